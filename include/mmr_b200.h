@@ -1,0 +1,168 @@
+/* mmr_b200.h -- C ABI of the B200-native route-fusion + capsule-routing hot path.
+ *
+ * This is the drop-in boundary for ONE path of AI-for-Health-Data/MultimodalRouting:
+ *   MULTModel.forward                     MIMIC-IV/MortModel/Paired_Cross_Attention/mult_model.py:116-193
+ *   TransformerEncoder(.Layer).forward    .../transformer.py:56-115,149-216
+ *   MultiheadAttention.forward            MIMIC-IV/PhenoModel/Paired_Cross_Attention/multihead_attention.py:48-148
+ *   RoutePrimaryProjector.forward         .../routing_and_heads.py:111-121
+ *   forward_capsule_from_route_dict       .../routing_and_heads.py:271-369
+ *   CapsuleMortalityHead.forward          Mort .../routing_and_heads.py:194-268, Pheno :194-272
+ *   CapsuleFC.forward                     .../capsule_layers.py:75-117
+ * The reference has no FFI of its own (it is eager PyTorch); the Python nn.Modules in
+ * multimodalrouting_b200/ bind these entry points through ctypes + torch.library.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the library never allocates or frees device memory and keeps no global mutable state
+ *     (apart from a thread-local last-error string); the caller owns inputs, outputs, packed
+ *     weights, saved-for-backward and scratch buffers (sizes from mmr_fusion_sizes);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - every function returns 0 on success, non-zero otherwise (mmr_last_error_string()).
+ *   - fixed model geometry (reference hyper-parameters): d=256, heads=8,
+ *     head_dim=32, ffn=1024, 10 routes, pc_dim=32, mc_caps_dim=64.
+ */
+#ifndef MMR_B200_H
+#define MMR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMR_OK 0
+#define MMR_ERR_INVALID_ARG 1
+#define MMR_ERR_UNSUPPORTED 2
+#define MMR_ERR_CUDA 3
+
+#define MMR_DTYPE_F32 0   /* fp32 SIMT arithmetic everywhere (parity mode, 1e-4)          */
+#define MMR_DTYPE_BF16 1  /* bf16 operands, fp32 accumulate / residual / softmax / LayerNorm */
+
+#define MMR_GEMM_AUTO 0   /* tcgen05 for bf16, SIMT for fp32 */
+#define MMR_GEMM_SIMT 1   /* debug: CUDA-core GEMM for every dtype */
+#define MMR_GEMM_TC 2
+
+#define MMR_VARIANT_MORT 0   /* routing uses act = route_mask, d = sum_r R*pose           */
+#define MMR_VARIANT_PHENO 1  /* routing uses act = alpha,      d = sum_r R*alpha*pose     */
+
+#define MMR_D 256
+#define MMR_HEADS 8
+#define MMR_HEAD_DIM 32
+#define MMR_FFN 1024
+#define MMR_ROUTES 10
+#define MMR_PC_DIM 32
+#define MMR_MC_DIM 64
+#define MMR_MAX_LAYERS 8
+#define MMR_MAX_LABELS 32
+
+typedef struct mmr_fusion_dims {
+  int32_t B;             /* patients */
+  int32_t TL, TN, TI;    /* tokens per modality */
+  int32_t dL, dN, dI;    /* input feature dims; != 256 enables the Conv1d(k=1) projection */
+  int32_t layers;        /* cross-modal encoder depth (reference: 4) */
+  int32_t dtype;         /* MMR_DTYPE_* */
+  int32_t gemm_engine;   /* MMR_GEMM_* */
+} mmr_fusion_dims;
+
+/* Number of parameter tensors of MULTModel in state_dict order (mult_model.py:30-57):
+ * proj_{l,n,i}.weight, trans_{l,n,i}.layer_norm.{weight,bias}, then per cross encoder
+ * (l_with_n, l_with_i, n_with_l, n_with_i, i_with_l, i_with_n) per layer
+ * {in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias, fc1.weight, fc1.bias,
+ *  fc2.weight, fc2.bias, layer_norms.0.{weight,bias}, layer_norms.1.{weight,bias}} and the
+ * encoder's final layer_norm.{weight,bias}; then proj_pair_{ln,li,ni}.{weight,bias},
+ * final_lni.{weight,bias}.  All fp32, contiguous. */
+int mmr_fusion_num_params(const mmr_fusion_dims* dims);
+
+/* Buffer sizes in bytes.  `saved` carries forward->backward state. */
+int mmr_fusion_sizes(const mmr_fusion_dims* dims, size_t* packed_bytes, size_t* saved_bytes,
+                     size_t* scratch_fwd_bytes, size_t* scratch_bwd_bytes);
+
+/* Replaces MULTModel.forward (mult_model.py:116-193).
+ * host_params: host array of mmr_fusion_num_params() device pointers (order above).
+ * x_*: fp32 [B,T,d_*]; m*: fp32 [B,T] (1 keep / 0 pad) or NULL; pos_table: fp32 [maxT,256]
+ * int-truncated sinusoid rows for positions 1..maxT (position_embedding.py:68-117).
+ * routes_out: fp32 [10,B,256] in ROUTES order L,N,I,LN,NL,LI,IL,NI,IN,LNI. */
+int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_params,
+                         const float* x_l, const float* x_n, const float* x_i,
+                         const float* mL, const float* mN, const float* mI,
+                         const float* pos_table, void* packed, void* saved, void* scratch,
+                         float* routes_out, void* stream);
+
+/* Backward of the above.  d_routes: fp32 [10,B,256].  host_param_grads: host array of device
+ * pointers (same order; NULL entries skipped) to ZERO-INITIALISED fp32 gradient tensors; the
+ * gradients are accumulated into them.  dx_*: fp32 [B,T,d_*] outputs or NULL. */
+int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_params,
+                         const float* x_l, const float* x_n, const float* x_i,
+                         const float* mL, const float* mN, const float* mI,
+                         const void* packed, const void* saved, void* scratch,
+                         const float* d_routes, void* const* host_param_grads,
+                         float* dx_l, float* dx_n, float* dx_i, void* stream);
+
+typedef struct mmr_routing_dims {
+  int32_t B;               /* patients */
+  int32_t K;               /* labels: 2 (mortality) / 25 (phenotypes); <= MMR_MAX_LABELS */
+  int32_t variant;         /* MMR_VARIANT_* */
+  int32_t num_routing;     /* agreement iterations (reference: 3) */
+  int32_t detach_priors;   /* routing_and_heads.py:352 */
+  int32_t from_poses;      /* 0: run projector on route embeddings; 1: poses/acts given (head only) */
+  float act_temperature;   /* routing_and_heads.py:330-339 (only applied when route_mask != NULL) */
+  float prior_floor, prior_ceiling;   /* 0.02 / 0.98 (env_config.py:157-158) */
+  int64_t emb_route_stride;   /* elements between routes of one patient in route_embs */
+  int64_t emb_batch_stride;   /* elements between patients */
+} mmr_routing_dims;
+
+typedef struct mmr_routing_params {
+  const float* proj_w[MMR_ROUTES];   /* [33,256] each, ROUTES order */
+  const float* proj_b[MMR_ROUTES];   /* [33] */
+  const float* caps_w;               /* [10,32,K,64] */
+  const float* pose_to_mc;           /* [64,32] */
+  const float* embedding;            /* [K,64] */
+  const float* bias;                 /* [K] */
+} mmr_routing_params;
+
+typedef struct mmr_routing_grads {   /* zero-initialised fp32 accumulators; NULL entries skipped */
+  float* proj_w[MMR_ROUTES];
+  float* proj_b[MMR_ROUTES];
+  float* caps_w;
+  float* pose_to_mc;
+  float* embedding;
+  float* bias;
+} mmr_routing_grads;
+
+size_t mmr_routing_scratch_bytes(const mmr_routing_dims* dims);
+
+/* Replaces forward_capsule_from_route_dict / CapsuleMortalityHead.forward.
+ * route_embs: fp32, element (r,b,c) at r*emb_route_stride + b*emb_batch_stride + c.
+ * When from_poses=1: poses_in fp32 [B,10,32], acts_in fp32 [B,10] are used instead (no clamp /
+ * temperature, exactly CapsuleMortalityHead.forward); acts_override fp32 [B,10] or NULL.
+ * route_mask: fp32 [B,10] or NULL.  Outputs fp32: logits [B,K], alpha [B,10], R [B,10,K],
+ * poses_out [B,10,32] and acts_out [B,10] (projector outputs; may be NULL). */
+int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_params* params,
+                            const float* route_embs, const float* poses_in, const float* acts_in,
+                            const float* acts_override, const float* route_mask,
+                            float* logits, float* alpha, float* R, float* poses_out,
+                            float* acts_out, void* stream);
+
+/* Backward: d_logits [B,K], d_R [B,10,K] or NULL.  d_route_embs uses the same strides as
+ * route_embs; d_poses [B,10,32] / d_acts [B,10] are written when from_poses=1. */
+int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_params* params,
+                            const float* route_embs, const float* poses_in, const float* acts_in,
+                            const float* acts_override, const float* route_mask,
+                            const float* d_logits, const float* d_R, void* scratch,
+                            const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
+                            float* d_acts, void* stream);
+
+/* Unit-test hook for the GEMM engines: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) with bf16 (dtype 1)
+ * or fp32 (dtype 0) operands, fp32 output.  trans=1 computes C[M,N] = A[Kr,M]^T * B[Kr,N]
+ * (the weight-gradient form, reduction over rows). */
+int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const void* A,
+                   const void* B, const float* bias, float* C, void* stream);
+
+int mmr_version(void);
+const char* mmr_last_error_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMR_B200_H */

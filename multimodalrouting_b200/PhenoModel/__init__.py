@@ -1,0 +1,3 @@
+"""Drop-in modules for MIMIC-IV/PhenoModel/Paired_Cross_Attention (variant 'pheno')."""
+from .. import capsule_layers, env_config, mult_model, multihead_attention, position_embedding, transformer  # noqa: F401
+from . import routing_and_heads  # noqa: F401

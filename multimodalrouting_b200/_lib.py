@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/mmr_b200.h (no torch types cross it)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_fp = C.c_void_p   # device pointers travel as void*
+
+
+class FusionDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("TL", C.c_int32), ("TN", C.c_int32), ("TI", C.c_int32),
+                ("dL", C.c_int32), ("dN", C.c_int32), ("dI", C.c_int32), ("layers", C.c_int32),
+                ("dtype", C.c_int32), ("gemm_engine", C.c_int32)]
+
+
+class RoutingDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("variant", C.c_int32), ("num_routing", C.c_int32),
+                ("detach_priors", C.c_int32), ("from_poses", C.c_int32), ("act_temperature", C.c_float),
+                ("prior_floor", C.c_float), ("prior_ceiling", C.c_float),
+                ("emb_route_stride", C.c_int64), ("emb_batch_stride", C.c_int64)]
+
+
+class RoutingParams(C.Structure):
+    _fields_ = [("proj_w", c_fp * 10), ("proj_b", c_fp * 10), ("caps_w", c_fp), ("pose_to_mc", c_fp),
+                ("embedding", c_fp), ("bias", c_fp)]
+
+
+class RoutingGrads(C.Structure):
+    _fields_ = [("proj_w", c_fp * 10), ("proj_b", c_fp * 10), ("caps_w", c_fp), ("pose_to_mc", c_fp),
+                ("embedding", c_fp), ("bias", c_fp)]
+
+
+EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
+           "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_routing_scratch_bytes",
+           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm"]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Loads csrc/libmmr_b200.so.  There is no fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the sm_100a kernels first (python -m multimodalrouting_b200.build "
+            "or __graft_entry__.build()).  There is no CPU / PyTorch fallback for this path.")
+    lib = C.CDLL(path)
+    lib.mmr_version.restype = C.c_int
+    lib.mmr_last_error_string.restype = C.c_char_p
+    lib.mmr_fusion_num_params.argtypes = [C.POINTER(FusionDims)]
+    lib.mmr_fusion_num_params.restype = C.c_int
+    lib.mmr_fusion_sizes.argtypes = [C.POINTER(FusionDims)] + [C.POINTER(C.c_size_t)] * 4
+    lib.mmr_fusion_sizes.restype = C.c_int
+    lib.mmr_route_fusion_fwd.argtypes = [C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 12
+    lib.mmr_route_fusion_fwd.restype = C.c_int
+    lib.mmr_route_fusion_bwd.argtypes = ([C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 10 +
+                                         [C.POINTER(c_fp)] + [c_fp] * 4)
+    lib.mmr_route_fusion_bwd.restype = C.c_int
+    lib.mmr_routing_scratch_bytes.argtypes = [C.POINTER(RoutingDims)]
+    lib.mmr_routing_scratch_bytes.restype = C.c_size_t
+    lib.mmr_capsule_routing_fwd.argtypes = [C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 11
+    lib.mmr_capsule_routing_fwd.restype = C.c_int
+    lib.mmr_capsule_routing_bwd.argtypes = ([C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 8 +
+                                            [C.POINTER(RoutingGrads)] + [c_fp] * 4)
+    lib.mmr_capsule_routing_bwd.restype = C.c_int
+    lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
+    lib.mmr_debug_gemm.restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mmr_last_error_string().decode("utf-8", "replace")
+        if rc in (1, 2):
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: {msg}")

@@ -1,0 +1,846 @@
+// C ABI (include/mmr_b200.h) and host orchestration of the sm_100a route-fusion + routing path.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string>
+
+#include "attention.cuh"
+#include "epilogue.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "mmr_common.cuh"
+#include "plan.cuh"
+#include "routing.cuh"
+#include "rows.cuh"
+
+using namespace mmr;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(MMR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+#define LAUNCH_OK(what)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(MMR_ERR_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// GEMM dispatch helpers
+template <class CT, int OP>
+static int run_gemm(const Plan& P, const GemmProblem& g, const EpiParams& e, int a_rows, int b_rows,
+                    cudaStream_t st, const char* what) {
+  if (P.tc) {
+    if (g.K % tc::BK != 0 || g.N % 256 != 0) return fail(MMR_ERR_UNSUPPORTED, std::string(what) + ": tcgen05 tile constraint");
+    cudaError_t err = tc::launch_gemm_tc<OP>(g, e, a_rows, b_rows, st);
+    if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 gemm ") + what + ": " + cudaGetErrorString(err));
+  } else {
+    launch_gemm_simt<CT, CT, OP, CT>(g, e, st);
+    LAUNCH_OK(what);
+  }
+  return MMR_OK;
+}
+
+template <class CT>
+static int run_wgrad(const Plan& P, const WgradProblem& w, int y_rows, int x_rows, cudaStream_t st, const char* what) {
+  if (P.tc) {
+    cudaError_t err = tc::launch_wgrad_tc(w, y_rows, x_rows, st);
+    if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 wgrad ") + what + ": " + cudaGetErrorString(err));
+  } else {
+    launch_wgrad_simt<CT, CT>(w, st);
+    LAUNCH_OK(what);
+  }
+  return MMR_OK;
+}
+
+static Segs single_seg(int rows, int T) {
+  Segs s;
+  memset(&s, 0, sizeof(s));
+  s.n = 1; s.row0[0] = 0; s.row0[1] = rows; s.rows[0] = rows; s.T[0] = T;
+  return s;
+}
+
+// plain fp32 GEMM  C[M,N] (ldc) = A[M,K] (lda) * W^T (+bias), W [N,K] (TRANSB=false) or [K,N] (true)
+template <bool TRANSB>
+static int fp32_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                       int M, int N, int K, cudaStream_t st, const char* what) {
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.segs = single_seg(M, 1);
+  g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = W; g.ldb = ldw;
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.bias = bias; e.out = C; e.ldo = ldc;
+  launch_gemm_simt<float, float, EPI_BIAS_F32, float, TRANSB>(g, e, st);
+  LAUNCH_OK(what);
+  return MMR_OK;
+}
+
+static int fp32_wgrad(const float* dY, int ldy, const float* X, int ldx, float* out, int ldo, int rows, int M, int N,
+                      cudaStream_t st, const char* what) {
+  if (out == nullptr) return MMR_OK;
+  WgradProblem w;
+  memset(&w, 0, sizeof(w));
+  w.segs = single_seg(rows, 1);
+  w.dY = dY; w.ldy = ldy; w.X = X; w.ldx = ldx; w.M = M; w.N = N; w.out[0] = out; w.ldo = ldo;
+  launch_wgrad_simt<float, float>(w, st);
+  LAUNCH_OK(what);
+  return MMR_OK;
+}
+
+template <class T>
+static int run_colsum(const Segs& segs, const void* src, int ld, int col0, int ncols, float* const* out, float scale,
+                      cudaStream_t st, const char* what) {
+  ColsumArgs c;
+  memset(&c, 0, sizeof(c));
+  c.segs = segs; c.src = src; c.ld = ld; c.col0 = col0; c.ncols = ncols; c.scale = scale;
+  bool any = false;
+  for (int i = 0; i < segs.n; ++i) { c.out[i] = out[i]; any = any || out[i] != nullptr; }
+  if (!any) return MMR_OK;
+  const int total = segs.row0[segs.n];
+  dim3 grid((ncols + 255) / 256, (total + 127) / 128);
+  colsum_kernel<T><<<grid, 256, 0, st>>>(c);
+  LAUNCH_OK(what);
+  return MMR_OK;
+}
+
+static bool has_pad(const Segs& s) {
+  for (int i = 0; i < s.n; ++i)
+    if (s.row0[i + 1] - s.row0[i] != s.rows[i]) return true;
+  return false;
+}
+static int zero_pad(const Segs& s, void* buf, size_t ld_bytes, cudaStream_t st) {
+  if (!has_pad(s)) return MMR_OK;
+  dim3 grid(127, s.n);
+  zero_pad_rows_kernel<<<grid, 128, 0, st>>>(s, reinterpret_cast<uint8_t*>(buf), ld_bytes);
+  LAUNCH_OK("zero_pad_rows");
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <class CT>
+static int pack_weights(const Plan& P, const void* const* prm, uint8_t* packed, cudaStream_t st) {
+  const ParamIndex ix{P.L};
+  const int L = P.L;
+  const float scaling = 1.0f / sqrtf((float)HD);
+  auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
+  CT* wq = reinterpret_cast<CT*>(packed + P.o_wq);   CT* wqT = reinterpret_cast<CT*>(packed + P.o_wqT);
+  CT* wo = reinterpret_cast<CT*>(packed + P.o_wo);   CT* woT = reinterpret_cast<CT*>(packed + P.o_woT);
+  CT* w1 = reinterpret_cast<CT*>(packed + P.o_w1);   CT* w1T = reinterpret_cast<CT*>(packed + P.o_w1T);
+  CT* w2 = reinterpret_cast<CT*>(packed + P.o_w2);   CT* w2T = reinterpret_cast<CT*>(packed + P.o_w2T);
+  CT* wkv = reinterpret_cast<CT*>(packed + P.o_wkv); CT* wkvT = reinterpret_cast<CT*>(packed + P.o_wkvT);
+  float* bq = reinterpret_cast<float*>(packed + P.o_bq);  float* bo = reinterpret_cast<float*>(packed + P.o_bo);
+  float* b1 = reinterpret_cast<float*>(packed + P.o_b1);  float* b2 = reinterpret_cast<float*>(packed + P.o_b2);
+  float* bkv = reinterpret_cast<float*>(packed + P.o_bkv);
+  for (int d = 0; d < NDIR; ++d) {
+    for (int l0 = 0; l0 < L; l0 += 4) {
+      PackJobs pj; memset(&pj, 0, sizeof(pj));
+      BiasJobs bj; memset(&bj, 0, sizeof(bj));
+      for (int l = l0; l < L && l < l0 + 4; ++l) {
+        const size_t ld_ = (size_t)l * 6 + d;
+        const float* win = f(ix.layer(d, l, 0));
+        const float* bin = f(ix.layer(d, l, 1));
+        const float* g0 = f(ix.layer(d, l, 8));
+        const float* be0 = f(ix.layer(d, l, 9));
+        PackJob* j = &pj.j[pj.n++];
+        *j = PackJob{win, D, D, D, nullptr, scaling, wq + ld_ * D * D, D, wqT + ld_ * D * D, D};
+        j = &pj.j[pj.n++];
+        *j = PackJob{win + (size_t)D * D, 2 * D, D, D, g0, 1.0f, wkv + ((size_t)d * L + l) * 2 * D * D, D,
+                     wkvT + (size_t)d * D * (L * 2 * D) + (size_t)l * 2 * D, L * 2 * D};
+        j = &pj.j[pj.n++];
+        *j = PackJob{f(ix.layer(d, l, 2)), D, D, D, nullptr, 1.0f, wo + ld_ * D * D, D, woT + ld_ * D * D, D};
+        j = &pj.j[pj.n++];
+        *j = PackJob{f(ix.layer(d, l, 4)), FF, D, D, nullptr, 1.0f, w1 + ld_ * FF * D, D, w1T + ld_ * D * FF, FF};
+        j = &pj.j[pj.n++];
+        *j = PackJob{f(ix.layer(d, l, 6)), D, FF, FF, nullptr, 1.0f, w2 + ld_ * D * FF, FF, w2T + ld_ * FF * D, D};
+        BiasJob* b = &bj.j[bj.n++];
+        *b = BiasJob{nullptr, 0, bin, nullptr, scaling, bq + ld_ * D, D};
+        b = &bj.j[bj.n++];
+        *b = BiasJob{win + (size_t)D * D, D, bin + D, be0, 1.0f, bkv + ((size_t)d * L + l) * 2 * D, 2 * D};
+        b = &bj.j[bj.n++];
+        *b = BiasJob{nullptr, 0, f(ix.layer(d, l, 3)), nullptr, 1.0f, bo + ld_ * D, D};
+        b = &bj.j[bj.n++];
+        *b = BiasJob{nullptr, 0, f(ix.layer(d, l, 5)), nullptr, 1.0f, b1 + ld_ * FF, FF};
+        b = &bj.j[bj.n++];
+        *b = BiasJob{nullptr, 0, f(ix.layer(d, l, 7)), nullptr, 1.0f, b2 + ld_ * D, D};
+      }
+      pack_kernel<CT><<<dim3(FF / 32, FF / 32, pj.n), 256, 0, st>>>(pj);
+      LAUNCH_OK("pack_kernel");
+      bias_fold_kernel<<<dim3(FF / 8, bj.n), 256, 0, st>>>(bj);
+      LAUNCH_OK("bias_fold_kernel");
+    }
+  }
+  return MMR_OK;
+}
+
+template <class CT>
+static int fusion_fwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
+                      const float* pos, uint8_t* packed, uint8_t* saved, uint8_t* scratch, float* routes,
+                      cudaStream_t st) {
+  const ParamIndex ix{P.L};
+  const int L = P.L, B = P.B;
+  auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
+  int rc = pack_weights<CT>(P, prm, packed, st);
+  if (rc) return rc;
+
+  float* fp = reinterpret_cast<float*>(scratch + P.f_p);
+  float* fy = reinterpret_cast<float*>(scratch + P.f_y);
+  float* fu = reinterpret_cast<float*>(scratch + P.f_u);
+  CT* xh = reinterpret_cast<CT*>(saved + P.s_xh);
+  float* maskq = reinterpret_cast<float*>(saved + P.s_maskq);
+  auto xin = [&](int l) { return reinterpret_cast<float*>(saved + P.s_xin + (size_t)l * P.l_xin); };
+  auto x1 = [&](int l) { return reinterpret_cast<float*>(saved + P.s_x1 + (size_t)l * P.l_xin); };
+  auto stat0 = [&](int l) { return reinterpret_cast<float*>(saved + P.s_stat0 + (size_t)l * P.l_stat); };
+  auto stat1 = [&](int l) { return reinterpret_cast<float*>(saved + P.s_stat1 + (size_t)l * P.l_stat); };
+  auto h0 = [&](int l) { return reinterpret_cast<CT*>(saved + P.s_h0 + (size_t)l * P.l_ct256); };
+  auto h1 = [&](int l) { return reinterpret_cast<CT*>(saved + P.s_h1 + (size_t)l * P.l_ct256); };
+  auto qb = [&](int l) { return reinterpret_cast<CT*>(saved + P.s_qb + (size_t)l * P.l_ct256); };
+  auto ob = [&](int l) { return reinterpret_cast<CT*>(saved + P.s_o + (size_t)l * P.l_ct256); };
+  auto ml = [&](int l) { return reinterpret_cast<float*>(saved + P.s_ml + (size_t)l * P.l_ml); };
+  auto ff = [&](int l) { return reinterpret_cast<CT*>(saved + P.s_f + (size_t)l * P.l_f); };
+  CT* kv = reinterpret_cast<CT*>(saved + P.s_kv);
+  float* ecat = reinterpret_cast<float*>(saved + P.s_epair);
+  float* zcat = reinterpret_cast<float*>(saved + P.s_routes);
+  float* cnt = reinterpret_cast<float*>(saved + P.s_cnt);
+  const int ldkv = L * 2 * D;
+
+  // 1. optional Conv1d(k=1) projections (mult_model.py:134-136)
+  const float* src[3];
+  for (int m = 0; m < NMOD; ++m) {
+    if (P.din[m] == D) { src[m] = x[m]; continue; }
+    float* dst = fp + (size_t)P.mod.row0[m] * D;
+    rc = fp32_linear<false>(x[m], P.din[m], f(ix.proj(m)), P.din[m], nullptr, dst, D, P.mod.rows[m], D, P.din[m], st, "proj");
+    if (rc) return rc;
+    src[m] = dst;
+  }
+  // 2. embedding, unimodal encoders, normalised K/V stream, layer-0 query streams
+  {
+    EmbedArgs a; memset(&a, 0, sizeof(a));
+    a.mod = P.mod; a.q = P.q; a.pos = pos;
+    for (int m = 0; m < NMOD; ++m) {
+      a.src[m] = src[m]; a.mask[m] = mask[m];
+      a.uni_g[m] = f(ix.uni_ln(m, 0)); a.uni_b[m] = f(ix.uni_ln(m, 1));
+    }
+    for (int d = 0; d < NDIR; ++d) { a.ln0_g[d] = f(ix.layer(d, 0, 8)); a.ln0_b[d] = f(ix.layer(d, 0, 9)); }
+    a.xh = xh; a.rstd_e = reinterpret_cast<float*>(saved + P.s_rstd_e); a.u = fu;
+    a.xin0 = xin(0); a.h0 = h0(0); a.stat0 = stat0(0); a.maskq = maskq;
+    embed_fwd_kernel<CT><<<P.MM / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+    LAUNCH_OK("embed_fwd");
+  }
+  // 3. K/V projections of every layer at once (LN0 affine folded into the weights)
+  {
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = P.kv;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.mod.row0[dir_kmod(d)]; g.b_row0[d] = d * ldkv; }
+    g.N = ldkv; g.K = D; g.A = xh; g.lda = D; g.B = packed + P.o_wkv; g.ldb = D;
+    EpiParams e; memset(&e, 0, sizeof(e));
+    e.bias = reinterpret_cast<const float*>(packed + P.o_bkv); e.out = kv; e.ldo = ldkv;
+    rc = run_gemm<CT, EPI_BIAS>(P, g, e, P.MM, NDIR * ldkv, st, "kv_proj");
+    if (rc) return rc;
+  }
+  const float* kmask[NDIR];
+  for (int d = 0; d < NDIR; ++d) kmask[d] = mask[dir_kmod(d)];
+  int maxTq = 0;
+  for (int d = 0; d < NDIR; ++d) maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d];
+  CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+
+  auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = P.q;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
+    g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = Bw; g.ldb = ldb;
+    return g;
+  };
+
+  for (int l = 0; l < L; ++l) {
+    {  // Q projection (scaled)
+      GemmProblem g = q_problem(h0(l), D, packed + P.o_wq, D, D, D, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.bias = reinterpret_cast<const float*>(packed + P.o_bq); e.out = qb(l); e.ldo = D;
+      rc = run_gemm<CT, EPI_BIAS>(P, g, e, P.MQ, L * 6 * D, st, "q_proj");
+      if (rc) return rc;
+    }
+    {  // attention
+      AttnArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.kv = P.kv;
+      for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
+      a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
+      dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+      attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      LAUNCH_OK("attn_fwd");
+      rc = zero_pad(P.q, ob(l), (size_t)D * sizeof(CT), st);
+      if (rc) return rc;
+    }
+    {  // out projection + residual + mask
+      GemmProblem g = q_problem(ob(l), D, packed + P.o_wo, D, D, D, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.bias = reinterpret_cast<const float*>(packed + P.o_bo); e.resid = xin(l); e.ldr = D; e.rowmask = maskq;
+      e.out = x1(l); e.ldo = D;
+      rc = run_gemm<CT, EPI_BIAS_RESID_MASK>(P, g, e, P.MQ, L * 6 * D, st, "out_proj");
+      if (rc) return rc;
+    }
+    {  // LN1
+      LnFwdArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.x = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
+      for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l, 10)); a.beta[d] = f(ix.layer(d, l, 11)); }
+      ln_rows_fwd_kernel<CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      LAUNCH_OK("ln1_fwd");
+    }
+    {  // fc1 + relu
+      GemmProblem g = q_problem(h1(l), D, packed + P.o_w1, D, FF, FF, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.bias = reinterpret_cast<const float*>(packed + P.o_b1); e.out = ff(l); e.ldo = FF;
+      rc = run_gemm<CT, EPI_BIAS_RELU>(P, g, e, P.MQ, L * 6 * FF, st, "fc1");
+      if (rc) return rc;
+    }
+    {  // fc2 + residual + mask
+      GemmProblem g = q_problem(ff(l), FF, packed + P.o_w2, FF, D, D, FF, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.bias = reinterpret_cast<const float*>(packed + P.o_b2); e.resid = x1(l); e.ldr = D; e.rowmask = maskq;
+      e.out = xin(l + 1); e.ldo = D;
+      rc = run_gemm<CT, EPI_BIAS_RESID_MASK>(P, g, e, P.MQ, L * 6 * D, st, "fc2");
+      if (rc) return rc;
+    }
+    if (l + 1 < L) {  // LN0 of the next layer
+      LnFwdArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.x = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
+      for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l + 1, 8)); a.beta[d] = f(ix.layer(d, l + 1, 9)); }
+      ln_rows_fwd_kernel<CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      LAUNCH_OK("ln0_fwd");
+    }
+  }
+  {  // encoder-final LayerNorm (transformer.py:108-113)
+    LnFwdArgs a; memset(&a, 0, sizeof(a));
+    a.q = P.q; a.x = xin(L); a.maskq = maskq; a.out = fy; a.stat = reinterpret_cast<float*>(saved + P.s_statf);
+    for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.enc_ln(d, 0)); a.beta[d] = f(ix.enc_ln(d, 1)); }
+    ln_rows_fwd_kernel<float><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+    LAUNCH_OK("lnf_fwd");
+  }
+  {  // masked-mean pooling of the 9 uni/bi-modal routes
+    PoolArgs a; memset(&a, 0, sizeof(a));
+    a.mod = P.mod; a.q = P.q; a.u = fu; a.y = fy; a.routes = routes; a.zcat = zcat; a.cnt = cnt; a.B = B;
+    for (int m = 0; m < NMOD; ++m) a.mask[m] = mask[m];
+    pool_fwd_kernel<<<dim3(B, 9), 256, 0, st>>>(a);
+    LAUNCH_OK("pool_fwd");
+  }
+  // pair projections and the trimodal composition (mult_model.py:174-178)
+  for (int p = 0; p < 3; ++p) {
+    rc = fp32_linear<false>(zcat + (size_t)p * B * 512, 512, f(ix.pair(p, 0)), 512, f(ix.pair(p, 1)), ecat + p * D, 3 * D,
+                            B, D, 512, st, "pair_proj");
+    if (rc) return rc;
+  }
+  rc = fp32_linear<false>(ecat, 3 * D, f(ix.final_lni(0)), 3 * D, f(ix.final_lni(1)), routes + (size_t)9 * B * D, D, B, D,
+                          3 * D, st, "final_lni");
+  return rc;
+}
+
+template <class CT>
+static int fusion_bwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
+                      const uint8_t* packed, const uint8_t* saved, uint8_t* scratch, const float* d_routes,
+                      void* const* grads, float* const dx[3], cudaStream_t st) {
+  const ParamIndex ix{P.L};
+  const int L = P.L, B = P.B;
+  auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
+  auto gr = [&](int i) { return reinterpret_cast<float*>(grads[i]); };
+  int rc;
+  CUDA_OK(cudaMemsetAsync(scratch + P.b_zero_begin, 0, P.b_zero_end - P.b_zero_begin, st));
+
+  const CT* xh = reinterpret_cast<const CT*>(saved + P.s_xh);
+  const float* maskq = reinterpret_cast<const float*>(saved + P.s_maskq);
+  auto xin = [&](int l) { return reinterpret_cast<const float*>(saved + P.s_xin + (size_t)l * P.l_xin); };
+  auto x1 = [&](int l) { return reinterpret_cast<const float*>(saved + P.s_x1 + (size_t)l * P.l_xin); };
+  auto stat0 = [&](int l) { return reinterpret_cast<const float*>(saved + P.s_stat0 + (size_t)l * P.l_stat); };
+  auto stat1 = [&](int l) { return reinterpret_cast<const float*>(saved + P.s_stat1 + (size_t)l * P.l_stat); };
+  auto h0 = [&](int l) { return reinterpret_cast<const CT*>(saved + P.s_h0 + (size_t)l * P.l_ct256); };
+  auto h1 = [&](int l) { return reinterpret_cast<const CT*>(saved + P.s_h1 + (size_t)l * P.l_ct256); };
+  auto qb = [&](int l) { return reinterpret_cast<const CT*>(saved + P.s_qb + (size_t)l * P.l_ct256); };
+  auto ob = [&](int l) { return reinterpret_cast<const CT*>(saved + P.s_o + (size_t)l * P.l_ct256); };
+  auto ml = [&](int l) { return reinterpret_cast<const float*>(saved + P.s_ml + (size_t)l * P.l_ml); };
+  auto ff = [&](int l) { return reinterpret_cast<const CT*>(saved + P.s_f + (size_t)l * P.l_f); };
+  const CT* kv = reinterpret_cast<const CT*>(saved + P.s_kv);
+  const float* ecat = reinterpret_cast<const float*>(saved + P.s_epair);
+  const float* zcat = reinterpret_cast<const float*>(saved + P.s_routes);
+  const float* cnt = reinterpret_cast<const float*>(saved + P.s_cnt);
+  const int ldkv = L * 2 * D;
+
+  float* g_a = reinterpret_cast<float*>(scratch + P.b_g);
+  float* g_b = reinterpret_cast<float*>(scratch + P.b_g1);
+  CT* gc = reinterpret_cast<CT*>(scratch + P.b_gc);
+  CT* dF = reinterpret_cast<CT*>(scratch + P.b_df);
+  CT* dH = reinterpret_cast<CT*>(scratch + P.b_dh);
+  CT* dO = reinterpret_cast<CT*>(scratch + P.b_do);
+  CT* dQ = reinterpret_cast<CT*>(scratch + P.b_dq);
+  CT* dKV = reinterpret_cast<CT*>(scratch + P.b_dkv);
+  float* dxh = reinterpret_cast<float*>(scratch + P.b_dxh);
+  float* dp = reinterpret_cast<float*>(scratch + P.b_dp);
+  float* dwq = reinterpret_cast<float*>(scratch + P.b_dwq);
+  float* dwkv = reinterpret_cast<float*>(scratch + P.b_dwkv);
+  float* dbq = reinterpret_cast<float*>(scratch + P.b_dbq);
+  float* dbkv = reinterpret_cast<float*>(scratch + P.b_dbkv);
+  float* decat = reinterpret_cast<float*>(scratch + P.b_depair);   // [B,768]
+  float* dzcat = reinterpret_cast<float*>(scratch + P.b_dzcat);    // [3,B,512]
+  float* dvec = reinterpret_cast<float*>(scratch + P.b_dvec);      // [MQ,8]
+
+  // ---- trimodal + pair projections (mult_model.py:174-178) ----
+  const float* dz_lni = d_routes + (size_t)9 * B * D;
+  rc = fp32_linear<true>(dz_lni, D, f(ix.final_lni(0)), 3 * D, nullptr, decat, 3 * D, B, 3 * D, D, st, "d_final_lni");
+  if (rc) return rc;
+  rc = fp32_wgrad(dz_lni, D, ecat, 3 * D, gr(ix.final_lni(0)), 3 * D, B, D, 3 * D, st, "w_final_lni");
+  if (rc) return rc;
+  {
+    Segs sb = single_seg(B, 1);
+    float* o1[6] = {gr(ix.final_lni(1)), nullptr, nullptr, nullptr, nullptr, nullptr};
+    rc = run_colsum<float>(sb, dz_lni, D, 0, D, o1, 1.0f, st, "b_final_lni");
+    if (rc) return rc;
+    for (int p = 0; p < 3; ++p) {
+      rc = fp32_linear<true>(decat + p * D, 3 * D, f(ix.pair(p, 0)), 512, nullptr, dzcat + (size_t)p * B * 512, 512, B, 512, D,
+                             st, "d_pair");
+      if (rc) return rc;
+      rc = fp32_wgrad(decat + p * D, 3 * D, zcat + (size_t)p * B * 512, 512, gr(ix.pair(p, 0)), 512, B, D, 512, st, "w_pair");
+      if (rc) return rc;
+      float* o2[6] = {gr(ix.pair(p, 1)), nullptr, nullptr, nullptr, nullptr, nullptr};
+      rc = run_colsum<float>(sb, decat, 3 * D, p * D, D, o2, 1.0f, st, "b_pair");
+      if (rc) return rc;
+    }
+  }
+  // ---- pooled gradient through the encoder-final LayerNorm ----
+  {
+    LnBwdArgs a; memset(&a, 0, sizeof(a));
+    a.q = P.q; a.x = xin(L); a.stat = reinterpret_cast<const float*>(saved + P.s_statf); a.maskq = maskq;
+    a.ld2 = 512; a.g_in = nullptr; a.g_out = g_a; a.gc_out = gc;
+    for (int d = 0; d < NDIR; ++d) {
+      a.dz[d] = d_routes + (size_t)route_of_dir(d) * B * D;
+      a.dz2[d] = dzcat + (size_t)pair_of_dir(d) * B * 512 + half_of_dir(d) * D;
+      a.cnt[d] = cnt + (size_t)dir_qmod(d) * B;
+      a.gamma[d] = f(ix.enc_ln(d, 0));
+      a.dgamma[d] = gr(ix.enc_ln(d, 0)); a.dbeta[d] = gr(ix.enc_ln(d, 1));
+      a.dbias[d] = gr(ix.layer(d, L - 1, 7));
+    }
+    ln_rows_bwd_kernel<CT, true><<<P.MQ / 64, 256, 0, st>>>(a);
+    LAUNCH_OK("lnf_bwd");
+  }
+  const float* kmask[NDIR];
+  for (int d = 0; d < NDIR; ++d) kmask[d] = mask[dir_kmod(d)];
+  int maxTq = 0, maxTk = 0;
+  for (int d = 0; d < NDIR; ++d) { maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d]; maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d]; }
+  CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+
+  auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = P.q;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
+    g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = Bw; g.ldb = ldb;
+    return g;
+  };
+  auto q_wgrad = [&](const void* dY, int ldy, int M, const void* X, int ldx, int N) {
+    WgradProblem w; memset(&w, 0, sizeof(w));
+    w.segs = P.q;
+    for (int d = 0; d < NDIR; ++d) w.x_row0[d] = P.q.row0[d];
+    w.dY = dY; w.ldy = ldy; w.X = X; w.ldx = ldx; w.M = M; w.N = N; w.ldo = N;
+    return w;
+  };
+
+  float* g_cur = g_a;   // gradient wrt the layer output (masked)
+  float* g_oth = g_b;
+  for (int l = L - 1; l >= 0; --l) {
+    {  // dF = (G W2) .* relu'   (fc2 data gradient)
+      GemmProblem g = q_problem(gc, D, packed + P.o_w2T, D, FF, FF, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.aux = ff(l); e.ldaux = FF; e.out = dF; e.ldo = FF;
+      rc = run_gemm<CT, EPI_RELUMASK>(P, g, e, P.MQ, L * 6 * FF, st, "d_fc2");
+      if (rc) return rc;
+    }
+    {  // dW2
+      WgradProblem w = q_wgrad(gc, D, D, ff(l), FF, FF);
+      for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 6));
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_fc2");
+      if (rc) return rc;
+    }
+    {  // dH1 = dF W1, masked
+      GemmProblem g = q_problem(dF, FF, packed + P.o_w1T, FF, D, D, FF, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.rowmask = maskq; e.out = dH; e.ldo = D;
+      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_fc1");
+      if (rc) return rc;
+    }
+    {  // dW1, db1
+      WgradProblem w = q_wgrad(dF, FF, FF, h1(l), D, D);
+      float* ob1[6];
+      for (int d = 0; d < NDIR; ++d) { w.out[d] = gr(ix.layer(d, l, 4)); ob1[d] = gr(ix.layer(d, l, 5)); }
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_fc1");
+      if (rc) return rc;
+      rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, st, "b_fc1");
+      if (rc) return rc;
+    }
+    {  // LN1 backward: g_oth = (g_cur + dLN1) * mask ; d out_proj.bias = colsum(g_oth)
+      LnBwdArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.dh = dH; a.x = x1(l); a.stat = stat1(l); a.maskq = maskq; a.g_in = g_cur; a.g_out = g_oth; a.gc_out = gc;
+      for (int d = 0; d < NDIR; ++d) {
+        a.gamma[d] = f(ix.layer(d, l, 10));
+        a.dgamma[d] = gr(ix.layer(d, l, 10)); a.dbeta[d] = gr(ix.layer(d, l, 11));
+        a.dbias[d] = gr(ix.layer(d, l, 3));
+      }
+      ln_rows_bwd_kernel<CT, false><<<P.MQ / 64, 256, 0, st>>>(a);
+      LAUNCH_OK("ln1_bwd");
+    }
+    {  // dO = G1 Wo
+      GemmProblem g = q_problem(gc, D, packed + P.o_woT, D, D, D, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.out = dO; e.ldo = D;
+      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_out_proj");
+      if (rc) return rc;
+    }
+    {  // dWo
+      WgradProblem w = q_wgrad(gc, D, D, ob(l), D, D);
+      for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 2));
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_out_proj");
+      if (rc) return rc;
+    }
+    {  // attention backward
+      AttnArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.kv = P.kv;
+      for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
+      a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = const_cast<CT*>(ob(l));
+      a.ml = const_cast<float*>(ml(l)); a.d_o = dO; a.dq = dQ; a.dkv = dKV; a.dvec = dvec;
+      dim3 g1((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+      attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      LAUNCH_OK("attn_bwd_dq");
+      dim3 g2((H * maxTk + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+      attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      LAUNCH_OK("attn_bwd_dkv");
+      rc = zero_pad(P.q, dQ, (size_t)D * sizeof(CT), st);
+      if (rc) return rc;
+    }
+    {  // dH0 = dQ Wq', masked
+      GemmProblem g = q_problem(dQ, D, packed + P.o_wqT, D, D, D, D, l);
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.rowmask = maskq; e.out = dH; e.ldo = D;
+      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_q_proj");
+      if (rc) return rc;
+    }
+    {  // dWq', dbq'
+      WgradProblem w = q_wgrad(dQ, D, D, h0(l), D, D);
+      float* obq[6];
+      for (int d = 0; d < NDIR; ++d) { w.out[d] = dwq + ((size_t)l * 6 + d) * D * D; obq[d] = dbq + ((size_t)l * 6 + d) * D; }
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_q_proj");
+      if (rc) return rc;
+      rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, st, "b_q_proj");
+      if (rc) return rc;
+    }
+    {  // LN0 backward: g_cur = (g_oth + dLN0) * mask ; d fc2.bias of the previous layer = colsum(g_cur)
+      LnBwdArgs a; memset(&a, 0, sizeof(a));
+      a.q = P.q; a.dh = dH; a.x = xin(l); a.stat = stat0(l); a.maskq = maskq; a.g_in = g_oth; a.g_out = g_cur; a.gc_out = gc;
+      for (int d = 0; d < NDIR; ++d) {
+        a.gamma[d] = f(ix.layer(d, l, 8));
+        a.dgamma[d] = gr(ix.layer(d, l, 8)); a.dbeta[d] = gr(ix.layer(d, l, 9));
+        a.dbias[d] = l > 0 ? gr(ix.layer(d, l - 1, 7)) : nullptr;
+      }
+      ln_rows_bwd_kernel<CT, false><<<P.MQ / 64, 256, 0, st>>>(a);
+      LAUNCH_OK("ln0_bwd");
+    }
+  }
+  // ---- K/V stream ----
+  rc = zero_pad(P.kv, dKV, (size_t)ldkv * sizeof(CT), st);
+  if (rc) return rc;
+  {
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = P.kv;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.kv.row0[d]; g.b_row0[d] = d * D; }
+    g.N = D; g.K = ldkv; g.A = dKV; g.lda = ldkv; g.B = packed + P.o_wkvT; g.ldb = ldkv;
+    EpiParams e; memset(&e, 0, sizeof(e));
+    e.out = dxh; e.ldo = D;
+    rc = run_gemm<CT, EPI_STORE_F32>(P, g, e, P.MK, NDIR * D, st, "d_kv_proj");
+    if (rc) return rc;
+    WgradProblem w; memset(&w, 0, sizeof(w));
+    w.segs = P.kv;
+    float* obkv[6];
+    for (int d = 0; d < NDIR; ++d) {
+      w.x_row0[d] = P.mod.row0[dir_kmod(d)];
+      w.out[d] = dwkv + (size_t)d * ldkv * D;
+      obkv[d] = dbkv + (size_t)d * ldkv;
+    }
+    w.dY = dKV; w.ldy = ldkv; w.X = xh; w.ldx = D; w.M = ldkv; w.N = D; w.ldo = D;
+    rc = run_wgrad<CT>(P, w, P.MK, P.MM, st, "w_kv_proj");
+    if (rc) return rc;
+    rc = run_colsum<CT>(P.kv, dKV, ldkv, 0, ldkv, obkv, 1.0f, st, "b_kv_proj");
+    if (rc) return rc;
+  }
+  // ---- unfold packed-weight gradients into in_proj_{weight,bias} and LN0 ----
+  {
+    UnfoldJobs uj; memset(&uj, 0, sizeof(uj));
+    uj.scaling = 1.0f / sqrtf((float)HD);
+    for (int d = 0; d < NDIR; ++d)
+      for (int l = 0; l < L; ++l) {
+        UnfoldJob& j = uj.j[uj.n++];
+        j.dwq = dwq + ((size_t)l * 6 + d) * D * D; j.dbq = dbq + ((size_t)l * 6 + d) * D;
+        j.dwkv = dwkv + ((size_t)d * L + l) * 2 * D * D; j.dbkv = dbkv + ((size_t)d * L + l) * 2 * D;
+        j.w_in = f(ix.layer(d, l, 0)); j.gamma0 = f(ix.layer(d, l, 8));
+        j.g_w_in = gr(ix.layer(d, l, 0)); j.g_b_in = gr(ix.layer(d, l, 1));
+        j.g_gamma0 = gr(ix.layer(d, l, 8)); j.g_beta0 = gr(ix.layer(d, l, 9));
+        if (uj.n == 24 || (d == NDIR - 1 && l == L - 1)) {
+          unfold_kernel<<<uj.n, 256, 0, st>>>(uj);
+          LAUNCH_OK("unfold");
+          uj.n = 0;
+        }
+      }
+  }
+  // ---- embedding backward ----
+  {
+    EmbedBwdArgs a; memset(&a, 0, sizeof(a));
+    a.mod = P.mod; a.q = P.q; a.kv = P.kv; a.xh = xh; a.rstd_e = reinterpret_cast<const float*>(saved + P.s_rstd_e);
+    a.g0 = g_cur; a.dxh = dxh; a.cnt = cnt; a.B = B;
+    for (int m = 0; m < NMOD; ++m) {
+      a.mask[m] = mask[m];
+      a.dz_uni[m] = d_routes + (size_t)m * B * D;
+      a.uni_g[m] = f(ix.uni_ln(m, 0));
+      a.d_uni_g[m] = gr(ix.uni_ln(m, 0)); a.d_uni_b[m] = gr(ix.uni_ln(m, 1));
+      a.dsrc[m] = (P.din[m] == D) ? dx[m] : dp + (size_t)P.mod.row0[m] * D;
+    }
+    embed_bwd_kernel<CT><<<P.MM / 64, 256, 0, st>>>(a);
+    LAUNCH_OK("embed_bwd");
+  }
+  for (int m = 0; m < NMOD; ++m) {
+    if (P.din[m] == D) continue;
+    const float* dpm = dp + (size_t)P.mod.row0[m] * D;
+    if (dx[m]) {
+      rc = fp32_linear<true>(dpm, D, f(ix.proj(m)), P.din[m], nullptr, dx[m], P.din[m], P.mod.rows[m], P.din[m], D, st, "d_proj");
+      if (rc) return rc;
+    }
+    rc = fp32_wgrad(dpm, D, x[m], P.din[m], gr(ix.proj(m)), P.din[m], P.mod.rows[m], D, P.din[m], st, "w_proj");
+    if (rc) return rc;
+  }
+  return MMR_OK;
+}
+
+// ================================================================================ C ABI ===
+extern "C" {
+
+int mmr_version(void) { return 100; }
+
+const char* mmr_last_error_string(void) { return g_err.c_str(); }
+
+int mmr_fusion_num_params(const mmr_fusion_dims* dims) {
+  if (!dims || dims->layers < 1 || dims->layers > MMR_MAX_LAYERS) return -1;
+  return ParamIndex{dims->layers}.count();
+}
+
+int mmr_fusion_sizes(const mmr_fusion_dims* dims, size_t* packed_bytes, size_t* saved_bytes, size_t* scratch_fwd_bytes,
+                     size_t* scratch_bwd_bytes) {
+  Plan P;
+  const char* why = "";
+  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
+  if (packed_bytes) *packed_bytes = P.packed_bytes;
+  if (saved_bytes) *saved_bytes = P.saved_bytes;
+  if (scratch_fwd_bytes) *scratch_fwd_bytes = P.scratch_fwd_bytes;
+  if (scratch_bwd_bytes) *scratch_bwd_bytes = P.scratch_bwd_bytes;
+  return MMR_OK;
+}
+
+int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                         const float* pos_table, void* packed, void* saved, void* scratch, float* routes_out,
+                         void* stream) {
+  Plan P;
+  const char* why = "";
+  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
+  if (!host_params || !x_l || !x_n || !x_i || !pos_table || !packed || !saved || !scratch || !routes_out)
+    return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  const float* x[3] = {x_l, x_n, x_i};
+  const float* mask[3] = {mL, mN, mI};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.bf16)
+    return fusion_fwd<bf16>(P, host_params, x, mask, pos_table, (uint8_t*)packed, (uint8_t*)saved, (uint8_t*)scratch,
+                            routes_out, st);
+  return fusion_fwd<float>(P, host_params, x, mask, pos_table, (uint8_t*)packed, (uint8_t*)saved, (uint8_t*)scratch,
+                           routes_out, st);
+}
+
+int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                         const void* packed, const void* saved, void* scratch, const float* d_routes,
+                         void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream) {
+  Plan P;
+  const char* why = "";
+  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
+  if (!host_params || !packed || !saved || !scratch || !d_routes || !host_param_grads || !x_l || !x_n || !x_i)
+    return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  const float* x[3] = {x_l, x_n, x_i};
+  const float* mask[3] = {mL, mN, mI};
+  float* dx[3] = {dx_l, dx_n, dx_i};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.bf16)
+    return fusion_bwd<bf16>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
+                            d_routes, host_param_grads, dx, st);
+  return fusion_bwd<float>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
+                           d_routes, host_param_grads, dx, st);
+}
+
+// ------------------------------------------------------------------------------- routing ---
+static int check_routing(const mmr_routing_dims* d) {
+  if (!d) return fail(MMR_ERR_INVALID_ARG, "dims is NULL");
+  if (d->B <= 0) return fail(MMR_ERR_INVALID_ARG, "B must be positive");
+  if (d->K < 1 || d->K > MMR_MAX_LABELS) return fail(MMR_ERR_UNSUPPORTED, "K must be in [1,32]");
+  if (d->num_routing < 1 || d->num_routing > RT_MAXIT) return fail(MMR_ERR_UNSUPPORTED, "num_routing must be in [1,4]");
+  if (d->variant != MMR_VARIANT_MORT && d->variant != MMR_VARIANT_PHENO) return fail(MMR_ERR_INVALID_ARG, "unknown variant");
+  if (!(d->act_temperature > 0.f)) return fail(MMR_ERR_INVALID_ARG, "act_temperature must be > 0");
+  return MMR_OK;
+}
+
+size_t mmr_routing_scratch_bytes(const mmr_routing_dims* d) {
+  if (!d || d->B <= 0 || d->K < 1) return 0;
+  const size_t B = d->B, K = d->K;
+  return align256(B * 10 * K * 64 * 4) + align256(B * 330 * 4) + align256(B * 320 * 4) + align256(K * 32 * 4) + 256;
+}
+
+static int routing_grid(int B, size_t smem_bytes) {
+  int per_sm = (int)((size_t)(227 * 1024) / (smem_bytes + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int g = 148 * per_sm;
+  return g < B ? g : B;
+}
+
+int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
+                            const float* poses_in, const float* acts_in, const float* acts_override,
+                            const float* route_mask, float* logits, float* alpha, float* R, float* poses_out,
+                            float* acts_out, void* stream) {
+  int rc = check_routing(dims);
+  if (rc) return rc;
+  if (!params || !logits || !alpha) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (dims->from_poses ? (!poses_in || !acts_in) : !route_embs) return fail(MMR_ERR_INVALID_ARG, "missing routing input");
+  RoutingArgs a; memset(&a, 0, sizeof(a));
+  a.d = *dims; a.p = *params;
+  a.route_embs = route_embs; a.poses_in = poses_in; a.acts_in = acts_in; a.acts_override = acts_override;
+  a.route_mask = route_mask; a.logits = logits; a.alpha = alpha; a.R = R; a.poses_out = poses_out; a.acts_out = acts_out;
+  const size_t smem = rt_smem_floats(dims->K, dims->num_routing, false) * 4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaFuncSetAttribute(routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  routing_fwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
+  LAUNCH_OK("routing_fwd");
+  return MMR_OK;
+}
+
+__global__ void proj_bias_grad_kernel(const float* dpc, int B, mmr_routing_grads g) {
+  __shared__ float red[8][33];
+  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  for (int b = warp; b < B; b += 8) {
+    const float* p = dpc + (size_t)b * 330 + r * 33;
+    a0 += p[lane];
+    if (lane == 0) a1 += p[32];
+  }
+  red[warp][lane] = a0;
+  if (lane == 0) red[warp][32] = a1;
+  __syncthreads();
+  if (threadIdx.x < 33 && g.proj_b[r]) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    g.proj_b[r][threadIdx.x] += s;
+  }
+}
+
+int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
+                            const float* poses_in, const float* acts_in, const float* acts_override,
+                            const float* route_mask, const float* d_logits, const float* d_R, void* scratch,
+                            const mmr_routing_grads* grads, float* d_route_embs, float* d_poses, float* d_acts,
+                            void* stream) {
+  int rc = check_routing(dims);
+  if (rc) return rc;
+  if (!params || !d_logits || !scratch || !grads) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (dims->from_poses ? (!poses_in || !acts_in) : !route_embs) return fail(MMR_ERR_INVALID_ARG, "missing routing input");
+  const size_t B = dims->B, K = dims->K, KD = K * 64;
+  uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
+  float* du = reinterpret_cast<float*>(s); s += align256(B * 10 * KD * 4);
+  float* dpc = reinterpret_cast<float*>(s); s += align256(B * 330 * 4);
+  float* posem = reinterpret_cast<float*>(s); s += align256(B * 320 * 4);
+  float* dG = reinterpret_cast<float*>(s);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(dG, 0, K * 32 * 4, st));
+  RoutingArgs a; memset(&a, 0, sizeof(a));
+  a.d = *dims; a.p = *params;
+  a.route_embs = route_embs; a.poses_in = poses_in; a.acts_in = acts_in; a.acts_override = acts_override;
+  a.route_mask = route_mask; a.d_logits = d_logits; a.d_R = d_R;
+  a.d_route_embs = d_route_embs; a.d_poses = d_poses; a.d_acts = d_acts;
+  a.du = du; a.dpc = dpc; a.dG = dG; a.dbias = grads->bias; a.poses_m = posem;
+  const size_t smem = rt_smem_floats(dims->K, dims->num_routing, true) * 4;
+  CUDA_OK(cudaFuncSetAttribute(routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  routing_bwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
+  LAUNCH_OK("routing_bwd");
+  routing_head_grads_kernel<<<1, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,
+                                               grads->embedding);
+  LAUNCH_OK("routing_head_grads");
+  if (grads->caps_w) {   // d w[r] = pose_masked[:, r, :]^T du[:, r, :]
+    WgradBatch w; memset(&w, 0, sizeof(w));
+    w.nbatch = 10; w.rows = dims->B; w.M = 32; w.N = (int)KD; w.ldy = 320; w.ldx = (int)(10 * KD); w.ldo = (int)KD;
+    for (int r = 0; r < 10; ++r) { w.dY[r] = posem + r * 32; w.X[r] = du + r * KD; w.out[r] = grads->caps_w + (size_t)r * 32 * KD; }
+    launch_wgrad_batched(w, st);
+    LAUNCH_OK("w_caps");
+  }
+  if (!dims->from_poses) {
+    WgradBatch w; memset(&w, 0, sizeof(w));
+    w.nbatch = 10; w.rows = dims->B; w.M = 33; w.N = 256; w.ldy = 330; w.ldx = (int)dims->emb_batch_stride; w.ldo = 256;
+    bool any = false;
+    for (int r = 0; r < 10; ++r) {
+      w.dY[r] = dpc + r * 33; w.X[r] = route_embs + (size_t)r * dims->emb_route_stride; w.out[r] = grads->proj_w[r];
+      any = any || grads->proj_w[r] != nullptr;
+    }
+    if (any) { launch_wgrad_batched(w, st); LAUNCH_OK("w_proj"); }
+    proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, dims->B, *grads);
+    LAUNCH_OK("b_proj");
+  }
+  return MMR_OK;
+}
+
+// ----------------------------------------------------------------------------- debug GEMM ---
+int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const void* A, const void* B,
+                   const float* bias, float* C, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0 || K <= 0) return fail(MMR_ERR_INVALID_ARG, "bad GEMM size");
+  const bool use_tc = engine == MMR_GEMM_TC;
+  if (use_tc && dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_UNSUPPORTED, "tcgen05 engine requires bf16");
+  if (!trans) {
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = single_seg(M, 1);
+    g.N = N; g.K = K; g.A = A; g.lda = K; g.B = B; g.ldb = K;
+    EpiParams e; memset(&e, 0, sizeof(e));
+    e.bias = bias; e.out = C; e.ldo = N;
+    if (use_tc) {
+      if (K % 64 || N % 256) return fail(MMR_ERR_UNSUPPORTED, "tcgen05 debug gemm needs K%64==0, N%256==0");
+      cudaError_t err = tc::launch_gemm_tc<EPI_BIAS_F32>(g, e, M, N, st);
+      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 gemm: ") + cudaGetErrorString(err));
+    } else {
+      if (K % 16 || N % 4) return fail(MMR_ERR_UNSUPPORTED, "simt debug gemm needs K%16==0, N%4==0");
+      if (dtype == MMR_DTYPE_BF16) launch_gemm_simt<bf16, bf16, EPI_BIAS_F32, bf16>(g, e, st);
+      else launch_gemm_simt<float, float, EPI_BIAS_F32, float>(g, e, st);
+      LAUNCH_OK("debug gemm");
+    }
+  } else {   // C[M,N] += A[K,M]^T B[K,N]
+    WgradProblem w; memset(&w, 0, sizeof(w));
+    w.segs = single_seg(K, 1);
+    w.segs.row0[1] = pad128(K);
+    w.dY = A; w.ldy = M; w.X = B; w.ldx = N; w.M = M; w.N = N; w.out[0] = C; w.ldo = N;
+    CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * N * 4, st));
+    if (use_tc) {
+      if (M % 128 || N % 256) return fail(MMR_ERR_UNSUPPORTED, "tcgen05 debug wgrad needs M%128==0, N%256==0");
+      cudaError_t err = tc::launch_wgrad_tc(w, K, K, st);
+      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 wgrad: ") + cudaGetErrorString(err));
+    } else {
+      if (dtype == MMR_DTYPE_BF16) launch_wgrad_simt<bf16, bf16>(w, st);
+      else launch_wgrad_simt<float, float>(w, st);
+      LAUNCH_OK("debug wgrad");
+    }
+  }
+  return MMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// CUDA-core GEMMs: the fp32 parity engine (and a debug engine for bf16 operands).
+// Same GemmProblem / epilogue contract as the tcgen05 engine in gemm_tc.cuh.
+#pragma once
+#include "epilogue.cuh"
+
+namespace mmr {
+
+// C[r, n] = sum_k A[a(r), k] * B[b(seg)+n, k];  64x64x16 tiles, 256 threads, 4x4 per thread.
+// Requires K % 16 == 0, N % 4 == 0, lda/ldb % 4 == 0.
+// TRANSB: B is a single row-major [K, N] matrix (B(n,k) = B[k*ldb + b_row0 + n]).
+template <class TA, class TB, int OP, class CT, bool TRANSB = false>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams e) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][68];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * 64;
+  const int n0 = blockIdx.x * 64;
+  const int seg = seg_of_row(g.segs, m0);
+  const int local0 = m0 - g.segs.row0[seg];
+  const int rows_valid = g.segs.rows[seg] - local0;  // may be <= 0 for pure padding tiles
+  const TA* A = reinterpret_cast<const TA*>(g.A);
+  const TB* B = reinterpret_cast<const TB*>(g.B);
+  const int lm = t >> 2, lk = (t & 3) * 4;
+  const bool a_ok = lm < rows_valid;
+  const bool b_ok = (n0 + lm) < g.N;
+  const TA* ap = A + (size_t)(g.a_row0[seg] + local0 + lm) * g.lda + lk;
+  const TB* bp = B + (size_t)(g.b_row0[seg] + n0 + lm) * g.ldb + lk;
+  const int tk = t >> 4, tn = (t & 15) * 4;             // TRANSB load mapping
+  const bool bt_ok = (n0 + tn) < g.N;
+  const TB* btp = B + (size_t)tk * g.ldb + g.b_row0[seg] + n0 + tn;
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+    float4 av = a_ok ? Vec4<TA>::ld(ap + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bv;
+    if (TRANSB) bv = bt_ok ? Vec4<TB>::ld(btp + (size_t)k0 * g.ldb) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else bv = b_ok ? Vec4<TB>::ld(bp + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    As[lk + 0][lm] = av.x; As[lk + 1][lm] = av.y; As[lk + 2][lm] = av.z; As[lk + 3][lm] = av.w;
+    if (TRANSB) {
+      *reinterpret_cast<float4*>(&Bs[tk][tn]) = bv;
+    } else {
+      Bs[lk + 0][lm] = bv.x; Bs[lk + 1][lm] = bv.y; Bs[lk + 2][lm] = bv.z; Bs[lk + 3][lm] = bv.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w};
+      const float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n < g.N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lr = ty * 4 + i;
+      const int crow = m0 + lr;
+      if (crow < g.segs.row0[seg + 1])
+        epi_apply<OP, CT>(e, crow, lr < rows_valid, g.b_row0[seg] + n, n,
+                          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  }
+}
+
+template <class TA, class TB, int OP, class CT, bool TRANSB = false>
+static void launch_gemm_simt(const GemmProblem& g, const EpiParams& e, cudaStream_t st) {
+  const int total_rows = g.segs.row0[g.segs.n];
+  dim3 grid((g.N + 63) / 64, (total_rows + 63) / 64);
+  gemm_simt_kernel<TA, TB, OP, CT, TRANSB><<<grid, 256, 0, st>>>(g, e);
+}
+
+// Weight-gradient tile: out[m, n] += sum_{r in [r_begin, r_end)} dY[r, m] * X[r, n]; fully guarded
+// scalar loads so that odd M/N/strides (projector 33x256, capsule votes) work.
+template <class TY, class TX>
+__device__ __forceinline__ void wgrad_tile(const TY* dY, int ldy, const TX* X, int ldx, int r_begin, int r_end,
+                                           int M, int N, int m0, int n0, float* out, int ldo) {
+  __shared__ float Ys[16][65];
+  __shared__ float Xs[16][65];
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int r0 = r_begin; r0 < r_end; r0 += 16) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + i * 256;  // 0..1023
+      const int k = idx >> 6, c = idx & 63;
+      const int r = r0 + k;
+      float yv = 0.f, xv = 0.f;
+      if (r < r_end) {
+        if (m0 + c < M) yv = to_f<TY>(dY[(size_t)r * ldy + m0 + c]);
+        if (n0 + c < N) xv = to_f<TX>(X[(size_t)r * ldx + n0 + c]);
+      }
+      Ys[k][c] = yv;
+      Xs[k][c] = xv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Ys[k][ty * 4 + i]; b[i] = Xs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  if (out == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(out + (size_t)m * ldo + n, acc[i][j]);
+    }
+  }
+}
+
+// grid.z = nseg * splits
+template <class TY, class TX>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradProblem w, int splits) {
+  const int seg = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int rows = w.segs.rows[seg];
+  const int chunk = (((rows + splits - 1) / splits) + 15) / 16 * 16;
+  const int r_begin = sp * chunk;
+  const int r_end = min(rows, r_begin + chunk);
+  const TY* dY = reinterpret_cast<const TY*>(w.dY) + (size_t)w.segs.row0[seg] * w.ldy;
+  const TX* X = reinterpret_cast<const TX*>(w.X) + (size_t)w.x_row0[seg] * w.ldx;
+  wgrad_tile<TY, TX>(dY, w.ldy, X, w.ldx, r_begin, r_end, w.M, w.N, blockIdx.y * 64, blockIdx.x * 64,
+                     w.out[seg], w.ldo);
+}
+
+// Batched fp32 weight gradients over one shared row range (capsule votes / projector): batch i has
+// its own operand bases.  grid.z = nbatch * splits.
+struct WgradBatch {
+  int nbatch, rows, M, N, ldy, ldx, ldo;
+  const float* dY[MMR_ROUTES];
+  const float* X[MMR_ROUTES];
+  float* out[MMR_ROUTES];
+};
+__global__ void __launch_bounds__(256) wgrad_batched_kernel(WgradBatch w, int splits) {
+  const int bi = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int chunk = (((w.rows + splits - 1) / splits) + 15) / 16 * 16;
+  const int r_begin = sp * chunk;
+  const int r_end = min(w.rows, r_begin + chunk);
+  wgrad_tile<float, float>(w.dY[bi], w.ldy, w.X[bi], w.ldx, r_begin, r_end, w.M, w.N, blockIdx.y * 64,
+                           blockIdx.x * 64, w.out[bi], w.ldo);
+}
+static void launch_wgrad_batched(const WgradBatch& w, cudaStream_t st) {
+  const int tiles = ((w.M + 63) / 64) * ((w.N + 63) / 64) * w.nbatch;
+  int splits = (148 * 4 + tiles - 1) / tiles;
+  const int max_splits = (w.rows + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  dim3 grid((w.N + 63) / 64, (w.M + 63) / 64, w.nbatch * splits);
+  wgrad_batched_kernel<<<grid, 256, 0, st>>>(w, splits);
+}
+
+template <class TY, class TX>
+static void launch_wgrad_simt(const WgradProblem& w, cudaStream_t st) {
+  int max_rows = 1;
+  for (int s = 0; s < w.segs.n; ++s) max_rows = max_rows > w.segs.rows[s] ? max_rows : w.segs.rows[s];
+  const int tiles = ((w.M + 63) / 64) * ((w.N + 63) / 64) * w.segs.n;
+  int splits = (148 * 4 + tiles - 1) / tiles;
+  const int max_splits = (max_rows + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  dim3 grid((w.N + 63) / 64, (w.M + 63) / 64, w.segs.n * splits);
+  wgrad_simt_kernel<TY, TX><<<grid, 256, 0, st>>>(w, splits);
+}
+
+}  // namespace mmr

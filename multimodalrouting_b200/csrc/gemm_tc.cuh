@@ -1,0 +1,401 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//  gemm_tc_kernel   C[r, n] = sum_k A[a(r), k] * B[b(seg)+n, k]     both operands K-major
+//  wgrad_tc_kernel  out[seg][m, n] += sum_r dY[r, m] * X[x(r), n]   both operands MN-major
+//
+// One CTA = one 128 x BN output tile.  Warp 0 lane 0 drives TMA (cp.async.bulk.tensor, 128B
+// swizzle) through a ring of mbarrier-guarded smem stages, warp 1 lane 0 issues tcgen05.mma with
+// smem descriptors and commits completion to mbarriers, warps 2-5 drain the 128 x BN fp32
+// accumulator from TMEM (tcgen05.ld 32x32b) and apply the element-wise epilogue.  Two CTAs per SM
+// are co-resident (2 x 256 TMEM columns) so one tile's epilogue overlaps the other's main loop.
+#pragma once
+#include <cuda.h>
+
+#include "epilogue.cuh"
+
+namespace mmr {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 bf16 = one 128-byte swizzle row
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must fault the launch (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (count 1) on the mbarrier once all previously issued tcgen05.mma of this thread retire
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1.
+//  K-major : 8-row groups of 128B rows, SBO = 1024 B, LBO unused.
+//  MN-major: 64-element (128B) MN atoms x 8 k-rows; SBO = 1024 B between k groups,
+//            LBO = 8192 B between MN atoms (each atom block is [64 k][64 mn] = 8 KB).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN> __host__ __device__ constexpr int stage_bytes() { return (BM + BN) * BK * 2; }
+template <int BN> __host__ __device__ constexpr int smem_bytes(int stages) { return stages * stage_bytes<BN>() + 1024 + 256; }
+
+struct Ctrl {   // lives after the stages
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------
+template <int BN, int OP>
+__global__ void __launch_bounds__(NTHREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               GemmProblem g, EpiParams e, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * stage_bytes<BN>());
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int seg = seg_of_row(g.segs, m0);
+  const int local0 = m0 - g.segs.row0[seg];
+  const int rows_valid = g.segs.rows[seg] - local0;
+  const int kblocks = g.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&ctrl->full[s]), 1);
+      mbar_init(smem_u32(&ctrl->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctrl->acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = ctrl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      const int a_row = g.a_row0[seg] + local0;
+      const int b_row = g.b_row0[seg] + n0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&ctrl->full[s]);
+        mbar_expect_tx(full, stage_bytes<BN>());
+        const uint32_t sa = sbase + s * stage_bytes<BN>();
+        const uint32_t sb = sa + BM * BK * 2;
+        tma_load_2d(sa, &tmA, kb * BK, a_row, full);
+        tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(smem_u32(&ctrl->full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = sbase + s * stage_bytes<BN>();
+        const uint32_t sb = sa + BM * BK * 2;
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the swizzle row
+          umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(smem_u32(&ctrl->empty[s]));
+      }
+      umma_commit(smem_u32(&ctrl->acc_full));
+    }
+  } else {
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int lr = q * 32 + lane;         // row inside the tile
+    const int crow = m0 + lr;
+    const bool in_seg = crow < g.segs.row0[seg + 1];
+    const bool valid = lr < rows_valid;
+    mbar_wait(smem_u32(&ctrl->acc_full), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      const int n = n0 + c * 32;
+      if (in_seg && n < g.N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          epi_apply<OP, bf16>(e, crow, valid, g.b_row0[seg] + n + 4 * j, n + 4 * j,
+                              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient: reduction over token rows; A = dY^T and B = X^T are MN-major views of the
+// row-major activations, fetched as [64 rows][64 cols] TMA boxes.  grid.z = nseg * splits.
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 2)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                WgradProblem w, int splits, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * stage_bytes<BN>());
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int rows_pad = w.segs.row0[seg + 1] - w.segs.row0[seg];   // multiple of 128; tail rows are zero
+  const int kb_total = rows_pad / BK;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  const int kb_begin = sp * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const int kblocks = kb_end - kb_begin;
+  if (kblocks <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&ctrl->full[s]), 1);
+      mbar_init(smem_u32(&ctrl->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctrl->acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = ctrl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+      for (int i = 0; i < kblocks; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&ctrl->full[s]);
+        mbar_expect_tx(full, stage_bytes<BN>());
+        const uint32_t sa = sbase + s * stage_bytes<BN>();
+        const uint32_t sb = sa + BM * BK * 2;
+        const int ry = w.segs.row0[seg] + (kb_begin + i) * BK;
+        const int rx = w.x_row0[seg] + (kb_begin + i) * BK;
+#pragma unroll
+        for (int a = 0; a < BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmY, m0 + a * 64, ry, full);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmX, n0 + b * 64, rx, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+      for (int i = 0; i < kblocks; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(smem_u32(&ctrl->full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = sbase + s * stage_bytes<BN>();
+        const uint32_t sb = sa + BM * BK * 2;
+        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)   // 16 k-rows of 128 B = 2048 B (>>4 = 128) per K=16 step
+          umma_bf16(tmem_acc, adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) != 0);
+        umma_commit(smem_u32(&ctrl->empty[s]));
+      }
+      umma_commit(smem_u32(&ctrl->acc_full));
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(smem_u32(&ctrl->acc_full), 0);
+    tc_fence_after();
+    float* out = w.out[seg];
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      const int n = n0 + c * 32;
+      if (out != nullptr && m < w.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j < w.N) atomicAdd(out + (size_t)m * w.ldo + n + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, BN);
+}
+
+// ---------------------------------------------------------------------------- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [outer, inner] (inner contiguous, leading dimension ld elements).
+static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// a_rows_total / b_rows_total: number of rows physically present in A / B (TMA bounds).
+template <int OP>
+static cudaError_t launch_gemm_tc(const GemmProblem& g, const EpiParams& e, int a_rows_total, int b_rows_total,
+                                  cudaStream_t st) {
+  constexpr int BN = 256;
+  static int stages_cfg = env_int("MMR_TC_STAGES", 2);
+  int stages = stages_cfg;
+  const int kblocks = g.K / BK;
+  if (stages > kblocks) stages = kblocks;
+  if (stages > 4) stages = 4;
+  if (stages < 1) stages = 1;
+  CUtensorMap tmA, tmB;
+  if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN)) return cudaErrorUnknown;
+  auto kern = gemm_tc_kernel<BN, OP>;
+  const int smem = smem_bytes<BN>(stages);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  const int total_rows = g.segs.row0[g.segs.n];
+  dim3 grid((g.N + BN - 1) / BN, (total_rows + BM - 1) / BM);
+  kern<<<grid, NTHREADS, smem, st>>>(tmA, tmB, g, e, stages);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_wgrad_tc(const WgradProblem& w, int y_rows_total, int x_rows_total, cudaStream_t st) {
+  constexpr int BN = 256;
+  static int stages_cfg = env_int("MMR_TC_WGRAD_STAGES", 2);
+  int stages = stages_cfg < 1 ? 1 : (stages_cfg > 4 ? 4 : stages_cfg);
+  CUtensorMap tmY, tmX;
+  if (!make_tmap(&tmY, w.dY, (uint64_t)w.ldy, (uint64_t)y_rows_total, (uint64_t)w.ldy, 64, BK)) return cudaErrorUnknown;
+  if (!make_tmap(&tmX, w.X, (uint64_t)w.ldx, (uint64_t)x_rows_total, (uint64_t)w.ldx, 64, BK)) return cudaErrorUnknown;
+  int max_kb = 1;
+  for (int s = 0; s < w.segs.n; ++s) {
+    int kb = (w.segs.row0[s + 1] - w.segs.row0[s]) / BK;
+    if (kb > max_kb) max_kb = kb;
+  }
+  const int tiles = ((w.M + BM - 1) / BM) * ((w.N + BN - 1) / BN) * w.segs.n;
+  int splits = (148 * 2 + tiles - 1) / tiles;
+  if (splits > max_kb / 4) splits = max_kb / 4;
+  if (splits < 1) splits = 1;
+  auto kern = wgrad_tc_kernel<BN>;
+  const int smem = smem_bytes<BN>(stages);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  dim3 grid((w.N + BN - 1) / BN, (w.M + BM - 1) / BM, w.segs.n * splits);
+  kern<<<grid, NTHREADS, smem, st>>>(tmY, tmX, w, splits, stages);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace mmr

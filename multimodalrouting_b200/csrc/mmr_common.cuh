@@ -1,0 +1,129 @@
+// Common device helpers for the B200 (sm_100a) route-fusion kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmr_b200.h"
+
+namespace mmr {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int D = MMR_D;          // model width
+constexpr int H = MMR_HEADS;
+constexpr int HD = MMR_HEAD_DIM;
+constexpr int FF = MMR_FFN;
+constexpr int NR = MMR_ROUTES;
+constexpr int PC = MMR_PC_DIM;
+constexpr int MC = MMR_MC_DIM;
+constexpr int NDIR = 6;
+constexpr int NMOD = 3;
+constexpr float LN_EPS = 1e-5f;
+constexpr float EMBED_SCALE = 16.0f;  // sqrt(256), transformer.py:33
+
+// Direction d: query modality / key modality (0=L,1=N,2=I): LN, LI, NL, NI, IL, IN
+__host__ __device__ inline int dir_qmod(int d) { return d >> 1; }
+__host__ __device__ inline int dir_kmod(int d) {
+  const int t[6] = {1, 2, 0, 2, 0, 1};
+  return t[d];
+}
+
+// A set of up to 6 row segments laid out back to back (128-row aligned starts).
+struct Segs {
+  int n;
+  int row0[7];   // padded start row of each segment; row0[n] = total padded rows
+  int rows[6];   // valid rows in the segment
+  int T[6];      // tokens per patient in this segment
+};
+
+__host__ __device__ inline int seg_of_row(const Segs& s, int row) {
+  int d = 0;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (i < s.n && row >= s.row0[i]) d = i;
+  return d;
+}
+
+// ---- element access: CT in {float, bf16}, 4 consecutive elements at a time -------------------
+template <class T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    float4 v;
+    v.x = __uint_as_float(r.x << 16);
+    v.y = __uint_as_float(r.x & 0xffff0000u);
+    v.z = __uint_as_float(r.y << 16);
+    v.w = __uint_as_float(r.y & 0xffff0000u);
+    return v;
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+template <class T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// round-trip through the compute type (identity for fp32): mimics autocast rounding points
+template <class T> __device__ __forceinline__ float round_ct(float v) { return to_f<T>(from_f<T>(v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// A 256-wide fp32 row held by one warp: lane owns columns [4*lane, 4*lane+4) and [128+4*lane, ...).
+struct Row8 {
+  float v[8];
+};
+template <class T> __device__ __forceinline__ Row8 row_load(const T* rowptr, int lane) {
+  Row8 r;
+  float4 a = Vec4<T>::ld(rowptr + 4 * lane);
+  float4 b = Vec4<T>::ld(rowptr + 128 + 4 * lane);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <class T> __device__ __forceinline__ void row_store(T* rowptr, int lane, const Row8& r) {
+  Vec4<T>::st(rowptr + 4 * lane, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+  Vec4<T>::st(rowptr + 128 + 4 * lane, make_float4(r.v[4], r.v[5], r.v[6], r.v[7]));
+}
+__device__ __forceinline__ int row_col(int lane, int i) { return (i < 4) ? 4 * lane + i : 128 + 4 * lane + (i - 4); }
+
+// LayerNorm statistics of a 256-wide row distributed over a warp (two-pass, like ATen).
+__device__ __forceinline__ void row_stats(const Row8& r, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += r.v[i];
+  mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float d = r.v[i] - mean;
+    q += d * d;
+  }
+  float var = warp_sum(q) * (1.0f / D);
+  rstd = rsqrtf(var + LN_EPS);
+}
+
+}  // namespace mmr

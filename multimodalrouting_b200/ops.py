@@ -1,0 +1,453 @@
+"""torch.library custom ops + autograd glue over the C ABI (include/mmr_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and autograd bookkeeping; all arithmetic
+of the hot path runs in the hand-written sm_100a kernels of csrc/.  There is no fallback path: if
+the shared library is missing or the tensors are not on a CUDA device the ops raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import FusionDims, RoutingDims, RoutingGrads, RoutingParams, c_fp
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+VARIANT = {"mort": 0, "pheno": 1}
+N_ROUTES = 10
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "multimodalrouting_b200 runs only on a CUDA (B200, sm_100a) device; got a "
+                f"{t.device} tensor.  There is no CPU fallback for the route-fusion path.")
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def resolve_dtype(mode: str = "auto") -> int:
+    """fp32 unless running under torch.autocast (any reduced dtype -> bf16 kernels), like the
+    reference's amp contexts (M/main.py:2633-2659).  MMR_B200_DTYPE=fp32|bf16 overrides."""
+    mode = os.environ.get("MMR_B200_DTYPE", mode)
+    if mode in ("bf16", "bfloat16"):
+        return DTYPE_BF16
+    if mode in ("fp32", "float32"):
+        return DTYPE_F32
+    if torch.is_autocast_enabled("cuda"):
+        return DTYPE_BF16
+    return DTYPE_F32
+
+
+def resolve_engine() -> int:
+    return {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tc": GEMM_TC}[os.environ.get("MMR_B200_GEMM", "auto")]
+
+
+def _fusion_dims(x_l, x_n, x_i, layers, dtype, engine) -> FusionDims:
+    B, TL, dL = x_l.shape
+    _, TN, dN = x_n.shape
+    _, TI, dI = x_i.shape
+    return FusionDims(B, TL, TN, TI, dL, dN, dI, layers, dtype, engine)
+
+
+def fusion_sizes(dims: FusionDims) -> Tuple[int, int, int, int]:
+    lib = _lib.load()
+    s = [C.c_size_t() for _ in range(4)]
+    _lib.check(lib.mmr_fusion_sizes(C.byref(dims), *[C.byref(v) for v in s]), "mmr_fusion_sizes")
+    return tuple(int(v.value) for v in s)
+
+
+def _ptr_table(ts: Sequence[Optional[Tensor]]):
+    arr = (c_fp * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+# --------------------------------------------------------------------------------------------
+# raw ops (opaque to torch.compile, with fake impls)
+@torch.library.custom_op("mmr_b200::route_fusion_fwd", mutates_args=())
+def route_fusion_fwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
+                     mI: Optional[Tensor], pos: Tensor, params: Sequence[Tensor], layers: int, dtype: int,
+                     engine: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _require_cuda(x_l, x_n, x_i, pos, *params)
+    lib = _lib.load()
+    dims = _fusion_dims(x_l, x_n, x_i, layers, dtype, engine)
+    n_expected = lib.mmr_fusion_num_params(C.byref(dims))
+    if n_expected != len(params):
+        raise ValueError(f"route_fusion_fwd expects {n_expected} parameter tensors, got {len(params)}")
+    packed_b, saved_b, sf_b, _ = fusion_sizes(dims)
+    dev = x_l.device
+    packed = torch.empty(packed_b, dtype=torch.uint8, device=dev)
+    saved = torch.empty(saved_b, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(sf_b, dtype=torch.uint8, device=dev)
+    routes = torch.empty(N_ROUTES, x_l.shape[0], 256, dtype=torch.float32, device=dev)
+    rc = lib.mmr_route_fusion_fwd(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
+                                  _ptr(mN), _ptr(mI), _ptr(pos), _ptr(packed), _ptr(saved), _ptr(scratch),
+                                  _ptr(routes), _stream())
+    _lib.check(rc, "mmr_route_fusion_fwd")
+    return routes, packed, saved
+
+
+@route_fusion_fwd.register_fake
+def _(x_l, x_n, x_i, mL, mN, mI, pos, params, layers, dtype, engine):
+    B = x_l.shape[0]
+    return (x_l.new_empty(N_ROUTES, B, 256, dtype=torch.float32), x_l.new_empty(1, dtype=torch.uint8),
+            x_l.new_empty(1, dtype=torch.uint8))
+
+
+@torch.library.custom_op("mmr_b200::route_fusion_bwd", mutates_args=())
+def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
+                     mI: Optional[Tensor], params: Sequence[Tensor], packed: Tensor, saved: Tensor,
+                     d_routes: Tensor, need: Sequence[bool], layers: int, dtype: int,
+                     engine: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns (dx_l, dx_n, dx_i, flat parameter gradients in `params` order)."""
+    lib = _lib.load()
+    dims = _fusion_dims(x_l, x_n, x_i, layers, dtype, engine)
+    _, _, _, sb_b = fusion_sizes(dims)
+    dev = x_l.device
+    scratch = torch.empty(sb_b, dtype=torch.uint8, device=dev)
+    sizes = [p.numel() for p in params]
+    # 16-byte aligned slots so vectorised accesses in the kernels stay legal
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o)
+        o += (n + 3) // 4 * 4
+    flat = torch.zeros(o, dtype=torch.float32, device=dev)
+    base = flat.data_ptr()
+    grads = (c_fp * len(params))()
+    for i, p in enumerate(params):
+        grads[i] = (base + 4 * offs[i]) if need[i] else None
+    dx = [torch.empty_like(x) for x in (x_l, x_n, x_i)]
+    rc = lib.mmr_route_fusion_bwd(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
+                                  _ptr(mN), _ptr(mI), _ptr(packed), _ptr(saved), _ptr(scratch), _ptr(d_routes),
+                                  grads, _ptr(dx[0]), _ptr(dx[1]), _ptr(dx[2]), _stream())
+    _lib.check(rc, "mmr_route_fusion_bwd")
+    return dx[0], dx[1], dx[2], flat
+
+
+@route_fusion_bwd.register_fake
+def _(x_l, x_n, x_i, mL, mN, mI, params, packed, saved, d_routes, need, layers, dtype, engine):
+    n = sum((p.numel() + 3) // 4 * 4 for p in params)
+    return (torch.empty_like(x_l), torch.empty_like(x_n), torch.empty_like(x_i),
+            x_l.new_empty(n, dtype=torch.float32))
+
+
+def _common_base(ts: Sequence[Optional[Tensor]], shape) -> Optional[Tuple[int, int, int]]:
+    """If the tensors are equally spaced fp32 [B,256] views of one buffer, return
+    (base_ptr, route_stride_elems, batch_stride_elems)."""
+    t0 = ts[0]
+    if any(t is None or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) for t in ts):
+        return None
+    if t0.stride(1) != 1 or any(t.stride() != t0.stride() for t in ts):
+        return None
+    p0 = t0.data_ptr()
+    if len(ts) == 1:
+        return p0, 0, t0.stride(0)
+    step = ts[1].data_ptr() - p0
+    if step <= 0 or step % 4 or any(t.data_ptr() - p0 != i * step for i, t in enumerate(ts)):
+        return None
+    return p0, step // 4, t0.stride(0)
+
+
+class RouteFusionFn(torch.autograd.Function):
+    """MULTModel.forward as one autograd node: 3 sequences + masks + 317 parameters -> 10 routes."""
+
+    @staticmethod
+    def forward(ctx, x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, *params):
+        xs = [_f32c(x.detach()) for x in (x_l, x_n, x_i)]
+        ms = [_f32c(m.detach()) if m is not None else None for m in (mL, mN, mI)]
+        ps = [p.detach() for p in params]
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise ValueError("route fusion parameters must be contiguous fp32 tensors")
+        routes, packed, saved = route_fusion_fwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], pos, ps, layers, dtype, engine)
+        ctx.save_for_backward(*xs, *[m for m in ms if m is not None], packed, saved, *ps)
+        ctx.mask_present = [m is not None for m in ms]
+        ctx.cfg = (layers, dtype, engine)
+        ctx.n_params = len(ps)
+        outs = tuple(routes[r] for r in range(N_ROUTES))
+        return outs
+
+    @staticmethod
+    def backward(ctx, *d_routes):
+        sv = list(ctx.saved_tensors)
+        xs = sv[:3]
+        k = 3
+        ms = []
+        for present in ctx.mask_present:
+            if present:
+                ms.append(sv[k]); k += 1
+            else:
+                ms.append(None)
+        packed, saved = sv[k], sv[k + 1]
+        ps = sv[k + 2:]
+        layers, dtype, engine = ctx.cfg
+        B = xs[0].shape[0]
+        base = _common_base(d_routes, (B, 256))
+        if base is not None and base[1] == B * 256 and base[2] == 256:
+            d_all = torch.as_strided(d_routes[0], (N_ROUTES, B, 256), (B * 256, 256, 1))
+        else:
+            d_all = torch.stack([g.float() if g is not None else torch.zeros(B, 256, device=xs[0].device)
+                                 for g in d_routes], dim=0).contiguous()
+        need = [bool(n) for n in ctx.needs_input_grad[10:]]
+        dxl, dxn, dxi, flat = route_fusion_bwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], ps, packed, saved, d_all,
+                                               need, layers, dtype, engine)
+        grads, o = [], 0
+        for p, nd in zip(ps, need):
+            n = p.numel()
+            grads.append(flat[o:o + n].view(p.shape) if nd else None)
+            o += (n + 3) // 4 * 4
+        gi = ctx.needs_input_grad
+        return (dxl if gi[0] else None, dxn if gi[1] else None, dxi if gi[2] else None,
+                None, None, None, None, None, None, None, *grads)
+
+
+def route_fusion(x_l, x_n, x_i, mL, mN, mI, pos, params: List[Tensor], layers: int, dtype: int,
+                 engine: int) -> Tuple[Tensor, ...]:
+    _require_cuda(x_l, x_n, x_i)
+    return RouteFusionFn.apply(x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, *params)
+
+
+# --------------------------------------------------------------------------------------------
+# capsule routing
+def _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs) -> RoutingDims:
+    return RoutingDims(B, K, variant, num_routing, int(detach_priors), int(from_poses), float(temp), float(floor),
+                       float(ceil), int(rs), int(bs))
+
+
+def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias) -> RoutingParams:
+    rp = RoutingParams()
+    for r in range(N_ROUTES):
+        rp.proj_w[r] = proj_w[r].data_ptr() if proj_w else None
+        rp.proj_b[r] = proj_b[r].data_ptr() if proj_b else None
+    rp.caps_w = caps_w.data_ptr()
+    rp.pose_to_mc = pose_to_mc.data_ptr()
+    rp.embedding = embedding.data_ptr()
+    rp.bias = bias.data_ptr()
+    return rp
+
+
+@torch.library.custom_op("mmr_b200::capsule_routing_fwd", mutates_args=())
+def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Optional[Tensor],
+                        acts_in: Optional[Tensor], acts_override: Optional[Tensor], route_mask: Optional[Tensor],
+                        proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
+                        embedding: Tensor, bias: Tensor, B: int, variant: int, num_routing: int,
+                        detach_priors: bool, temp: float, floor: float, ceil: float
+                        ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10])."""
+    _require_cuda(caps_w, embs, poses_in)
+    lib = _lib.load()
+    K = embedding.shape[0]
+    from_poses = embs is None
+    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs)
+    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
+    dev = caps_w.device
+    logits = torch.empty(B, K, dtype=torch.float32, device=dev)
+    alpha = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
+    R = torch.empty(B, N_ROUTES, K, dtype=torch.float32, device=dev)
+    poses = torch.empty(B, N_ROUTES, 32, dtype=torch.float32, device=dev)
+    acts = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
+    rc = lib.mmr_capsule_routing_fwd(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
+                                     _ptr(acts_override), _ptr(route_mask), _ptr(logits), _ptr(alpha), _ptr(R),
+                                     None if from_poses else _ptr(poses), None if from_poses else _ptr(acts),
+                                     _stream())
+    _lib.check(rc, "mmr_capsule_routing_fwd")
+    return logits, alpha, R, poses, acts
+
+
+@capsule_routing_fwd.register_fake
+def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b, caps_w, pose_to_mc, embedding,
+      bias, B, variant, num_routing, detach_priors, temp, floor, ceil):
+    K = embedding.shape[0]
+    e = caps_w
+    return (e.new_empty(B, K), e.new_empty(B, N_ROUTES), e.new_empty(B, N_ROUTES, K),
+            e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES))
+
+
+@torch.library.custom_op("mmr_b200::capsule_routing_bwd", mutates_args=())
+def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Optional[Tensor],
+                        acts_in: Optional[Tensor], acts_override: Optional[Tensor], route_mask: Optional[Tensor],
+                        proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
+                        embedding: Tensor, bias: Tensor, d_logits: Tensor, d_R: Optional[Tensor], B: int,
+                        variant: int, num_routing: int, detach_priors: bool, temp: float, floor: float,
+                        ceil: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns (d_embs [10,B,256] | empty, d_poses [B,10,32] | empty, d_acts [B,10] | empty, flat grads)
+    flat grads layout: proj_w[10] (33*256 each) | proj_b[10] (36 each, 33 used) | caps_w | pose_to_mc |
+    embedding | bias."""
+    lib = _lib.load()
+    K = embedding.shape[0]
+    from_poses = embs is None
+    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs)
+    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
+    dev = caps_w.device
+    scratch = torch.empty(int(lib.mmr_routing_scratch_bytes(C.byref(dims))), dtype=torch.uint8, device=dev)
+    n_flat = routing_flat_layout(K)["total"]
+    flat = torch.zeros(n_flat, dtype=torch.float32, device=dev)
+    lay = routing_flat_layout(K)
+    base = flat.data_ptr()
+    g = RoutingGrads()
+    for r in range(N_ROUTES):
+        g.proj_w[r] = None if from_poses else base + 4 * (lay["proj_w"] + r * 33 * 256)
+        g.proj_b[r] = None if from_poses else base + 4 * (lay["proj_b"] + r * 36)
+    g.caps_w = base + 4 * lay["caps_w"]
+    g.pose_to_mc = base + 4 * lay["pose_to_mc"]
+    g.embedding = base + 4 * lay["embedding"]
+    g.bias = base + 4 * lay["bias"]
+    if from_poses:
+        d_embs = torch.empty(0, dtype=torch.float32, device=dev)
+        d_poses = torch.empty(B, N_ROUTES, 32, dtype=torch.float32, device=dev)
+        d_acts = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
+    else:
+        d_embs = torch.empty(N_ROUTES, B, 256, dtype=torch.float32, device=dev)
+        d_poses = torch.empty(0, dtype=torch.float32, device=dev)
+        d_acts = torch.empty(0, dtype=torch.float32, device=dev)
+    # d_route_embs shares the (route, batch) strides of the input embeddings in the C ABI; RoutingFn
+    # normalises the inputs to the dense [10,B,256] layout, so the output is dense as well.
+    rc = lib.mmr_capsule_routing_bwd(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
+                                     _ptr(acts_override), _ptr(route_mask), _ptr(d_logits), _ptr(d_R),
+                                     _ptr(scratch), C.byref(g), None if from_poses else _ptr(d_embs),
+                                     _ptr(d_poses) if from_poses else None,
+                                     _ptr(d_acts) if from_poses else None, _stream())
+    _lib.check(rc, "mmr_capsule_routing_bwd")
+    return d_embs, d_poses, d_acts, flat
+
+
+@capsule_routing_bwd.register_fake
+def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b, caps_w, pose_to_mc, embedding,
+      bias, d_logits, d_R, B, variant, num_routing, detach_priors, temp, floor, ceil):
+    K = embedding.shape[0]
+    e = caps_w
+    n = routing_flat_layout(K)["total"]
+    if embs is None:
+        return e.new_empty(0), e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES), e.new_empty(n)
+    return e.new_empty(N_ROUTES, B, 256), e.new_empty(0), e.new_empty(0), e.new_empty(n)
+
+
+def routing_flat_layout(K: int):
+    lay, o = {}, 0
+    lay["proj_w"] = o; o += N_ROUTES * 33 * 256
+    lay["proj_b"] = o; o += N_ROUTES * 36
+    lay["caps_w"] = o; o += N_ROUTES * 32 * K * 64
+    lay["pose_to_mc"] = o; o += 64 * 32
+    lay["embedding"] = o; o += K * 64
+    lay["bias"] = o; o += (K + 3) // 4 * 4
+    lay["total"] = o
+    return lay
+
+
+class RoutingFn(torch.autograd.Function):
+    """forward_capsule_from_route_dict (embs given) or CapsuleMortalityHead.forward (poses given)."""
+
+    @staticmethod
+    def forward(ctx, cfg, acts_override, route_mask, caps_w, pose_to_mc, embedding, bias, *rest):
+        variant, num_routing, detach_priors, temp, floor, ceil, from_poses = cfg
+        if from_poses:
+            poses_in, acts_in = rest
+            B = poses_in.shape[0]
+            poses_c, acts_c = _f32c(poses_in.detach()), _f32c(acts_in.detach())
+            embs_dense, proj_w, proj_b = None, [], []
+            rs = bs = 0
+        else:
+            embs = rest[:N_ROUTES]
+            proj_w = [p.detach() for p in rest[N_ROUTES:2 * N_ROUTES]]
+            proj_b = [p.detach() for p in rest[2 * N_ROUTES:3 * N_ROUTES]]
+            B = embs[0].shape[0]
+            base = _common_base([e.detach() for e in embs], (B, 256))
+            if base is not None and base[1] == B * 256 and base[2] == 256:
+                embs_dense = torch.as_strided(embs[0].detach(), (N_ROUTES, B, 256), (B * 256, 256, 1))
+            else:
+                embs_dense = torch.stack([_f32c(e.detach()) for e in embs], dim=0)
+            rs, bs = B * 256, 256
+            poses_c = acts_c = None
+        rm = _f32c(route_mask.detach()) if route_mask is not None else None
+        ao = _f32c(acts_override.detach()) if acts_override is not None else None
+        logits, alpha, R, poses, acts = capsule_routing_fwd(
+            embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w.detach(), pose_to_mc.detach(),
+            embedding.detach(), bias.detach(), B, variant, num_routing, detach_priors, temp, floor, ceil)
+        ctx.cfg = cfg
+        ctx.B = B
+        ctx.has = (embs_dense is not None, rm is not None, ao is not None)
+        tensors = [t for t in (embs_dense, poses_c, acts_c, ao, rm) if t is not None]
+        ctx.n_in = len(tensors)
+        ctx.save_for_backward(*tensors, caps_w.detach(), pose_to_mc.detach(), embedding.detach(), bias.detach(),
+                              *proj_w, *proj_b)
+        ctx.mark_non_differentiable(alpha, poses, acts)
+        return logits, alpha, R, poses, acts
+
+    @staticmethod
+    def backward(ctx, d_logits, _d_alpha, d_R, _d_poses, _d_acts):
+        variant, num_routing, detach_priors, temp, floor, ceil, from_poses = ctx.cfg
+        sv = list(ctx.saved_tensors)
+        has_embs, has_rm, has_ao = ctx.has
+        k = 0
+        embs_dense = poses_c = acts_c = ao = rm = None
+        if has_embs:
+            embs_dense = sv[k]; k += 1
+        else:
+            poses_c, acts_c = sv[k], sv[k + 1]; k += 2
+        if has_ao:
+            ao = sv[k]; k += 1
+        if has_rm:
+            rm = sv[k]; k += 1
+        caps_w, pose_to_mc, embedding, bias = sv[k:k + 4]
+        k += 4
+        proj_w = sv[k:k + N_ROUTES] if has_embs else []
+        proj_b = sv[k + N_ROUTES:k + 2 * N_ROUTES] if has_embs else []
+        B, K = ctx.B, embedding.shape[0]
+        if d_logits is None:
+            d_logits = torch.zeros(B, K, device=caps_w.device)
+        rs, bs = (B * 256, 256) if has_embs else (0, 0)
+        d_embs, d_poses, d_acts, flat = capsule_routing_bwd(
+            embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w, pose_to_mc, embedding, bias,
+            _f32c(d_logits), _f32c(d_R) if d_R is not None else None, B, variant, num_routing, detach_priors, temp,
+            floor, ceil)
+        lay = routing_flat_layout(K)
+        g_caps = flat[lay["caps_w"]:lay["caps_w"] + caps_w.numel()].view(caps_w.shape)
+        g_mc = flat[lay["pose_to_mc"]:lay["pose_to_mc"] + 64 * 32].view(64, 32)
+        g_emb = flat[lay["embedding"]:lay["embedding"] + K * 64].view(K, 64)
+        g_bias = flat[lay["bias"]:lay["bias"] + K]
+        head = (None, None, None, g_caps, g_mc, g_emb, g_bias)
+        if from_poses:
+            return head + (d_poses, d_acts)
+        g_pw = [flat[lay["proj_w"] + r * 33 * 256: lay["proj_w"] + (r + 1) * 33 * 256].view(33, 256)
+                for r in range(N_ROUTES)]
+        g_pb = [flat[lay["proj_b"] + r * 36: lay["proj_b"] + r * 36 + 33] for r in range(N_ROUTES)]
+        return head + tuple(d_embs[r] for r in range(N_ROUTES)) + tuple(g_pw) + tuple(g_pb)
+
+
+def debug_gemm(engine: int, dtype: int, trans: bool, A: Tensor, B: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """Unit-test hook: C = A @ B^T (+bias)  or, trans, C = A^T @ B (reduction over rows)."""
+    _require_cuda(A, B)
+    lib = _lib.load()
+    if trans:
+        Kr, M = A.shape
+        N = B.shape[1]
+        K = Kr
+    else:
+        M, K = A.shape
+        N = B.shape[0]
+    Cc = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    rc = lib.mmr_debug_gemm(engine, dtype, int(trans), M, N, K, _ptr(A), _ptr(B), _ptr(bias), _ptr(Cc), _stream())
+    _lib.check(rc, "mmr_debug_gemm")
+    return Cc

@@ -1,0 +1,40 @@
+"""-m gpu: the tcgen05/TMEM/TMA GEMM engine -- unit parity against fp64 matmul and end-to-end bf16
+parity of the full path running on it (the default engine for bf16)."""
+import pytest
+import torch
+
+from helpers import max_rel
+from test_gpu_fusion import _bf16_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (300, 512, 1024), (1000, 1024, 256), (4096, 256, 2048)])
+def test_tc_gemm_tn(M, N, K):
+    from multimodalrouting_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    A = torch.randn(M, K, generator=g).cuda().bfloat16()
+    B = torch.randn(N, K, generator=g).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    C = ops.debug_gemm(ops.GEMM_TC, ops.DTYPE_BF16, False, A, B, bias)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t() + bias.double()
+    assert max_rel(C, ref) < 1e-5
+
+
+@pytest.mark.parametrize("Kr,M,N", [(64, 128, 256), (128, 128, 256), (1000, 256, 1024), (5000, 1024, 256), (777, 2048, 256)])
+def test_tc_gemm_wgrad(Kr, M, N):
+    from multimodalrouting_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    Y = torch.randn(Kr, M, generator=g).cuda().bfloat16()
+    X = torch.randn(Kr, N, generator=g).cuda().bfloat16()
+    W = ops.debug_gemm(ops.GEMM_TC, ops.DTYPE_BF16, True, Y, X, None)
+    torch.cuda.synchronize()
+    ref = Y.double().t() @ X.double()
+    assert max_rel(W, ref) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "pheno_missing",
+                                  "mort_nomask", "pheno_rm1d", "pheno_odd"])
+def test_bf16_tc_engine(name):
+    _bf16_case(name, "tc")

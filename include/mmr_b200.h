@@ -159,6 +159,15 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
 int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const void* A,
                    const void* B, const float* bias, float* C, void* stream);
 
+/* Instrumentation (bench / profiling only).  mmr_launch_count: kernels launched by this library
+ * since load.  mmr_prof_enable(1) brackets every launch group with CUDA events on the launching
+ * stream; mmr_prof_collect synchronises them and returns summed device milliseconds and group counts
+ * for 8 classes: 0 tcgen05 gemm, 1 tcgen05 wgrad, 2 attention fwd, 3 attention bwd, 4 SIMT gemm,
+ * 5 routing, 6 whole fusion fwd call, 7 whole fusion bwd call. */
+long long mmr_launch_count(void);
+int mmr_prof_enable(int on);
+int mmr_prof_collect(double* ms_by_class, long long* n_by_class);
+
 int mmr_version(void);
 const char* mmr_last_error_string(void);
 

@@ -36,7 +36,8 @@ class RoutingGrads(C.Structure):
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_routing_scratch_bytes",
-           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm"]
+           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_launch_count",
+           "mmr_prof_enable", "mmr_prof_collect"]
 
 
 def lib_path() -> str:
@@ -74,6 +75,9 @@ def load():
     lib.mmr_capsule_routing_bwd.restype = C.c_int
     lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
     lib.mmr_debug_gemm.restype = C.c_int
+    lib.mmr_launch_count.restype = C.c_longlong
+    lib.mmr_prof_enable.argtypes = [C.c_int]
+    lib.mmr_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _LIB = lib
     return lib
 

@@ -17,6 +17,31 @@ using namespace mmr;
 
 static thread_local std::string g_err;
 
+// ---- instrumentation: launch counter + optional per-class CUDA-event timing (bench / profiling only)
+#include <atomic>
+#include <mutex>
+#include <vector>
+enum ProfClass { PC_GEMM_TC = 0, PC_WGRAD_TC = 1, PC_ATTN_FWD = 2, PC_ATTN_BWD = 3, PC_GEMM_SIMT = 4,
+                 PC_ROUTING = 5, PC_FUSION_FWD = 6, PC_FUSION_BWD = 7, PC_N = 8 };
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { cudaEvent_t a, b; int cls; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+struct ProfScope {
+  cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int cls; bool on;
+  ProfScope(int c, cudaStream_t s) : st(s), cls(c), on(g_prof_on.load() != 0) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof_recs.push_back(ProfRec{a, b, cls});
+    }
+  }
+};
+
 static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -32,6 +57,7 @@ static int fail(int code, const std::string& msg) {
     cudaError_t _e = cudaGetLastError();                                                     \
     if (_e != cudaSuccess)                                                                   \
       return fail(MMR_ERR_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString(_e)); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
   } while (0)
 
 // ------------------------------------------------------------------------------------------
@@ -41,9 +67,12 @@ static int run_gemm(const Plan& P, const GemmProblem& g, const EpiParams& e, int
                     cudaStream_t st, const char* what) {
   if (P.tc) {
     if (g.K % tc::BK != 0 || g.N % 256 != 0) return fail(MMR_ERR_UNSUPPORTED, std::string(what) + ": tcgen05 tile constraint");
+    ProfScope ps(PC_GEMM_TC, st);
     cudaError_t err = tc::launch_gemm_tc<OP>(g, e, a_rows, b_rows, st);
     if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 gemm ") + what + ": " + cudaGetErrorString(err));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
+    ProfScope ps(PC_GEMM_SIMT, st);
     launch_gemm_simt<CT, CT, OP, CT>(g, e, st);
     LAUNCH_OK(what);
   }
@@ -53,9 +82,12 @@ static int run_gemm(const Plan& P, const GemmProblem& g, const EpiParams& e, int
 template <class CT>
 static int run_wgrad(const Plan& P, const WgradProblem& w, int y_rows, int x_rows, cudaStream_t st, const char* what) {
   if (P.tc) {
+    ProfScope ps(PC_WGRAD_TC, st);
     cudaError_t err = tc::launch_wgrad_tc(w, y_rows, x_rows, st);
     if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 wgrad ") + what + ": " + cudaGetErrorString(err));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
+    ProfScope ps(PC_GEMM_SIMT, st);
     launch_wgrad_simt<CT, CT>(w, st);
     LAUNCH_OK(what);
   }
@@ -275,7 +307,10 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
       dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
-      attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      {
+        ProfScope ps(PC_ATTN_FWD, st);
+        attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      }
       LAUNCH_OK("attn_fwd");
       rc = zero_pad(P.q, ob(l), (size_t)D * sizeof(CT), st);
       if (rc) return rc;
@@ -513,10 +548,13 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = const_cast<CT*>(ob(l));
       a.ml = const_cast<float*>(ml(l)); a.d_o = dO; a.dq = dQ; a.dkv = dKV; a.dvec = dvec;
       dim3 g1((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
-      attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
-      LAUNCH_OK("attn_bwd_dq");
       dim3 g2((H * maxTk + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
-      attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      {
+        ProfScope ps(PC_ATTN_BWD, st);
+        attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+      }
+      LAUNCH_OK("attn_bwd_dq");
       LAUNCH_OK("attn_bwd_dkv");
       rc = zero_pad(P.q, dQ, (size_t)D * sizeof(CT), st);
       if (rc) return rc;
@@ -584,7 +622,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         UnfoldJob& j = uj.j[uj.n++];
         j.dwq = dwq + ((size_t)l * 6 + d) * D * D; j.dbq = dbq + ((size_t)l * 6 + d) * D;
         j.dwkv = dwkv + ((size_t)d * L + l) * 2 * D * D; j.dbkv = dbkv + ((size_t)d * L + l) * 2 * D;
-        j.w_in = f(ix.layer(d, l, 0)); j.gamma0 = f(ix.layer(d, l, 8));
+        j.w_in = f(ix.layer(d, l, 0)); j.gamma0 = f(ix.layer(d, l, 8)); j.beta0 = f(ix.layer(d, l, 9));
         j.g_w_in = gr(ix.layer(d, l, 0)); j.g_b_in = gr(ix.layer(d, l, 1));
         j.g_gamma0 = gr(ix.layer(d, l, 8)); j.g_beta0 = gr(ix.layer(d, l, 9));
         if (uj.n == 24 || (d == NDIR - 1 && l == L - 1)) {
@@ -627,6 +665,33 @@ extern "C" {
 
 int mmr_version(void) { return 100; }
 
+long long mmr_launch_count(void) { return g_launches.load(); }
+
+int mmr_prof_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return MMR_OK;
+}
+
+// Synchronises the recorded events and returns the summed device time (ms) and launch-group count
+// per class: 0 tcgen05 gemm, 1 tcgen05 wgrad, 2 attention fwd, 3 attention bwd, 4 SIMT gemm,
+// 5 routing, 6 whole fusion fwd call, 7 whole fusion bwd call.
+int mmr_prof_collect(double* ms_by_class, long long* n_by_class) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < PC_N; ++i) { if (ms_by_class) ms_by_class[i] = 0.0; if (n_by_class) n_by_class[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (ms_by_class) ms_by_class[r.cls] += ms;
+      if (n_by_class) n_by_class[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  return MMR_OK;
+}
+
 const char* mmr_last_error_string(void) { return g_err.c_str(); }
 
 int mmr_fusion_num_params(const mmr_fusion_dims* dims) {
@@ -658,6 +723,7 @@ int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_pa
   const float* x[3] = {x_l, x_n, x_i};
   const float* mask[3] = {mL, mN, mI};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope ps(PC_FUSION_FWD, st);
   if (P.bf16)
     return fusion_fwd<bf16>(P, host_params, x, mask, pos_table, (uint8_t*)packed, (uint8_t*)saved, (uint8_t*)scratch,
                             routes_out, st);
@@ -678,6 +744,7 @@ int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_pa
   const float* mask[3] = {mL, mN, mI};
   float* dx[3] = {dx_l, dx_n, dx_i};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope ps(PC_FUSION_BWD, st);
   if (P.bf16)
     return fusion_bwd<bf16>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
                             d_routes, host_param_grads, dx, st);
@@ -725,6 +792,7 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
   const size_t smem = rt_smem_floats(dims->K, dims->num_routing, false) * 4;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_OK(cudaFuncSetAttribute(routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PC_ROUTING, st);
   routing_fwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
   LAUNCH_OK("routing_fwd");
   return MMR_OK;
@@ -774,6 +842,7 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   a.du = du; a.dpc = dpc; a.dG = dG; a.dbias = grads->bias; a.poses_m = posem;
   const size_t smem = rt_smem_floats(dims->K, dims->num_routing, true) * 4;
   CUDA_OK(cudaFuncSetAttribute(routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PC_ROUTING, st);
   routing_bwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
   LAUNCH_OK("routing_bwd");
   routing_head_grads_kernel<<<1, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,

@@ -428,28 +428,29 @@ __global__ void __launch_bounds__(256) bias_fold_kernel(BiasJobs jobs) {
 // plus the K/V-path contribution to layer_norms.0.{weight,bias}.
 //   Wq' = s*Wq                      -> dWq = s*dWq',  dbq = s*dbq'
 //   Wkv' = Wkv*diag(gamma0)         -> dWkv = dWkv'*diag(gamma0), dgamma0 += colsum(dWkv' .* Wkv)
-//   bkv' = bkv + Wkv*beta0          -> dbkv = dbkv', dbeta0 += Wkv^T dbkv'
+//   bkv' = bkv + Wkv*beta0          -> dbkv = dbkv', dbeta0 += Wkv^T dbkv', dWkv += dbkv' beta0^T
 struct UnfoldJob {
   const float* dwq; const float* dbq;        // [256,256], [256]
   const float* dwkv; const float* dbkv;      // [512,256], [512]
-  const float* w_in; const float* gamma0;    // in_proj_weight [768,256], ln0 weight [256]
+  const float* w_in; const float* gamma0; const float* beta0;   // in_proj_weight [768,256], ln0 weight/bias [256]
   float* g_w_in; float* g_b_in; float* g_gamma0; float* g_beta0;
 };
-struct UnfoldJobs { UnfoldJob j[48]; int n; float scaling; };
+struct UnfoldJobs { UnfoldJob j[24]; int n; float scaling; };
 __global__ void __launch_bounds__(256) unfold_kernel(UnfoldJobs jobs) {
   const UnfoldJob& j = jobs.j[blockIdx.x];
   const int c = threadIdx.x;
   const float s = jobs.scaling;
   if (j.g_w_in)
     for (int o = 0; o < D; ++o) j.g_w_in[(size_t)o * D + c] += s * j.dwq[(size_t)o * D + c];
-  const float gm = j.gamma0[c];
+  const float gm = j.gamma0[c], be = j.beta0[c];
   float dg = 0.f, db = 0.f;
   for (int o = 0; o < 2 * D; ++o) {
     const float dw = j.dwkv[(size_t)o * D + c];
     const float w = j.w_in[(size_t)(D + o) * D + c];
-    if (j.g_w_in) j.g_w_in[(size_t)(D + o) * D + c] += dw * gm;
+    const float dbo = j.dbkv[o];
+    if (j.g_w_in) j.g_w_in[(size_t)(D + o) * D + c] += dw * gm + dbo * be;
     dg += dw * w;
-    db += j.dbkv[o] * w;
+    db += dbo * w;
   }
   if (j.g_gamma0) atomicAdd(j.g_gamma0 + c, dg);
   if (j.g_beta0) atomicAdd(j.g_beta0 + c, db);

@@ -161,6 +161,9 @@ def _common_base(ts: Sequence[Optional[Tensor]], shape) -> Optional[Tuple[int, i
         return None
     if t0.stride(1) != 1 or any(t.stride() != t0.stride() for t in ts):
         return None
+    st0 = t0.untyped_storage().data_ptr()
+    if any(t.untyped_storage().data_ptr() != st0 for t in ts):
+        return None     # separately allocated tensors may be equally spaced by accident
     p0 = t0.data_ptr()
     if len(ts) == 1:
         return p0, 0, t0.stride(0)

@@ -75,3 +75,35 @@ def check_grad_checksums(got: dict, gold: dict, tol: float, what=""):
         if abs(cn - gn) > tol * scale + 1e-9 or abs(cp - gp) > 6 * tol * scale + 1e-9:
             bad.append((n, f"norm {cn:.6e} vs {gn:.6e}; proj {cp:.6e} vs {gp:.6e}"))
     assert not bad, f"{what}: {len(bad)} gradient checksum mismatches, first: {bad[:5]}"
+
+
+def fp64_truth(c, sdm, sdp, sdh, inp):
+    """The oracle evaluated in float64: the exact-arithmetic answer.  Routing with sharpened votes is
+    ill-conditioned for some patients (a 1e-6 input perturbation can move logits by 3e-4), so the
+    reference's own fp32 output carries that much rounding noise; tests therefore accept an
+    implementation that is as close to the fp64 truth as the reference's fp32 result is."""
+    from oracle import route_fusion_oracle as orc
+    d = lambda sd: {k: v.double() for k, v in sd.items()}
+    f = lambda t: None if t is None else t.double()
+    logits, alpha, routes, R = orc.full_forward(
+        d(sdm), d(sdp), d(sdh), inp["x_l"].double(), inp["x_n"].double(), inp["x_i"].double(),
+        f(inp["mL"]), f(inp["mN"]), f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
+        act_temperature=c["temp"], detach_priors=c["detach"])
+    return {"logits": logits, "alpha": alpha, "R": R,
+            "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
+
+
+def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
+    """Per-patient condition estimate of the routing stage: relative change of (logits, R) caused by a
+    relative perturbation eps of the route embeddings, divided by eps (fp64)."""
+    from oracle import route_fusion_oracle as orc
+    d = lambda sd: {k: v.double() for k, v in sd.items()}
+    rm = None if inp["route_mask"] is None else inp["route_mask"].double()
+    base = {r: routes_bt[:, i].double() for i, r in enumerate(synth.ROUTES)}
+    g = torch.Generator().manual_seed(1234)
+    pert = {r: v * (1 + eps * torch.randn(v.shape, generator=g, dtype=torch.float64)) for r, v in base.items()}
+    l0, _, R0 = orc.routing_forward(d(sdp), d(sdh), base, variant=c["variant"], route_mask=rm, act_temperature=c["temp"])
+    l1, _, R1 = orc.routing_forward(d(sdp), d(sdh), pert, variant=c["variant"], route_mask=rm, act_temperature=c["temp"])
+    dl = (l1 - l0).abs().amax(dim=1) / l0.abs().max().clamp_min(1e-12)
+    dR = (R1 - R0).abs().amax(dim=(1, 2)) / R0.abs().max().clamp_min(1e-12)
+    return torch.maximum(dl, dR) / eps

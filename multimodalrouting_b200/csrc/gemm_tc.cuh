@@ -91,6 +91,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-byte vector reduction into global memory (split-K accumulation of weight gradients)
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1.
 //  K-major : 8-row groups of 128B rows, SBO = 1024 B, LBO unused.
 //  MN-major: 64-element (128B) MN atoms x 8 k-rows; SBO = 1024 B between k groups,
@@ -188,24 +193,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(smem_u32(&ctrl->acc_full));
     }
   } else {
+    // TMEM -> registers (one accumulator row per thread) -> shared-memory transpose -> global.
+    // After acc_full every pipeline stage is idle, so the staging tile reuses stage memory.  Each warp
+    // owns rows [32q, 32q+32): it writes its 32x32 chunk as float4 rows (row stride 36 floats: conflict
+    // free for 128-bit accesses) and re-reads it so that 8 lanes cover 128 contiguous bytes of one
+    // output row; residual / aux loads and the stores are then fully coalesced.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int lr = q * 32 + lane;         // row inside the tile
-    const int crow = m0 + lr;
-    const bool in_seg = crow < g.segs.row0[seg + 1];
-    const bool valid = lr < rows_valid;
     mbar_wait(smem_u32(&ctrl->acc_full), 0);
     tc_fence_after();
+    float* stg = reinterpret_cast<float*>(sgen) + q * (32 * 36);
+    const int rg = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      const int n = n0 + c * 32;
-      if (in_seg && n < g.N) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          epi_apply<OP, bf16>(e, crow, valid, g.b_row0[seg] + n + 4 * j, n + 4 * j,
-                              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const int n = n0 + c * 32 + c4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int lr = q * 32 + 4 * i + rg;
+        const int crow = m0 + lr;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * i + rg) * 36 + c4);
+        if (crow < g.segs.row0[seg + 1] && n < g.N)
+          epi_apply<OP, bf16>(e, crow, lr < rows_valid, g.b_row0[seg] + n, n, a4);
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -290,20 +305,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
   } else {
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
     mbar_wait(smem_u32(&ctrl->acc_full), 0);
     tc_fence_after();
     float* out = w.out[seg];
+    float* stg = reinterpret_cast<float*>(sgen) + q * (32 * 36);
+    const int rg = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      const int n = n0 + c * 32;
-      if (out != nullptr && m < w.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n + j < w.N) atomicAdd(out + (size_t)m * w.ldo + n + j, v[j]);
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const int n = n0 + c * 32 + c4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + q * 32 + 4 * i + rg;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * i + rg) * 36 + c4);
+        if (out != nullptr && m < w.M && n < w.N) red_add_v4(out + (size_t)m * w.ldo + n, a4);
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

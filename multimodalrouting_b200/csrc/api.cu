@@ -61,19 +61,41 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// GEMM dispatch helpers
-template <class CT, int OP>
-static int run_gemm(const Plan& P, const GemmProblem& g, const EpiParams& e, int a_rows, int b_rows,
+// GEMM dispatch helpers.  One logical epilogue (EpiSpec) is lowered to the SIMT engine's element-wise
+// functor or to the tcgen05 engine's store-only epilogue.
+enum GOp { G_BIAS, G_BIAS_RELU, G_RELU_BWD, G_MASK, G_F32 };
+struct EpiSpec {
+  const float* bias = nullptr;      // G_BIAS, G_BIAS_RELU
+  const float* rowmask = nullptr;   // G_MASK
+  const void* relu_src = nullptr;   // G_RELU_BWD, SIMT engine: fc1 output (CT) [rows, ld_relu]
+  int ld_relu = 0;
+  uint32_t* bits = nullptr;         // tcgen05 engine: ReLU sign bits [rows, ld_bits] (written by G_BIAS_RELU)
+  int ld_bits = 0;
+  void* out = nullptr;
+  int ldo = 0;
+};
+
+template <class CT, int GOP>
+static int run_gemm(const Plan& P, const GemmProblem& g, const EpiSpec& sp, int a_rows, int b_rows,
                     cudaStream_t st, const char* what) {
   if (P.tc) {
     if (g.K % tc::BK != 0 || g.N % 256 != 0) return fail(MMR_ERR_UNSUPPORTED, std::string(what) + ": tcgen05 tile constraint");
+    tc::TcEpi e; memset(&e, 0, sizeof(e));
+    e.bias = sp.bias; e.rowmask = sp.rowmask; e.bits_in = sp.bits; e.bits_out = sp.bits; e.ld_bits = sp.ld_bits;
+    e.out = sp.out; e.ldo = sp.ldo;
+    constexpr int TOP = GOP == G_BIAS ? tc::TEPI_BIAS : GOP == G_BIAS_RELU ? tc::TEPI_BIAS_RELU_BITS
+                      : GOP == G_RELU_BWD ? tc::TEPI_BITS_IN : GOP == G_MASK ? tc::TEPI_MASK : tc::TEPI_F32;
     ProfScope ps(PC_GEMM_TC, st);
-    cudaError_t err = tc::launch_gemm_tc<OP>(g, e, a_rows, b_rows, st);
+    cudaError_t err = tc::launch_gemm_tc<TOP>(g, e, a_rows, b_rows, st);
     if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 gemm ") + what + ": " + cudaGetErrorString(err));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
+    EpiParams e; memset(&e, 0, sizeof(e));
+    e.bias = sp.bias; e.rowmask = sp.rowmask; e.aux = sp.relu_src; e.ldaux = sp.ld_relu; e.out = sp.out; e.ldo = sp.ldo;
+    constexpr int SOP = GOP == G_BIAS ? EPI_BIAS : GOP == G_BIAS_RELU ? EPI_BIAS_RELU
+                      : GOP == G_RELU_BWD ? EPI_RELUMASK : GOP == G_MASK ? EPI_MASK : EPI_STORE_F32;
     ProfScope ps(PC_GEMM_SIMT, st);
-    launch_gemm_simt<CT, CT, OP, CT>(g, e, st);
+    launch_gemm_simt<CT, CT, SOP, CT>(g, e, st);
     LAUNCH_OK(what);
   }
   return MMR_OK;
@@ -227,6 +249,8 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   float* fp = reinterpret_cast<float*>(scratch + P.f_p);
   float* fy = reinterpret_cast<float*>(scratch + P.f_y);
   float* fu = reinterpret_cast<float*>(scratch + P.f_u);
+  CT* delta = reinterpret_cast<CT*>(scratch + P.f_delta);
+  auto bits = [&](int l) { return reinterpret_cast<uint32_t*>(saved + P.s_bits + (size_t)l * P.l_bits); };
   CT* xh = reinterpret_cast<CT*>(saved + P.s_xh);
   float* maskq = reinterpret_cast<float*>(saved + P.s_maskq);
   auto xin = [&](int l) { return reinterpret_cast<float*>(saved + P.s_xin + (size_t)l * P.l_xin); };
@@ -274,9 +298,9 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     g.segs = P.kv;
     for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.mod.row0[dir_kmod(d)]; g.b_row0[d] = d * ldkv; }
     g.N = ldkv; g.K = D; g.A = xh; g.lda = D; g.B = packed + P.o_wkv; g.ldb = D;
-    EpiParams e; memset(&e, 0, sizeof(e));
+    EpiSpec e;
     e.bias = reinterpret_cast<const float*>(packed + P.o_bkv); e.out = kv; e.ldo = ldkv;
-    rc = run_gemm<CT, EPI_BIAS>(P, g, e, P.MM, NDIR * ldkv, st, "kv_proj");
+    rc = run_gemm<CT, G_BIAS>(P, g, e, P.MM, NDIR * ldkv, st, "kv_proj");
     if (rc) return rc;
   }
   const float* kmask[NDIR];
@@ -296,9 +320,9 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   for (int l = 0; l < L; ++l) {
     {  // Q projection (scaled)
       GemmProblem g = q_problem(h0(l), D, packed + P.o_wq, D, D, D, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
+      EpiSpec e;
       e.bias = reinterpret_cast<const float*>(packed + P.o_bq); e.out = qb(l); e.ldo = D;
-      rc = run_gemm<CT, EPI_BIAS>(P, g, e, P.MQ, L * 6 * D, st, "q_proj");
+      rc = run_gemm<CT, G_BIAS>(P, g, e, P.MQ, L * 6 * D, st, "q_proj");
       if (rc) return rc;
     }
     {  // attention
@@ -315,49 +339,49 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       rc = zero_pad(P.q, ob(l), (size_t)D * sizeof(CT), st);
       if (rc) return rc;
     }
-    {  // out projection + residual + mask
+    {  // out projection (+bias); the residual add + mask is fused into the LN1 kernel below
       GemmProblem g = q_problem(ob(l), D, packed + P.o_wo, D, D, D, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
-      e.bias = reinterpret_cast<const float*>(packed + P.o_bo); e.resid = xin(l); e.ldr = D; e.rowmask = maskq;
-      e.out = x1(l); e.ldo = D;
-      rc = run_gemm<CT, EPI_BIAS_RESID_MASK>(P, g, e, P.MQ, L * 6 * D, st, "out_proj");
+      EpiSpec e;
+      e.bias = reinterpret_cast<const float*>(packed + P.o_bo); e.out = delta; e.ldo = D;
+      rc = run_gemm<CT, G_BIAS>(P, g, e, P.MQ, L * 6 * D, st, "out_proj");
       if (rc) return rc;
     }
-    {  // LN1
+    {  // x1 = (x + attn)*mask ; h1 = LN1(x1)*mask
       LnFwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.x = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
+      a.q = P.q; a.x = xin(l); a.delta = delta; a.x_out = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l, 10)); a.beta[d] = f(ix.layer(d, l, 11)); }
-      ln_rows_fwd_kernel<CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      ln_rows_fwd_kernel<CT, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
       LAUNCH_OK("ln1_fwd");
     }
     {  // fc1 + relu
       GemmProblem g = q_problem(h1(l), D, packed + P.o_w1, D, FF, FF, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
+      EpiSpec e;
       e.bias = reinterpret_cast<const float*>(packed + P.o_b1); e.out = ff(l); e.ldo = FF;
-      rc = run_gemm<CT, EPI_BIAS_RELU>(P, g, e, P.MQ, L * 6 * FF, st, "fc1");
+      e.bits = bits(l); e.ld_bits = FF / 32;
+      rc = run_gemm<CT, G_BIAS_RELU>(P, g, e, P.MQ, L * 6 * FF, st, "fc1");
       if (rc) return rc;
     }
-    {  // fc2 + residual + mask
+    {  // fc2 (+bias); residual add + mask fused into the following LayerNorm kernel
       GemmProblem g = q_problem(ff(l), FF, packed + P.o_w2, FF, D, D, FF, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
-      e.bias = reinterpret_cast<const float*>(packed + P.o_b2); e.resid = x1(l); e.ldr = D; e.rowmask = maskq;
-      e.out = xin(l + 1); e.ldo = D;
-      rc = run_gemm<CT, EPI_BIAS_RESID_MASK>(P, g, e, P.MQ, L * 6 * D, st, "fc2");
+      EpiSpec e;
+      e.bias = reinterpret_cast<const float*>(packed + P.o_b2); e.out = delta; e.ldo = D;
+      rc = run_gemm<CT, G_BIAS>(P, g, e, P.MQ, L * 6 * D, st, "fc2");
       if (rc) return rc;
     }
-    if (l + 1 < L) {  // LN0 of the next layer
+    if (l + 1 < L) {  // x_{l+1} = (x1 + ffn)*mask ; h0 = LN0_{l+1}(x_{l+1})*mask
       LnFwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.x = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
+      a.q = P.q; a.x = x1(l); a.delta = delta; a.x_out = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l + 1, 8)); a.beta[d] = f(ix.layer(d, l + 1, 9)); }
-      ln_rows_fwd_kernel<CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      ln_rows_fwd_kernel<CT, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
       LAUNCH_OK("ln0_fwd");
     }
   }
-  {  // encoder-final LayerNorm (transformer.py:108-113)
+  {  // x_L = (x1 + ffn)*mask, then the encoder-final LayerNorm (transformer.py:108-113)
     LnFwdArgs a; memset(&a, 0, sizeof(a));
-    a.q = P.q; a.x = xin(L); a.maskq = maskq; a.out = fy; a.stat = reinterpret_cast<float*>(saved + P.s_statf);
+    a.q = P.q; a.x = x1(L - 1); a.delta = delta; a.x_out = xin(L); a.maskq = maskq; a.out = fy;
+    a.stat = reinterpret_cast<float*>(saved + P.s_statf);
     for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.enc_ln(d, 0)); a.beta[d] = f(ix.enc_ln(d, 1)); }
-    ln_rows_fwd_kernel<float><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+    ln_rows_fwd_kernel<float, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
     LAUNCH_OK("lnf_fwd");
   }
   {  // masked-mean pooling of the 9 uni/bi-modal routes
@@ -490,9 +514,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   for (int l = L - 1; l >= 0; --l) {
     {  // dF = (G W2) .* relu'   (fc2 data gradient)
       GemmProblem g = q_problem(gc, D, packed + P.o_w2T, D, FF, FF, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
-      e.aux = ff(l); e.ldaux = FF; e.out = dF; e.ldo = FF;
-      rc = run_gemm<CT, EPI_RELUMASK>(P, g, e, P.MQ, L * 6 * FF, st, "d_fc2");
+      EpiSpec e;
+      e.relu_src = ff(l); e.ld_relu = FF; e.out = dF; e.ldo = FF;
+      e.bits = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(saved + P.s_bits + (size_t)l * P.l_bits)); e.ld_bits = FF / 32;
+      rc = run_gemm<CT, G_RELU_BWD>(P, g, e, P.MQ, L * 6 * FF, st, "d_fc2");
       if (rc) return rc;
     }
     {  // dW2
@@ -503,9 +528,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     }
     {  // dH1 = dF W1, masked
       GemmProblem g = q_problem(dF, FF, packed + P.o_w1T, FF, D, D, FF, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
+      EpiSpec e;
       e.rowmask = maskq; e.out = dH; e.ldo = D;
-      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_fc1");
+      rc = run_gemm<CT, G_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_fc1");
       if (rc) return rc;
     }
     {  // dW1, db1
@@ -530,9 +555,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     }
     {  // dO = G1 Wo
       GemmProblem g = q_problem(gc, D, packed + P.o_woT, D, D, D, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
+      EpiSpec e;
       e.out = dO; e.ldo = D;
-      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_out_proj");
+      rc = run_gemm<CT, G_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_out_proj");
       if (rc) return rc;
     }
     {  // dWo
@@ -561,9 +586,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     }
     {  // dH0 = dQ Wq', masked
       GemmProblem g = q_problem(dQ, D, packed + P.o_wqT, D, D, D, D, l);
-      EpiParams e; memset(&e, 0, sizeof(e));
+      EpiSpec e;
       e.rowmask = maskq; e.out = dH; e.ldo = D;
-      rc = run_gemm<CT, EPI_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_q_proj");
+      rc = run_gemm<CT, G_MASK>(P, g, e, P.MQ, L * 6 * D, st, "d_q_proj");
       if (rc) return rc;
     }
     {  // dWq', dbq'
@@ -595,9 +620,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     g.segs = P.kv;
     for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.kv.row0[d]; g.b_row0[d] = d * D; }
     g.N = D; g.K = ldkv; g.A = dKV; g.lda = ldkv; g.B = packed + P.o_wkvT; g.ldb = ldkv;
-    EpiParams e; memset(&e, 0, sizeof(e));
+    EpiSpec e;
     e.out = dxh; e.ldo = D;
-    rc = run_gemm<CT, EPI_STORE_F32>(P, g, e, P.MK, NDIR * D, st, "d_kv_proj");
+    rc = run_gemm<CT, G_F32>(P, g, e, P.MK, NDIR * D, st, "d_kv_proj");
     if (rc) return rc;
     WgradProblem w; memset(&w, 0, sizeof(w));
     w.segs = P.kv;
@@ -885,7 +910,9 @@ int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const 
     e.bias = bias; e.out = C; e.ldo = N;
     if (use_tc) {
       if (K % 64 || N % 256) return fail(MMR_ERR_UNSUPPORTED, "tcgen05 debug gemm needs K%64==0, N%256==0");
-      cudaError_t err = tc::launch_gemm_tc<EPI_BIAS_F32>(g, e, M, N, st);
+      tc::TcEpi te; memset(&te, 0, sizeof(te));
+      te.bias = bias; te.out = C; te.ldo = N;
+      cudaError_t err = tc::launch_gemm_tc<tc::TEPI_BIAS_F32>(g, te, M, N, st);
       if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 gemm: ") + cudaGetErrorString(err));
     } else {
       if (K % 16 || N % 4) return fail(MMR_ERR_UNSUPPORTED, "simt debug gemm needs K%16==0, N%4==0");

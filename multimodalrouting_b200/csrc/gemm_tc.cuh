@@ -3,11 +3,11 @@
 //  gemm_tc_kernel   C[r, n] = sum_k A[a(r), k] * B[b(seg)+n, k]     both operands K-major
 //  wgrad_tc_kernel  out[seg][m, n] += sum_r dY[r, m] * X[x(r), n]   both operands MN-major
 //
-// One CTA = one 128 x BN output tile.  Warp 0 lane 0 drives TMA (cp.async.bulk.tensor, 128B
-// swizzle) through a ring of mbarrier-guarded smem stages, warp 1 lane 0 issues tcgen05.mma with
-// smem descriptors and commits completion to mbarriers, warps 2-5 drain the 128 x BN fp32
-// accumulator from TMEM (tcgen05.ld 32x32b) and apply the element-wise epilogue.  Two CTAs per SM
-// are co-resident (2 x 256 TMEM columns) so one tile's epilogue overlaps the other's main loop.
+// Warp 0 lane 0 drives TMA (cp.async.bulk.tensor, 128B swizzle) through a ring of mbarrier-guarded
+// smem stages, warp 1 lane 0 issues tcgen05.mma with smem descriptors and commits completion to
+// mbarriers, warps 2-5 drain the 128 x BN fp32 accumulator from TMEM (tcgen05.ld 32x32b).  The
+// forward/data-gradient GEMM is persistent (one CTA per SM, two TMEM accumulators, store-only
+// epilogue); the weight-gradient GEMM runs one CTA per (tile, split-K chunk), two CTAs per SM.
 #pragma once
 #include <cuda.h>
 
@@ -121,111 +121,223 @@ template <int BN> __host__ __device__ constexpr int smem_bytes(int stages) { ret
 struct Ctrl {   // lives after the stages
   uint64_t full[8];
   uint64_t empty[8];
-  uint64_t acc_full;
+  uint64_t acc_full;      // wgrad kernel (single accumulator)
+  uint64_t tfull[2];      // persistent GEMM: accumulator buffer ready for the epilogue
+  uint64_t tempty[2];     // persistent GEMM: accumulator buffer drained
   uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Epilogue of the persistent tcgen05 GEMM.  Everything that needs a global LOAD is row- or
+// column-uniform (bias per column, keep-mask per row, 32 ReLU-mask bits per row and 32-column chunk)
+// and is fetched once per tile before the accumulator is ready; after the shared-memory transpose the
+// epilogue only stores, so no memory latency sits on the per-chunk critical path.
+enum TcOp {
+  TEPI_BIAS = 0,            // out<bf16> = acc + bias
+  TEPI_BIAS_RELU_BITS = 1,  // out<bf16> = relu(acc + bias); bits_out = (acc + bias > 0)
+  TEPI_BITS_IN = 2,         // out<bf16> = acc * bits_in
+  TEPI_MASK = 3,            // out<bf16> = acc * rowmask   (rowmask may be null)
+  TEPI_F32 = 4,             // out<f32>  = acc
+  TEPI_BIAS_F32 = 5,        // out<f32>  = acc + bias      (bias may be null; unit tests)
+};
+struct TcEpi {
+  const float* bias;          // stacked like the B rows (b_row0[seg] + n), or null
+  const float* rowmask;       // [rows] in C row space, or null
+  const uint32_t* bits_in;    // [rows, ld_bits] words; word n/32 holds columns n..n+31
+  uint32_t* bits_out;
+  int ld_bits;
+  void* out;
+  int ldo;
+};
+
+constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile (row stride 36 floats)
+
+template <int BN> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
+  return stages * stage_bytes<BN>() + 4 * STG_FLOATS * 4 + 4 * BN * 4 + 1024 + 256;
+}
+
 // ------------------------------------------------------------------------------------------
+// Persistent, warp-specialised GEMM: grid = #SMs, each CTA walks 128 x BN output tiles.
+//   warp 0 : TMA producer, runs ahead across tile boundaries through the smem ring
+//   warp 1 : tcgen05.mma issuer, alternates between two BN-column TMEM accumulators
+//   warps 2-5 : epilogue, drain accumulator i while the MMA warp fills accumulator i+1
 template <int BN, int OP>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               GemmProblem g, EpiParams e, int stages) {
+               GemmProblem g, TcEpi e, int stages) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * stage_bytes<BN>());
+  float* stg_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>());
+  float* bias_all = stg_all + 4 * STG_FLOATS;
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 4 * BN);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int seg = seg_of_row(g.segs, m0);
-  const int local0 = m0 - g.segs.row0[seg];
-  const int rows_valid = g.segs.rows[seg] - local0;
   const int kblocks = g.K / BK;
+  const int nN = g.N / BN;
+  const int ntiles = ((g.segs.row0[g.segs.n] + BM - 1) / BM) * nN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&ctrl->full[s]), 1);
       mbar_init(smem_u32(&ctrl->empty[s]), 1);
     }
-    mbar_init(smem_u32(&ctrl->acc_full), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&ctrl->tfull[b]), 1);
+      mbar_init(smem_u32(&ctrl->tempty[b]), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), BN);
+  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = ctrl->tmem_base;
+  const uint32_t tmem_base = ctrl->tmem_base;
 
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      const int a_row = g.a_row0[seg] + local0;
-      const int b_row = g.b_row0[seg] + n0;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
-        const uint32_t full = smem_u32(&ctrl->full[s]);
-        mbar_expect_tx(full, stage_bytes<BN>());
-        const uint32_t sa = sbase + s * stage_bytes<BN>();
-        const uint32_t sb = sa + BM * BK * 2;
-        tma_load_2d(sa, &tmA, kb * BK, a_row, full);
-        tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / nN) * BM, n0 = (t % nN) * BN;
+        const int seg = seg_of_row(g.segs, m0);
+        const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
+        const int b_row = g.b_row0[seg] + n0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&ctrl->full[s]);
+          mbar_expect_tx(full, stage_bytes<BN>());
+          const uint32_t sa = sbase + s * stage_bytes<BN>();
+          const uint32_t sb = sa + BM * BK * 2;
+          tma_load_2d(sa, &tmA, kb * BK, a_row, full);
+          tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(smem_u32(&ctrl->full[s]), ph);
+      uint32_t it = 0, i = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1;
+        mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = sbase + s * stage_bytes<BN>();
-        const uint32_t sb = sa + BM * BK * 2;
-        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-        const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(smem_u32(&ctrl->full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = sbase + s * stage_bytes<BN>();
+          const uint32_t sb = sa + BM * BK * 2;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the swizzle row
-          umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(smem_u32(&ctrl->empty[s]));
+          for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the swizzle row
+            umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&ctrl->empty[s]));
+        }
+        umma_commit(smem_u32(&ctrl->tfull[buf]));
       }
-      umma_commit(smem_u32(&ctrl->acc_full));
     }
   } else {
-    // TMEM -> registers (one accumulator row per thread) -> shared-memory transpose -> global.
-    // After acc_full every pipeline stage is idle, so the staging tile reuses stage memory.  Each warp
-    // owns rows [32q, 32q+32): it writes its 32x32 chunk as float4 rows (row stride 36 floats: conflict
-    // free for 128-bit accesses) and re-reads it so that 8 lanes cover 128 contiguous bytes of one
-    // output row; residual / aux loads and the stores are then fully coalesced.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    mbar_wait(smem_u32(&ctrl->acc_full), 0);
-    tc_fence_after();
-    float* stg = reinterpret_cast<float*>(sgen) + q * (32 * 36);
+    float* stg = stg_all + q * STG_FLOATS;
+    float* bias_s = bias_all + q * BN;
     const int rg = lane >> 3, c4 = (lane & 7) * 4;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      const int m0 = (t / nN) * BM, n0 = (t % nN) * BN;
+      const int seg = seg_of_row(g.segs, m0);
+      const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
+      const int lr = q * 32 + lane;                 // row owned in the register phase
+      const bool row_ok = lr < rows_valid;
+      // ---- per-tile operands, fetched while the accumulator is still being computed ----
+      float rmask = 1.f;
+      uint32_t bits[BN / 32];
+      if (OP == TEPI_MASK) rmask = (e.rowmask != nullptr && row_ok) ? e.rowmask[m0 + lr] : 1.f;
+      if (OP == TEPI_BITS_IN) {
+        const uint4* bp = reinterpret_cast<const uint4*>(e.bits_in + (size_t)(m0 + lr) * e.ld_bits + n0 / 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      const int n = n0 + c * 32 + c4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int lr = q * 32 + 4 * i + rg;
-        const int crow = m0 + lr;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * i + rg) * 36 + c4);
-        if (crow < g.segs.row0[seg + 1] && n < g.N)
-          epi_apply<OP, bf16>(e, crow, lr < rows_valid, g.b_row0[seg] + n, n, a4);
+        for (int w4 = 0; w4 < BN / 128; ++w4) {
+          uint4 b4 = row_ok ? bp[w4] : make_uint4(0, 0, 0, 0);
+          bits[4 * w4] = b4.x; bits[4 * w4 + 1] = b4.y; bits[4 * w4 + 2] = b4.z; bits[4 * w4 + 3] = b4.w;
+        }
       }
+      if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
+        const float* bsrc = e.bias ? e.bias + g.b_row0[seg] + n0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
+        __syncwarp();
+      }
+      const uint32_t buf = i & 1;
+      mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_acc + c * 32, v);
+        // ---- register phase: thread = row, 32 consecutive columns ----
+        if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bias_s[c * 32 + j];
+        }
+        if (OP == TEPI_BIAS_RELU_BITS) {
+          uint32_t wbits = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            wbits |= (v[j] > 0.f ? 1u : 0u) << j;
+            v[j] = fmaxf(v[j], 0.f);
+          }
+          if (row_ok) e.bits_out[(size_t)(m0 + lr) * e.ld_bits + n0 / 32 + c] = wbits;
+        }
+        if (OP == TEPI_BITS_IN) {
+          const uint32_t wbits = bits[c];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((wbits >> j) & 1u) ? v[j] : 0.f;
+        }
+        if (OP == TEPI_MASK) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= rmask;
+        }
+        if (!row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        // ---- transpose through shared memory, then coalesced stores ----
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int n = n0 + c * 32 + c4;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int crow = m0 + q * 32 + 4 * r8 + rg;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * r8 + rg) * 36 + c4);
+          if (crow < g.segs.row0[seg + 1]) {
+            if (OP == TEPI_F32 || OP == TEPI_BIAS_F32)
+              Vec4<float>::st(reinterpret_cast<float*>(e.out) + (size_t)crow * e.ldo + n, a4);
+            else
+              Vec4<bf16>::st(reinterpret_cast<bf16*>(e.out) + (size_t)crow * e.ldo + n, a4);
+          }
+        }
+        __syncwarp();
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctrl->tempty[buf]));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_acc, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -372,24 +484,30 @@ inline int env_int(const char* name, int dflt) {
 
 // a_rows_total / b_rows_total: number of rows physically present in A / B (TMA bounds).
 template <int OP>
-static cudaError_t launch_gemm_tc(const GemmProblem& g, const EpiParams& e, int a_rows_total, int b_rows_total,
+static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                   cudaStream_t st) {
   constexpr int BN = 256;
-  static int stages_cfg = env_int("MMR_TC_STAGES", 2);
+  static int stages_cfg = env_int("MMR_TC_STAGES", 4);
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
   int stages = stages_cfg;
-  const int kblocks = g.K / BK;
-  if (stages > kblocks) stages = kblocks;
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
   CUtensorMap tmA, tmB;
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN)) return cudaErrorUnknown;
   auto kern = gemm_tc_kernel<BN, OP>;
-  const int smem = smem_bytes<BN>(stages);
+  const int smem = gemm_smem_bytes<BN>(stages);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   const int total_rows = g.segs.row0[g.segs.n];
-  dim3 grid((g.N + BN - 1) / BN, (total_rows + BM - 1) / BM);
+  const int ntiles = ((total_rows + BM - 1) / BM) * (g.N / BN);
+  const int grid = ntiles < sm_count ? ntiles : sm_count;
   kern<<<grid, NTHREADS, smem, st>>>(tmA, tmB, g, e, stages);
   return cudaGetLastError();
 }

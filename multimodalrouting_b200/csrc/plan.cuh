@@ -51,6 +51,7 @@ struct Plan {
   size_t s_xin, s_stat0, s_h0, s_qb, s_o, s_ml, s_x1, s_stat1, s_h1, s_f;   // per layer (stride *_l)
   size_t l_xin, l_stat, l_ct256, l_ml, l_f;
   size_t s_statf;                         // fp32 [MQ,2]
+  size_t s_bits, l_bits;                  // u32 [L][MQ,32] ReLU sign bits of fc1 (tcgen05 engine)
   size_t s_kv;                            // CT [MK, L*512]
   size_t s_epair;                         // fp32 [3,B,256] pair embeddings eLN,eLI,eNI
   size_t s_routes;                        // fp32 [10,B,256] copy of the outputs (pair/trimodal bwd)
@@ -61,6 +62,7 @@ struct Plan {
   size_t f_p;                             // fp32 [MM,256] projected inputs (when din != 256)
   size_t f_y;                             // fp32 [MQ,256] final-LN outputs before pooling
   size_t f_u;                             // fp32 [MM,256] unimodal encoder outputs
+  size_t f_delta;                         // CT [MQ,256] out_proj / fc2 outputs before the residual add
   size_t scratch_fwd_bytes;
 
   // ---- backward scratch ---------------------------------------------------------------------
@@ -133,12 +135,13 @@ inline bool build_plan(const mmr_fusion_dims* d, Plan* p, const char** why) {
   p->s_o = take(L * p->l_ct256); p->s_ml = take(L * p->l_ml); p->s_x1 = take(L * p->l_xin);
   p->s_stat1 = take(L * p->l_stat); p->s_h1 = take(L * p->l_ct256); p->s_f = take(L * p->l_f);
   p->s_statf = take(MQ * 2 * 4);
+  p->l_bits = align256(MQ * (FF / 32) * 4); p->s_bits = take(L * p->l_bits);
   p->s_kv = take(MK * L * 2 * D * ct);
   p->s_epair = take(3 * B * D * 4); p->s_routes = take(10 * B * D * 4); p->s_cnt = take(3 * B * 4);
   p->saved_bytes = o;
 
   o = 0;
-  p->f_p = take(MM * D * 4); p->f_y = take(MQ * D * 4); p->f_u = take(MM * D * 4);
+  p->f_p = take(MM * D * 4); p->f_y = take(MQ * D * 4); p->f_u = take(MM * D * 4); p->f_delta = take(MQ * D * ct);
   p->scratch_fwd_bytes = o;
 
   o = 0;

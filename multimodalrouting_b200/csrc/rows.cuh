@@ -96,14 +96,18 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
 
 // -------------------------------------------------------------------------------------------
 // LayerNorm forward over the query row space: out = (LN(x)*gamma+beta)*maskq; stats saved.
+// With `delta` (the bias-added output of out_proj / fc2 in the compute type) the residual add and
+// query masking of transformer.py:196-199,211-215 are fused in: x = (x_prev + delta)*maskq is
+// written to x_out before being normalised.
 struct LnFwdArgs {
   Segs q;
   const float* x; const float* maskq;
+  const void* delta; float* x_out;
   const float* gamma[NDIR]; const float* beta[NDIR];
   void* out; float* stat;
 };
 
-template <class OT>
+template <class OT, class CT>
 __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(LnFwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
@@ -111,6 +115,12 @@ __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(LnFwdArgs a) {
   const int d = seg_of_row(a.q, r);
   const float mval = a.maskq[r];
   Row8 x = row_load<float>(a.x + (size_t)r * D, lane);
+  if (a.delta) {
+    Row8 dl = row_load<CT>(reinterpret_cast<const CT*>(a.delta) + (size_t)r * D, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x.v[i] = (x.v[i] + dl.v[i]) * mval;
+    row_store<float>(a.x_out + (size_t)r * D, lane, x);
+  }
   float mean, rstd;
   row_stats(x, mean, rstd);
   Row8 g = row_load<float>(a.gamma[d], lane), b = row_load<float>(a.beta[d], lane), o;

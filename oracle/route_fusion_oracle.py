@@ -100,7 +100,8 @@ def _attention(sd, pfx, q_in, k_in, v_in, key_pad, heads):
     if key_pad is not None:
         s = s.view(B, heads, Tq, Tk).masked_fill(
             key_pad.view(B, 1, 1, Tk), torch.finfo(s.dtype).min).view(B * heads, Tq, Tk)
-    p = F.softmax(s.float(), dim=-1).to(dtype=s.dtype)       # fp32 softmax, cast back
+    sf = s if s.dtype == torch.float64 else s.float()        # fp32 softmax (fp64 when evaluating the exact answer)
+    p = F.softmax(sf, dim=-1).to(dtype=s.dtype)              # cast back
     o = torch.bmm(p, v)                                      # [B*H,Tq,hd]
     o = o.view(B, heads, Tq, hd).permute(0, 2, 1, 3).reshape(B, Tq, C)
     return F.linear(o, sd[pfx + "out_proj.weight"], sd[pfx + "out_proj.bias"])

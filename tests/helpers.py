@@ -107,3 +107,27 @@ def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
     dl = (l1 - l0).abs().amax(dim=1) / l0.abs().max().clamp_min(1e-12)
     dR = (R1 - R0).abs().amax(dim=(1, 2)) / R0.abs().max().clamp_min(1e-12)
     return torch.maximum(dl, dR) / eps
+
+
+def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
+    """All parameter / input gradients of the oracle (same loss + R probe as gpu_common.run_case) in
+    `dtype`; float64 gives the exact-arithmetic gradients used by the conditioning-aware criterion."""
+    from oracle import route_fusion_oracle as orc
+    cv = lambda sd: {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    f = lambda t: None if t is None else t.to(dtype)
+    a, b, h = cv(sdm), cv(sdp), cv(sdh)
+    xs = {k: inp[k].to(dtype).clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+    logits, _, _, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
+                                       f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
+                                       act_temperature=c["temp"], detach_priors=c["detach"])
+    total = synth.loss_fn(logits, inp["y"].to(dtype), c["variant"])
+    if r_probe is not None:
+        total = total + 0.05 * (R * r_probe.to(dtype)).sum()
+    total.backward()
+    g = {}
+    for sd in (a, b, h):
+        for k, v in sd.items():
+            g[k] = v.grad
+    for k, v in xs.items():
+        g[k] = v.grad
+    return g

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "attention.cuh"
+#include "attention_mma.cuh"
 #include "epilogue.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -114,6 +115,13 @@ static int run_wgrad(const Plan& P, const WgradProblem& w, int y_rows, int x_row
     LAUNCH_OK(what);
   }
   return MMR_OK;
+}
+
+// bf16 path: tensor-core attention (attention_mma.cuh); fp32 parity path and MMR_ATTN=simt: SIMT kernels
+template <class CT> static bool mma_attention() { return false; }
+template <> bool mma_attention<bf16>() {
+  const char* e = getenv("MMR_ATTN");   // read per call so tests can switch engines inside one process
+  return !(e && !strcmp(e, "simt"));
 }
 
 static Segs single_seg(int rows, int T) {
@@ -308,6 +316,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   int maxTq = 0;
   for (int d = 0; d < NDIR; ++d) maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d];
   CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::FWD_SMEM));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -330,10 +339,15 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       a.q = P.q; a.kv = P.kv;
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
-      dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
       {
         ProfScope ps(PC_ATTN_FWD, st);
-        attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        if (mma_attention<CT>()) {
+          dim3 grid(2 * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
+          amma::attn_fwd_kernel<<<grid, amma::THREADS, amma::FWD_SMEM, st>>>(a);
+        } else {
+          dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+          attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        }
       }
       LAUNCH_OK("attn_fwd");
       rc = zero_pad(P.q, ob(l), (size_t)D * sizeof(CT), st);
@@ -493,6 +507,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   for (int d = 0; d < NDIR; ++d) { maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d]; maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d]; }
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::BWD_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::BWD_SMEM));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -572,12 +588,19 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = const_cast<CT*>(ob(l));
       a.ml = const_cast<float*>(ml(l)); a.d_o = dO; a.dq = dQ; a.dkv = dKV; a.dvec = dvec;
-      dim3 g1((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
-      dim3 g2((H * maxTk + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
       {
         ProfScope ps(PC_ATTN_BWD, st);
-        attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
-        attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        if (mma_attention<CT>()) {
+          dim3 g1(2 * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
+          dim3 g2(2 * ((maxTk + amma::RC - 1) / amma::RC), B, NDIR);
+          amma::attn_bwd_dq_kernel<<<g1, amma::THREADS, amma::BWD_SMEM, st>>>(a);
+          amma::attn_bwd_dkv_kernel<<<g2, amma::THREADS, amma::BWD_SMEM, st>>>(a);
+        } else {
+          dim3 g1((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+          dim3 g2((H * maxTk + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
+          attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+          attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+        }
       }
       LAUNCH_OK("attn_bwd_dq");
       LAUNCH_OK("attn_bwd_dkv");

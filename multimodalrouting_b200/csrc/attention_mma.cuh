@@ -1,0 +1,497 @@
+// Tensor-core (mma.sync m16n8k16, bf16 -> fp32) per-patient cross attention for the bf16 path,
+// forward and backward, all six directions in one launch (multihead_attention.py:93-143).
+//
+// One CTA handles one (direction, patient, head-group of 4, 64-row chunk): the 128-column slice of
+// the Q / K / V (/ dO) rows is staged in shared memory with cp.async (coalesced 256 B row segments),
+// fragments come from ldmatrix, and the [rows x keys] score tile lives in registers.  Warp w owns
+// head (w & 3) of the group and the 16-row tiles {2*(w>>2), 2*(w>>2)+1} of the chunk.  Sequences
+// longer than 64 are walked in 64-row chunks (online softmax in the forward pass).
+//
+// Masking semantics of the reference: scores are rounded to bf16, padded keys are
+// filled with finfo(bf16).min (NOT -inf), softmax is fp32; a patient whose keys are all padded
+// attends uniformly.  Tile-padding keys (>= Tk) are excluded outright.
+#pragma once
+#include "attention.cuh"
+
+namespace mmr {
+namespace amma {
+
+constexpr int HG = 4;              // heads per CTA
+constexpr int THREADS = 256;
+constexpr int LDS = 136;           // smem row stride in bf16 elements (128 + 8: conflict-free ldmatrix)
+constexpr int RC = 64;             // rows (queries or keys) per chunk
+constexpr float NEG_BF16 = -3.3895313892515355e38f;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Stage `nvalid` rows x 128 columns (src row stride ld elements) into dst[rows][LDS]; rows
+// [nvalid, nrows) are zero-filled so that padded B-operand rows never inject NaN/Inf.
+__device__ __forceinline__ void stage(bf16* dst, const bf16* src, size_t ld, int nvalid, int nrows) {
+  for (int idx = threadIdx.x; idx < nrows * 16; idx += THREADS) {
+    const int r = idx >> 4, c = (idx & 15) * 8;
+    bf16* d = dst + r * LDS + c;
+    if (r < nvalid) cp_async16(smem_addr(d), src + (size_t)r * ld + c);
+    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// A fragment (16 rows x 16 k) of a row-major smem tile at (row0, col0)
+__device__ __forceinline__ void frag_a(const bf16* s, int row0, int col0, int lane, uint32_t (&r)[4]) {
+  ldsm_x4(smem_addr(s + (row0 + (lane & 15)) * LDS + col0 + (lane >> 4) * 8), r);
+}
+// B fragments for C[m][n] += A[m][k] * X[n][k] (X row-major, n = row, k = col): 8 rows n0.., k = col0..col0+31
+//   r[0],r[1] = (b0,b1) of k-step 0, r[2],r[3] = (b0,b1) of k-step 1
+__device__ __forceinline__ void frag_b_nk(const bf16* s, int n0, int col0, int lane, uint32_t (&r)[4]) {
+  ldsm_x4(smem_addr(s + (n0 + (lane & 7)) * LDS + col0 + (lane >> 3) * 8), r);
+}
+// B fragments for C[m][n] += A[m][k] * X[k][n] (X row-major, k = row, n = col): 16 rows k0.., cols n0..n0+15
+//   r[0],r[1] = (b0,b1) of n-tile n0, r[2],r[3] = (b0,b1) of n-tile n0+8
+__device__ __forceinline__ void frag_b_kn(const bf16* s, int k0, int n0, int lane, uint32_t (&r)[4]) {
+  ldsm_x4_t(smem_addr(s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8), r);
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// copy `nrows` x 128 columns from smem tile to global (row stride ld), coalesced 16-byte stores
+__device__ __forceinline__ void unstage(bf16* dst, size_t ld, const bf16* src, int nrows) {
+  for (int idx = threadIdx.x; idx < nrows * 16; idx += THREADS) {
+    const int r = idx >> 4, c = (idx & 15) * 8;
+    *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c) = *reinterpret_cast<const uint4*>(src + r * LDS + c);
+  }
+}
+
+// write a 16x8 fp32 C fragment tile as bf16 into smem at (row0, col0)
+__device__ __forceinline__ void put_c(bf16* s, int row0, int col0, int lane, const float (&c)[4], float s0 = 1.f, float s1 = 1.f) {
+  const int g = lane >> 2, t = lane & 3;
+  *reinterpret_cast<uint32_t*>(s + (row0 + g) * LDS + col0 + 2 * t) = pack_bf16(c[0] * s0, c[1] * s0);
+  *reinterpret_cast<uint32_t*>(s + (row0 + g + 8) * LDS + col0 + 2 * t) = pack_bf16(c[2] * s1, c[3] * s1);
+}
+
+constexpr int FWD_SMEM = 3 * RC * LDS * 2 + RC * 4;
+constexpr int BWD_SMEM = 4 * RC * LDS * 2 + RC * 4 + RC * HG * 3 * 4;
+
+// grid: (2 * ceil(maxTq/64), B, 6)
+__global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Ks = Qs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] 1 keep / 0 padded / -1 beyond Tk
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, qc = blockIdx.x >> 1;
+  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  const int q0 = qc * RC;
+  if (q0 >= Tq) return;
+  const int nq = min(RC, Tq - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp & 3, half = warp >> 2, h = hg * HG + hl;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const bf16* qsrc = reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * 128;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * 128;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
+  const int nq16 = (nq + 15) & ~15;
+  stage(Qs, qsrc, D, nq, nq16);
+  const bool single = Tk <= RC;
+
+  float o[2][4][4];
+  float mrun[2][2], lrun[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    mrun[i][0] = mrun[i][1] = -INFINITY;
+    lrun[i][0] = lrun[i][1] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][n][j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < Tk; k0 += RC) {
+    const int nk = min(RC, Tk - k0);
+    const int nk16 = (nk + 15) & ~15;
+    __syncthreads();   // previous chunk fully consumed
+    stage(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
+    stage(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
+    if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[k0 + threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
+    cp_async_wait_all();
+    __syncthreads();
+    const int NT = nk16 >> 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int mt = half * 2 + i;
+      if (mt * 16 >= nq) continue;
+      uint32_t qa[2][4];
+      frag_a(Qs, mt * 16, hl * 32, lane, qa[0]);
+      frag_a(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < NT) {
+          uint32_t kb[4];
+          frag_b_nk(Ks, nt * 8, hl * 32, lane, kb);
+          mma16816(s[nt], qa[0], kb[0], kb[1]);
+          mma16816(s[nt], qa[1], kb[2], kb[3]);
+        }
+      }
+      // bf16 rounding of the scores, key masking, chunk row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float mk = (nt < NT) ? Ms[nt * 8 + 2 * t + j] : -1.f;
+          float v0 = rbf(s[nt][j]), v1 = rbf(s[nt][2 + j]);
+          if (mk == 0.f) { v0 = NEG_BF16; v1 = NEG_BF16; }
+          if (mk < 0.f) { v0 = -INFINITY; v1 = -INFINITY; }
+          s[nt][j] = v0; s[nt][2 + j] = v1;
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      const float mn0 = fmaxf(mrun[i][0], mx0), mn1 = fmaxf(mrun[i][1], mx1);
+      const float c0 = __expf(mrun[i][0] - mn0), c1 = __expf(mrun[i][1] - mn1);   // exp(-inf) = 0 on the first chunk
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float p0 = __expf(s[nt][j] - mn0), p1 = __expf(s[nt][2 + j] - mn1);
+          s[nt][j] = p0; s[nt][2 + j] = p1;
+          sum0 += p0; sum1 += p1;
+        }
+      }
+      sum0 = quad_sum(sum0); sum1 = quad_sum(sum1);
+      lrun[i][0] = lrun[i][0] * c0 + sum0;
+      lrun[i][1] = lrun[i][1] * c1 + sum1;
+      mrun[i][0] = mn0; mrun[i][1] = mn1;
+      float ps0 = 1.f, ps1 = 1.f;
+      if (single) { ps0 = 1.0f / sum0; ps1 = 1.0f / sum1; }   // exact reference order: normalise, then round to bf16
+      else {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { o[i][n][0] *= c0; o[i][n][1] *= c0; o[i][n][2] *= c1; o[i][n][3] *= c1; }
+      }
+      // O += P V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 16 < nk16) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(s[2 * kk][0] * ps0, s[2 * kk][1] * ps0);
+          pa[1] = pack_bf16(s[2 * kk][2] * ps1, s[2 * kk][3] * ps1);
+          pa[2] = pack_bf16(s[2 * kk + 1][0] * ps0, s[2 * kk + 1][1] * ps0);
+          pa[3] = pack_bf16(s[2 * kk + 1][2] * ps1, s[2 * kk + 1][3] * ps1);
+#pragma unroll
+          for (int nc = 0; nc < 2; ++nc) {
+            uint32_t vb[4];
+            frag_b_kn(Vs, kk * 16, hl * 32 + nc * 16, lane, vb);
+            mma16816(o[i][2 * nc], pa, vb[0], vb[1]);
+            mma16816(o[i][2 * nc + 1], pa, vb[2], vb[3]);
+          }
+        }
+      }
+    }
+  }
+  // epilogue: normalise, stage O through the (warp-private) Q slots, write statistics
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nq) continue;
+    const float il0 = 1.0f / lrun[i][0], il1 = 1.0f / lrun[i][1];
+    const float s0 = single ? 1.f : il0, s1 = single ? 1.f : il1;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) put_c(Qs, mt * 16, hl * 32 + n * 8, lane, o[i][n], s0, s1);
+    if (t == 0) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (r0 < nq) { float* p = a.ml + ((qrow0 + r0) * H + h) * 2; p[0] = mrun[i][0]; p[1] = il0; }
+      if (r1 < nq) { float* p = a.ml + ((qrow0 + r1) * H + h) * 2; p[0] = mrun[i][1]; p[1] = il1; }
+    }
+  }
+  __syncthreads();
+  unstage(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * 128, D, Qs, nq);
+}
+
+// ------------------------------------------------------------------------------------------
+// dQ pass.  CTA = (direction, patient, head group, 64-query chunk); loops over key chunks.
+//   P = exp(S - m) / l ; dP = dO V^T ; dS = P .* (dP - D) on kept keys ; dQ = dS K
+// Also writes D = rowsum(dO .* O) to a.dvec for the dK/dV pass.
+__global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Gs = Qs + RC * LDS;      // dO
+  bf16* Ks = Gs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);
+  float* St = Ms + RC;           // [64][HG][3]: m, 1/l, D
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, qc = blockIdx.x >> 1;
+  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  const int q0 = qc * RC;
+  if (q0 >= Tq) return;
+  const int nq = min(RC, Tq - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp & 3, half = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * 128;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
+  const int nq16 = (nq + 15) & ~15;
+  stage(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * 128, D, nq, nq16);
+  stage(Gs, reinterpret_cast<const bf16*>(a.d_o) + qrow0 * D + hg * 128, D, nq, nq16);
+  // row statistics: (row, head) pairs of this CTA; D from global O / dO (64-byte head slices)
+  for (int idx = threadIdx.x; idx < nq * HG; idx += THREADS) {
+    const int r = idx >> 2, hh = idx & 3;
+    const size_t row = qrow0 + r;
+    const int hglob = hg * HG + hh;
+    const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.o) + row * D + hglob * HD);
+    const uint4* pg = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.d_o) + row * D + hglob * HD);
+    float dv = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 x = po[i], y = pg[i];
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dv = fmaf(__uint_as_float(xs[j] << 16), __uint_as_float(ys[j] << 16), dv);
+        dv = fmaf(__uint_as_float(xs[j] & 0xffff0000u), __uint_as_float(ys[j] & 0xffff0000u), dv);
+      }
+    }
+    const float* ml = a.ml + (row * H + hglob) * 2;
+    St[idx * 3] = ml[0]; St[idx * 3 + 1] = ml[1]; St[idx * 3 + 2] = dv;
+    a.dvec[row * H + hglob] = dv;
+  }
+  float dq[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[i][n][j] = 0.f;
+
+  for (int k0 = 0; k0 < Tk; k0 += RC) {
+    const int nk = min(RC, Tk - k0);
+    const int nk16 = (nk + 15) & ~15;
+    __syncthreads();
+    stage(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
+    stage(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
+    if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[k0 + threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int mt = half * 2 + i;
+      if (mt * 16 >= nq) continue;
+      uint32_t qa[2][4], ga[2][4];
+      frag_a(Qs, mt * 16, hl * 32, lane, qa[0]);
+      frag_a(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+      frag_a(Gs, mt * 16, hl * 32, lane, ga[0]);
+      frag_a(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
+      const int r0 = min(mt * 16 + g, nq - 1), r1 = min(mt * 16 + g + 8, nq - 1);
+      const float m0 = St[(r0 * HG + hl) * 3], il0 = St[(r0 * HG + hl) * 3 + 1], D0 = St[(r0 * HG + hl) * 3 + 2];
+      const float m1 = St[(r1 * HG + hl) * 3], il1 = St[(r1 * HG + hl) * 3 + 1], D1 = St[(r1 * HG + hl) * 3 + 2];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 16 >= nk16) continue;
+        uint32_t dsa[4];   // dS of this 16-key step as an A fragment
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int nt = 2 * kk + e;
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t kb[4], vb[4];
+          frag_b_nk(Ks, nt * 8, hl * 32, lane, kb);
+          frag_b_nk(Vs, nt * 8, hl * 32, lane, vb);
+          mma16816(s, qa[0], kb[0], kb[1]);
+          mma16816(s, qa[1], kb[2], kb[3]);
+          mma16816(dp, ga[0], vb[0], vb[1]);
+          mma16816(dp, ga[1], vb[2], vb[3]);
+          float ds[4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float mk = Ms[nt * 8 + 2 * t + j];
+            const float p0 = __expf(rbf(s[j]) - m0) * il0, p1 = __expf(rbf(s[2 + j]) - m1) * il1;
+            ds[j] = mk > 0.f ? p0 * (dp[j] - D0) : 0.f;
+            ds[2 + j] = mk > 0.f ? p1 * (dp[2 + j] - D1) : 0.f;
+          }
+          dsa[e * 2] = pack_bf16(ds[0], ds[1]);
+          dsa[e * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+#pragma unroll
+        for (int nc = 0; nc < 2; ++nc) {
+          uint32_t kb[4];
+          frag_b_kn(Ks, kk * 16, hl * 32 + nc * 16, lane, kb);
+          mma16816(dq[i][2 * nc], dsa, kb[0], kb[1]);
+          mma16816(dq[i][2 * nc + 1], dsa, kb[2], kb[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();   // all reads of Qs done before it is reused as the dQ staging tile
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nq) continue;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) put_c(Qs, mt * 16, hl * 32 + n * 8, lane, dq[i][n]);
+  }
+  __syncthreads();
+  unstage(reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * 128, D, Qs, nq);
+}
+
+// ------------------------------------------------------------------------------------------
+// dK / dV pass (transposed tiles).  CTA = (direction, patient, head group, 64-key chunk); loops
+// over query chunks.  S^T = K Q^T ; dP^T = V dO^T ; dV = P^T dO ; dK = dS^T Q.
+// A padded key still receives dV (its probability is only zero when another key is kept) but no dK.
+__global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Ks = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Vs = Ks + RC * LDS;
+  bf16* Qs = Vs + RC * LDS;
+  bf16* Gs = Qs + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Gs + RC * LDS);
+  float* St = Ms + RC;           // [64 queries][HG][3]
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, kc = blockIdx.x >> 1;
+  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  const int k0 = kc * RC;
+  if (k0 >= Tk) return;
+  const int nk = min(RC, Tk - k0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp & 3, half = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * Tk + k0;
+  const size_t qbase = (size_t)a.q.row0[d] + (size_t)b * Tq;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * 128;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk + k0 : nullptr;
+  const int nk16 = (nk + 15) & ~15;
+  stage(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
+
+  float dk[2][4][4], dv[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dk[i][n][j] = 0.f; dv[i][n][j] = 0.f; }
+
+  for (int q0 = 0; q0 < Tq; q0 += RC) {
+    const int nq = min(RC, Tq - q0);
+    const int nq16 = (nq + 15) & ~15;
+    __syncthreads();
+    stage(Qs, reinterpret_cast<const bf16*>(a.qb) + (qbase + q0) * D + hg * 128, D, nq, nq16);
+    stage(Gs, reinterpret_cast<const bf16*>(a.d_o) + (qbase + q0) * D + hg * 128, D, nq, nq16);
+    for (int idx = threadIdx.x; idx < RC * HG; idx += THREADS) {
+      const int r = idx >> 2, hh = idx & 3;
+      float m = 0.f, il = 0.f, dd = 0.f;
+      if (r < nq) {
+        const size_t rr = (qbase + q0 + r) * H + hg * HG + hh;
+        m = a.ml[rr * 2]; il = a.ml[rr * 2 + 1]; dd = a.dvec[rr];
+      }
+      St[idx * 3] = m; St[idx * 3 + 1] = il; St[idx * 3 + 2] = dd;   // il = 0 for tile-padding queries -> P = 0
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int mt = half * 2 + i;
+      if (mt * 16 >= nk) continue;
+      uint32_t ka[2][4], va[2][4];
+      frag_a(Ks, mt * 16, hl * 32, lane, ka[0]);
+      frag_a(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
+      frag_a(Vs, mt * 16, hl * 32, lane, va[0]);
+      frag_a(Vs, mt * 16, hl * 32 + 16, lane, va[1]);
+      const float mk0 = Ms[mt * 16 + g], mk1 = Ms[mt * 16 + g + 8];   // key flags of this thread's two rows
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 16 >= nq16) continue;
+        uint32_t pa[4], dsa[4];   // P^T and dS^T of this 16-query step as A fragments
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int nt = 2 * kk + e;
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t qb[4], gb[4];
+          frag_b_nk(Qs, nt * 8, hl * 32, lane, qb);
+          frag_b_nk(Gs, nt * 8, hl * 32, lane, gb);
+          mma16816(s, ka[0], qb[0], qb[1]);
+          mma16816(s, ka[1], qb[2], qb[3]);
+          mma16816(dp, va[0], gb[0], gb[1]);
+          mma16816(dp, va[1], gb[2], gb[3]);
+          float p[4], ds[4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float* st = St + ((nt * 8 + 2 * t + j) * HG + hl) * 3;
+            const float m = st[0], il = st[1], dd = st[2];
+            float s0 = rbf(s[j]), s1 = rbf(s[2 + j]);
+            if (mk0 == 0.f) s0 = NEG_BF16;
+            if (mk1 == 0.f) s1 = NEG_BF16;
+            const float p0 = mk0 < 0.f ? 0.f : __expf(s0 - m) * il;
+            const float p1 = mk1 < 0.f ? 0.f : __expf(s1 - m) * il;
+            p[j] = p0; p[2 + j] = p1;
+            ds[j] = mk0 > 0.f ? p0 * (dp[j] - dd) : 0.f;
+            ds[2 + j] = mk1 > 0.f ? p1 * (dp[2 + j] - dd) : 0.f;
+          }
+          pa[e * 2] = pack_bf16(p[0], p[1]);
+          pa[e * 2 + 1] = pack_bf16(p[2], p[3]);
+          dsa[e * 2] = pack_bf16(ds[0], ds[1]);
+          dsa[e * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+#pragma unroll
+        for (int nc = 0; nc < 2; ++nc) {
+          uint32_t gb[4], qb[4];
+          frag_b_kn(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
+          frag_b_kn(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
+          mma16816(dv[i][2 * nc], pa, gb[0], gb[1]);
+          mma16816(dv[i][2 * nc + 1], pa, gb[2], gb[3]);
+          mma16816(dk[i][2 * nc], dsa, qb[0], qb[1]);
+          mma16816(dk[i][2 * nc + 1], dsa, qb[2], qb[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nk) continue;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      put_c(Ks, mt * 16, hl * 32 + n * 8, lane, dk[i][n]);
+      put_c(Vs, mt * 16, hl * 32 + n * 8, lane, dv[i][n]);
+    }
+  }
+  __syncthreads();
+  bf16* out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * 128;
+  unstage(out, a.ldkv, Ks, nk);
+  unstage(out + D, a.ldkv, Vs, nk);
+}
+
+}  // namespace amma
+}  // namespace mmr

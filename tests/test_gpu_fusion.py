@@ -101,3 +101,39 @@ def _bf16_case(name, engine):
 @pytest.mark.parametrize("name", ["mort_cfg1", "pheno_sharp4", "mort_missing", "pheno_odd"])
 def test_bf16_simt_engine(name):
     _bf16_case(name, "simt")
+
+
+@pytest.mark.parametrize("TL,TN,TI,missing", [(150, 70, 33, True), (48, 16, 49, True), (64, 65, 17, False)])
+def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
+    """Tensor-core attention (mma.sync tiles, 64-row chunks with online softmax) against the SIMT
+    attention kernels on the same bf16 path, including sequences longer than one chunk, plus the fp32
+    oracle as the anchor for the route embeddings."""
+    from oracle import route_fusion_oracle as orc
+    c = dict(variant="pheno", K=5, orig_d_n=256, B=3, seed=909, sharp=1.0, temp=1.0, detach=False,
+             missing=missing, mask_mode="full", TL=TL, TN=TN, TI=TI)
+    sdm, sdp, sdh, inp = rebuild_case(c)
+    outs = {}
+    for eng in ("simt", "mma"):
+        os.environ["MMR_ATTN"] = eng
+        try:
+            outs[eng] = run_case(c, sdm, sdp, sdh, inp, autocast=True)
+        finally:
+            os.environ.pop("MMR_ATTN", None)
+    a, b = outs["mma"], outs["simt"]
+    assert max_rel(a["routes"], b["routes"]) < 5e-3
+    assert max_rel(a["logits"], b["logits"]) < 2e-2
+    for k, g in b["grads"].items():
+        if g is None:
+            assert a["grads"][k] is None
+            continue
+        assert bool(torch.isfinite(a["grads"][k]).all()), k
+        assert max_rel(a["grads"][k], g) < 8e-2, f"grad {k}"   # two bf16 roundings of the same math
+    logits, alpha, routes, R = orc.full_forward(sdm, sdp, sdh, inp["x_l"], inp["x_n"], inp["x_i"], inp["mL"],
+                                                inp["mN"], inp["mI"], variant="pheno", route_mask=inp["route_mask"])
+    ref = torch.stack([routes[r] for r in synth_routes()], dim=1)
+    assert max_rel(a["routes"], ref) < 2e-2
+
+
+def synth_routes():
+    from oracle import synth
+    return synth.ROUTES

@@ -110,6 +110,10 @@ typedef struct mmr_routing_dims {
   float prior_floor, prior_ceiling;   /* 0.02 / 0.98 (env_config.py:157-158) */
   int64_t emb_route_stride;   /* elements between routes of one patient in route_embs */
   int64_t emb_batch_stride;   /* elements between patients */
+  int32_t vote_dtype;         /* MMR_DTYPE_F32: votes held in fp32 (parity mode); MMR_DTYPE_BF16: the reduced-
+                                 precision mode -- votes held as saturating fp16 (11-bit mantissa, tighter than the
+                                 reference's bf16 autocast einsums); all accumulation is fp32 in both modes */
+  int32_t reserved;
 } mmr_routing_dims;
 
 typedef struct mmr_routing_params {
@@ -158,6 +162,12 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
  * (the weight-gradient form, reduction over rows). */
 int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const void* A,
                    const void* B, const float* bias, float* C, void* stream);
+
+/* Tuning hook: average device milliseconds of `iters` launches of the persistent tcgen05 GEMM
+ * C[M,N] = A[M,K] * B[N,K]^T (bf16 operands) with epilogue op 0 (+bias -> bf16), 1 (+bias, ReLU, sign
+ * bits), 2 (sign-bit mask) or 4 (fp32 out).  M is padded to 128 rows by the caller's buffers. */
+int mmr_bench_gemm(int op, int M, int N, int K, const void* A, const void* B, const float* bias,
+                   void* C, uint32_t* bits, int iters, float* ms_out, void* stream);
 
 /* Instrumentation (bench / profiling only).  mmr_launch_count: kernels launched by this library
  * since load.  mmr_prof_enable(1) brackets every launch group with CUDA events on the launching

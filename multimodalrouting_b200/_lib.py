@@ -21,7 +21,8 @@ class RoutingDims(C.Structure):
     _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("variant", C.c_int32), ("num_routing", C.c_int32),
                 ("detach_priors", C.c_int32), ("from_poses", C.c_int32), ("act_temperature", C.c_float),
                 ("prior_floor", C.c_float), ("prior_ceiling", C.c_float),
-                ("emb_route_stride", C.c_int64), ("emb_batch_stride", C.c_int64)]
+                ("emb_route_stride", C.c_int64), ("emb_batch_stride", C.c_int64),
+                ("vote_dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RoutingParams(C.Structure):
@@ -36,7 +37,7 @@ class RoutingGrads(C.Structure):
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_routing_scratch_bytes",
-           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_launch_count",
+           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect"]
 
 
@@ -75,6 +76,8 @@ def load():
     lib.mmr_capsule_routing_bwd.restype = C.c_int
     lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
     lib.mmr_debug_gemm.restype = C.c_int
+    lib.mmr_bench_gemm.argtypes = [C.c_int] * 4 + [c_fp] * 5 + [C.c_int, C.POINTER(C.c_float), c_fp]
+    lib.mmr_bench_gemm.restype = C.c_int
     lib.mmr_launch_count.restype = C.c_longlong
     lib.mmr_prof_enable.argtypes = [C.c_int]
     lib.mmr_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]

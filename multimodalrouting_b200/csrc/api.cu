@@ -808,6 +808,7 @@ static int check_routing(const mmr_routing_dims* d) {
   if (d->num_routing < 1 || d->num_routing > RT_MAXIT) return fail(MMR_ERR_UNSUPPORTED, "num_routing must be in [1,4]");
   if (d->variant != MMR_VARIANT_MORT && d->variant != MMR_VARIANT_PHENO) return fail(MMR_ERR_INVALID_ARG, "unknown variant");
   if (!(d->act_temperature > 0.f)) return fail(MMR_ERR_INVALID_ARG, "act_temperature must be > 0");
+  if (d->vote_dtype != MMR_DTYPE_F32 && d->vote_dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_INVALID_ARG, "unknown vote_dtype");
   return MMR_OK;
 }
 
@@ -817,13 +818,59 @@ size_t mmr_routing_scratch_bytes(const mmr_routing_dims* d) {
   return align256(B * 10 * K * 64 * 4) + align256(B * 330 * 4) + align256(B * 320 * 4) + align256(K * 32 * 4) + 256;
 }
 
-static int routing_grid(int B, size_t smem_bytes) {
-  int per_sm = (int)((size_t)(227 * 1024) / (smem_bytes + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int g = 148 * per_sm;
-  return g < B ? g : B;
+}  // extern "C"
+
+// Tile size (patients per CTA) and vote storage type.  The largest tile that fits in shared memory is
+// used as long as it still leaves >= 100 tiles (so the SMs stay busy); small batches use small tiles.
+struct RtLaunch { int PB; bool bf16; size_t smem; int grid; };
+static RtLaunch routing_launch_cfg(const mmr_routing_dims* d, bool bwd) {
+  RtLaunch L;
+  L.bf16 = d->vote_dtype == MMR_DTYPE_BF16;
+  const size_t ut = L.bf16 ? 2 : 4;
+  const int cand[4] = {8, 4, 2, 1};
+  L.PB = 1;
+  for (int i = 0; i < 4; ++i) {
+    const int pb = cand[i];
+    const size_t smem = rt_smem_bytes(d->K, d->num_routing, bwd, pb, ut, d->from_poses != 0);
+    if (smem > (size_t)227 * 1024) continue;
+    if (pb > 1 && (d->B + pb - 1) / pb < 100) continue;
+    L.PB = pb;
+    break;
+  }
+  L.smem = rt_smem_bytes(d->K, d->num_routing, bwd, L.PB, ut, d->from_poses != 0);
+  int per_sm = (int)((size_t)(227 * 1024) / (L.smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int ntiles = (d->B + L.PB - 1) / L.PB;
+  L.grid = ntiles < 148 * per_sm ? ntiles : 148 * per_sm;
+  return L;
 }
+
+template <int PB, class UT>
+static cudaError_t launch_routing(const RoutingArgs& a, const RtLaunch& L, bool bwd, cudaStream_t st) {
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(routing_bwd_kernel<PB, UT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    routing_bwd_kernel<PB, UT><<<L.grid, RT_THREADS, L.smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(routing_fwd_kernel<PB, UT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    routing_fwd_kernel<PB, UT><<<L.grid, RT_THREADS, L.smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+static cudaError_t dispatch_routing(const RoutingArgs& a, const RtLaunch& L, bool bwd, cudaStream_t st) {
+#define MMR_RT_CASE(pb)                                                          \
+  case pb:                                                                       \
+    return L.bf16 ? launch_routing<pb, __half>(a, L, bwd, st) : launch_routing<pb, float>(a, L, bwd, st);
+  switch (L.PB) {
+    MMR_RT_CASE(1) MMR_RT_CASE(2) MMR_RT_CASE(4) MMR_RT_CASE(8)
+  }
+#undef MMR_RT_CASE
+  return cudaErrorInvalidValue;
+}
+
+extern "C" {
 
 int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
                             const float* poses_in, const float* acts_in, const float* acts_override,
@@ -837,12 +884,11 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
   a.d = *dims; a.p = *params;
   a.route_embs = route_embs; a.poses_in = poses_in; a.acts_in = acts_in; a.acts_override = acts_override;
   a.route_mask = route_mask; a.logits = logits; a.alpha = alpha; a.R = R; a.poses_out = poses_out; a.acts_out = acts_out;
-  const size_t smem = rt_smem_floats(dims->K, dims->num_routing, false) * 4;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUDA_OK(cudaFuncSetAttribute(routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const RtLaunch L = routing_launch_cfg(dims, false);
   ProfScope ps(PC_ROUTING, st);
-  routing_fwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
-  LAUNCH_OK("routing_fwd");
+  CUDA_OK(dispatch_routing(a, L, false, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return MMR_OK;
 }
 
@@ -888,11 +934,10 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   a.route_mask = route_mask; a.d_logits = d_logits; a.d_R = d_R;
   a.d_route_embs = d_route_embs; a.d_poses = d_poses; a.d_acts = d_acts;
   a.du = du; a.dpc = dpc; a.dG = dG; a.dbias = grads->bias; a.poses_m = posem;
-  const size_t smem = rt_smem_floats(dims->K, dims->num_routing, true) * 4;
-  CUDA_OK(cudaFuncSetAttribute(routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const RtLaunch L = routing_launch_cfg(dims, true);
   ProfScope ps(PC_ROUTING, st);
-  routing_bwd_kernel<<<routing_grid(dims->B, smem), RT_THREADS, smem, st>>>(a);
-  LAUNCH_OK("routing_bwd");
+  CUDA_OK(dispatch_routing(a, L, true, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   routing_head_grads_kernel<<<1, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,
                                                grads->embedding);
   LAUNCH_OK("routing_head_grads");
@@ -959,6 +1004,40 @@ int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const 
       LAUNCH_OK("debug wgrad");
     }
   }
+  return MMR_OK;
+}
+
+
+/* Tuning hook: times `iters` back-to-back launches of the persistent tcgen05 GEMM  C[M,N] = A[M,K] B[N,K]^T with the
+ * epilogue `op` (0 bias->bf16, 1 bias+relu+sign bits, 2 sign-bit mask, 4 fp32 out) using CUDA events on `stream`;
+ * returns the average milliseconds per launch. */
+int mmr_bench_gemm(int op, int M, int N, int K, const void* A, const void* B, const float* bias, void* C,
+                   uint32_t* bits, int iters, float* ms_out, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0 || N % 256 || K % 64 || iters < 1) return fail(MMR_ERR_INVALID_ARG, "bad bench gemm size");
+  GemmProblem g; memset(&g, 0, sizeof(g));
+  g.segs = single_seg(M, 1);
+  g.segs.row0[1] = pad128(M);
+  g.N = N; g.K = K; g.A = A; g.lda = K; g.B = B; g.ldb = K;
+  tc::TcEpi te; memset(&te, 0, sizeof(te));
+  te.bias = bias; te.out = C; te.ldo = N; te.bits_in = bits; te.bits_out = bits; te.ld_bits = N / 32;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaError_t err = cudaSuccess;
+  for (int i = -1; i < iters && err == cudaSuccess; ++i) {
+    if (i == 0) cudaEventRecord(e0, st);
+    if (op == 0) err = tc::launch_gemm_tc<tc::TEPI_BIAS>(g, te, M, N, st);
+    else if (op == 1) err = tc::launch_gemm_tc<tc::TEPI_BIAS_RELU_BITS>(g, te, M, N, st);
+    else if (op == 2) err = tc::launch_gemm_tc<tc::TEPI_BITS_IN>(g, te, M, N, st);
+    else err = tc::launch_gemm_tc<tc::TEPI_F32>(g, te, M, N, st);
+  }
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("bench gemm: ") + cudaGetErrorString(err));
+  if (ms_out) *ms_out = ms / iters;
   return MMR_OK;
 }
 

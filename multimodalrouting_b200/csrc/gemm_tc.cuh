@@ -153,27 +153,96 @@ struct TcEpi {
   int ldo;
 };
 
-constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile (row stride 36 floats)
+constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile of the weight-gradient epilogue
 
 template <int BN> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-  return stages * stage_bytes<BN>() + 4 * STG_FLOATS * 4 + 4 * BN * 4 + 1024 + 256;
+  return stages * stage_bytes<BN>() + 8 * (BN / 2) * 4 + 1024 + 256;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// One 32-column chunk of one accumulator row: apply the epilogue op and store it.  The thread owns
+// the row, so its 32 columns are 64 (bf16) / 128 (fp32) contiguous bytes written as 16-byte vectors.
+template <int OP>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* bias_c, float rmask, uint32_t wbits_in,
+                                          uint32_t& wbits_out, bool row_ok, void* out_row, int col) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_c + j);   // shared-memory broadcast
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (OP == TEPI_BIAS_RELU_BITS) {
+    uint32_t wb = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      wb |= (v[j] > 0.f ? 1u : 0u) << j;
+      v[j] = fmaxf(v[j], 0.f);
+    }
+    wbits_out = wb;
+  }
+  if (OP == TEPI_BITS_IN) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((wbits_in >> j) & 1u) ? v[j] : 0.f;
+  }
+  if (OP == TEPI_MASK) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rmask;
+  }
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if (OP == TEPI_F32 || OP == TEPI_BIAS_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_row) + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                        pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // Persistent, warp-specialised GEMM: grid = #SMs, each CTA walks 128 x BN output tiles.
-//   warp 0 : TMA producer, runs ahead across tile boundaries through the smem ring
-//   warp 1 : tcgen05.mma issuer, alternates between two BN-column TMEM accumulators
-//   warps 2-5 : epilogue, drain accumulator i while the MMA warp fills accumulator i+1
+//   warp 0    : TMA producer, runs ahead across tile boundaries through the smem ring
+//   warp 1    : tcgen05.mma issuer, alternates between two BN-column TMEM accumulators
+//   warps 2-9 : epilogue; warp w drains TMEM lane quarter (w & 3), column half ((w - 2) >> 2) of
+//               accumulator i while the MMA warp fills accumulator i+1
 template <int BN, int OP>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                GemmProblem g, TcEpi e, int stages) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  float* stg_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>());
-  float* bias_all = stg_all + 4 * STG_FLOATS;
-  Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 4 * BN);
+  float* bias_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>());
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 8 * (BN / 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = g.K / BK;
   const int nN = g.N / BN;
@@ -186,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&ctrl->tfull[b]), 1);
-      mbar_init(smem_u32(&ctrl->tempty[b]), 4);
+      mbar_init(smem_u32(&ctrl->tempty[b]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -247,92 +316,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    float* stg = stg_all + q * STG_FLOATS;
-    float* bias_s = bias_all + q * BN;
-    const int rg = lane >> 3, c4 = (lane & 7) * 4;
+    const int ch = (warp - 2) >> 2;       // column half
+    constexpr int HC = BN / 2;            // columns per epilogue warp
+    float* bias_s = bias_all + (warp - 2) * HC;
+    const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
     uint32_t i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
-      const int m0 = (t / nN) * BM, n0 = (t % nN) * BN;
+      const int m0 = (t / nN) * BM, n0 = (t % nN) * BN + ch * HC;
       const int seg = seg_of_row(g.segs, m0);
       const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
-      const int lr = q * 32 + lane;                 // row owned in the register phase
+      const int lr = q * 32 + lane;                 // accumulator row owned by this thread
       const bool row_ok = lr < rows_valid;
       // ---- per-tile operands, fetched while the accumulator is still being computed ----
       float rmask = 1.f;
-      uint32_t bits[BN / 32];
+      uint32_t bits[HC / 32];
       if (OP == TEPI_MASK) rmask = (e.rowmask != nullptr && row_ok) ? e.rowmask[m0 + lr] : 1.f;
       if (OP == TEPI_BITS_IN) {
         const uint4* bp = reinterpret_cast<const uint4*>(e.bits_in + (size_t)(m0 + lr) * e.ld_bits + n0 / 32);
 #pragma unroll
-        for (int w4 = 0; w4 < BN / 128; ++w4) {
+        for (int w4 = 0; w4 < HC / 128; ++w4) {
           uint4 b4 = row_ok ? bp[w4] : make_uint4(0, 0, 0, 0);
           bits[4 * w4] = b4.x; bits[4 * w4 + 1] = b4.y; bits[4 * w4 + 2] = b4.z; bits[4 * w4 + 3] = b4.w;
         }
       }
       if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
         const float* bsrc = e.bias ? e.bias + g.b_row0[seg] + n0 : nullptr;
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
+        for (int j = 0; j < HC / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
         __syncwarp();
       }
+      uint8_t* out_row = reinterpret_cast<uint8_t*>(e.out) + (size_t)(m0 + lr) * e.ldo * (f32_out ? 4 : 2);
       const uint32_t buf = i & 1;
       mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_acc + c * 32, v);
-        // ---- register phase: thread = row, 32 consecutive columns ----
-        if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
+      const uint32_t tmem_acc = tmem_base + buf * BN + ch * HC + ((uint32_t)(q * 32) << 16);
+      uint32_t wout[HC / 32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += bias_s[c * 32 + j];
+      for (int cc = 0; cc < HC / 64; ++cc) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tmem_acc + cc * 64, r0);
+        tmem_ld32_nowait(tmem_acc + cc * 64 + 32, r1);
+        tmem_ld_wait();
+        if (cc == HC / 64 - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&ctrl->tempty[buf]));
         }
-        if (OP == TEPI_BIAS_RELU_BITS) {
-          uint32_t wbits = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            wbits |= (v[j] > 0.f ? 1u : 0u) << j;
-            v[j] = fmaxf(v[j], 0.f);
-          }
-          if (row_ok) e.bits_out[(size_t)(m0 + lr) * e.ld_bits + n0 / 32 + c] = wbits;
-        }
-        if (OP == TEPI_BITS_IN) {
-          const uint32_t wbits = bits[c];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((wbits >> j) & 1u) ? v[j] : 0.f;
-        }
-        if (OP == TEPI_MASK) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= rmask;
-        }
-        if (!row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        // ---- transpose through shared memory, then coalesced stores ----
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int n = n0 + c * 32 + c4;
-#pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-          const int crow = m0 + q * 32 + 4 * r8 + rg;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * r8 + rg) * 36 + c4);
-          if (crow < g.segs.row0[seg + 1]) {
-            if (OP == TEPI_F32 || OP == TEPI_BIAS_F32)
-              Vec4<float>::st(reinterpret_cast<float*>(e.out) + (size_t)crow * e.ldo + n, a4);
-            else
-              Vec4<bf16>::st(reinterpret_cast<bf16*>(e.out) + (size_t)crow * e.ldo + n, a4);
-          }
-        }
-        __syncwarp();
+        epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], row_ok,
+                      out_row, n0 + cc * 64);
+        epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, OP == TEPI_BITS_IN ? bits[2 * cc + 1] : 0u, wout[2 * cc + 1],
+                      row_ok, out_row, n0 + cc * 64 + 32);
       }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctrl->tempty[buf]));
+      if (OP == TEPI_BIAS_RELU_BITS && row_ok) {
+        uint4* bo = reinterpret_cast<uint4*>(e.bits_out + (size_t)(m0 + lr) * e.ld_bits + n0 / 32);
+#pragma unroll
+        for (int w4 = 0; w4 < HC / 128; ++w4) bo[w4] = make_uint4(wout[4 * w4], wout[4 * w4 + 1], wout[4 * w4 + 2], wout[4 * w4 + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -508,7 +548,7 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   const int total_rows = g.segs.row0[g.segs.n];
   const int ntiles = ((total_rows + BM - 1) / BM) * (g.N / BN);
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  kern<<<grid, NTHREADS, smem, st>>>(tmA, tmB, g, e, stages);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g, e, stages);
   return cudaGetLastError();
 }
 

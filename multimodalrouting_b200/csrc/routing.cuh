@@ -1,6 +1,10 @@
-// Capsule-style routing + heads: one persistent CTA walks patients; all per-patient routing state
-// (10 route embeddings, primary capsules, 10 x K x 64 votes, per-iteration decision poses and
-// routing coefficients) lives in shared memory across all agreement iterations.
+// Capsule-style routing + heads.  One CTA owns a tile of PB patients and keeps ALL of their routing
+// state in shared memory across the agreement iterations: the 10 route embeddings, the primary
+// capsules, the 10 x K x 64 votes (fp32 in the fp32 parity mode, saturating fp16 in the bf16 mode -- the
+// reference computes these einsums in bf16 under autocast), per-iteration decision poses and routing
+// coefficients.  The vote weights w[10,32,K,64] (2 MB at K=25) and the projector weights stream
+// through the CTA ONCE per tile (coalesced 16-byte loads, PB FMAs per loaded value), so their L2
+// traffic is amortised over the tile instead of being re-read per patient.
 //   RoutePrimaryProjector.forward         routing_and_heads.py:111-121
 //   forward_capsule_from_route_dict       routing_and_heads.py:314-352 (mask / temperature / clamp)
 //   CapsuleMortalityHead.forward          Mort :194-268 / Pheno :194-272
@@ -29,46 +33,54 @@ struct RoutingArgs {
   float* dbias;     // [K] or null
 };
 
-// shared-memory carve (floats)
-struct RtSmem {
-  float* e;      // [10][256]
-  float* pose;   // [10][32]  masked poses
-  float* zl;     // [10] projector activation logits
-  float* a0;     // [10] sigmoid / override
-  float* a2;     // [10] after temperature (pre-clamp)
-  float* a3;     // [10] prior after clamp
-  float* alpha;  // [10] prim_act * mask
-  float* act;    // [10] activation used inside routing
-  float* rm;     // [10]
+// per-patient persistent state (floats)
+constexpr int RT_PP_FWD = 320 + 7 * 16;            // pose, zl, a0, a2, a3, alpha, act, rm
+constexpr int RT_PP_BWD = RT_PP_FWD + 320 + 48;    // + dpose, misc (d alpha | d act | d act-logit)
+
+struct RtPatient {   // views into the per-patient block
+  float* pose; float* zl; float* a0; float* a2; float* a3; float* alpha; float* act; float* rm;
+  float* dpose; float* misc;
+};
+__device__ __forceinline__ RtPatient rt_patient(float* base, int p, bool bwd) {
+  float* q = base + (size_t)p * (bwd ? RT_PP_BWD : RT_PP_FWD);
+  RtPatient s;
+  s.pose = q; q += 320;
+  s.zl = q; q += 16; s.a0 = q; q += 16; s.a2 = q; q += 16; s.a3 = q; q += 16;
+  s.alpha = q; q += 16; s.act = q; q += 16; s.rm = q; q += 16;
+  s.dpose = q; s.misc = q + 320;
+  return s;
+}
+
+// scratch shared by the patients of a tile (one patient walks the iterations at a time)
+struct RtScratch {
   float* G;      // [K][32]
-  float* u;      // [10][K*64]
   float* v;      // [nit][K*64]
   float* q;      // [nit][10*K]
   float* Rn;     // [10*K]
   float* dp;     // [K][32] decision poses d_bkp
-  // backward only
-  float* dv;     // [nit][K*64]
-  float* ds;     // [nit][10*K]
-  float* ddp;    // [K][32]
-  float* dpose;  // [10][32]
-  float* misc;   // [64]
+  float* dv;     // bwd [nit][K*64]
+  float* ds;     // bwd [nit][10*K]
+  float* ddp;    // bwd [K][32]
+  float* tr;     // bwd [10*K]
 };
-
-__host__ __device__ inline size_t rt_smem_floats(int K, int nit, bool bwd) {
-  size_t n = 10 * 256 + 10 * 32 + 7 * 16 + K * 32 + 10 * K * 64 + (size_t)nit * K * 64 + (size_t)nit * 10 * K + 10 * K + K * 32;
-  if (bwd) n += (size_t)nit * K * 64 + (size_t)nit * 10 * K + K * 32 + 10 * 32 + 64;
-  return n + 64;
+__host__ __device__ inline size_t rt_scratch_floats(int K, int nit, bool bwd) {
+  size_t n = (size_t)K * 32 + (size_t)nit * K * 64 + (size_t)nit * 10 * K + 10 * K + K * 32;
+  if (bwd) n += (size_t)nit * K * 64 + (size_t)nit * 10 * K + K * 32 + 10 * K;
+  return (n + 3) / 4 * 4;
 }
-
-__device__ inline RtSmem rt_carve(float* base, int K, int nit, bool bwd) {
-  RtSmem s;
+// vote region per patient: max(votes in UT, the 10 route embeddings in fp32 that alias it during the projector phase)
+__host__ __device__ inline size_t rt_u_bytes(int K, size_t ut_size, bool from_poses) {
+  const size_t u = (size_t)10 * K * 64 * ut_size, e = from_poses ? 0 : (size_t)10 * 256 * 4;
+  return ((u > e ? u : e) + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t rt_smem_bytes(int K, int nit, bool bwd, int PB, size_t ut_size, bool from_poses) {
+  return rt_scratch_floats(K, nit, bwd) * 4 + (size_t)PB * (bwd ? RT_PP_BWD : RT_PP_FWD) * 4 +
+         (size_t)PB * rt_u_bytes(K, ut_size, from_poses) + 16;
+}
+__device__ inline RtScratch rt_carve(float* base, int K, int nit, bool bwd) {
+  RtScratch s;
   float* p = base;
-  s.e = p; p += 10 * 256;
-  s.pose = p; p += 10 * 32;
-  s.zl = p; p += 16; s.a0 = p; p += 16; s.a2 = p; p += 16; s.a3 = p; p += 16;
-  s.alpha = p; p += 16; s.act = p; p += 16; s.rm = p; p += 16;
   s.G = p; p += K * 32;
-  s.u = p; p += 10 * K * 64;
   s.v = p; p += nit * K * 64;
   s.q = p; p += nit * 10 * K;
   s.Rn = p; p += 10 * K;
@@ -77,55 +89,72 @@ __device__ inline RtSmem rt_carve(float* base, int K, int nit, bool bwd) {
     s.dv = p; p += nit * K * 64;
     s.ds = p; p += nit * 10 * K;
     s.ddp = p; p += K * 32;
-    s.dpose = p; p += 10 * 32;
-    s.misc = p; p += 64;
+    s.tr = p; p += 10 * K;
   } else {
-    s.dv = s.ds = s.ddp = s.dpose = s.misc = nullptr;
+    s.dv = s.ds = s.ddp = s.tr = nullptr;
   }
   return s;
 }
 
 // G[k][p] = sum_m pose_to_mc[m][p] * embedding[k][m]   (logits = sum_p d[k][p]*G[k][p] + bias[k])
-__device__ inline void rt_build_G(const RoutingArgs& a, const RtSmem& s) {
+__device__ inline void rt_build_G(const RoutingArgs& a, float* G) {
   const int K = a.d.K;
   for (int i = threadIdx.x; i < K * 32; i += RT_THREADS) {
     const int k = i >> 5, p = i & 31;
     float acc = 0.f;
     for (int m = 0; m < MC; ++m) acc = fmaf(a.p.pose_to_mc[m * PC + p], a.p.embedding[k * MC + m], acc);
-    s.G[i] = acc;
+    G[i] = acc;
   }
 }
 
-// Forward for patient b entirely in shared memory.  Leaves every intermediate in `s`.
-__device__ inline void rt_forward(const RoutingArgs& a, const RtSmem& s, int b) {
-  const int K = a.d.K, KD = K * 64, nit = a.d.num_routing;
+// ---- tile phase 1: projector + activation chain for the np patients b0 .. b0+np-1 ---------------
+template <int PB>
+__device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg, size_t ustride, bool bwd, int b0, int np) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_mask = a.route_mask != nullptr;
-  __syncthreads();
-  if (tid < 10) s.rm[tid] = has_mask ? a.route_mask[(size_t)b * 10 + tid] : 1.f;
+  for (int i = tid; i < PB * 10; i += RT_THREADS) {
+    const int p = i / 10, r = i % 10;
+    RtPatient s = rt_patient(pp, p, bwd);
+    s.rm[r] = (p < np && has_mask) ? a.route_mask[(size_t)(b0 + p) * 10 + r] : 1.f;
+  }
   if (!a.d.from_poses) {
-    for (int i = tid; i < 10 * 64; i += RT_THREADS) {
-      const int r = i >> 6, c = (i & 63) * 4;
-      *reinterpret_cast<float4*>(s.e + r * 256 + c) = *reinterpret_cast<const float4*>(
-          a.route_embs + (size_t)r * a.d.emb_route_stride + (size_t)b * a.d.emb_batch_stride + c);
+    // route embeddings -> the (not yet used) vote region
+    for (int i = tid; i < PB * 10 * 64; i += RT_THREADS) {
+      const int p = i / 640, r = (i % 640) >> 6, c = (i & 63) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < np)
+        v = *reinterpret_cast<const float4*>(a.route_embs + (size_t)r * a.d.emb_route_stride +
+                                             (size_t)(b0 + p) * a.d.emb_batch_stride + c);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ureg + p * ustride) + r * 256 + c) = v;
     }
     __syncthreads();
-    // projector: 10 x 33 dot products of length 256, one warp each
+    // 10 x 33 dot products of length 256: one warp per output, the weight row is shared by the tile
     for (int o = warp; o < 330; o += RT_THREADS / 32) {
       const int r = o / 33, j = o % 33;
       const float* w = a.p.proj_w[r] + (size_t)j * 256;
-      float acc = 0.f;
+      float wv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fmaf(w[lane + 32 * i], s.e[r * 256 + lane + 32 * i], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        acc += a.p.proj_b[r][j];
-        if (j < 32) s.pose[r * 32 + j] = acc; else s.zl[r] = acc;
+      for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + lane + 32 * i);
+      const float bias = a.p.proj_b[r][j];
+#pragma unroll
+      for (int p = 0; p < PB; ++p) {
+        const float* e = reinterpret_cast<const float*>(ureg + p * ustride) + r * 256;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(wv[i], e[lane + 32 * i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          RtPatient s = rt_patient(pp, p, bwd);
+          if (j < 32) s.pose[r * 32 + j] = acc + bias; else s.zl[r] = acc + bias;
+        }
       }
     }
     __syncthreads();
-    if (tid < 10) {
-      const int r = tid;
+    for (int i = tid; i < PB * 10; i += RT_THREADS) {
+      const int p = i / 10, r = i % 10;
+      if (p >= np) continue;
+      RtPatient s = rt_patient(pp, p, bwd);
+      const int b = b0 + p;
       const float rm = s.rm[r];
       float a0 = 1.0f / (1.0f + expf(-s.zl[r]));
       if (a.acts_out) a.acts_out[(size_t)b * 10 + r] = a0;
@@ -144,32 +173,73 @@ __device__ inline void rt_forward(const RoutingArgs& a, const RtSmem& s, int b) 
       s.alpha[r] = has_mask ? x * rm : x;
     }
     if (a.poses_out)
-      for (int i = tid; i < 320; i += RT_THREADS) a.poses_out[(size_t)b * 320 + i] = s.pose[i];
+      for (int i = tid; i < np * 320; i += RT_THREADS) {
+        const int p = i / 320, j = i % 320;
+        a.poses_out[(size_t)(b0 + p) * 320 + j] = rt_patient(pp, p, bwd).pose[j];
+      }
     __syncthreads();
   } else {
-    for (int i = tid; i < 320; i += RT_THREADS) s.pose[i] = a.poses_in[(size_t)b * 320 + i];
-    if (tid < 10) {
-      const float x = a.acts_in[(size_t)b * 10 + tid];
-      s.a0[tid] = s.a2[tid] = s.a3[tid] = x;
-      s.alpha[tid] = has_mask ? x * s.rm[tid] : x;
+    for (int i = tid; i < PB * 320; i += RT_THREADS) {
+      const int p = i / 320, j = i % 320;
+      rt_patient(pp, p, bwd).pose[j] = p < np ? a.poses_in[(size_t)(b0 + p) * 320 + j] : 0.f;
+    }
+    for (int i = tid; i < PB * 10; i += RT_THREADS) {
+      const int p = i / 10, r = i % 10;
+      RtPatient s = rt_patient(pp, p, bwd);
+      const float x = p < np ? a.acts_in[(size_t)(b0 + p) * 10 + r] : 0.f;
+      s.a0[r] = s.a2[r] = s.a3[r] = x;
+      s.alpha[r] = has_mask ? x * s.rm[r] : x;
     }
     __syncthreads();
   }
   // mask poses, pick the routing activation
-  for (int i = tid; i < 320; i += RT_THREADS) s.pose[i] *= s.rm[i >> 5];
-  if (tid < 10) s.act[tid] = (a.d.variant == MMR_VARIANT_PHENO) ? s.alpha[tid] : s.rm[tid];
+  for (int i = tid; i < PB * 320; i += RT_THREADS) {
+    const int p = i / 320, j = i % 320;
+    RtPatient s = rt_patient(pp, p, bwd);
+    s.pose[j] *= s.rm[j >> 5];
+  }
+  for (int i = tid; i < PB * 10; i += RT_THREADS) {
+    const int p = i / 10, r = i % 10;
+    RtPatient s = rt_patient(pp, p, bwd);
+    s.act[r] = (a.d.variant == MMR_VARIANT_PHENO) ? s.alpha[r] : s.rm[r];
+  }
   __syncthreads();
-  // votes u[r][c] = sum_a pose[r][a] * w[r][a][c],  c = k*64 + d
-  for (int c = tid; c < KD; c += RT_THREADS) {
+}
+
+// ---- tile phase 2: votes u[p][r][c] = sum_a pose[p][r][a] * w[r][a][c],  c = k*64 + d ------------
+// A thread owns 4 consecutive columns; every 16-byte weight load feeds PB*4 FMAs.
+template <int PB, class UT>
+__device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* ureg, size_t ustride, bool bwd) {
+  const int KD = a.d.K * 64;
+  const int ppstride = bwd ? RT_PP_BWD : RT_PP_FWD;
+  for (int cg = threadIdx.x; cg < KD / 4; cg += RT_THREADS) {
     for (int r = 0; r < 10; ++r) {
-      const float* w = a.p.caps_w + (size_t)r * 32 * KD + c;
-      float acc = 0.f;
+      float4 acc[PB];
+#pragma unroll
+      for (int p = 0; p < PB; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* w = reinterpret_cast<const float4*>(a.p.caps_w + (size_t)r * 32 * KD) + cg;
 #pragma unroll 8
-      for (int aa = 0; aa < 32; ++aa) acc = fmaf(s.pose[r * 32 + aa], w[(size_t)aa * KD], acc);
-      s.u[r * KD + c] = acc;
+      for (int aa = 0; aa < 32; ++aa) {
+        const float4 w4 = __ldg(w + (size_t)aa * (KD / 4));
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+          const float x = pp[p * ppstride + r * 32 + aa];
+          acc[p].x = fmaf(x, w4.x, acc[p].x); acc[p].y = fmaf(x, w4.y, acc[p].y);
+          acc[p].z = fmaf(x, w4.z, acc[p].z); acc[p].w = fmaf(x, w4.w, acc[p].w);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < PB; ++p) Vec4<UT>::st(reinterpret_cast<UT*>(ureg + p * ustride) + r * KD + 4 * cg, acc[p]);
     }
   }
   __syncthreads();
+}
+
+// ---- per-patient agreement iterations; leaves q / v / Rn / dp in the shared scratch -------------
+template <class UT>
+__device__ inline void rt_iterate(const RoutingArgs& a, const RtScratch& s, const RtPatient& pt, const UT* u) {
+  const int K = a.d.K, KD = K * 64, nit = a.d.num_routing;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float scale = 0.125f;   // 1/sqrt(64)
   const float invK = 1.0f / (float)K;
   for (int it = 0; it < nit; ++it) {
@@ -180,8 +250,8 @@ __device__ inline void rt_forward(const RoutingArgs& a, const RtSmem& s, int b) 
       const float* vp = s.v + (it - 1) * KD;
       for (int o = warp; o < 10 * K; o += RT_THREADS / 32) {
         const int r = o / K, k = o % K;
-        const float* uu = s.u + r * KD + k * 64;
-        float acc = uu[lane] * vp[k * 64 + lane] + uu[lane + 32] * vp[k * 64 + lane + 32];
+        const UT* uu = u + r * KD + k * 64;
+        float acc = to_f<UT>(uu[lane]) * vp[k * 64 + lane] + to_f<UT>(uu[lane + 32]) * vp[k * 64 + lane + 32];
         acc = warp_sum(acc);
         if (lane == 0) q[o] = acc * scale;
       }
@@ -206,10 +276,10 @@ __device__ inline void rt_forward(const RoutingArgs& a, const RtSmem& s, int b) 
         const int k = c >> 6;
         float acc = 0.f;
         if (it == 0) {
-          for (int r = 0; r < 10; ++r) acc += s.u[r * KD + c];
+          for (int r = 0; r < 10; ++r) acc += to_f<UT>(u[r * KD + c]);
           acc *= invK;
         } else {
-          for (int r = 0; r < 10; ++r) acc = fmaf(q[r * K + k] * s.act[r], s.u[r * KD + c], acc);
+          for (int r = 0; r < 10; ++r) acc = fmaf(q[r * K + k] * pt.act[r], to_f<UT>(u[r * KD + c]), acc);
         }
         vo[c] = acc;
       }
@@ -220,81 +290,67 @@ __device__ inline void rt_forward(const RoutingArgs& a, const RtSmem& s, int b) 
   const float* ql = s.q + (nit - 1) * 10 * K;
   if (tid < K) {
     float den = 0.f;
-    for (int r = 0; r < 10; ++r) den += ql[r * K + tid] * s.rm[r];
+    for (int r = 0; r < 10; ++r) den += ql[r * K + tid] * pt.rm[r];
     den = fmaxf(den, 1e-10f);
-    for (int r = 0; r < 10; ++r) s.Rn[r * K + tid] = ql[r * K + tid] * s.rm[r] / den;
+    for (int r = 0; r < 10; ++r) s.Rn[r * K + tid] = ql[r * K + tid] * pt.rm[r] / den;
   }
   __syncthreads();
   for (int i = tid; i < K * 32; i += RT_THREADS) {
     const int k = i >> 5, p = i & 31;
     float acc = 0.f;
     for (int r = 0; r < 10; ++r) {
-      const float cr = (a.d.variant == MMR_VARIANT_PHENO) ? s.alpha[r] : 1.f;
-      acc = fmaf(s.Rn[r * K + k] * cr, s.pose[r * 32 + p], acc);
+      const float cr = (a.d.variant == MMR_VARIANT_PHENO) ? pt.alpha[r] : 1.f;
+      acc = fmaf(s.Rn[r * K + k] * cr, pt.pose[r * 32 + p], acc);
     }
     s.dp[i] = acc;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(RT_THREADS) routing_fwd_kernel(RoutingArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int K = a.d.K;
-  RtSmem s = rt_carve(smem, K, a.d.num_routing, false);
-  rt_build_G(a, s);
+template <int PB, class UT>
+__global__ void __launch_bounds__(RT_THREADS, 1) routing_fwd_kernel(RoutingArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int K = a.d.K, nit = a.d.num_routing;
+  float* sf = reinterpret_cast<float*>(smem_raw);
+  RtScratch s = rt_carve(sf, K, nit, false);
+  float* pp = sf + rt_scratch_floats(K, nit, false);
+  uint8_t* ureg = reinterpret_cast<uint8_t*>(pp + PB * RT_PP_FWD);
+  const size_t ustride = rt_u_bytes(K, sizeof(UT), a.d.from_poses != 0);
+  rt_build_G(a, s.G);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int b = blockIdx.x; b < a.d.B; b += gridDim.x) {
-    rt_forward(a, s, b);
-    for (int k = warp; k < K; k += RT_THREADS / 32) {
-      float acc = s.dp[k * 32 + lane] * s.G[k * 32 + lane];
-      acc = warp_sum(acc);
-      if (lane == 0) a.logits[(size_t)b * K + k] = acc + a.p.bias[k];
+  const int ntiles = (a.d.B + PB - 1) / PB;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * PB, np = min(PB, a.d.B - b0);
+    __syncthreads();
+    rt_project<PB>(a, pp, ureg, ustride, false, b0, np);
+    rt_votes<PB, UT>(a, pp, ureg, ustride, false);
+    for (int p = 0; p < np; ++p) {
+      const int b = b0 + p;
+      RtPatient pt = rt_patient(pp, p, false);
+      rt_iterate<UT>(a, s, pt, reinterpret_cast<const UT*>(ureg + p * ustride));
+      for (int k = warp; k < K; k += RT_THREADS / 32) {
+        float acc = s.dp[k * 32 + lane] * s.G[k * 32 + lane];
+        acc = warp_sum(acc);
+        if (lane == 0) a.logits[(size_t)b * K + k] = acc + a.p.bias[k];
+      }
+      if (tid < 10) a.alpha[(size_t)b * 10 + tid] = pt.alpha[tid];
+      if (a.R)
+        for (int i = tid; i < 10 * K; i += RT_THREADS) a.R[(size_t)b * 10 * K + i] = s.Rn[i];
+      __syncthreads();
     }
-    if (tid < 10) a.alpha[(size_t)b * 10 + tid] = s.alpha[tid];
-    if (a.R)
-      for (int i = tid; i < 10 * K; i += RT_THREADS) a.R[(size_t)b * 10 * K + i] = s.Rn[i];
   }
 }
 
-// 32 per-lane partial sums -> lane i ends with the warp-wide total of index i (31 shuffles).
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float send = (lane & 16) ? v[i] : v[i + 16];
-    const float keep = (lane & 16) ? v[i + 16] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = (lane & 8) ? v[i] : v[i + 8];
-    const float keep = (lane & 8) ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = (lane & 4) ? v[i] : v[i + 4];
-    const float keep = (lane & 4) ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = (lane & 2) ? v[i] : v[i + 2];
-    const float keep = (lane & 2) ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    const float send = (lane & 1) ? v[0] : v[1];
-    const float keep = (lane & 1) ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  return v[0];
-}
-
-__global__ void __launch_bounds__(RT_THREADS) routing_bwd_kernel(RoutingArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <int PB, class UT>
+__global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int K = a.d.K, KD = K * 64, nit = a.d.num_routing;
-  RtSmem s = rt_carve(smem, K, nit, true);
-  rt_build_G(a, s);
+  float* sf = reinterpret_cast<float*>(smem_raw);
+  RtScratch s = rt_carve(sf, K, nit, true);
+  float* pp = sf + rt_scratch_floats(K, nit, true);
+  uint8_t* ureg = reinterpret_cast<uint8_t*>(pp + PB * RT_PP_BWD);
+  const size_t ustride = rt_u_bytes(K, sizeof(UT), a.d.from_poses != 0);
+  rt_build_G(a, s.G);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool pheno = a.d.variant == MMR_VARIANT_PHENO;
   const bool has_mask = a.route_mask != nullptr;
@@ -302,176 +358,216 @@ __global__ void __launch_bounds__(RT_THREADS) routing_bwd_kernel(RoutingArgs a) 
   // per-CTA accumulators for dG / dbias (flushed once at the end)
   float accG[4] = {0.f, 0.f, 0.f, 0.f};   // element i = tid + 256*j of [K][32]  (K*32 <= 1024)
   float accB = 0.f;                         // tid < K
-  for (int b = blockIdx.x; b < a.d.B; b += gridDim.x) {
-    rt_forward(a, s, b);
-    const float* dl = a.d_logits + (size_t)b * K;
-    // (a,b) head: dG, dbias, ddp = dlogit[k]*G[k][p]
-    for (int j = 0; j < 4; ++j) {
-      const int i = tid + 256 * j;
-      if (i < K * 32) {
-        const float g = dl[i >> 5];
-        accG[j] = fmaf(g, s.dp[i], accG[j]);
-        s.ddp[i] = g * s.G[i];
+  const int ntiles = (a.d.B + PB - 1) / PB;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * PB, np = min(PB, a.d.B - b0);
+    __syncthreads();
+    rt_project<PB>(a, pp, ureg, ustride, true, b0, np);
+    rt_votes<PB, UT>(a, pp, ureg, ustride, true);
+    for (int p = 0; p < np; ++p) {
+      const int b = b0 + p;
+      RtPatient pt = rt_patient(pp, p, true);
+      UT* u = reinterpret_cast<UT*>(ureg + p * ustride);
+      rt_iterate<UT>(a, s, pt, u);
+      const float* dl = a.d_logits + (size_t)b * K;
+      // (a,b) head: dG, dbias, ddp = dlogit[k]*G[k][p]
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + 256 * j;
+        if (i < K * 32) {
+          const float g = dl[i >> 5];
+          accG[j] = fmaf(g, s.dp[i], accG[j]);
+          s.ddp[i] = g * s.G[i];
+        }
       }
-    }
-    if (tid < K) accB += dl[tid];
-    for (int i = tid; i < 320; i += RT_THREADS) { s.dpose[i] = 0.f; a.poses_m[(size_t)b * 320 + i] = s.pose[i]; }
-    __syncthreads();
-    // (c) t_rk = sum_p ddp[k][p]*pose[r][p];  dRt = dR + c_r*t_rk  (stored in ds[nit-1] temporarily)
-    // The dv slab of the last iteration is never used by the iteration backward (the last
-    // decision pose is not consumed), so it serves as scratch for t_rk.
-    float* dRt = s.ds + (nit - 1) * 10 * K;
-    float* tr = s.dv + (nit - 1) * KD;
-    for (int o = tid; o < 10 * K; o += RT_THREADS) {
-      const int r = o / K, k = o % K;
-      float t = 0.f;
-      for (int p = 0; p < 32; ++p) t = fmaf(s.ddp[k * 32 + p], s.pose[r * 32 + p], t);
-      const float cr = pheno ? s.alpha[r] : 1.f;
-      const float dr = a.d_R ? a.d_R[(size_t)b * 10 * K + o] : 0.f;
-      tr[o] = t;
-      dRt[o] = dr + cr * t;
-    }
-    __syncthreads();
-    // dpose from the final aggregation, dalpha (pheno)
-    for (int i = tid; i < 320; i += RT_THREADS) {
-      const int r = i >> 5, p = i & 31;
-      const float cr = pheno ? s.alpha[r] : 1.f;
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc = fmaf(s.Rn[r * K + k], s.ddp[k * 32 + p], acc);
-      s.dpose[i] = cr * acc;
-    }
-    if (tid < 10) {
-      float da = 0.f;
-      if (pheno)
-        for (int k = 0; k < K; ++k) da = fmaf(s.Rn[tid * K + k], tr[tid * K + k], da);
-      s.misc[tid] = da;          // d alpha
-      s.misc[16 + tid] = 0.f;    // d act (filled by the iterations)
-    }
-    __syncthreads();
-    // (d) through R = qm / den
-    const float* ql = s.q + (nit - 1) * 10 * K;
-    if (tid < K) {
-      const int k = tid;
-      float den = 0.f, dot = 0.f;
-      for (int r = 0; r < 10; ++r) { den += ql[r * K + k] * s.rm[r]; dot = fmaf(dRt[r * K + k], s.Rn[r * K + k], dot); }
-      const bool clamped = den < 1e-10f;
-      const float dd = clamped ? 1e-10f : den;
-      for (int r = 0; r < 10; ++r) {
-        const float g = clamped ? dRt[r * K + k] : (dRt[r * K + k] - dot);
-        dRt[r * K + k] = g / dd * s.rm[r];     // now holds dq of the last iteration
-      }
-    }
-    __syncthreads();
-    // (e) agreement iterations, last to first.  ds[it] holds dq_it on entry and ds_it on exit.
-    for (int it = nit - 1; it >= 1; --it) {
-      float* dq = s.ds + it * 10 * K;
-      const float* q = s.q + it * 10 * K;
-      if (tid < 10) {
-        const int r = tid;
-        float aa = 0.f, sq = 0.f;
-        for (int k = 0; k < K; ++k) { aa = fmaf(dq[r * K + k], q[r * K + k], aa); sq += q[r * K + k]; }
-        const float T = 1.0f;   // sum of the softmax (== 1 up to rounding) + 1e-10
-        float bb = 0.f;
-        for (int k = 0; k < K; ++k) bb = fmaf((dq[r * K + k] - aa) / T, q[r * K + k], bb);
-        for (int k = 0; k < K; ++k) dq[r * K + k] = q[r * K + k] * ((dq[r * K + k] - aa) / T - bb);
-        (void)sq;
+      if (tid < K) accB += dl[tid];
+      for (int i = tid; i < 320; i += RT_THREADS) a.poses_m[(size_t)b * 320 + i] = pt.pose[i];
+      __syncthreads();
+      // (c) t_rk = sum_p ddp[k][p]*pose[r][p];  dRt = dR + c_r*t_rk  (held in ds[nit-1])
+      float* dRt = s.ds + (nit - 1) * 10 * K;
+      for (int o = tid; o < 10 * K; o += RT_THREADS) {
+        const int r = o / K, k = o % K;
+        float t = 0.f;
+        for (int c = 0; c < 32; ++c) t = fmaf(s.ddp[k * 32 + c], pt.pose[r * 32 + c], t);
+        const float cr = pheno ? pt.alpha[r] : 1.f;
+        const float dr = a.d_R ? a.d_R[(size_t)b * 10 * K + o] : 0.f;
+        s.tr[o] = t;
+        dRt[o] = dr + cr * t;
       }
       __syncthreads();
-      // dv_{it-1}[c] = scale * sum_r ds[r][k] * u[r][c]
-      float* dvp = s.dv + (it - 1) * KD;
-      for (int c = tid; c < KD; c += RT_THREADS) {
-        const int k = c >> 6;
+      // dpose from the final aggregation, dalpha (pheno)
+      for (int i = tid; i < 320; i += RT_THREADS) {
+        const int r = i >> 5, c = i & 31;
+        const float cr = pheno ? pt.alpha[r] : 1.f;
         float acc = 0.f;
-        for (int r = 0; r < 10; ++r) acc = fmaf(dq[r * K + k], s.u[r * KD + c], acc);
-        dvp[c] = acc * scale;
+        for (int k = 0; k < K; ++k) acc = fmaf(s.Rn[r * K + k], s.ddp[k * 32 + c], acc);
+        pt.dpose[i] = cr * acc;
+      }
+      if (tid < 10) {
+        float da = 0.f;
+        if (pheno)
+          for (int k = 0; k < K; ++k) da = fmaf(s.Rn[tid * K + k], s.tr[tid * K + k], da);
+        pt.misc[tid] = da;          // d alpha
+        pt.misc[16 + tid] = 0.f;    // d act (filled by the iterations)
       }
       __syncthreads();
-      if (it - 1 >= 1) {
-        // v_{it-1} = sum_r q_{it-1}*act*u  ->  dq_{it-1}[r][k] = act[r]*w_rk, dact[r] += sum_k q*w_rk
-        float* dqp = s.ds + (it - 1) * 10 * K;
-        const float* qp = s.q + (it - 1) * 10 * K;
-        for (int o = warp; o < 10 * K; o += RT_THREADS / 32) {
-          const int r = o / K, k = o % K;
-          const float* uu = s.u + r * KD + k * 64;
-          float w = uu[lane] * dvp[k * 64 + lane] + uu[lane + 32] * dvp[k * 64 + lane + 32];
-          w = warp_sum(w);
-          if (lane == 0) {
-            dqp[o] = s.act[r] * w;
-            atomicAdd(&s.misc[16 + r], qp[o] * w);
-          }
+      // (d) through R = qm / den
+      const float* ql = s.q + (nit - 1) * 10 * K;
+      if (tid < K) {
+        const int k = tid;
+        float den = 0.f, dot = 0.f;
+        for (int r = 0; r < 10; ++r) { den += ql[r * K + k] * pt.rm[r]; dot = fmaf(dRt[r * K + k], s.Rn[r * K + k], dot); }
+        const bool clamped = den < 1e-10f;
+        const float dd = clamped ? 1e-10f : den;
+        for (int r = 0; r < 10; ++r) {
+          const float g = clamped ? dRt[r * K + k] : (dRt[r * K + k] - dot);
+          dRt[r * K + k] = g / dd * pt.rm[r];     // now holds dq of the last iteration
+        }
+      }
+      __syncthreads();
+      // (e) agreement iterations, last to first.  ds[it] holds dq_it on entry and ds_it on exit.
+      for (int it = nit - 1; it >= 1; --it) {
+        float* dq = s.ds + it * 10 * K;
+        const float* q = s.q + it * 10 * K;
+        if (tid < 10) {
+          const int r = tid;
+          float aa = 0.f;
+          for (int k = 0; k < K; ++k) aa = fmaf(dq[r * K + k], q[r * K + k], aa);
+          float bb = 0.f;   // renormalisation by (sum softmax + 1e-10) == 1 up to rounding
+          for (int k = 0; k < K; ++k) bb = fmaf(dq[r * K + k] - aa, q[r * K + k], bb);
+          for (int k = 0; k < K; ++k) dq[r * K + k] = q[r * K + k] * ((dq[r * K + k] - aa) - bb);
         }
         __syncthreads();
+        // dv_{it-1}[c] = scale * sum_r ds[r][k] * u[r][c]
+        float* dvp = s.dv + (it - 1) * KD;
+        for (int c = tid; c < KD; c += RT_THREADS) {
+          const int k = c >> 6;
+          float acc = 0.f;
+          for (int r = 0; r < 10; ++r) acc = fmaf(dq[r * K + k], to_f<UT>(u[r * KD + c]), acc);
+          dvp[c] = acc * scale;
+        }
+        __syncthreads();
+        if (it - 1 >= 1) {
+          // v_{it-1} = sum_r q_{it-1}*act*u  ->  dq_{it-1}[r][k] = act[r]*w_rk, dact[r] += sum_k q*w_rk
+          float* dqp = s.ds + (it - 1) * 10 * K;
+          const float* qp = s.q + (it - 1) * 10 * K;
+          for (int o = warp; o < 10 * K; o += RT_THREADS / 32) {
+            const int r = o / K, k = o % K;
+            const UT* uu = u + r * KD + k * 64;
+            float w = to_f<UT>(uu[lane]) * dvp[k * 64 + lane] + to_f<UT>(uu[lane + 32]) * dvp[k * 64 + lane + 32];
+            w = warp_sum(w);
+            if (lane == 0) {
+              dqp[o] = pt.act[r] * w;
+              atomicAdd(&pt.misc[16 + r], qp[o] * w);
+            }
+          }
+          __syncthreads();
+        }
       }
-    }
-    // (f) du[r][c] and dpose[r][a] += sum_c du[r][c]*w[r][a][c]
-    for (int r = 0; r < 10; ++r) {
-      float part[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) part[i] = 0.f;
+      // (f) du[r][c], written to global (fp32, operand of the vote-weight gradient) and in place of u
       for (int c = tid; c < KD; c += RT_THREADS) {
         const int k = c >> 6;
-        float du = 0.f;
-        if (nit >= 2) du = invK * s.dv[c];
-        for (int it = 1; it < nit; ++it) {
-          du = fmaf(s.ds[it * 10 * K + r * K + k], scale * s.v[(it - 1) * KD + c], du);
-          if (it < nit - 1) du = fmaf(s.q[it * 10 * K + r * K + k] * s.act[r], s.dv[it * KD + c], du);
+        for (int r = 0; r < 10; ++r) {
+          float du = 0.f;
+          if (nit >= 2) du = invK * s.dv[c];
+          for (int it = 1; it < nit; ++it) {
+            du = fmaf(s.ds[it * 10 * K + r * K + k], scale * s.v[(it - 1) * KD + c], du);
+            if (it < nit - 1) du = fmaf(s.q[it * 10 * K + r * K + k] * pt.act[r], s.dv[it * KD + c], du);
+          }
+          a.du[((size_t)b * 10 + r) * KD + c] = du;
+          u[r * KD + c] = from_f<UT>(du);
         }
-        a.du[((size_t)b * 10 + r) * KD + c] = du;
-        const float* w = a.p.caps_w + (size_t)r * 32 * KD + c;
-#pragma unroll
-        for (int aa = 0; aa < 32; ++aa) part[aa] = fmaf(du, w[(size_t)aa * KD], part[aa]);
       }
-      const float tot = warp_transpose_reduce(part, lane);
-      atomicAdd(&s.dpose[r * 32 + lane], tot);
+      __syncthreads();
+    }
+    // (f') dpose[p][r][a] += sum_c du[p][r][c]*w[r][a][c]: a thread owns (column quarter, r, a); lanes of a
+    // warp share r, so the du reads are shared-memory broadcasts and each weight load feeds PB dot products.
+    for (int item = tid; item < 4 * 320; item += RT_THREADS) {
+      const int cq = item / 320, ra = item % 320, r = ra >> 5;
+      const int c4_lo = (KD / 4) * cq / 4, c4_hi = (KD / 4) * (cq + 1) / 4;
+      const float4* w = reinterpret_cast<const float4*>(a.p.caps_w + (size_t)ra * KD);
+      float acc[PB];
+#pragma unroll
+      for (int p = 0; p < PB; ++p) acc[p] = 0.f;
+#pragma unroll 4
+      for (int c4 = c4_lo; c4 < c4_hi; ++c4) {
+        const float4 w4 = __ldg(w + c4);
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+          const float4 d4 = Vec4<UT>::ld(reinterpret_cast<const UT*>(ureg + p * ustride) + r * KD + 4 * c4);
+          acc[p] = fmaf(d4.x, w4.x, fmaf(d4.y, w4.y, fmaf(d4.z, w4.z, fmaf(d4.w, w4.w, acc[p]))));
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < PB; ++p)
+        if (p < np) atomicAdd(&rt_patient(pp, p, true).dpose[ra], acc[p]);
     }
     __syncthreads();
     // (g) activation chain and projector data-gradient
-    if (tid < 10) {
-      const int r = tid;
-      const float rm = s.rm[r];
-      float dal = s.misc[r] + (pheno ? s.misc[16 + r] : 0.f);   // d alpha (alpha = a3*rm)
-      float g = has_mask ? dal * rm : dal;                       // d a3
+    for (int i = tid; i < np * 10; i += RT_THREADS) {
+      const int p = i / 10, r = i % 10, b = b0 + p;
+      RtPatient pt = rt_patient(pp, p, true);
+      const float rm = pt.rm[r];
+      float dal = pt.misc[r] + (pheno ? pt.misc[16 + r] : 0.f);   // d alpha (alpha = a3*rm)
+      float g = has_mask ? dal * rm : dal;                         // d a3
       if (a.d.from_poses) {
         if (a.d_acts) a.d_acts[(size_t)b * 10 + r] = g;
-        s.misc[32 + r] = 0.f;
+        pt.misc[32 + r] = 0.f;
       } else {
         if (a.d.detach_priors) g = 0.f;
         const bool keep = has_mask ? (rm != 0.f) : true;
-        if (keep) { const float x = s.a2[r]; if (x < a.d.prior_floor || x > a.d.prior_ceiling) g = 0.f; }
+        if (keep) { const float x = pt.a2[r]; if (x < a.d.prior_floor || x > a.d.prior_ceiling) g = 0.f; }
         if (a.d.act_temperature != 1.0f && has_mask && keep) {
-          const float a1 = s.a0[r] * rm;
+          const float a1 = pt.a0[r] * rm;
           if (a1 < 1e-6f || a1 > 1.0f - 1e-6f) g = 0.f;
-          else { const float y = s.a2[r]; g *= y * (1.0f - y) / a.d.act_temperature / (a1 * (1.0f - a1)); }
+          else { const float y = pt.a2[r]; g *= y * (1.0f - y) / a.d.act_temperature / (a1 * (1.0f - a1)); }
         }
         if (has_mask) g *= rm;
         if (a.acts_override) g = 0.f;
-        else g *= s.a0[r] * (1.0f - s.a0[r]);
-        s.misc[32 + r] = g;   // d (activation logit)
+        else g *= pt.a0[r] * (1.0f - pt.a0[r]);
+        pt.misc[32 + r] = g;   // d (activation logit)
       }
     }
     __syncthreads();
     if (a.d.from_poses) {
       if (a.d_poses)
-        for (int i = tid; i < 320; i += RT_THREADS) a.d_poses[(size_t)b * 320 + i] = s.dpose[i] * s.rm[i >> 5];
+        for (int i = tid; i < np * 320; i += RT_THREADS) {
+          const int p = i / 320, j = i % 320;
+          RtPatient pt = rt_patient(pp, p, true);
+          a.d_poses[(size_t)(b0 + p) * 320 + j] = pt.dpose[j] * pt.rm[j >> 5];
+        }
     } else {
-      for (int i = tid; i < 330; i += RT_THREADS) {
-        const int r = i / 33, j = i % 33;
-        const float g = (j < 32) ? s.dpose[r * 32 + j] * s.rm[r] : s.misc[32 + r];
-        a.dpc[(size_t)b * 330 + i] = g;
-        s.e[i] = g;     // route embeddings are no longer needed: reuse as dpc[10][33]
+      // dpc[p][r][j] (j < 32: pose, j = 32: activation logit); staged in the pose slots (no longer needed)
+      for (int i = tid; i < np * 330; i += RT_THREADS) {
+        const int p = i / 330, o = i % 330, r = o / 33, j = o % 33;
+        RtPatient pt = rt_patient(pp, p, true);
+        const float g = (j < 32) ? pt.dpose[r * 32 + j] * pt.rm[r] : pt.misc[32 + r];
+        a.dpc[(size_t)(b0 + p) * 330 + o] = g;
       }
       __syncthreads();
       if (a.d_route_embs) {
+        // d e[p][r][c] = sum_j dpc[p][r][j] * W_r[j][c]; thread = column c, weights shared by the tile
         for (int r = 0; r < 10; ++r) {
           const float* w = a.p.proj_w[r] + tid;
-          float acc = 0.f;
+          float acc[PB];
+#pragma unroll
+          for (int p = 0; p < PB; ++p) acc[p] = 0.f;
 #pragma unroll 3
-          for (int j = 0; j < 33; ++j) acc = fmaf(s.e[r * 33 + j], w[(size_t)j * 256], acc);
-          a.d_route_embs[(size_t)r * a.d.emb_route_stride + (size_t)b * a.d.emb_batch_stride + tid] = acc;
+          for (int j = 0; j < 33; ++j) {
+            const float wv = __ldg(w + (size_t)j * 256);
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+              RtPatient pt = rt_patient(pp, p, true);
+              const float g = (j < 32) ? pt.dpose[r * 32 + j] * pt.rm[r] : pt.misc[32 + r];
+              acc[p] = fmaf(g, wv, acc[p]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < PB; ++p)
+            if (p < np)
+              a.d_route_embs[(size_t)r * a.d.emb_route_stride + (size_t)(b0 + p) * a.d.emb_batch_stride + tid] = acc[p];
         }
       }
     }
-    __syncthreads();
   }
   for (int j = 0; j < 4; ++j) {
     const int i = tid + 256 * j;

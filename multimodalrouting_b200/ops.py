@@ -234,9 +234,9 @@ def route_fusion(x_l, x_n, x_i, mL, mN, mI, pos, params: List[Tensor], layers: i
 
 # --------------------------------------------------------------------------------------------
 # capsule routing
-def _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs) -> RoutingDims:
+def _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt) -> RoutingDims:
     return RoutingDims(B, K, variant, num_routing, int(detach_priors), int(from_poses), float(temp), float(floor),
-                       float(ceil), int(rs), int(bs))
+                       float(ceil), int(rs), int(bs), int(vdt), 0)
 
 
 def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias) -> RoutingParams:
@@ -256,14 +256,14 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                         acts_in: Optional[Tensor], acts_override: Optional[Tensor], route_mask: Optional[Tensor],
                         proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
                         embedding: Tensor, bias: Tensor, B: int, variant: int, num_routing: int,
-                        detach_priors: bool, temp: float, floor: float, ceil: float
+                        detach_priors: bool, temp: float, floor: float, ceil: float, vdt: int
                         ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10])."""
     _require_cuda(caps_w, embs, poses_in)
     lib = _lib.load()
     K = embedding.shape[0]
     from_poses = embs is None
-    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs)
+    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt)
     rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
     dev = caps_w.device
     logits = torch.empty(B, K, dtype=torch.float32, device=dev)
@@ -281,7 +281,7 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
 
 @capsule_routing_fwd.register_fake
 def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b, caps_w, pose_to_mc, embedding,
-      bias, B, variant, num_routing, detach_priors, temp, floor, ceil):
+      bias, B, variant, num_routing, detach_priors, temp, floor, ceil, vdt):
     K = embedding.shape[0]
     e = caps_w
     return (e.new_empty(B, K), e.new_empty(B, N_ROUTES), e.new_empty(B, N_ROUTES, K),
@@ -294,14 +294,14 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                         proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
                         embedding: Tensor, bias: Tensor, d_logits: Tensor, d_R: Optional[Tensor], B: int,
                         variant: int, num_routing: int, detach_priors: bool, temp: float, floor: float,
-                        ceil: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                        ceil: float, vdt: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Returns (d_embs [10,B,256] | empty, d_poses [B,10,32] | empty, d_acts [B,10] | empty, flat grads)
     flat grads layout: proj_w[10] (33*256 each) | proj_b[10] (36 each, 33 used) | caps_w | pose_to_mc |
     embedding | bias."""
     lib = _lib.load()
     K = embedding.shape[0]
     from_poses = embs is None
-    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs)
+    dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt)
     rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
     dev = caps_w.device
     scratch = torch.empty(int(lib.mmr_routing_scratch_bytes(C.byref(dims))), dtype=torch.uint8, device=dev)
@@ -338,7 +338,7 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
 
 @capsule_routing_bwd.register_fake
 def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b, caps_w, pose_to_mc, embedding,
-      bias, d_logits, d_R, B, variant, num_routing, detach_priors, temp, floor, ceil):
+      bias, d_logits, d_R, B, variant, num_routing, detach_priors, temp, floor, ceil, vdt):
     K = embedding.shape[0]
     e = caps_w
     n = routing_flat_layout(K)["total"]
@@ -365,6 +365,7 @@ class RoutingFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, acts_override, route_mask, caps_w, pose_to_mc, embedding, bias, *rest):
         variant, num_routing, detach_priors, temp, floor, ceil, from_poses = cfg
+        vdt = resolve_dtype()      # votes in bf16 under autocast (like the reference's einsums), else fp32
         if from_poses:
             poses_in, acts_in = rest
             B = poses_in.shape[0]
@@ -387,8 +388,9 @@ class RoutingFn(torch.autograd.Function):
         ao = _f32c(acts_override.detach()) if acts_override is not None else None
         logits, alpha, R, poses, acts = capsule_routing_fwd(
             embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w.detach(), pose_to_mc.detach(),
-            embedding.detach(), bias.detach(), B, variant, num_routing, detach_priors, temp, floor, ceil)
+            embedding.detach(), bias.detach(), B, variant, num_routing, detach_priors, temp, floor, ceil, vdt)
         ctx.cfg = cfg
+        ctx.vdt = vdt
         ctx.B = B
         ctx.has = (embs_dense is not None, rm is not None, ao is not None)
         tensors = [t for t in (embs_dense, poses_c, acts_c, ao, rm) if t is not None]
@@ -424,7 +426,7 @@ class RoutingFn(torch.autograd.Function):
         d_embs, d_poses, d_acts, flat = capsule_routing_bwd(
             embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w, pose_to_mc, embedding, bias,
             _f32c(d_logits), _f32c(d_R) if d_R is not None else None, B, variant, num_routing, detach_priors, temp,
-            floor, ceil)
+            floor, ceil, ctx.vdt)
         lay = routing_flat_layout(K)
         g_caps = flat[lay["caps_w"]:lay["caps_w"] + caps_w.numel()].view(caps_w.shape)
         g_mc = flat[lay["pose_to_mc"]:lay["pose_to_mc"] + 64 * 32].view(64, 32)

@@ -122,12 +122,15 @@ def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
     a, b = outs["mma"], outs["simt"]
     assert max_rel(a["routes"], b["routes"]) < 5e-3
     assert max_rel(a["logits"], b["logits"]) < 2e-2
+    # gradients: both engines are bf16 roundings of the same math; anchor them on the fp32 oracle
+    g32 = oracle_grads(c, sdm, sdp, sdh, inp, None, torch.float32)
     for k, g in b["grads"].items():
         if g is None:
             assert a["grads"][k] is None
             continue
         assert bool(torch.isfinite(a["grads"][k]).all()), k
-        assert max_rel(a["grads"][k], g) < 8e-2, f"grad {k}"   # two bf16 roundings of the same math
+        e_mma, e_simt = max_rel(a["grads"][k], g32[k]), max_rel(g, g32[k])
+        assert e_mma <= max(8e-2, 2.0 * e_simt), f"grad {k}: mma {e_mma:.2e} simt {e_simt:.2e}"
     logits, alpha, routes, R = orc.full_forward(sdm, sdp, sdh, inp["x_l"], inp["x_n"], inp["x_i"], inp["mL"],
                                                 inp["mN"], inp["mI"], variant="pheno", route_mask=inp["route_mask"])
     ref = torch.stack([routes[r] for r in synth_routes()], dim=1)

@@ -156,9 +156,20 @@ struct TcEpi {
 constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile of the weight-gradient epilogue
 
+constexpr int CSTG_BYTES = 8192;      // per epilogue warp: 32 rows x 256 bytes, two 128B-swizzled TMA store boxes
 template <int BN> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-  return stages * stage_bytes<BN>() + 8 * (BN / 2) * 4 + 1024 + 256;
+  return stages * stage_bytes<BN>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
 }
+
+// TMA store of one [32 rows x 128 bytes] box from shared memory (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -179,11 +190,13 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// One 32-column chunk of one accumulator row: apply the epilogue op and store it.  The thread owns
-// the row, so its 32 columns are 64 (bf16) / 128 (fp32) contiguous bytes written as 16-byte vectors.
+// One 32-column chunk of one accumulator row: apply the epilogue op and write it into the warp's
+// staging box (row = lane, 128-byte rows, 16-byte units XOR-swizzled by row & 7 like the TMA map).
+//   bf16: `unit0` = first 16-byte unit of the chunk inside its box (0 or 4), 4 units
+//   fp32: the chunk is a whole box row (8 units)
 template <int OP>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* bias_c, float rmask, uint32_t wbits_in,
-                                          uint32_t& wbits_out, bool row_ok, void* out_row, int col) {
+                                          uint32_t& wbits_out, bool row_ok, uint32_t box_row_addr, int unit0, int lane) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -215,16 +228,21 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
+  const uint32_t sw = (uint32_t)(lane & 7);
   if (OP == TEPI_F32 || OP == TEPI_BIAS_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + col);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = box_row_addr + (((uint32_t)j ^ sw) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    }
   } else {
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_row) + col);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
-                        pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t addr = box_row_addr + (((uint32_t)(unit0 + j) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2_bf16(v[8 * j], v[8 * j + 1])),
+                   "r"(pack2_bf16(v[8 * j + 2], v[8 * j + 3])), "r"(pack2_bf16(v[8 * j + 4], v[8 * j + 5])),
+                   "r"(pack2_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+    }
   }
 }
 
@@ -237,11 +255,12 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 template <int BN, int OP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               GemmProblem g, TcEpi e, int stages) {
+               const __grid_constant__ CUtensorMap tmC, GemmProblem g, TcEpi e, int stages) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  float* bias_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>());
+  const uint32_t cstg_base = sbase + stages * stage_bytes<BN>();   // 1024-byte aligned (stages are multiples of 1 KB)
+  float* bias_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>() + 8 * CSTG_BYTES);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 8 * (BN / 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = g.K / BK;
@@ -269,6 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m0 = (t / nN) * BM, n0 = (t % nN) * BN;
@@ -346,11 +366,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < HC / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
         __syncwarp();
       }
-      uint8_t* out_row = reinterpret_cast<uint8_t*>(e.out) + (size_t)(m0 + lr) * e.ldo * (f32_out ? 4 : 2);
       const uint32_t buf = i & 1;
       mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * BN + ch * HC + ((uint32_t)(q * 32) << 16);
+      const uint32_t stg = cstg_base + (warp - 2) * CSTG_BYTES;     // two 4 KB boxes
+      const uint32_t stg_row = stg + lane * 128;
       uint32_t wout[HC / 32];
 #pragma unroll
       for (int cc = 0; cc < HC / 64; ++cc) {
@@ -363,10 +384,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&ctrl->tempty[buf]));
         }
-        epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], row_ok,
-                      out_row, n0 + cc * 64);
-        epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, OP == TEPI_BITS_IN ? bits[2 * cc + 1] : 0u, wout[2 * cc + 1],
-                      row_ok, out_row, n0 + cc * 64 + 32);
+        // the staging boxes may still be read by the previous TMA store of this warp
+        if (f32_out || cc == 0) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+        if (f32_out) {   // 64 fp32 columns = two [32 x 32] boxes per round
+          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, 0u, wout[2 * cc], row_ok, stg_row, 0, lane);
+          epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, 0u, wout[2 * cc + 1], row_ok, stg_row + 4096, 0, lane);
+        } else {         // 64 bf16 columns = one [32 x 64] box per round
+          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], row_ok,
+                        stg_row + cc * 4096, 0, lane);
+          epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, OP == TEPI_BITS_IN ? bits[2 * cc + 1] : 0u, wout[2 * cc + 1],
+                        row_ok, stg_row + cc * 4096, 4, lane);
+        }
+        if (f32_out || cc == HC / 64 - 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (f32_out) {
+              tma_store_2d(&tmC, stg, n0 + cc * 64, m0 + q * 32);
+              tma_store_2d(&tmC, stg + 4096, n0 + cc * 64 + 32, m0 + q * 32);
+            } else {
+#pragma unroll
+              for (int bx = 0; bx < HC / 64; ++bx) tma_store_2d(&tmC, stg + bx * 4096, n0 + bx * 64, m0 + q * 32);
+            }
+            tma_store_commit();
+          }
+        }
       }
       if (OP == TEPI_BIAS_RELU_BITS && row_ok) {
         uint4* bo = reinterpret_cast<uint4*>(e.bits_out + (size_t)(m0 + lr) * e.ld_bits + n0 / 32);
@@ -375,6 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores must complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
@@ -502,18 +548,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor [outer, inner] (inner contiguous, leading dimension ld elements).
+// 2-D row-major tensor [outer, inner] (inner contiguous, leading dimension ld elements), bf16 or fp32.
 static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -527,7 +573,7 @@ template <int OP>
 static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                   cudaStream_t st) {
   constexpr int BN = 256;
-  static int stages_cfg = env_int("MMR_TC_STAGES", 4);
+  static int stages_cfg = env_int("MMR_TC_STAGES", 3);
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -536,9 +582,12 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
     if (sm_count <= 0) sm_count = 148;
   }
   int stages = stages_cfg;
-  if (stages > 4) stages = 4;
+  if (stages > 3) stages = 3;     // 3 x 48 KB operand stages + 64 KB of TMA-store staging
   if (stages < 1) stages = 1;
-  CUtensorMap tmA, tmB;
+  constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
+  CUtensorMap tmA, tmB, tmC;
+  if (!make_tmap(&tmC, e.out, (uint64_t)e.ldo, (uint64_t)g.segs.row0[g.segs.n], (uint64_t)e.ldo, f32_out ? 32 : 64, 32, f32_out))
+    return cudaErrorUnknown;
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN)) return cudaErrorUnknown;
   auto kern = gemm_tc_kernel<BN, OP>;
@@ -548,7 +597,7 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   const int total_rows = g.segs.row0[g.segs.n];
   const int ntiles = ((total_rows + BM - 1) / BM) * (g.N / BN);
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g, e, stages);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g, e, stages);
   return cudaGetLastError();
 }
 

@@ -102,6 +102,14 @@ static int run_gemm(const Plan& P, const GemmProblem& g, const EpiSpec& sp, int 
   return MMR_OK;
 }
 
+// tcgen05 engine: bias gradients (column sums of dY) ride along in the weight-gradient kernel
+static bool fuse_colsum(const Plan& P, WgradProblem& w, float* const* dbias) {
+  if (!P.tc || getenv("MMR_NO_FUSED_COLSUM")) return false;
+  for (int i = 0; i < w.segs.n; ++i) w.dbias[i] = dbias[i];
+  w.colsum = 1;
+  return true;
+}
+
 template <class CT>
 static int run_wgrad(const Plan& P, const WgradProblem& w, int y_rows, int x_rows, cudaStream_t st, const char* what) {
   if (P.tc) {
@@ -553,9 +561,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       WgradProblem w = q_wgrad(dF, FF, FF, h1(l), D, D);
       float* ob1[6];
       for (int d = 0; d < NDIR; ++d) { w.out[d] = gr(ix.layer(d, l, 4)); ob1[d] = gr(ix.layer(d, l, 5)); }
+      const bool fused = fuse_colsum(P, w, ob1);
       rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_fc1");
       if (rc) return rc;
-      rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, st, "b_fc1");
+      if (!fused) rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, st, "b_fc1");
       if (rc) return rc;
     }
     {  // LN1 backward: g_oth = (g_cur + dLN1) * mask ; d out_proj.bias = colsum(g_oth)
@@ -618,9 +627,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       WgradProblem w = q_wgrad(dQ, D, D, h0(l), D, D);
       float* obq[6];
       for (int d = 0; d < NDIR; ++d) { w.out[d] = dwq + ((size_t)l * 6 + d) * D * D; obq[d] = dbq + ((size_t)l * 6 + d) * D; }
+      const bool fused = fuse_colsum(P, w, obq);
       rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_q_proj");
       if (rc) return rc;
-      rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, st, "b_q_proj");
+      if (!fused) rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, st, "b_q_proj");
       if (rc) return rc;
     }
     {  // LN0 backward: g_cur = (g_oth + dLN0) * mask ; d fc2.bias of the previous layer = colsum(g_cur)
@@ -656,9 +666,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       obkv[d] = dbkv + (size_t)d * ldkv;
     }
     w.dY = dKV; w.ldy = ldkv; w.X = xh; w.ldx = D; w.M = ldkv; w.N = D; w.ldo = D;
+    const bool fused = fuse_colsum(P, w, obkv);
     rc = run_wgrad<CT>(P, w, P.MK, P.MM, st, "w_kv_proj");
     if (rc) return rc;
-    rc = run_colsum<CT>(P.kv, dKV, ldkv, 0, ldkv, obkv, 1.0f, st, "b_kv_proj");
+    if (!fused) rc = run_colsum<CT>(P.kv, dKV, ldkv, 0, ldkv, obkv, 1.0f, st, "b_kv_proj");
     if (rc) return rc;
   }
   // ---- unfold packed-weight gradients into in_proj_{weight,bias} and LN0 ----
@@ -674,7 +685,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         j.g_w_in = gr(ix.layer(d, l, 0)); j.g_b_in = gr(ix.layer(d, l, 1));
         j.g_gamma0 = gr(ix.layer(d, l, 8)); j.g_beta0 = gr(ix.layer(d, l, 9));
         if (uj.n == 24 || (d == NDIR - 1 && l == L - 1)) {
-          unfold_kernel<<<uj.n, 256, 0, st>>>(uj);
+          unfold_kernel<<<dim3(3 * D / UNFOLD_ROWS, uj.n), 256, 0, st>>>(uj);
           LAUNCH_OK("unfold");
           uj.n = 0;
         }

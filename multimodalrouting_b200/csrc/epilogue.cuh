@@ -90,6 +90,8 @@ struct WgradProblem {
   int M, N;
   float* out[6];      // per segment fp32 [M, ldo] accumulators (zero-initialised by the caller)
   int ldo;
+  float* dbias[6];    // optional per segment fp32 [M]: += column sums of dY (bias gradient), fused into the
+  int colsum;         // tcgen05 weight-gradient kernel when `colsum` is set (launch-uniform)
 };
 
 }  // namespace mmr

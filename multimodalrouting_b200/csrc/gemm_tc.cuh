@@ -451,7 +451,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&ctrl->full[s]), 1);
-      mbar_init(smem_u32(&ctrl->empty[s]), 1);
+      mbar_init(smem_u32(&ctrl->empty[s]), w.colsum ? 5 : 1);   // MMA commit (+ the 4 column-sum warps)
     }
     mbar_init(smem_u32(&ctrl->acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -503,6 +503,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
   } else {
     const int q = warp & 3;
+    if (w.colsum) {
+      // Bias gradient fused in: while the MMA warp consumes the stages, the (otherwise idle) epilogue warps
+      // sum the dY tile over its 64 reduction rows.  Warp q takes rows [16q, 16q+16) of every stage, lane l the
+      // 4 columns 4l..4l+3 (atom l/16, 16-byte unit (l%16)/2 of the 128B-swizzled [64 k][64 m] atom).
+      const bool mine = blockIdx.x == 0 && w.dbias[seg] != nullptr;
+      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t unit = (lane & 15) >> 1, sub = (lane & 1) * 8, atom = lane >> 4;
+      for (int i = 0; i < kblocks; ++i) {
+        const int s = i % stages;
+        mbar_wait(smem_u32(&ctrl->full[s]), (i / stages) & 1);
+        if (mine) {
+          const uint32_t sa = sbase + s * stage_bytes<BN>() + atom * 8192;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            const uint32_t k = q * 16 + kk;
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(sa + k * 128 + ((unit ^ (k & 7)) << 4) + sub));
+            cs[0] += __uint_as_float(lo << 16); cs[1] += __uint_as_float(lo & 0xffff0000u);
+            cs[2] += __uint_as_float(hi << 16); cs[3] += __uint_as_float(hi & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty[s]));
+      }
+      if (mine) {
+        float* db = w.dbias[seg] + m0 + 4 * lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (m0 + 4 * lane + j < w.M) atomicAdd(db + j, cs[j]);
+      }
+    }
     mbar_wait(smem_u32(&ctrl->acc_full), 0);
     tc_fence_after();
     float* out = w.out[seg];

@@ -218,7 +218,7 @@ __device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* 
 #pragma unroll
       for (int p = 0; p < PB; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4* w = reinterpret_cast<const float4*>(a.p.caps_w + (size_t)r * 32 * KD) + cg;
-#pragma unroll 8
+#pragma unroll 16
       for (int aa = 0; aa < 32; ++aa) {
         const float4 w4 = __ldg(w + (size_t)aa * (KD / 4));
 #pragma unroll
@@ -235,6 +235,31 @@ __device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* 
   __syncthreads();
 }
 
+// dot_d u[k*64 + d] * v[k*64 + d] with the d index rotated by 2k so that the lanes of a warp (consecutive k)
+// hit distinct shared-memory banks although their rows are 64 elements apart.
+template <class UT> __device__ __forceinline__ float rt_dot64(const UT* urow, const float* vrow, int k);
+template <> __device__ __forceinline__ float rt_dot64<float>(const float* urow, const float* vrow, int k) {
+  float acc = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < 64; d += 2) {
+    const int dd = (d + 2 * k) & 63;
+    const float2 a = *reinterpret_cast<const float2*>(urow + dd), b = *reinterpret_cast<const float2*>(vrow + dd);
+    acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+  }
+  return acc;
+}
+template <> __device__ __forceinline__ float rt_dot64<__half>(const __half* urow, const float* vrow, int k) {
+  float acc = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < 64; d += 2) {
+    const int dd = (d + 2 * k) & 63;
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(urow + dd));
+    const float2 b = *reinterpret_cast<const float2*>(vrow + dd);
+    acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+  }
+  return acc;
+}
+
 // ---- per-patient agreement iterations; leaves q / v / Rn / dp in the shared scratch -------------
 template <class UT>
 __device__ inline void rt_iterate(const RoutingArgs& a, const RtScratch& s, const RtPatient& pt, const UT* u) {
@@ -248,25 +273,18 @@ __device__ inline void rt_iterate(const RoutingArgs& a, const RtScratch& s, cons
       for (int i = tid; i < 10 * K; i += RT_THREADS) q[i] = invK;
     } else {
       const float* vp = s.v + (it - 1) * KD;
-      for (int o = warp; o < 10 * K; o += RT_THREADS / 32) {
+      for (int o = tid; o < 10 * K; o += RT_THREADS) {      // one thread per (route, label) agreement
         const int r = o / K, k = o % K;
-        const UT* uu = u + r * KD + k * 64;
-        float acc = to_f<UT>(uu[lane]) * vp[k * 64 + lane] + to_f<UT>(uu[lane + 32]) * vp[k * 64 + lane + 32];
-        acc = warp_sum(acc);
-        if (lane == 0) q[o] = acc * scale;
+        q[o] = scale * rt_dot64<UT>(u + r * KD + k * 64, vp + k * 64, k);
       }
       __syncthreads();
-      if (tid < 10) {
-        float* qr = q + tid * K;
-        float mx = -INFINITY;
-        for (int k = 0; k < K; ++k) mx = fmaxf(mx, qr[k]);
-        float sum = 0.f;
-        for (int k = 0; k < K; ++k) { const float ex = expf(qr[k] - mx); qr[k] = ex; sum += ex; }
-        const float inv = 1.0f / sum;
-        float t = 0.f;
-        for (int k = 0; k < K; ++k) { qr[k] *= inv; t += qr[k]; }
-        const float rn = 1.0f / (t + 1e-10f);
-        for (int k = 0; k < K; ++k) qr[k] *= rn;
+      for (int r = warp; r < 10; r += RT_THREADS / 32) {    // softmax over labels: one warp per route (K <= 32)
+        const float x = lane < K ? q[r * K + lane] : -INFINITY;
+        const float mx = warp_max(x);
+        const float ex = lane < K ? expf(x - mx) : 0.f;
+        const float pr = ex * (1.0f / warp_sum(ex));
+        const float t = warp_sum(pr);
+        if (lane < K) q[r * K + lane] = pr * (1.0f / (t + 1e-10f));
       }
     }
     __syncthreads();
@@ -387,7 +405,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
       for (int o = tid; o < 10 * K; o += RT_THREADS) {
         const int r = o / K, k = o % K;
         float t = 0.f;
-        for (int c = 0; c < 32; ++c) t = fmaf(s.ddp[k * 32 + c], pt.pose[r * 32 + c], t);
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {      // rotated by k: conflict-free although the ddp rows are 32 words apart
+          const int cc = (c + k) & 31;
+          t = fmaf(s.ddp[k * 32 + cc], pt.pose[r * 32 + cc], t);
+        }
         const float cr = pheno ? pt.alpha[r] : 1.f;
         const float dr = a.d_R ? a.d_R[(size_t)b * 10 * K + o] : 0.f;
         s.tr[o] = t;
@@ -428,13 +450,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
       for (int it = nit - 1; it >= 1; --it) {
         float* dq = s.ds + it * 10 * K;
         const float* q = s.q + it * 10 * K;
-        if (tid < 10) {
-          const int r = tid;
-          float aa = 0.f;
-          for (int k = 0; k < K; ++k) aa = fmaf(dq[r * K + k], q[r * K + k], aa);
-          float bb = 0.f;   // renormalisation by (sum softmax + 1e-10) == 1 up to rounding
-          for (int k = 0; k < K; ++k) bb = fmaf(dq[r * K + k] - aa, q[r * K + k], bb);
-          for (int k = 0; k < K; ++k) dq[r * K + k] = q[r * K + k] * ((dq[r * K + k] - aa) - bb);
+        for (int r = warp; r < 10; r += RT_THREADS / 32) {   // one warp per route, lane = label
+          const float g = lane < K ? dq[r * K + lane] : 0.f, qq = lane < K ? q[r * K + lane] : 0.f;
+          const float aa = warp_sum(g * qq);
+          const float bb = warp_sum((g - aa) * qq);   // renormalisation by (sum softmax + 1e-10) == 1 up to rounding
+          if (lane < K) dq[r * K + lane] = qq * ((g - aa) - bb);
         }
         __syncthreads();
         // dv_{it-1}[c] = scale * sum_r ds[r][k] * u[r][c]
@@ -450,15 +470,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
           // v_{it-1} = sum_r q_{it-1}*act*u  ->  dq_{it-1}[r][k] = act[r]*w_rk, dact[r] += sum_k q*w_rk
           float* dqp = s.ds + (it - 1) * 10 * K;
           const float* qp = s.q + (it - 1) * 10 * K;
-          for (int o = warp; o < 10 * K; o += RT_THREADS / 32) {
+          for (int o = tid; o < 10 * K; o += RT_THREADS) {
             const int r = o / K, k = o % K;
-            const UT* uu = u + r * KD + k * 64;
-            float w = to_f<UT>(uu[lane]) * dvp[k * 64 + lane] + to_f<UT>(uu[lane + 32]) * dvp[k * 64 + lane + 32];
-            w = warp_sum(w);
-            if (lane == 0) {
-              dqp[o] = pt.act[r] * w;
-              atomicAdd(&pt.misc[16 + r], qp[o] * w);
-            }
+            const float w = rt_dot64<UT>(u + r * KD + k * 64, dvp + k * 64, k);
+            dqp[o] = pt.act[r] * w;
+            atomicAdd(&pt.misc[16 + r], qp[o] * w);
           }
           __syncthreads();
         }

@@ -446,25 +446,32 @@ struct UnfoldJob {
   float* g_w_in; float* g_b_in; float* g_gamma0; float* g_beta0;
 };
 struct UnfoldJobs { UnfoldJob j[24]; int n; float scaling; };
+constexpr int UNFOLD_ROWS = 32;   // in_proj rows per block; grid = (768 / 32, jobs)
 __global__ void __launch_bounds__(256) unfold_kernel(UnfoldJobs jobs) {
-  const UnfoldJob& j = jobs.j[blockIdx.x];
+  const UnfoldJob& j = jobs.j[blockIdx.y];
   const int c = threadIdx.x;
   const float s = jobs.scaling;
-  if (j.g_w_in)
-    for (int o = 0; o < D; ++o) j.g_w_in[(size_t)o * D + c] += s * j.dwq[(size_t)o * D + c];
-  const float gm = j.gamma0[c], be = j.beta0[c];
-  float dg = 0.f, db = 0.f;
-  for (int o = 0; o < 2 * D; ++o) {
-    const float dw = j.dwkv[(size_t)o * D + c];
-    const float w = j.w_in[(size_t)(D + o) * D + c];
-    const float dbo = j.dbkv[o];
-    if (j.g_w_in) j.g_w_in[(size_t)(D + o) * D + c] += dw * gm + dbo * be;
-    dg += dw * w;
-    db += dbo * w;
+  const int r0 = blockIdx.x * UNFOLD_ROWS;        // row of in_proj_weight [768,256]
+  if (r0 < D) {                                   // query block: Wq' = s*Wq
+    if (j.g_w_in)
+#pragma unroll 4
+      for (int o = r0; o < r0 + UNFOLD_ROWS; ++o) j.g_w_in[(size_t)o * D + c] += s * j.dwq[(size_t)o * D + c];
+  } else {                                        // key / value blocks (LN0 affine folded into the weights)
+    const float gm = j.gamma0[c], be = j.beta0[c];
+    float dg = 0.f, db = 0.f;
+#pragma unroll 4
+    for (int o = r0 - D; o < r0 - D + UNFOLD_ROWS; ++o) {
+      const float dw = j.dwkv[(size_t)o * D + c];
+      const float w = j.w_in[(size_t)(D + o) * D + c];
+      const float dbo = j.dbkv[o];
+      if (j.g_w_in) j.g_w_in[(size_t)(D + o) * D + c] += dw * gm + dbo * be;
+      dg += dw * w;
+      db += dbo * w;
+    }
+    if (j.g_gamma0) atomicAdd(j.g_gamma0 + c, dg);
+    if (j.g_beta0) atomicAdd(j.g_beta0 + c, db);
   }
-  if (j.g_gamma0) atomicAdd(j.g_gamma0 + c, dg);
-  if (j.g_beta0) atomicAdd(j.g_beta0 + c, db);
-  if (j.g_b_in) {
+  if (blockIdx.x == 0 && j.g_b_in) {
     j.g_b_in[c] += s * j.dbq[c];
     j.g_b_in[D + c] += j.dbkv[c];
     j.g_b_in[2 * D + c] += j.dbkv[D + c];

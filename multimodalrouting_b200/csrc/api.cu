@@ -125,6 +125,7 @@ static int run_wgrad(const Plan& P, const WgradProblem& w, int y_rows, int x_row
   return MMR_OK;
 }
 
+constexpr int AHG = 2;   // heads per attention CTA (attention_mma.cuh)
 // bf16 path: tensor-core attention (attention_mma.cuh); fp32 parity path and MMR_ATTN=simt: SIMT kernels
 template <class CT> static bool mma_attention() { return false; }
 template <> bool mma_attention<bf16>() {
@@ -324,7 +325,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   int maxTq = 0;
   for (int d = 0; d < NDIR; ++d) maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d];
   CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-  CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::FWD_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -350,8 +351,8 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       {
         ProfScope ps(PC_ATTN_FWD, st);
         if (mma_attention<CT>()) {
-          dim3 grid(2 * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
-          amma::attn_fwd_kernel<<<grid, amma::THREADS, amma::FWD_SMEM, st>>>(a);
+          dim3 grid(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
+          amma::attn_fwd_kernel<AHG><<<grid, amma::Cfg<AHG>::THREADS, amma::fwd_smem<AHG>(), st>>>(a);
         } else {
           dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
           attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
@@ -515,8 +516,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   for (int d = 0; d < NDIR; ++d) { maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d]; maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d]; }
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::BWD_SMEM));
-  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::BWD_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -600,10 +602,16 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       {
         ProfScope ps(PC_ATTN_BWD, st);
         if (mma_attention<CT>()) {
-          dim3 g1(2 * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
-          dim3 g2(2 * ((maxTk + amma::RC - 1) / amma::RC), B, NDIR);
-          amma::attn_bwd_dq_kernel<<<g1, amma::THREADS, amma::BWD_SMEM, st>>>(a);
-          amma::attn_bwd_dkv_kernel<<<g2, amma::THREADS, amma::BWD_SMEM, st>>>(a);
+          if (maxTq <= amma::RC && maxTk <= amma::RC && !getenv("MMR_ATTN_BWD_SPLIT")) {
+            // one chunk per sequence: fused dQ + dK/dV kernel (operands staged once, no O / D round trip)
+            amma::attn_bwd_fused_kernel<AHG><<<dim3(amma::Cfg<AHG>::NHG, B, NDIR), amma::Cfg<AHG>::THREADS,
+                                               amma::bwd_fused_smem<AHG>(), st>>>(a);
+          } else {
+          dim3 g1(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
+          dim3 g2(amma::Cfg<AHG>::NHG * ((maxTk + amma::RC - 1) / amma::RC), B, NDIR);
+          amma::attn_bwd_dq_kernel<AHG><<<g1, amma::Cfg<AHG>::THREADS, amma::bwd_smem<AHG>(), st>>>(a);
+          amma::attn_bwd_dkv_kernel<AHG><<<g2, amma::Cfg<AHG>::THREADS, amma::bwd_smem<AHG>(), st>>>(a);
+          }
         } else {
           dim3 g1((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
           dim3 g2((H * maxTk + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);

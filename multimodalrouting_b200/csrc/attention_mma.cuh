@@ -16,9 +16,16 @@
 namespace mmr {
 namespace amma {
 
-constexpr int HG = 4;              // heads per CTA
-constexpr int THREADS = 256;
-constexpr int LDS = 136;           // smem row stride in bf16 elements (128 + 8: conflict-free ldmatrix)
+// HG = heads per CTA (2 or 4): 2*HG warps, HG*32-column row slices (64*HG bytes), smem row stride HG*32+8
+// elements (the +8 keeps ldmatrix conflict-free).  HG=2 gives 128-thread CTAs with ~30-40 KB of shared memory,
+// so 4 CTAs per SM overlap each other's load / compute / store phases.
+template <int HG> struct Cfg {
+  static constexpr int THREADS = HG * 64;
+  static constexpr int LDS = HG * 32 + 8;
+  static constexpr int NHG = 8 / HG;       // head groups per patient
+  static constexpr int CPR = HG * 4;       // 16-byte chunks per staged row
+  static constexpr int COLS = HG * 32;
+};
 constexpr int RC = 64;             // rows (queries or keys) per chunk
 constexpr float NEG_BF16 = -3.3895313892515355e38f;
 
@@ -50,9 +57,11 @@ __device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2
 
 // Stage `nvalid` rows x 128 columns (src row stride ld elements) into dst[rows][LDS]; rows
 // [nvalid, nrows) are zero-filled so that padded B-operand rows never inject NaN/Inf.
+template <int HG>
 __device__ __forceinline__ void stage(bf16* dst, const bf16* src, size_t ld, int nvalid, int nrows) {
-  for (int idx = threadIdx.x; idx < nrows * 16; idx += THREADS) {
-    const int r = idx >> 4, c = (idx & 15) * 8;
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, CPR = Cfg<HG>::CPR;
+  for (int idx = threadIdx.x; idx < nrows * CPR; idx += THREADS) {
+    const int r = idx / CPR, c = (idx % CPR) * 8;
     bf16* d = dst + r * LDS + c;
     if (r < nvalid) cp_async16(smem_addr(d), src + (size_t)r * ld + c);
     else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
@@ -60,19 +69,32 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* src, size_t ld, int
 }
 
 // A fragment (16 rows x 16 k) of a row-major smem tile at (row0, col0)
+template <int LDS>
 __device__ __forceinline__ void frag_a(const bf16* s, int row0, int col0, int lane, uint32_t (&r)[4]) {
   ldsm_x4(smem_addr(s + (row0 + (lane & 15)) * LDS + col0 + (lane >> 4) * 8), r);
 }
 // B fragments for C[m][n] += A[m][k] * X[n][k] (X row-major, n = row, k = col): 8 rows n0.., k = col0..col0+31
 //   r[0],r[1] = (b0,b1) of k-step 0, r[2],r[3] = (b0,b1) of k-step 1
+template <int LDS>
 __device__ __forceinline__ void frag_b_nk(const bf16* s, int n0, int col0, int lane, uint32_t (&r)[4]) {
   ldsm_x4(smem_addr(s + (n0 + (lane & 7)) * LDS + col0 + (lane >> 3) * 8), r);
 }
 // B fragments for C[m][n] += A[m][k] * X[k][n] (X row-major, k = row, n = col): 16 rows k0.., cols n0..n0+15
 //   r[0],r[1] = (b0,b1) of n-tile n0, r[2],r[3] = (b0,b1) of n-tile n0+8
+template <int LDS>
 __device__ __forceinline__ void frag_b_kn(const bf16* s, int k0, int n0, int lane, uint32_t (&r)[4]) {
   ldsm_x4_t(smem_addr(s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8), r);
 }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float L2E = 1.4426950408889634f;
+// additive key bias: 0 for a kept key, finfo(bf16).min for a padded key (a bf16 score plus it IS finfo.min in
+// fp32, i.e. masked_fill), -inf for tile padding beyond Tk
+__device__ __forceinline__ float key_bias(float mk) { return mk > 0.f ? 0.f : (mk == 0.f ? NEG_BF16 : -INFINITY); }
 
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -84,44 +106,49 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // copy `nrows` x 128 columns from smem tile to global (row stride ld), coalesced 16-byte stores
+template <int HG>
 __device__ __forceinline__ void unstage(bf16* dst, size_t ld, const bf16* src, int nrows) {
-  for (int idx = threadIdx.x; idx < nrows * 16; idx += THREADS) {
-    const int r = idx >> 4, c = (idx & 15) * 8;
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, CPR = Cfg<HG>::CPR;
+  for (int idx = threadIdx.x; idx < nrows * CPR; idx += THREADS) {
+    const int r = idx / CPR, c = (idx % CPR) * 8;
     *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c) = *reinterpret_cast<const uint4*>(src + r * LDS + c);
   }
 }
 
 // write a 16x8 fp32 C fragment tile as bf16 into smem at (row0, col0)
+template <int LDS>
 __device__ __forceinline__ void put_c(bf16* s, int row0, int col0, int lane, const float (&c)[4], float s0 = 1.f, float s1 = 1.f) {
   const int g = lane >> 2, t = lane & 3;
   *reinterpret_cast<uint32_t*>(s + (row0 + g) * LDS + col0 + 2 * t) = pack_bf16(c[0] * s0, c[1] * s0);
   *reinterpret_cast<uint32_t*>(s + (row0 + g + 8) * LDS + col0 + 2 * t) = pack_bf16(c[2] * s1, c[3] * s1);
 }
 
-constexpr int FWD_SMEM = 3 * RC * LDS * 2 + RC * 4;
-constexpr int BWD_SMEM = 4 * RC * LDS * 2 + RC * 4 + RC * HG * 3 * 4;
+template <int HG> constexpr int fwd_smem() { return 3 * RC * Cfg<HG>::LDS * 2 + RC * 4; }
+template <int HG> constexpr int bwd_smem() { return 4 * RC * Cfg<HG>::LDS * 2 + RC * 4 + RC * HG * 3 * 4; }
 
-// grid: (2 * ceil(maxTq/64), B, 6)
-__global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
+// grid: (NHG * ceil(maxTq/64), B, 6)
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn_fwd_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Ks = Qs + RC * LDS;
   bf16* Vs = Ks + RC * LDS;
   float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] 1 keep / 0 padded / -1 beyond Tk
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, qc = blockIdx.x >> 1;
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
   const int Tq = a.q.T[d], Tk = a.kv.T[d];
   const int q0 = qc * RC;
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = warp & 3, half = warp >> 2, h = hg * HG + hl;
+  const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
   const int g = lane >> 2, t = lane & 3;
   const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
-  const bf16* qsrc = reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * 128;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * 128;
+  const bf16* qsrc = reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
   const int nq16 = (nq + 15) & ~15;
-  stage(Qs, qsrc, D, nq, nq16);
+  stage<HG>(Qs, qsrc, D, nq, nq16);
   const bool single = Tk <= RC;
 
   float o[2][4][4];
@@ -140,55 +167,48 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
     const int nk = min(RC, Tk - k0);
     const int nk16 = (nk + 15) & ~15;
     __syncthreads();   // previous chunk fully consumed
-    stage(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
-    stage(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
-    if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[k0 + threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
+    stage<HG>(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
+    stage<HG>(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
+    if (threadIdx.x < RC)
+      Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[k0 + threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
     cp_async_wait_all();
     __syncthreads();
-    const int NT = nk16 >> 3;
+    const int NT = (nk + 7) >> 3;      // 8-key score tiles that hold at least one real key
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int mt = half * 2 + i;
       if (mt * 16 >= nq) continue;
       uint32_t qa[2][4];
-      frag_a(Qs, mt * 16, hl * 32, lane, qa[0]);
-      frag_a(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+      frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
+      frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
       float s[8][4];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         if (nt < NT) {
           uint32_t kb[4];
-          frag_b_nk(Ks, nt * 8, hl * 32, lane, kb);
+          frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
           mma16816(s[nt], qa[0], kb[0], kb[1]);
           mma16816(s[nt], qa[1], kb[2], kb[3]);
-        }
-      }
-      // bf16 rounding of the scores, key masking, chunk row max
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float mk = (nt < NT) ? Ms[nt * 8 + 2 * t + j] : -1.f;
-          float v0 = rbf(s[nt][j]), v1 = rbf(s[nt][2 + j]);
-          if (mk == 0.f) { v0 = NEG_BF16; v1 = NEG_BF16; }
-          if (mk < 0.f) { v0 = -INFINITY; v1 = -INFINITY; }
-          s[nt][j] = v0; s[nt][2 + j] = v1;
-          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+          const float2 kbias = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
+          s[nt][0] = rbf(s[nt][0]) + kbias.x; s[nt][1] = rbf(s[nt][1]) + kbias.y;
+          s[nt][2] = rbf(s[nt][2]) + kbias.x; s[nt][3] = rbf(s[nt][3]) + kbias.y;
+          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
         }
       }
       mx0 = quad_max(mx0); mx1 = quad_max(mx1);
       const float mn0 = fmaxf(mrun[i][0], mx0), mn1 = fmaxf(mrun[i][1], mx1);
-      const float c0 = __expf(mrun[i][0] - mn0), c1 = __expf(mrun[i][1] - mn1);   // exp(-inf) = 0 on the first chunk
+      const float c0 = ex2((mrun[i][0] - mn0) * L2E), c1 = ex2((mrun[i][1] - mn1) * L2E);   // 0 on the first chunk
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float p0 = __expf(s[nt][j] - mn0), p1 = __expf(s[nt][2 + j] - mn1);
-          s[nt][j] = p0; s[nt][2 + j] = p1;
-          sum0 += p0; sum1 += p1;
+        if (nt < NT) {
+          s[nt][0] = ex2((s[nt][0] - mn0) * L2E); s[nt][1] = ex2((s[nt][1] - mn0) * L2E);
+          s[nt][2] = ex2((s[nt][2] - mn1) * L2E); s[nt][3] = ex2((s[nt][3] - mn1) * L2E);
+          sum0 += s[nt][0] + s[nt][1];
+          sum1 += s[nt][2] + s[nt][3];
         }
       }
       sum0 = quad_sum(sum0); sum1 = quad_sum(sum1);
@@ -201,10 +221,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
         for (int n = 0; n < 4; ++n) { o[i][n][0] *= c0; o[i][n][1] *= c0; o[i][n][2] *= c1; o[i][n][3] *= c1; }
       }
-      // O += P V
+      // O += P V   (score tiles >= NT are exactly zero)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        if (kk * 16 < nk16) {
+        if (2 * kk < NT) {
           uint32_t pa[4];
           pa[0] = pack_bf16(s[2 * kk][0] * ps0, s[2 * kk][1] * ps0);
           pa[1] = pack_bf16(s[2 * kk][2] * ps1, s[2 * kk][3] * ps1);
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
           for (int nc = 0; nc < 2; ++nc) {
             uint32_t vb[4];
-            frag_b_kn(Vs, kk * 16, hl * 32 + nc * 16, lane, vb);
+            frag_b_kn<LDS>(Vs, kk * 16, hl * 32 + nc * 16, lane, vb);
             mma16816(o[i][2 * nc], pa, vb[0], vb[1]);
             mma16816(o[i][2 * nc + 1], pa, vb[2], vb[3]);
           }
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
     const float il0 = 1.0f / lrun[i][0], il1 = 1.0f / lrun[i][1];
     const float s0 = single ? 1.f : il0, s1 = single ? 1.f : il1;
 #pragma unroll
-    for (int n = 0; n < 4; ++n) put_c(Qs, mt * 16, hl * 32 + n * 8, lane, o[i][n], s0, s1);
+    for (int n = 0; n < 4; ++n) put_c<LDS>(Qs, mt * 16, hl * 32 + n * 8, lane, o[i][n], s0, s1);
     if (t == 0) {
       const int r0 = mt * 16 + g, r1 = r0 + 8;
       if (r0 < nq) { float* p = a.ml + ((qrow0 + r0) * H + h) * 2; p[0] = mrun[i][0]; p[1] = il0; }
@@ -237,14 +257,16 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_kernel(AttnArgs a) {
     }
   }
   __syncthreads();
-  unstage(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * 128, D, Qs, nq);
+  unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
 }
 
 // ------------------------------------------------------------------------------------------
 // dQ pass.  CTA = (direction, patient, head group, 64-query chunk); loops over key chunks.
 //   P = exp(S - m) / l ; dP = dO V^T ; dS = P .* (dP - D) on kept keys ; dQ = dS K
 // Also writes D = rowsum(dO .* O) to a.dvec for the dK/dV pass.
-__global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn_bwd_dq_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Gs = Qs + RC * LDS;      // dO
@@ -252,23 +274,23 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
   bf16* Vs = Ks + RC * LDS;
   float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);
   float* St = Ms + RC;           // [64][HG][3]: m, 1/l, D
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, qc = blockIdx.x >> 1;
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
   const int Tq = a.q.T[d], Tk = a.kv.T[d];
   const int q0 = qc * RC;
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = warp & 3, half = warp >> 2;
+  const int hl = warp % HG, half = warp / HG;
   const int g = lane >> 2, t = lane & 3;
   const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * 128;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
   const int nq16 = (nq + 15) & ~15;
-  stage(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * 128, D, nq, nq16);
-  stage(Gs, reinterpret_cast<const bf16*>(a.d_o) + qrow0 * D + hg * 128, D, nq, nq16);
+  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Gs, reinterpret_cast<const bf16*>(a.d_o) + qrow0 * D + hg * COLS, D, nq, nq16);
   // row statistics: (row, head) pairs of this CTA; D from global O / dO (64-byte head slices)
   for (int idx = threadIdx.x; idx < nq * HG; idx += THREADS) {
-    const int r = idx >> 2, hh = idx & 3;
+    const int r = idx / HG, hh = idx % HG;
     const size_t row = qrow0 + r;
     const int hglob = hg * HG + hh;
     const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.o) + row * D + hglob * HD);
@@ -300,8 +322,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
     const int nk = min(RC, Tk - k0);
     const int nk16 = (nk + 15) & ~15;
     __syncthreads();
-    stage(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
-    stage(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
+    stage<HG>(Ks, kvsrc + (size_t)k0 * a.ldkv, a.ldkv, nk, nk16);
+    stage<HG>(Vs, kvsrc + (size_t)k0 * a.ldkv + D, a.ldkv, nk, nk16);
     if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[k0 + threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
     cp_async_wait_all();
     __syncthreads();
@@ -310,10 +332,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
       const int mt = half * 2 + i;
       if (mt * 16 >= nq) continue;
       uint32_t qa[2][4], ga[2][4];
-      frag_a(Qs, mt * 16, hl * 32, lane, qa[0]);
-      frag_a(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
-      frag_a(Gs, mt * 16, hl * 32, lane, ga[0]);
-      frag_a(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
+      frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
+      frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+      frag_a<LDS>(Gs, mt * 16, hl * 32, lane, ga[0]);
+      frag_a<LDS>(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
       const int r0 = min(mt * 16 + g, nq - 1), r1 = min(mt * 16 + g + 8, nq - 1);
       const float m0 = St[(r0 * HG + hl) * 3], il0 = St[(r0 * HG + hl) * 3 + 1], D0 = St[(r0 * HG + hl) * 3 + 2];
       const float m1 = St[(r1 * HG + hl) * 3], il1 = St[(r1 * HG + hl) * 3 + 1], D1 = St[(r1 * HG + hl) * 3 + 2];
@@ -326,8 +348,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
           const int nt = 2 * kk + e;
           float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
           uint32_t kb[4], vb[4];
-          frag_b_nk(Ks, nt * 8, hl * 32, lane, kb);
-          frag_b_nk(Vs, nt * 8, hl * 32, lane, vb);
+          frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
+          frag_b_nk<LDS>(Vs, nt * 8, hl * 32, lane, vb);
           mma16816(s, qa[0], kb[0], kb[1]);
           mma16816(s, qa[1], kb[2], kb[3]);
           mma16816(dp, ga[0], vb[0], vb[1]);
@@ -346,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
 #pragma unroll
         for (int nc = 0; nc < 2; ++nc) {
           uint32_t kb[4];
-          frag_b_kn(Ks, kk * 16, hl * 32 + nc * 16, lane, kb);
+          frag_b_kn<LDS>(Ks, kk * 16, hl * 32 + nc * 16, lane, kb);
           mma16816(dq[i][2 * nc], dsa, kb[0], kb[1]);
           mma16816(dq[i][2 * nc + 1], dsa, kb[2], kb[3]);
         }
@@ -359,17 +381,19 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_kernel(AttnArgs a) {
     const int mt = half * 2 + i;
     if (mt * 16 >= nq) continue;
 #pragma unroll
-    for (int n = 0; n < 4; ++n) put_c(Qs, mt * 16, hl * 32 + n * 8, lane, dq[i][n]);
+    for (int n = 0; n < 4; ++n) put_c<LDS>(Qs, mt * 16, hl * 32 + n * 8, lane, dq[i][n]);
   }
   __syncthreads();
-  unstage(reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * 128, D, Qs, nq);
+  unstage<HG>(reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * COLS, D, Qs, nq);
 }
 
 // ------------------------------------------------------------------------------------------
 // dK / dV pass (transposed tiles).  CTA = (direction, patient, head group, 64-key chunk); loops
 // over query chunks.  S^T = K Q^T ; dP^T = V dO^T ; dV = P^T dO ; dK = dS^T Q.
 // A padded key still receives dV (its probability is only zero when another key is kept) but no dK.
-__global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn_bwd_dkv_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Ks = reinterpret_cast<bf16*>(smem_raw);
   bf16* Vs = Ks + RC * LDS;
@@ -377,21 +401,21 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
   bf16* Gs = Qs + RC * LDS;
   float* Ms = reinterpret_cast<float*>(Gs + RC * LDS);
   float* St = Ms + RC;           // [64 queries][HG][3]
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x & 1, kc = blockIdx.x >> 1;
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, kc = blockIdx.x / NHG;
   const int Tq = a.q.T[d], Tk = a.kv.T[d];
   const int k0 = kc * RC;
   if (k0 >= Tk) return;
   const int nk = min(RC, Tk - k0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = warp & 3, half = warp >> 2;
+  const int hl = warp % HG, half = warp / HG;
   const int g = lane >> 2, t = lane & 3;
   const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * Tk + k0;
   const size_t qbase = (size_t)a.q.row0[d] + (size_t)b * Tq;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * 128;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk + k0 : nullptr;
   const int nk16 = (nk + 15) & ~15;
-  stage(Ks, kvsrc, a.ldkv, nk, nk16);
-  stage(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
   if (threadIdx.x < RC) Ms[threadIdx.x] = threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
 
   float dk[2][4][4], dv[2][4][4];
@@ -406,10 +430,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
     const int nq = min(RC, Tq - q0);
     const int nq16 = (nq + 15) & ~15;
     __syncthreads();
-    stage(Qs, reinterpret_cast<const bf16*>(a.qb) + (qbase + q0) * D + hg * 128, D, nq, nq16);
-    stage(Gs, reinterpret_cast<const bf16*>(a.d_o) + (qbase + q0) * D + hg * 128, D, nq, nq16);
+    stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + (qbase + q0) * D + hg * COLS, D, nq, nq16);
+    stage<HG>(Gs, reinterpret_cast<const bf16*>(a.d_o) + (qbase + q0) * D + hg * COLS, D, nq, nq16);
     for (int idx = threadIdx.x; idx < RC * HG; idx += THREADS) {
-      const int r = idx >> 2, hh = idx & 3;
+      const int r = idx / HG, hh = idx % HG;
       float m = 0.f, il = 0.f, dd = 0.f;
       if (r < nq) {
         const size_t rr = (qbase + q0 + r) * H + hg * HG + hh;
@@ -424,10 +448,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
       const int mt = half * 2 + i;
       if (mt * 16 >= nk) continue;
       uint32_t ka[2][4], va[2][4];
-      frag_a(Ks, mt * 16, hl * 32, lane, ka[0]);
-      frag_a(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
-      frag_a(Vs, mt * 16, hl * 32, lane, va[0]);
-      frag_a(Vs, mt * 16, hl * 32 + 16, lane, va[1]);
+      frag_a<LDS>(Ks, mt * 16, hl * 32, lane, ka[0]);
+      frag_a<LDS>(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
+      frag_a<LDS>(Vs, mt * 16, hl * 32, lane, va[0]);
+      frag_a<LDS>(Vs, mt * 16, hl * 32 + 16, lane, va[1]);
       const float mk0 = Ms[mt * 16 + g], mk1 = Ms[mt * 16 + g + 8];   // key flags of this thread's two rows
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
@@ -438,8 +462,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
           const int nt = 2 * kk + e;
           float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
           uint32_t qb[4], gb[4];
-          frag_b_nk(Qs, nt * 8, hl * 32, lane, qb);
-          frag_b_nk(Gs, nt * 8, hl * 32, lane, gb);
+          frag_b_nk<LDS>(Qs, nt * 8, hl * 32, lane, qb);
+          frag_b_nk<LDS>(Gs, nt * 8, hl * 32, lane, gb);
           mma16816(s, ka[0], qb[0], qb[1]);
           mma16816(s, ka[1], qb[2], qb[3]);
           mma16816(dp, va[0], gb[0], gb[1]);
@@ -466,8 +490,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
 #pragma unroll
         for (int nc = 0; nc < 2; ++nc) {
           uint32_t gb[4], qb[4];
-          frag_b_kn(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
-          frag_b_kn(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
+          frag_b_kn<LDS>(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
+          frag_b_kn<LDS>(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
           mma16816(dv[i][2 * nc], pa, gb[0], gb[1]);
           mma16816(dv[i][2 * nc + 1], pa, gb[2], gb[3]);
           mma16816(dk[i][2 * nc], dsa, qb[0], qb[1]);
@@ -483,14 +507,198 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_kernel(AttnArgs a) {
     if (mt * 16 >= nk) continue;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      put_c(Ks, mt * 16, hl * 32 + n * 8, lane, dk[i][n]);
-      put_c(Vs, mt * 16, hl * 32 + n * 8, lane, dv[i][n]);
+      put_c<LDS>(Ks, mt * 16, hl * 32 + n * 8, lane, dk[i][n]);
+      put_c<LDS>(Vs, mt * 16, hl * 32 + n * 8, lane, dv[i][n]);
     }
   }
   __syncthreads();
-  bf16* out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * 128;
-  unstage(out, a.ldkv, Ks, nk);
-  unstage(out + D, a.ldkv, Vs, nk);
+  bf16* out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * COLS;
+  unstage<HG>(out, a.ldkv, Ks, nk);
+  unstage<HG>(out + D, a.ldkv, Vs, nk);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused backward for sequences that fit one chunk (Tq <= 64 and Tk <= 64: all MIMIC-IV shapes).
+// CTA = (direction, patient, head group): Q, dO, K, V are staged ONCE; pass A (rows = queries) produces dQ
+// and the softmax-backward row term D_i = sum_j P_ij dP_ij (== rowsum(dO .* O), so O is never re-read);
+// pass B (rows = keys, transposed tiles) produces dK and dV.  grid: (NHG, B, 6)
+template <int HG> constexpr int bwd_fused_smem() { return 5 * RC * Cfg<HG>::LDS * 2 + 2 * RC * 4 + RC * HG * 4 * 4; }
+
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn_bwd_fused_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, COLS = Cfg<HG>::COLS;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Gs = Qs + RC * LDS;      // dO
+  bf16* Ks = Gs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  bf16* Ds = Vs + RC * LDS;      // dQ staging
+  float* Bs = reinterpret_cast<float*>(Ds + RC * LDS);   // [64] additive key bias
+  float* Kp = Bs + RC;                                   // [64] 1 for kept keys else 0
+  float4* St = reinterpret_cast<float4*>(Kp + RC);       // [64 queries][HG]: m, 1/l, D, -
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x;
+  const int nq = a.q.T[d], nk = a.kv.T[d];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp % HG, half = warp / HG;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * nq;
+  const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * nk;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * COLS;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
+  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
+  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Gs, reinterpret_cast<const bf16*>(a.d_o) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  if (threadIdx.x < RC) {
+    const float mk = threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
+    Bs[threadIdx.x] = key_bias(mk);
+    Kp[threadIdx.x] = mk > 0.f ? 1.f : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < RC * HG; idx += THREADS) {
+    const int r = idx / HG, hh = idx % HG;
+    float2 ml = make_float2(0.f, 0.f);     // 1/l = 0 for tile-padding queries -> P = 0
+    if (r < nq) ml = *reinterpret_cast<const float2*>(a.ml + ((qrow0 + r) * H + hg * HG + hh) * 2);
+    St[idx] = make_float4(ml.x, ml.y, 0.f, 0.f);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int NTK = (nk + 7) >> 3, NTQ = (nq + 7) >> 3;
+
+  // ---- pass A: rows = queries ------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nq) continue;
+    uint32_t qa[2][4], ga[2][4];
+    frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
+    frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+    frag_a<LDS>(Gs, mt * 16, hl * 32, lane, ga[0]);
+    frag_a<LDS>(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const float4 st0 = St[r0 * HG + hl], st1 = St[r1 * HG + hl];
+    float s[8][4], dp[8][4];
+    float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
+      if (nt < NTK) {
+        uint32_t kb[4], vb[4];
+        frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
+        frag_b_nk<LDS>(Vs, nt * 8, hl * 32, lane, vb);
+        mma16816(s[nt], qa[0], kb[0], kb[1]);
+        mma16816(s[nt], qa[1], kb[2], kb[3]);
+        mma16816(dp[nt], ga[0], vb[0], vb[1]);
+        mma16816(dp[nt], ga[1], vb[2], vb[3]);
+        const float2 kbias = *reinterpret_cast<const float2*>(Bs + nt * 8 + 2 * t);
+        s[nt][0] = ex2((rbf(s[nt][0]) + kbias.x - st0.x) * L2E) * st0.y;
+        s[nt][1] = ex2((rbf(s[nt][1]) + kbias.y - st0.x) * L2E) * st0.y;
+        s[nt][2] = ex2((rbf(s[nt][2]) + kbias.x - st1.x) * L2E) * st1.y;
+        s[nt][3] = ex2((rbf(s[nt][3]) + kbias.y - st1.x) * L2E) * st1.y;
+        D0 = fmaf(s[nt][0], dp[nt][0], fmaf(s[nt][1], dp[nt][1], D0));
+        D1 = fmaf(s[nt][2], dp[nt][2], fmaf(s[nt][3], dp[nt][3], D1));
+      }
+    }
+    D0 = quad_sum(D0); D1 = quad_sum(D1);
+    if (t == 0) { St[r0 * HG + hl].z = D0; St[r1 * HG + hl].z = D1; }
+    float dq[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (2 * kk >= NTK) continue;
+      uint32_t dsa[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nt = 2 * kk + e;
+        const float2 keep = *reinterpret_cast<const float2*>(Kp + nt * 8 + 2 * t);   // tiles >= NTK: P = 0 already
+        dsa[e * 2] = pack_bf16(s[nt][0] * (dp[nt][0] - D0) * keep.x, s[nt][1] * (dp[nt][1] - D0) * keep.y);
+        dsa[e * 2 + 1] = pack_bf16(s[nt][2] * (dp[nt][2] - D1) * keep.x, s[nt][3] * (dp[nt][3] - D1) * keep.y);
+      }
+#pragma unroll
+      for (int nc = 0; nc < 2; ++nc) {
+        uint32_t kb[4];
+        frag_b_kn<LDS>(Ks, kk * 16, hl * 32 + nc * 16, lane, kb);
+        mma16816(dq[2 * nc], dsa, kb[0], kb[1]);
+        mma16816(dq[2 * nc + 1], dsa, kb[2], kb[3]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) put_c<LDS>(Ds, mt * 16, hl * 32 + n * 8, lane, dq[n]);
+  }
+  __syncthreads();   // D of every (query, head) visible; dQ staged
+
+  // ---- pass B: rows = keys (transposed tiles) ---------------------------------------------
+  float dk[2][4][4], dv[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dk[i][n][j] = 0.f; dv[i][n][j] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nk) continue;
+    uint32_t ka[2][4], va[2][4];
+    frag_a<LDS>(Ks, mt * 16, hl * 32, lane, ka[0]);
+    frag_a<LDS>(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
+    frag_a<LDS>(Vs, mt * 16, hl * 32, lane, va[0]);
+    frag_a<LDS>(Vs, mt * 16, hl * 32 + 16, lane, va[1]);
+    const float kb0 = Bs[mt * 16 + g], kb1 = Bs[mt * 16 + g + 8];      // this thread's two key rows
+    const float kp0 = Kp[mt * 16 + g], kp1 = Kp[mt * 16 + g + 8];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (2 * kk >= NTQ) continue;
+      uint32_t pa[4], dsa[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nt = 2 * kk + e;
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t qb[4], gb[4];
+        frag_b_nk<LDS>(Qs, nt * 8, hl * 32, lane, qb);
+        frag_b_nk<LDS>(Gs, nt * 8, hl * 32, lane, gb);
+        mma16816(s, ka[0], qb[0], qb[1]);
+        mma16816(s, ka[1], qb[2], qb[3]);
+        mma16816(dp, va[0], gb[0], gb[1]);
+        mma16816(dp, va[1], gb[2], gb[3]);
+        const float4 sa = St[(nt * 8 + 2 * t) * HG + hl], sb = St[(nt * 8 + 2 * t + 1) * HG + hl];   // query columns
+        const float p0 = ex2((rbf(s[0]) + kb0 - sa.x) * L2E) * sa.y, p1 = ex2((rbf(s[1]) + kb0 - sb.x) * L2E) * sb.y;
+        const float p2 = ex2((rbf(s[2]) + kb1 - sa.x) * L2E) * sa.y, p3 = ex2((rbf(s[3]) + kb1 - sb.x) * L2E) * sb.y;
+        pa[e * 2] = pack_bf16(p0, p1);
+        pa[e * 2 + 1] = pack_bf16(p2, p3);
+        dsa[e * 2] = pack_bf16(p0 * (dp[0] - sa.z) * kp0, p1 * (dp[1] - sb.z) * kp0);
+        dsa[e * 2 + 1] = pack_bf16(p2 * (dp[2] - sa.z) * kp1, p3 * (dp[3] - sb.z) * kp1);
+      }
+#pragma unroll
+      for (int nc = 0; nc < 2; ++nc) {
+        uint32_t gb[4], qb[4];
+        frag_b_kn<LDS>(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
+        frag_b_kn<LDS>(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
+        mma16816(dv[i][2 * nc], pa, gb[0], gb[1]);
+        mma16816(dv[i][2 * nc + 1], pa, gb[2], gb[3]);
+        mma16816(dk[i][2 * nc], dsa, qb[0], qb[1]);
+        mma16816(dk[i][2 * nc + 1], dsa, qb[2], qb[3]);
+      }
+    }
+  }
+  __syncthreads();   // every warp is done reading K / V before they become the dK / dV staging tiles
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nk) continue;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      put_c<LDS>(Ks, mt * 16, hl * 32 + n * 8, lane, dk[i][n]);
+      put_c<LDS>(Vs, mt * 16, hl * 32 + n * 8, lane, dv[i][n]);
+    }
+  }
+  __syncthreads();
+  unstage<HG>(reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * COLS, D, Ds, nq);
+  bf16* out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * COLS;
+  unstage<HG>(out, a.ldkv, Ks, nk);
+  unstage<HG>(out + D, a.ldkv, Vs, nk);
 }
 
 }  // namespace amma

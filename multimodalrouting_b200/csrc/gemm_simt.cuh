@@ -5,13 +5,16 @@
 
 namespace mmr {
 
-// C[r, n] = sum_k A[a(r), k] * B[b(seg)+n, k];  64x64x16 tiles, 256 threads, 4x4 per thread.
-// Requires K % 16 == 0, N % 4 == 0, lda/ldb % 4 == 0.
+// C[r, n] = sum_k A[a(r), k] * B[b(seg)+n, k];  64x64xBK tiles, 256 threads, 4x4 per thread.
+// Requires K % BK == 0 (BK = 64 when K % 64 == 0, else 16), N % 4 == 0, lda/ldb % 4 == 0.  BK = 64 issues four
+// independent 16-byte loads per operand per thread and quarters the number of barrier-separated steps, which
+// is what the small (M = batch) pair / trimodal projections are bound by.
 // TRANSB: B is a single row-major [K, N] matrix (B(n,k) = B[k*ldb + b_row0 + n]).
-template <class TA, class TB, int OP, class CT, bool TRANSB = false>
+template <class TA, class TB, int OP, class CT, bool TRANSB, int BK>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams e) {
-  __shared__ __align__(16) float As[16][68];
-  __shared__ __align__(16) float Bs[16][68];
+  constexpr int NL = BK / 16;     // 16-wide k slabs per step
+  __shared__ __align__(16) float As[BK][68];
+  __shared__ __align__(16) float Bs[BK][68];
   const int t = threadIdx.x;
   const int m0 = blockIdx.y * 64;
   const int n0 = blockIdx.x * 64;
@@ -34,22 +37,30 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int k0 = 0; k0 < g.K; k0 += 16) {
-    float4 av = a_ok ? Vec4<TA>::ld(ap + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 bv;
-    if (TRANSB) bv = bt_ok ? Vec4<TB>::ld(btp + (size_t)k0 * g.ldb) : make_float4(0.f, 0.f, 0.f, 0.f);
-    else bv = b_ok ? Vec4<TB>::ld(bp + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    As[lk + 0][lm] = av.x; As[lk + 1][lm] = av.y; As[lk + 2][lm] = av.z; As[lk + 3][lm] = av.w;
-    if (TRANSB) {
-      *reinterpret_cast<float4*>(&Bs[tk][tn]) = bv;
-    } else {
-      Bs[lk + 0][lm] = bv.x; Bs[lk + 1][lm] = bv.y; Bs[lk + 2][lm] = bv.z; Bs[lk + 3][lm] = bv.w;
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    float4 av[NL], bv[NL];
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      av[u] = a_ok ? Vec4<TA>::ld(ap + k0 + 16 * u) : zero4;
+      if (TRANSB) bv[u] = bt_ok ? Vec4<TB>::ld(btp + (size_t)(k0 + 16 * u) * g.ldb) : zero4;
+      else bv[u] = b_ok ? Vec4<TB>::ld(bp + k0 + 16 * u) : zero4;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int u = 0; u < NL; ++u) {
+      const int kk = 16 * u + lk;
+      As[kk + 0][lm] = av[u].x; As[kk + 1][lm] = av[u].y; As[kk + 2][lm] = av[u].z; As[kk + 3][lm] = av[u].w;
+      if (TRANSB) {
+        *reinterpret_cast<float4*>(&Bs[16 * u + tk][tn]) = bv[u];
+      } else {
+        Bs[kk + 0][lm] = bv[u].x; Bs[kk + 1][lm] = bv[u].y; Bs[kk + 2][lm] = bv[u].z; Bs[kk + 3][lm] = bv[u].w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
       float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
       float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
       const float ar[4] = {a.x, a.y, a.z, a.w};
@@ -77,7 +88,8 @@ template <class TA, class TB, int OP, class CT, bool TRANSB = false>
 static void launch_gemm_simt(const GemmProblem& g, const EpiParams& e, cudaStream_t st) {
   const int total_rows = g.segs.row0[g.segs.n];
   dim3 grid((g.N + 63) / 64, (total_rows + 63) / 64);
-  gemm_simt_kernel<TA, TB, OP, CT, TRANSB><<<grid, 256, 0, st>>>(g, e);
+  if (g.K % 64 == 0) gemm_simt_kernel<TA, TB, OP, CT, TRANSB, 64><<<grid, 256, 0, st>>>(g, e);
+  else gemm_simt_kernel<TA, TB, OP, CT, TRANSB, 16><<<grid, 256, 0, st>>>(g, e);
 }
 
 // Weight-gradient tile: out[m, n] += sum_{r in [r_begin, r_end)} dY[r, m] * X[r, n]; fully guarded

@@ -429,17 +429,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Weight gradient: reduction over token rows; A = dY^T and B = X^T are MN-major views of the
 // row-major activations, fetched as [64 rows][64 cols] TMA boxes.  grid.z = nseg * splits.
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 2)
+// MT = 128-row output tiles per CTA: MT = 2 (a 256 x 256 tile, two TMEM accumulators fed by the same X stage)
+// cuts the L2 -> SM operand traffic by a third -- the measured bound of this kernel (profiles/r1_wgrad.md).
+// split-K chunks per segment (proportional to the segment's rows so that all CTAs reduce similar row counts):
+// blockIdx.z in [first[seg], first[seg+1]) works on segment seg
+struct WgradSplits { int first[7]; };
+
+template <int MT, int BN> __host__ __device__ constexpr int wgrad_stage_bytes() { return (MT * BM + BN) * BK * 2; }
+template <int MT, int BN> __host__ __device__ constexpr int wgrad_smem_bytes(int stages) {
+  return stages * wgrad_stage_bytes<MT, BN>() + 1024 + 256;
+}
+
+template <int MT, int BN>
+__global__ void __launch_bounds__(NTHREADS, MT == 1 ? 2 : 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
-                WgradProblem w, int splits, int stages) {
+                WgradProblem w, WgradSplits sp_tab, int stages) {
+  constexpr int STAGE = wgrad_stage_bytes<MT, BN>();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * stage_bytes<BN>());
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = blockIdx.z / splits, sp = blockIdx.z % splits;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int seg = 0;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (i < w.segs.n && (int)blockIdx.z >= sp_tab.first[i]) seg = i;
+  const int sp = blockIdx.z - sp_tab.first[seg], splits = sp_tab.first[seg + 1] - sp_tab.first[seg];
+  const int m0 = blockIdx.y * (MT * BM), n0 = blockIdx.x * BN;
   const int rows_pad = w.segs.row0[seg + 1] - w.segs.row0[seg];   // multiple of 128; tail rows are zero
   const int kb_total = rows_pad / BK;
   const int kb_per = (kb_total + splits - 1) / splits;
@@ -456,7 +472,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     mbar_init(smem_u32(&ctrl->acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), BN);
+  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), MT * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -471,13 +487,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const uint32_t ph = (i / stages) & 1;
         mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
         const uint32_t full = smem_u32(&ctrl->full[s]);
-        mbar_expect_tx(full, stage_bytes<BN>());
-        const uint32_t sa = sbase + s * stage_bytes<BN>();
-        const uint32_t sb = sa + BM * BK * 2;
+        mbar_expect_tx(full, STAGE);
+        const uint32_t sa = sbase + s * STAGE;
+        const uint32_t sb = sa + MT * BM * BK * 2;
         const int ry = w.segs.row0[seg] + (kb_begin + i) * BK;
         const int rx = w.x_row0[seg] + (kb_begin + i) * BK;
 #pragma unroll
-        for (int a = 0; a < BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmY, m0 + a * 64, ry, full);
+        for (int a = 0; a < MT * BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmY, m0 + a * 64, ry, full);
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmX, n0 + b * 64, rx, full);
       }
@@ -490,13 +506,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const uint32_t ph = (i / stages) & 1;
         mbar_wait(smem_u32(&ctrl->full[s]), ph);
         tc_fence_after();
-        const uint32_t sa = sbase + s * stage_bytes<BN>();
-        const uint32_t sb = sa + BM * BK * 2;
-        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+        const uint32_t sa = sbase + s * STAGE;
+        const uint32_t sb = sa + MT * BM * BK * 2;
         const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)   // 16 k-rows of 128 B = 2048 B (>>4 = 128) per K=16 step
-          umma_bf16(tmem_acc, adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) != 0);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t adesc = make_smem_desc(sa + mt * (BM * BK * 2), 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // 16 k-rows of 128 B = 2048 B (>>4 = 128) per K=16 step
+            umma_bf16(tmem_acc + mt * BN, adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) != 0);
+        }
         umma_commit(smem_u32(&ctrl->empty[s]));
       }
       umma_commit(smem_u32(&ctrl->acc_full));
@@ -506,32 +525,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if (w.colsum) {
       // Bias gradient fused in: while the MMA warp consumes the stages, the (otherwise idle) epilogue warps
       // sum the dY tile over its 64 reduction rows.  Warp q takes rows [16q, 16q+16) of every stage, lane l the
-      // 4 columns 4l..4l+3 (atom l/16, 16-byte unit (l%16)/2 of the 128B-swizzled [64 k][64 m] atom).
+      // 4 columns 4l..4l+3 of each 128-column group (atom l/16, 16-byte unit (l%16)/2 of the 128B-swizzled
+      // [64 k][64 m] atom).
       const bool mine = blockIdx.x == 0 && w.dbias[seg] != nullptr;
-      float cs[4] = {0.f, 0.f, 0.f, 0.f};
+      float cs[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) cs[mt][0] = cs[mt][1] = cs[mt][2] = cs[mt][3] = 0.f;
       const uint32_t unit = (lane & 15) >> 1, sub = (lane & 1) * 8, atom = lane >> 4;
       for (int i = 0; i < kblocks; ++i) {
         const int s = i % stages;
         mbar_wait(smem_u32(&ctrl->full[s]), (i / stages) & 1);
         if (mine) {
-          const uint32_t sa = sbase + s * stage_bytes<BN>() + atom * 8192;
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) {
-            const uint32_t k = q * 16 + kk;
-            uint32_t lo, hi;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(sa + k * 128 + ((unit ^ (k & 7)) << 4) + sub));
-            cs[0] += __uint_as_float(lo << 16); cs[1] += __uint_as_float(lo & 0xffff0000u);
-            cs[2] += __uint_as_float(hi << 16); cs[3] += __uint_as_float(hi & 0xffff0000u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sa = sbase + s * STAGE + (mt * 2 + atom) * 8192;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+              const uint32_t k = q * 16 + kk;
+              uint32_t lo, hi;
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(sa + k * 128 + ((unit ^ (k & 7)) << 4) + sub));
+              cs[mt][0] += __uint_as_float(lo << 16); cs[mt][1] += __uint_as_float(lo & 0xffff0000u);
+              cs[mt][2] += __uint_as_float(hi << 16); cs[mt][3] += __uint_as_float(hi & 0xffff0000u);
+            }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty[s]));
       }
       if (mine) {
-        float* db = w.dbias[seg] + m0 + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (m0 + 4 * lane + j < w.M) atomicAdd(db + j, cs[j]);
+        for (int mt = 0; mt < MT; ++mt) {
+          const int mcol = m0 + mt * BM + 4 * lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (mcol + j < w.M) atomicAdd(w.dbias[seg] + mcol + j, cs[mt][j]);
+        }
       }
     }
     mbar_wait(smem_u32(&ctrl->acc_full), 0);
@@ -540,17 +568,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     float* stg = reinterpret_cast<float*>(sgen) + q * (32 * 36);
     const int rg = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < MT * BN / 32; ++c) {
+      const int mt = c / (BN / 32), cn = c % (BN / 32);
       float v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
-      const int n = n0 + c * 32 + c4;
+      const int n = n0 + cn * 32 + c4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int m = m0 + q * 32 + 4 * i + rg;
+        const int m = m0 + mt * BM + q * 32 + 4 * i + rg;
         const float4 a4 = *reinterpret_cast<const float4*>(stg + (4 * i + rg) * 36 + c4);
         if (out != nullptr && m < w.M && n < w.N) red_add_v4(out + (size_t)m * w.ldo + n, a4);
       }
@@ -559,7 +588,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_acc, BN);
+  if (warp == 1) tmem_dealloc(tmem_acc, MT * BN);
 }
 
 // ---------------------------------------------------------------------------- host side ----
@@ -632,10 +661,42 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   return cudaGetLastError();
 }
 
-static cudaError_t launch_wgrad_tc(const WgradProblem& w, int y_rows_total, int x_rows_total, cudaStream_t st) {
+template <int MT>
+static cudaError_t launch_wgrad_tc_mt(const WgradProblem& w, const CUtensorMap& tmY, const CUtensorMap& tmX, int max_kb,
+                                      cudaStream_t st) {
   constexpr int BN = 256;
-  static int stages_cfg = env_int("MMR_TC_WGRAD_STAGES", 2);
-  int stages = stages_cfg < 1 ? 1 : (stages_cfg > 4 ? 4 : stages_cfg);
+  static int stages_cfg = env_int("MMR_TC_WGRAD_STAGES", MT == 1 ? 2 : 3);
+  const int max_stages = MT == 1 ? 4 : 3;
+  const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
+  const int tiles_per_seg = ((w.M + MT * BM - 1) / (MT * BM)) * ((w.N + BN - 1) / BN);
+  const int ctas_per_wave = 148 * (MT == 1 ? 2 : 1);
+  // distribute ~one wave of CTAs over the segments in proportion to their reduction length
+  long long total_kb = 0;
+  for (int s = 0; s < w.segs.n; ++s) total_kb += (w.segs.row0[s + 1] - w.segs.row0[s]) / BK;
+  const int units = ctas_per_wave / tiles_per_seg > w.segs.n ? ctas_per_wave / tiles_per_seg : w.segs.n;
+  static int prop = env_int("MMR_TC_WGRAD_PROP", 0);
+  WgradSplits tab;
+  tab.first[0] = 0;
+  for (int s = 0; s < w.segs.n; ++s) {
+    const int kb = (w.segs.row0[s + 1] - w.segs.row0[s]) / BK;
+    int sp = prop ? (int)(((long long)units * kb + total_kb / 2) / (total_kb > 0 ? total_kb : 1))
+                  : (ctas_per_wave + tiles_per_seg * w.segs.n - 1) / (tiles_per_seg * w.segs.n);
+    if (sp > kb / 4) sp = kb / 4;       // at least 4 k-blocks (256 rows) per chunk
+    if (sp < 1) sp = 1;
+    tab.first[s + 1] = tab.first[s] + sp;
+  }
+  for (int s = w.segs.n; s < 6; ++s) tab.first[s + 1] = tab.first[w.segs.n];
+  (void)max_kb;
+  auto kern = wgrad_tc_kernel<MT, BN>;
+  const int smem = wgrad_smem_bytes<MT, BN>(stages);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  dim3 grid((w.N + BN - 1) / BN, (w.M + MT * BM - 1) / (MT * BM), tab.first[w.segs.n]);
+  kern<<<grid, NTHREADS, smem, st>>>(tmY, tmX, w, tab, stages);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_wgrad_tc(const WgradProblem& w, int y_rows_total, int x_rows_total, cudaStream_t st) {
   CUtensorMap tmY, tmX;
   if (!make_tmap(&tmY, w.dY, (uint64_t)w.ldy, (uint64_t)y_rows_total, (uint64_t)w.ldy, 64, BK)) return cudaErrorUnknown;
   if (!make_tmap(&tmX, w.X, (uint64_t)w.ldx, (uint64_t)x_rows_total, (uint64_t)w.ldx, 64, BK)) return cudaErrorUnknown;
@@ -644,17 +705,9 @@ static cudaError_t launch_wgrad_tc(const WgradProblem& w, int y_rows_total, int 
     int kb = (w.segs.row0[s + 1] - w.segs.row0[s]) / BK;
     if (kb > max_kb) max_kb = kb;
   }
-  const int tiles = ((w.M + BM - 1) / BM) * ((w.N + BN - 1) / BN) * w.segs.n;
-  int splits = (148 * 2 + tiles - 1) / tiles;
-  if (splits > max_kb / 4) splits = max_kb / 4;
-  if (splits < 1) splits = 1;
-  auto kern = wgrad_tc_kernel<BN>;
-  const int smem = smem_bytes<BN>(stages);
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  dim3 grid((w.N + BN - 1) / BN, (w.M + BM - 1) / BM, w.segs.n * splits);
-  kern<<<grid, NTHREADS, smem, st>>>(tmY, tmX, w, splits, stages);
-  return cudaGetLastError();
+  static int mt_cfg = env_int("MMR_TC_WGRAD_MT", 2);
+  if (mt_cfg == 2 && w.M % (2 * BM) == 0) return launch_wgrad_tc_mt<2>(w, tmY, tmX, max_kb, st);
+  return launch_wgrad_tc_mt<1>(w, tmY, tmX, max_kb, st);
 }
 
 }  // namespace tc

@@ -65,25 +65,58 @@ def total_flops_per_patient():
 
 
 class ClockSampler:
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML every ~5 ms; nvidia-smi fallback)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.samples, self.stop = [], False
+        self.sm, self.mx, self.reasons, self.stop = [], 0.0, set(), False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                          ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                              "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        f = [x.strip() for x in out.split(",")]
+        self.sm.append(float(f[1])); self.mx = max(self.mx, float(f[2]))
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -94,18 +127,9 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[1])); mx = max(mx, float(s[2]))
-                for n, v in zip(names, s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_models(device, seed=42):
@@ -204,6 +228,9 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)                 # library banners (e.g. NCCL's version line) must not pollute the one JSON line
     import torch.distributed as dist
     from multimodalrouting_b200 import _lib
     from multimodalrouting_b200.dist import allreduce_gradients
@@ -213,7 +240,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=180))
     lib = _lib.load()
     rh, mult, proj, head, sds = build_models(dev)
     modules = (mult, proj, head)
@@ -282,12 +309,13 @@ def main():
 
     # per-class device time of OUR kernels (CUDA events on the launching stream), separate pass
     prof = None
+    nprof = 3
     if rank == 0:
         lib.mmr_prof_enable(1)
-        nprof = 3
-        for _ in range(nprof):
-            step(False)
-        torch.cuda.synchronize()
+    for _ in range(nprof):          # every rank steps (the gradient all-reduce is a collective)
+        step(False)
+    torch.cuda.synchronize()
+    if rank == 0:
         msc = (C.c_double * 8)(); nc = (C.c_longlong * 8)()
         lib.mmr_prof_collect(msc, nc)
         lib.mmr_prof_enable(0)
@@ -326,7 +354,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_time_ms_per_step": prof}
-    print(json.dumps(line), flush=True)
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -191,7 +191,7 @@ static bool has_pad(const Segs& s) {
 }
 static int zero_pad(const Segs& s, void* buf, size_t ld_bytes, cudaStream_t st) {
   if (!has_pad(s)) return MMR_OK;
-  dim3 grid(127, s.n);
+  dim3 grid(255, s.n);
   zero_pad_rows_kernel<<<grid, 128, 0, st>>>(s, reinterpret_cast<uint8_t*>(buf), ld_bytes);
   LAUNCH_OK("zero_pad_rows");
   return MMR_OK;

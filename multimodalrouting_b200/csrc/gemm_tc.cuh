@@ -91,6 +91,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA-pair (cta_group::2) primitives: two SMs of a TPC cooperate on one 256-row tile ------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are credited to the mbarrier at `bar`
+// (a shared::cluster address -- the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at the same offset in BOTH CTAs of the pair once the issued MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // 16-byte vector reduction into global memory (split-K accumulation of weight gradients)
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -110,9 +158,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128.
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 template <int BN> __host__ __device__ constexpr int stage_bytes() { return (BM + BN) * BK * 2; }
@@ -157,9 +205,6 @@ constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilo
 constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile of the weight-gradient epilogue
 
 constexpr int CSTG_BYTES = 8192;      // per epilogue warp: 32 rows x 256 bytes, two 128B-swizzled TMA store boxes
-template <int BN> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-  return stages * stage_bytes<BN>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
-}
 
 // TMA store of one [32 rows x 128 bytes] box from shared memory (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int x, int y) {
@@ -252,20 +297,34 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 //   warp 1    : tcgen05.mma issuer, alternates between two BN-column TMEM accumulators
 //   warps 2-9 : epilogue; warp w drains TMEM lane quarter (w & 3), column half ((w - 2) >> 2) of
 //               accumulator i while the MMA warp fills accumulator i+1
-template <int BN, int OP>
+// CL = 2: CTA pairs (cluster of two SMs, tcgen05 cta_group::2).  The pair owns a 256 x BN tile; each CTA
+// stages its own 128 A rows and only HALF of the B tile (BN/2 weight rows), the leader CTA's single thread
+// issues M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  Operand bytes entering
+// each SM per k-block drop from 48 KB to 32 KB (the measured bound, profiles/r1_gemm_epilogue.md) and a
+// fourth stage fits.  Requires every segment to hold an even number of 128-row tiles.
+template <int BN, int CL> __host__ __device__ constexpr int gemm_stage_bytes() { return (BM + BN / CL) * BK * 2; }
+template <int BN, int CL> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
+  return stages * gemm_stage_bytes<BN, CL>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
+}
+
+template <int BN, int OP, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmProblem g, TcEpi e, int stages) {
+  constexpr int STAGE = gemm_stage_bytes<BN, CL>();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t cstg_base = sbase + stages * stage_bytes<BN>();   // 1024-byte aligned (stages are multiples of 1 KB)
-  float* bias_all = reinterpret_cast<float*>(sgen + stages * stage_bytes<BN>() + 8 * CSTG_BYTES);
+  const uint32_t cstg_base = sbase + stages * STAGE;   // 1024-byte aligned (stages are multiples of 1 KB)
+  float* bias_all = reinterpret_cast<float*>(sgen + stages * STAGE + 8 * CSTG_BYTES);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 8 * (BN / 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
   const int kblocks = g.K / BK;
   const int nN = g.N / BN;
-  const int ntiles = ((g.segs.row0[g.segs.n] + BM - 1) / BM) * nN;
+  // work items: 128-row tiles (CL = 1) or 256-row tile pairs (CL = 2), n-block fastest
+  const int nwork = ((g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM)) * nN;
+  const int w0 = blockIdx.x / CL, wstep = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -274,13 +333,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&ctrl->tfull[b]), 1);
-      mbar_init(smem_u32(&ctrl->tempty[b]), 8);
+      mbar_init(smem_u32(&ctrl->tempty[b]), 8 * CL);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctrl->tmem_base), 2 * BN);
+  if (warp == 1) {
+    if (CL == 2) tmem_alloc_pair(smem_u32(&ctrl->tmem_base), 2 * BN);
+    else tmem_alloc(smem_u32(&ctrl->tmem_base), 2 * BN);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
@@ -290,29 +352,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t / nN) * BM, n0 = (t % nN) * BN;
+      for (int t = w0; t < nwork; t += wstep) {
+        const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN;
         const int seg = seg_of_row(g.segs, m0);
         const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
-        const int b_row = g.b_row0[seg] + n0;
+        const int b_row = g.b_row0[seg] + n0 + (int)rank * (BN / CL);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
           mbar_wait(smem_u32(&ctrl->empty[s]), ph ^ 1);
-          const uint32_t full = smem_u32(&ctrl->full[s]);
-          mbar_expect_tx(full, stage_bytes<BN>());
-          const uint32_t sa = sbase + s * stage_bytes<BN>();
+          const uint32_t sa = sbase + s * STAGE;
           const uint32_t sb = sa + BM * BK * 2;
-          tma_load_2d(sa, &tmA, kb * BK, a_row, full);
-          tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+          if (CL == 2) {
+            // both CTAs credit the LEADER's barrier (peer bit of the shared::cluster address cleared)
+            const uint32_t full = mapa_u32(smem_u32(&ctrl->full[s]), 0);
+            if (rank == 0) mbar_expect_tx(smem_u32(&ctrl->full[s]), 2 * STAGE);
+            tma_load_2d_pair(sa, &tmA, kb * BK, a_row, full);
+            tma_load_2d_pair(sb, &tmB, kb * BK, b_row, full);
+          } else {
+            const uint32_t full = smem_u32(&ctrl->full[s]);
+            mbar_expect_tx(full, STAGE);
+            tma_load_2d(sa, &tmA, kb * BK, a_row, full);
+            tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       uint32_t it = 0, i = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      for (int t = w0; t < nwork; t += wstep, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -322,16 +392,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (it / stages) & 1;
           mbar_wait(smem_u32(&ctrl->full[s]), ph);
           tc_fence_after();
-          const uint32_t sa = sbase + s * stage_bytes<BN>();
+          const uint32_t sa = sbase + s * STAGE;
           const uint32_t sb = sa + BM * BK * 2;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the swizzle row
-            umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&ctrl->empty[s]));
+          for (int k = 0; k < BK / 16; ++k) {   // +32 bytes (>>4 = 2) per K=16 step inside the swizzle row
+            if (CL == 2) umma_bf16_pair(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (CL == 2) umma_commit_pair(smem_u32(&ctrl->empty[s]));
+          else umma_commit(smem_u32(&ctrl->empty[s]));
         }
-        umma_commit(smem_u32(&ctrl->tfull[buf]));
+        if (CL == 2) umma_commit_pair(smem_u32(&ctrl->tfull[buf]));
+        else umma_commit(smem_u32(&ctrl->tfull[buf]));
       }
     }
   } else {
@@ -341,8 +415,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = bias_all + (warp - 2) * HC;
     const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
     uint32_t i = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
-      const int m0 = (t / nN) * BM, n0 = (t % nN) * BN + ch * HC;
+    for (int t = w0; t < nwork; t += wstep, ++i) {
+      const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN + ch * HC;
       const int seg = seg_of_row(g.segs, m0);
       const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
       const int lr = q * 32 + lane;                 // accumulator row owned by this thread
@@ -379,10 +453,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32_nowait(tmem_acc + cc * 64, r0);
         tmem_ld32_nowait(tmem_acc + cc * 64 + 32, r1);
         tmem_ld_wait();
-        if (cc == HC / 64 - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (cc == HC / 64 - 1) {   // accumulator fully read: hand the TMEM buffer back to the (leader's) MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&ctrl->tempty[buf]));
+          if (lane == 0) {
+            if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->tempty[buf]), 0));
+            else mbar_arrive(smem_u32(&ctrl->tempty[buf]));
+          }
         }
         // the staging boxes may still be read by the previous TMA store of this warp
         if (f32_out || cc == 0) {
@@ -422,8 +499,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores must complete before the CTA exits
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (CL == 2) cluster_sync_all(); else __syncthreads();   // the peer may still read this CTA's smem / arrive on its barriers
+  if (warp == 1) {
+    if (CL == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,12 +708,45 @@ inline int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
+template <int OP, int CL>
+static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
+                                     int sm_count, cudaStream_t st) {
+  constexpr int BN = 256;
+  static int stages_cfg = env_int("MMR_TC_STAGES", CL == 2 ? 4 : 3);
+  const int max_stages = CL == 2 ? 4 : 3;      // 32 KB (pair) / 48 KB operand stages + 64 KB of TMA-store staging
+  const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
+  constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
+  CUtensorMap tmA, tmB, tmC;
+  if (!make_tmap(&tmC, e.out, (uint64_t)e.ldo, (uint64_t)g.segs.row0[g.segs.n], (uint64_t)e.ldo, f32_out ? 32 : 64, 32, f32_out))
+    return cudaErrorUnknown;
+  if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;
+  auto kern = gemm_tc_kernel<BN, OP, CL>;
+  const int smem = gemm_smem_bytes<BN, CL>(stages);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  const int total_rows = g.segs.row0[g.segs.n];
+  const int nwork = ((total_rows + CL * BM - 1) / (CL * BM)) * (g.N / BN);
+  int grid = nwork * CL < sm_count ? nwork * CL : sm_count;
+  grid -= grid % CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e, stages);
+}
+
 // a_rows_total / b_rows_total: number of rows physically present in A / B (TMA bounds).
 template <int OP>
 static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                   cudaStream_t st) {
-  constexpr int BN = 256;
-  static int stages_cfg = env_int("MMR_TC_STAGES", 3);
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -641,24 +754,14 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  int stages = stages_cfg;
-  if (stages > 3) stages = 3;     // 3 x 48 KB operand stages + 64 KB of TMA-store staging
-  if (stages < 1) stages = 1;
-  constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
-  CUtensorMap tmA, tmB, tmC;
-  if (!make_tmap(&tmC, e.out, (uint64_t)e.ldo, (uint64_t)g.segs.row0[g.segs.n], (uint64_t)e.ldo, f32_out ? 32 : 64, 32, f32_out))
-    return cudaErrorUnknown;
-  if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
-  if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN)) return cudaErrorUnknown;
-  auto kern = gemm_tc_kernel<BN, OP>;
-  const int smem = gemm_smem_bytes<BN>(stages);
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  const int total_rows = g.segs.row0[g.segs.n];
-  const int ntiles = ((total_rows + BM - 1) / BM) * (g.N / BN);
-  const int grid = ntiles < sm_count ? ntiles : sm_count;
-  kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g, e, stages);
-  return cudaGetLastError();
+  // CTA pairs need every segment to start on a 256-row boundary and hold an even number of 128-row tiles
+  // (measured, tools/bench_gemm.py: pairs win for K >= 512, single CTAs for the K = 256 shapes)
+  static int pair_cfg = env_int("MMR_TC_PAIR", 1);
+  static int pair_min_k = env_int("MMR_TC_PAIR_MIN_K", 512);
+  bool pair_ok = pair_cfg != 0 && g.K >= pair_min_k;
+  for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
+  if (pair_ok) return launch_gemm_tc_cl<OP, 2>(g, e, a_rows_total, b_rows_total, sm_count, st);
+  return launch_gemm_tc_cl<OP, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
 }
 
 template <int MT>

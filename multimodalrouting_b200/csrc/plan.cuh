@@ -7,6 +7,8 @@
 namespace mmr {
 
 inline int pad128(int x) { return (x + 127) / 128 * 128; }
+// row-space segments are 256-row aligned: CTA pairs (tcgen05 cta_group::2) own 256-row tiles
+inline int pad_seg(int x) { return (x + 255) / 256 * 256; }
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 // Index of parameter tensors in the host pointer table (MULTModel state_dict order).
@@ -101,14 +103,14 @@ inline bool build_plan(const mmr_fusion_dims* d, Plan* p, const char** why) {
   p->ct = p->bf16 ? 2 : 4;
   p->mod.n = NMOD;
   int r = 0;
-  for (int m = 0; m < NMOD; ++m) { p->mod.row0[m] = r; p->mod.rows[m] = p->B * p->T[m]; p->mod.T[m] = p->T[m]; r += pad128(p->mod.rows[m]); }
+  for (int m = 0; m < NMOD; ++m) { p->mod.row0[m] = r; p->mod.rows[m] = p->B * p->T[m]; p->mod.T[m] = p->T[m]; r += pad_seg(p->mod.rows[m]); }
   p->mod.row0[NMOD] = r; p->MM = r;
   p->q.n = NDIR; p->kv.n = NDIR;
   int rq = 0, rk = 0;
   for (int dd = 0; dd < NDIR; ++dd) {
     const int qm = dir_qmod(dd), km = dir_kmod(dd);
-    p->q.row0[dd] = rq; p->q.rows[dd] = p->B * p->T[qm]; p->q.T[dd] = p->T[qm]; rq += pad128(p->q.rows[dd]);
-    p->kv.row0[dd] = rk; p->kv.rows[dd] = p->B * p->T[km]; p->kv.T[dd] = p->T[km]; rk += pad128(p->kv.rows[dd]);
+    p->q.row0[dd] = rq; p->q.rows[dd] = p->B * p->T[qm]; p->q.T[dd] = p->T[qm]; rq += pad_seg(p->q.rows[dd]);
+    p->kv.row0[dd] = rk; p->kv.rows[dd] = p->B * p->T[km]; p->kv.T[dd] = p->T[km]; rk += pad_seg(p->kv.rows[dd]);
   }
   p->q.row0[NDIR] = rq; p->MQ = rq;
   p->kv.row0[NDIR] = rk; p->MK = rk;

@@ -14,7 +14,8 @@
 
 namespace mmr {
 
-constexpr int RT_THREADS = 256;
+constexpr int RT_THREADS = 512;    // 16 warps: one CTA per SM, latency hidden by warps rather than by CTAs
+constexpr int RT_GSLOTS = 1024 / RT_THREADS;   // K*32 <= 1024 head-gradient accumulators spread over the CTA
 constexpr int RT_MAXIT = 4;
 
 struct RoutingArgs {
@@ -218,14 +219,20 @@ __device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* 
 #pragma unroll
       for (int p = 0; p < PB; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4* w = reinterpret_cast<const float4*>(a.p.caps_w + (size_t)r * 32 * KD) + cg;
-#pragma unroll 16
-      for (int aa = 0; aa < 32; ++aa) {
-        const float4 w4 = __ldg(w + (size_t)aa * (KD / 4));
+#pragma unroll 2
+      for (int a4 = 0; a4 < 32; a4 += 4) {
+        float4 w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w4[j] = __ldg(w + (size_t)(a4 + j) * (KD / 4));
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
-          const float x = pp[p * ppstride + r * 32 + aa];
-          acc[p].x = fmaf(x, w4.x, acc[p].x); acc[p].y = fmaf(x, w4.y, acc[p].y);
-          acc[p].z = fmaf(x, w4.z, acc[p].z); acc[p].w = fmaf(x, w4.w, acc[p].w);
+          const float4 x = *reinterpret_cast<const float4*>(pp + p * ppstride + r * 32 + a4);   // broadcast
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[p].x = fmaf(xs[j], w4[j].x, acc[p].x); acc[p].y = fmaf(xs[j], w4[j].y, acc[p].y);
+            acc[p].z = fmaf(xs[j], w4[j].z, acc[p].z); acc[p].w = fmaf(xs[j], w4[j].w, acc[p].w);
+          }
         }
       }
 #pragma unroll
@@ -374,7 +381,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
   const bool has_mask = a.route_mask != nullptr;
   const float scale = 0.125f, invK = 1.0f / (float)K;
   // per-CTA accumulators for dG / dbias (flushed once at the end)
-  float accG[4] = {0.f, 0.f, 0.f, 0.f};   // element i = tid + 256*j of [K][32]  (K*32 <= 1024)
+  float accG[RT_GSLOTS];                    // element i = tid + RT_THREADS*j of [K][32]  (K*32 <= 1024)
+#pragma unroll
+  for (int j = 0; j < RT_GSLOTS; ++j) accG[j] = 0.f;
   float accB = 0.f;                         // tid < K
   const int ntiles = (a.d.B + PB - 1) / PB;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -389,8 +398,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
       rt_iterate<UT>(a, s, pt, u);
       const float* dl = a.d_logits + (size_t)b * K;
       // (a,b) head: dG, dbias, ddp = dlogit[k]*G[k][p]
-      for (int j = 0; j < 4; ++j) {
-        const int i = tid + 256 * j;
+#pragma unroll
+      for (int j = 0; j < RT_GSLOTS; ++j) {
+        const int i = tid + RT_THREADS * j;
         if (i < K * 32) {
           const float g = dl[i >> 5];
           accG[j] = fmaf(g, s.dp[i], accG[j]);
@@ -562,8 +572,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
       __syncthreads();
       if (a.d_route_embs) {
         // d e[p][r][c] = sum_j dpc[p][r][j] * W_r[j][c]; thread = column c, weights shared by the tile
-        for (int r = 0; r < 10; ++r) {
-          const float* w = a.p.proj_w[r] + tid;
+        for (int r = tid >> 8; r < 10; r += RT_THREADS / 256) {
+          const int col = tid & 255;
+          const float* w = a.p.proj_w[r] + col;
           float acc[PB];
 #pragma unroll
           for (int p = 0; p < PB; ++p) acc[p] = 0.f;
@@ -580,13 +591,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
 #pragma unroll
           for (int p = 0; p < PB; ++p)
             if (p < np)
-              a.d_route_embs[(size_t)r * a.d.emb_route_stride + (size_t)(b0 + p) * a.d.emb_batch_stride + tid] = acc[p];
+              a.d_route_embs[(size_t)r * a.d.emb_route_stride + (size_t)(b0 + p) * a.d.emb_batch_stride + col] = acc[p];
         }
       }
     }
   }
-  for (int j = 0; j < 4; ++j) {
-    const int i = tid + 256 * j;
+#pragma unroll
+  for (int j = 0; j < RT_GSLOTS; ++j) {
+    const int i = tid + RT_THREADS * j;
     if (i < K * 32 && a.dG) atomicAdd(a.dG + i, accG[j]);
   }
   if (tid < K && a.dbias) atomicAdd(a.dbias + tid, accB);

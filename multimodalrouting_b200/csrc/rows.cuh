@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
   atomicAdd(a.out[seg] + c, s * a.scale);
 }
 
-// Zero the padding rows [rows, pad128(rows)) of every segment of a [*, ld_bytes] buffer.
+// Zero the padding rows [rows, pad_seg(rows)) of every segment of a [*, ld_bytes] buffer.
 __global__ void zero_pad_rows_kernel(Segs s, uint8_t* buf, size_t ld_bytes) {
   const int seg = blockIdx.y;
   const int npad = (s.row0[seg + 1] - s.row0[seg]) - s.rows[seg];

@@ -31,6 +31,17 @@ for idx, (name, op, N, K) in enumerate(shapes):
     fl = 2.0 * M * N * K
     by = M * K * 2 + M * N * (4 if op == 4 else 2) + N * K * 2
     print(f"{name}: {ms.value*1e3:8.1f} us  {fl/ms.value/1e9:8.1f} TFLOP/s  {by/ms.value/1e6:8.1f} GB/s (algorithmic)")
+    if os.environ.get("CUBLAS", "1") == "1":      # library reference point for the same shape (not on the product path)
+        Bt = B.t()
+        for _ in range(3):
+            torch.matmul(A, Bt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ITERS):
+            torch.matmul(A, Bt)
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / ITERS
+        print(f"    cuBLAS bf16 (no epilogue): {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TFLOP/s")
     ref = (A[:256].float() @ B.float().t())
     if op in (0, 1):
         ref = ref + bias

@@ -212,11 +212,21 @@ static int pack_weights(const Plan& P, const void* const* prm, uint8_t* packed, 
   float* bq = reinterpret_cast<float*>(packed + P.o_bq);  float* bo = reinterpret_cast<float*>(packed + P.o_bo);
   float* b1 = reinterpret_cast<float*>(packed + P.o_b1);  float* b2 = reinterpret_cast<float*>(packed + P.o_b2);
   float* bkv = reinterpret_cast<float*>(packed + P.o_bkv);
+  PackJobs pj; memset(&pj, 0, sizeof(pj));
+  BiasJobs bj; memset(&bj, 0, sizeof(bj));
+  auto flush = [&]() -> int {
+    if (pj.n == 0) return MMR_OK;
+    pack_kernel<CT><<<dim3((FF / 32) * (D / 32), pj.n), 256, 0, st>>>(pj);
+    LAUNCH_OK("pack_kernel");
+    bias_fold_kernel<<<dim3(FF / 8, bj.n), 256, 0, st>>>(bj);
+    LAUNCH_OK("bias_fold_kernel");
+    pj.n = 0; bj.n = 0;
+    return MMR_OK;
+  };
   for (int d = 0; d < NDIR; ++d) {
-    for (int l0 = 0; l0 < L; l0 += 4) {
-      PackJobs pj; memset(&pj, 0, sizeof(pj));
-      BiasJobs bj; memset(&bj, 0, sizeof(bj));
-      for (int l = l0; l < L && l < l0 + 4; ++l) {
+    for (int l = 0; l < L; ++l) {
+      if (pj.n + 5 > 60) { int rc = flush(); if (rc) return rc; }
+      {
         const size_t ld_ = (size_t)l * 6 + d;
         const float* win = f(ix.layer(d, l, 0));
         const float* bin = f(ix.layer(d, l, 1));
@@ -244,11 +254,11 @@ static int pack_weights(const Plan& P, const void* const* prm, uint8_t* packed, 
         b = &bj.j[bj.n++];
         *b = BiasJob{nullptr, 0, f(ix.layer(d, l, 7)), nullptr, 1.0f, b2 + ld_ * D, D};
       }
-      pack_kernel<CT><<<dim3(FF / 32, FF / 32, pj.n), 256, 0, st>>>(pj);
-      LAUNCH_OK("pack_kernel");
-      bias_fold_kernel<<<dim3(FF / 8, bj.n), 256, 0, st>>>(bj);
-      LAUNCH_OK("bias_fold_kernel");
     }
+  }
+  {
+    int rc = flush();
+    if (rc) return rc;
   }
   return MMR_OK;
 }
@@ -957,7 +967,7 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   ProfScope ps(PC_ROUTING, st);
   CUDA_OK(dispatch_routing(a, L, true, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  routing_head_grads_kernel<<<1, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,
+  routing_head_grads_kernel<<<(MC * PC + (int)K * MC + 255) / 256, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,
                                                grads->embedding);
   LAUNCH_OK("routing_head_grads");
   if (grads->caps_w) {   // d w[r] = pose_masked[:, r, :]^T du[:, r, :]

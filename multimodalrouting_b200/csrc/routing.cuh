@@ -605,23 +605,24 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs 
 }
 
 // dG[k][p] -> d pose_to_mc[m][p] += sum_k dG[k][p]*emb[k][m];  d emb[k][m] += sum_p dG[k][p]*Wmc[m][p]
+// one thread per output element (MC*PC + K*MC of them)
 __global__ void routing_head_grads_kernel(const float* dG, const float* pose_to_mc, const float* embedding, int K,
                                           float* d_pose_to_mc, float* d_embedding) {
-  const int tid = threadIdx.x;
-  if (d_pose_to_mc)
-    for (int i = tid; i < MC * PC; i += blockDim.x) {
-      const int m = i / PC, p = i % PC;
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc = fmaf(dG[k * 32 + p], embedding[k * MC + m], acc);
-      d_pose_to_mc[i] += acc;
-    }
-  if (d_embedding)
-    for (int i = tid; i < K * MC; i += blockDim.x) {
-      const int k = i / MC, m = i % MC;
-      float acc = 0.f;
-      for (int p = 0; p < PC; ++p) acc = fmaf(dG[k * 32 + p], pose_to_mc[m * PC + p], acc);
-      d_embedding[i] += acc;
-    }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < MC * PC) {
+    if (!d_pose_to_mc) return;
+    const int m = i / PC, p = i % PC;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(dG[k * 32 + p], embedding[k * MC + m], acc);
+    d_pose_to_mc[i] += acc;
+  } else if (i < MC * PC + K * MC) {
+    if (!d_embedding) return;
+    const int j = i - MC * PC;
+    const int k = j / MC, m = j % MC;
+    float acc = 0.f;
+    for (int p = 0; p < PC; ++p) acc = fmaf(dG[k * 32 + p], pose_to_mc[m * PC + p], acc);
+    d_embedding[j] += acc;
+  }
 }
 
 }  // namespace mmr

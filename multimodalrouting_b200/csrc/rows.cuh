@@ -394,14 +394,15 @@ struct PackJob {
   void* dst; int dst_ld;
   void* dstT; int dstT_ld;
 };
-struct PackJobs { PackJob j[24]; int n; };
+struct PackJobs { PackJob j[60]; int n; };
 
 template <class CT>
 __global__ void __launch_bounds__(256) pack_kernel(PackJobs jobs) {
   __shared__ float tile[32][33];
-  const PackJob& j = jobs.j[blockIdx.z];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  if (r0 >= j.rows || c0 >= j.cols) return;
+  const PackJob& j = jobs.j[blockIdx.y];
+  const int tiles_c = j.cols / 32;                 // grid.x = 256 tiles covers every job ([1024,256] / [256,1024] max)
+  const int r0 = ((int)blockIdx.x / tiles_c) * 32, c0 = ((int)blockIdx.x % tiles_c) * 32;
+  if (r0 >= j.rows) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   CT* dst = reinterpret_cast<CT*>(j.dst);
   CT* dstT = reinterpret_cast<CT*>(j.dstT);
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackJobs jobs) {
 
 // bias fold: dst[o] = scale * (b[o] + sum_i W[o][i] * beta[i]); one warp per output row.
 struct BiasJob { const float* w; int ld; const float* b; const float* beta; float scale; float* dst; int rows; };
-struct BiasJobs { BiasJob j[48]; int n; };
+struct BiasJobs { BiasJob j[60]; int n; };
 __global__ void __launch_bounds__(256) bias_fold_kernel(BiasJobs jobs) {
   const BiasJob& j = jobs.j[blockIdx.y];
   const int lane = threadIdx.x & 31;

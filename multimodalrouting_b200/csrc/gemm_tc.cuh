@@ -239,9 +239,22 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 // staging box (row = lane, 128-byte rows, 16-byte units XOR-swizzled by row & 7 like the TMA map).
 //   bf16: `unit0` = first 16-byte unit of the chunk inside its box (0 or 4), 4 units
 //   fp32: the chunk is a whole box row (8 units)
+// relu(a), relu(b) rounded to bf16 and packed (lo = a): one F2FP instruction for two elements
+__device__ __forceinline__ uint32_t pack2_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// wb |= (v > 0) << j   as FSETP + predicated LOP3
+__device__ __forceinline__ void or_bit_if_pos(uint32_t& wb, float v, uint32_t bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(wb) : "f"(v), "r"(bit));
+}
+
 template <int OP>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* bias_c, float rmask, uint32_t wbits_in,
-                                          uint32_t& wbits_out, bool row_ok, uint32_t box_row_addr, int unit0, int lane) {
+                                          uint32_t& wbits_out, bool zero_row, uint32_t box_row_addr, int unit0, int lane) {
+  // `zero_row`: this thread's row is segment padding (only possible in the last tile of a segment; the caller
+  // passes a tile-uniform false otherwise so the selects below fold away at run time)
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -255,11 +268,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
   if (OP == TEPI_BIAS_RELU_BITS) {
     uint32_t wb = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      wb |= (v[j] > 0.f ? 1u : 0u) << j;
-      v[j] = fmaxf(v[j], 0.f);
-    }
-    wbits_out = wb;
+    for (int j = 0; j < 32; ++j) or_bit_if_pos(wb, v[j], 1u << j);
+    wbits_out = wb;          // the ReLU itself is folded into the bf16 pack below
   }
   if (OP == TEPI_BITS_IN) {
 #pragma unroll
@@ -269,7 +279,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= rmask;
   }
-  if (!row_ok) {
+  if (zero_row) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
@@ -284,9 +294,15 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t addr = box_row_addr + (((uint32_t)(unit0 + j) ^ sw) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2_bf16(v[8 * j], v[8 * j + 1])),
-                   "r"(pack2_bf16(v[8 * j + 2], v[8 * j + 3])), "r"(pack2_bf16(v[8 * j + 4], v[8 * j + 5])),
-                   "r"(pack2_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+      uint32_t w0, w1, w2, w3;
+      if (OP == TEPI_BIAS_RELU_BITS) {
+        w0 = pack2_bf16_relu(v[8 * j], v[8 * j + 1]); w1 = pack2_bf16_relu(v[8 * j + 2], v[8 * j + 3]);
+        w2 = pack2_bf16_relu(v[8 * j + 4], v[8 * j + 5]); w3 = pack2_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+      } else {
+        w0 = pack2_bf16(v[8 * j], v[8 * j + 1]); w1 = pack2_bf16(v[8 * j + 2], v[8 * j + 3]);
+        w2 = pack2_bf16(v[8 * j + 4], v[8 * j + 5]); w3 = pack2_bf16(v[8 * j + 6], v[8 * j + 7]);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
     }
   }
 }
@@ -421,6 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
       const int lr = q * 32 + lane;                 // accumulator row owned by this thread
       const bool row_ok = lr < rows_valid;
+      const bool zrow = (rows_valid < BM) && !row_ok;   // tile-uniform fast path when the tile has no padding rows
       // ---- per-tile operands, fetched while the accumulator is still being computed ----
       float rmask = 1.f;
       uint32_t bits[HC / 32];
@@ -467,13 +484,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
         if (f32_out) {   // 64 fp32 columns = two [32 x 32] boxes per round
-          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, 0u, wout[2 * cc], row_ok, stg_row, 0, lane);
-          epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, 0u, wout[2 * cc + 1], row_ok, stg_row + 4096, 0, lane);
+          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, 0u, wout[2 * cc], zrow, stg_row, 0, lane);
+          epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, 0u, wout[2 * cc + 1], zrow, stg_row + 4096, 0, lane);
         } else {         // 64 bf16 columns = one [32 x 64] box per round
-          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], row_ok,
+          epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], zrow,
                         stg_row + cc * 4096, 0, lane);
           epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, OP == TEPI_BITS_IN ? bits[2 * cc + 1] : 0u, wout[2 * cc + 1],
-                        row_ok, stg_row + cc * 4096, 4, lane);
+                        zrow, stg_row + cc * 4096, 4, lane);
         }
         if (f32_out || cc == HC / 64 - 1) {
           fence_async_smem();
@@ -503,6 +520,275 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (CL == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
     else tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Chained GEMM pair with the 1024-wide intermediate kept on chip between the two products:
+//     mid[r, 0:1024] = epi1( A[r, 0:256] * B1[seg]^T )        (written to HBM once, never re-read here)
+//     out[r, 0:256]  = epi2( mid[r, :]   * B2[seg]^T )
+//   forward : A = LN1(x1) , B1 = fc1.weight, epi1 = +bias, ReLU, sign bits ; B2 = fc2.weight, epi2 = +bias
+//   backward: A = dY(fc2) , B1 = fc2.weight^T, epi1 = ReLU' bit mask (dF)  ; B2 = fc1.weight^T, epi2 = row mask
+// (transformer.py:204-215 and its autograd).  Per 128-row tile the A block (64 KB) is staged once; the 1024
+// intermediate columns are produced in four 256-column chunks: GEMM1 -> TMEM acc1 -> epilogue warps (bias / ReLU
+// / mask in registers) -> bf16 into a 128B-swizzled shared-memory block F that is BOTH the TMA-store source
+// for `mid` and the K-major A operand of GEMM2, which accumulates into TMEM acc2.  Unfused, `mid` (237 MB at
+// B=512) is written by one kernel and re-read by the next; here the second read never leaves the SM.
+// CL = 2 runs CTA pairs (tcgen05 cta_group::2): each CTA stages only half of every weight tile.
+struct ChainProblem {
+  Segs segs;            // row space of A / mid / out (same rows)
+  int b1_row0[6];       // first row of the segment's [1024, 256] block in the stacked B1
+  int b2_row0[6];       // first row of the segment's [256, 1024] block in the stacked B2
+  const float* bias1;   // [stack of 1024] indexed like B1 rows, or null   (forward)
+  const float* bias2;   // [stack of 256]  indexed like B2 rows, or null   (forward)
+  const float* rowmask; // [rows] or null                                   (backward epi2)
+  uint32_t* bits;       // [rows, 32] ReLU sign bits: written (forward) / read (backward)
+};
+struct ChainCtrl {
+  uint64_t a_full, a_empty;
+  uint64_t b_full[8], b_empty[8];
+  uint64_t acc1_full, acc1_empty, f_full, f_empty, acc2_full, acc2_empty;
+  uint32_t tmem_base;
+};
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CHAIN_THREADS = 64 + 32 * CH_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, 16 epilogue warps
+constexpr int CH_MID = 1024, CH_K = 256, CH_N = 256;     // fixed geometry of the reference FFN (d=256, 4d)
+constexpr int CH_A_BYTES = BM * CH_K * 2;                 // 64 KB: 4 k-blocks of [128 x 64]
+constexpr int CH_F_BYTES = BM * 256 * 2;                  // 64 KB: one 256-column chunk of the intermediate
+template <int CL> __host__ __device__ constexpr int chain_bstage_bytes() { return (256 / CL) * BK * 2; }
+template <int CL> __host__ __device__ constexpr int chain_smem_bytes(int stages) {
+  return CH_A_BYTES + CH_F_BYTES + stages * chain_bstage_bytes<CL>() + CH_EPI_WARPS * 64 * 4 + 1024 + 512;
+}
+
+template <int OP1, int OP2, int CL>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmMid,
+                const __grid_constant__ CUtensorMap tmOut, ChainProblem g, int stages) {
+  constexpr int BST = chain_bstage_bytes<CL>();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t sA = sbase, sF = sbase + CH_A_BYTES, sB = sF + CH_F_BYTES;
+  float* bias_all = reinterpret_cast<float*>(sgen + CH_A_BYTES + CH_F_BYTES + stages * BST);
+  ChainCtrl* ctrl = reinterpret_cast<ChainCtrl*>(bias_all + CH_EPI_WARPS * 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
+  const int nwork = (g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM);
+  const int w0 = blockIdx.x / CL, wstep = gridDim.x / CL;
+  auto bar = [&](uint64_t* b) { return smem_u32(b); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(&ctrl->a_full), 1); mbar_init(bar(&ctrl->a_empty), 1);
+    for (int s = 0; s < stages; ++s) { mbar_init(bar(&ctrl->b_full[s]), 1); mbar_init(bar(&ctrl->b_empty[s]), 1); }
+    mbar_init(bar(&ctrl->acc1_full), 1); mbar_init(bar(&ctrl->acc1_empty), CH_EPI_WARPS * CL);
+    mbar_init(bar(&ctrl->f_full), CH_EPI_WARPS * CL); mbar_init(bar(&ctrl->f_empty), 1);
+    mbar_init(bar(&ctrl->acc2_full), 1); mbar_init(bar(&ctrl->acc2_empty), CH_EPI_WARPS * CL);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (CL == 2) tmem_alloc_pair(smem_u32(&ctrl->tmem_base), 512);
+    else tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
+  }
+  tc_fence_before();
+  if (CL == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  // epilogue -> MMA handshakes land on the leader CTA's barriers
+  auto arrive_leader = [&](uint64_t* b) {
+    if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(b), 0));
+    else mbar_arrive(smem_u32(b));
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer.  Weight tiles follow the MMA issue order:
+    //       W1(0) | W1(1) W2(0) | W1(2) W2(1) | W1(3) W2(2) | W2(3)   (each item = 4 k-blocks of [256/CL x 64])
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
+      uint32_t it = 0, ti = 0;
+      for (int t = w0; t < nwork; t += wstep, ++ti) {
+        const int m0 = (t * CL + (int)rank) * BM;
+        const int seg = seg_of_row(g.segs, m0);
+        mbar_wait(bar(&ctrl->a_empty), (ti & 1) ^ 1);
+        {
+          const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->a_full), 0) : bar(&ctrl->a_full);
+          if (rank == 0) mbar_expect_tx(bar(&ctrl->a_full), CL * CH_A_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < CH_K / BK; ++kb) {
+            if (CL == 2) tma_load_2d_pair(sA + kb * (BM * BK * 2), &tmA, kb * BK, m0, full);
+            else tma_load_2d(sA + kb * (BM * BK * 2), &tmA, kb * BK, m0, full);
+          }
+        }
+        for (int item = 0; item < 8; ++item) {
+          // items: 0:W1(0) 1:W1(1) 2:W2(0) 3:W1(2) 4:W2(1) 5:W1(3) 6:W2(2) 7:W2(3)
+          const bool is2 = (item == 2 || item == 4 || item >= 6);
+          const int c = item == 0 ? 0 : item == 1 ? 1 : item == 2 ? 0 : item == 3 ? 2 : item == 4 ? 1 : item == 5 ? 3 : item == 6 ? 2 : 3;
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (it / stages) & 1;
+            mbar_wait(bar(&ctrl->b_empty[s]), ph ^ 1);
+            const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->b_full[s]), 0) : bar(&ctrl->b_full[s]);
+            if (rank == 0) mbar_expect_tx(bar(&ctrl->b_full[s]), CL * BST);
+            const uint32_t dst = sB + s * BST;
+            // GEMM1 tile: rows = intermediate columns c*256.. of B1, k = kb*64 of 256
+            // GEMM2 tile: rows = output columns of B2 (256), k = c*256 + kb*64 of 1024
+            const int x = is2 ? c * 256 + kb * BK : kb * BK;
+            const int y = (is2 ? g.b2_row0[seg] : g.b1_row0[seg] + c * 256) + (int)rank * (256 / CL);
+            const CUtensorMap* tm = is2 ? &tmB2 : &tmB1;
+            if (CL == 2) tma_load_2d_pair(dst, tm, x, y, full);
+            else tma_load_2d(dst, tm, x, y, full);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, 0, 0, CL * BM);
+      uint32_t it = 0, ti = 0, n1 = 0, n2 = 0;   // n1 / n2: GEMM1 / GEMM2 chunk counters (barrier phases)
+      auto commit = [&](uint64_t* b) {
+        if (CL == 2) umma_commit_pair(smem_u32(b)); else umma_commit(smem_u32(b));
+      };
+      auto gemm_kblocks = [&](uint32_t a_base, uint32_t acc, bool fresh) {
+        for (int kb = 0; kb < 4; ++kb, ++it) {
+          const int s = it % stages;
+          mbar_wait(bar(&ctrl->b_full[s]), (it / stages) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(a_base + kb * (BM * BK * 2), 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sB + s * BST, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t accum = (fresh && kb == 0 && k == 0) ? 0u : 1u;
+            if (CL == 2) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            else umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+          }
+          commit(&ctrl->b_empty[s]);
+        }
+      };
+      for (int t = w0; t < nwork; t += wstep, ++ti) {
+        mbar_wait(bar(&ctrl->a_full), ti & 1);
+        tc_fence_after();
+        for (int c = 0; c <= 4; ++c) {
+          if (c < 4) {            // GEMM1(c): acc1 = A * B1[chunk c]^T
+            mbar_wait(bar(&ctrl->acc1_empty), (n1 & 1) ^ 1);
+            tc_fence_after();
+            gemm_kblocks(sA, acc1, true);
+            commit(&ctrl->acc1_full);
+            if (c == 3) commit(&ctrl->a_empty);
+            ++n1;
+          }
+          if (c > 0) {            // GEMM2(c-1): acc2 += F(c-1) * B2[:, chunk c-1]^T
+            mbar_wait(bar(&ctrl->f_full), n2 & 1);
+            if (c == 1) mbar_wait(bar(&ctrl->acc2_empty), (ti & 1) ^ 1);
+            tc_fence_after();
+            gemm_kblocks(sF, acc2, c == 1);
+            commit(&ctrl->f_empty);
+            if (c == 4) commit(&ctrl->acc2_full);
+            ++n2;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== 16 epilogue warps: warp w owns TMEM lane quarter (w & 3) and the 64-column slice cq = (w - 2) >> 2
+    //       of each 256-column chunk, i.e. exactly one [32 rows x 64 cols] box of k-block cq of F
+    const int q = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    float* bias_s = bias_all + (warp - 2) * 64;
+    uint32_t ti = 0, n1 = 0;
+    for (int t = w0; t < nwork; t += wstep, ++ti) {
+      const int m0 = (t * CL + (int)rank) * BM;
+      const int seg = seg_of_row(g.segs, m0);
+      const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
+      const int lr = q * 32 + lane;
+      const bool row_ok = lr < rows_valid;
+      const bool zrow = (rows_valid < BM) && !row_ok;
+      const uint32_t f_box = sF + (uint32_t)cq * (BM * BK * 2) + (uint32_t)q * 4096;   // this warp's 4 KB box of F
+      const uint32_t f_row = f_box + (uint32_t)lane * 128;
+      float rmask = 1.f;
+      if (OP2 == TEPI_MASK) rmask = (g.rowmask != nullptr && row_ok) ? g.rowmask[m0 + lr] : 1.f;
+      for (int c = 0; c < 4; ++c, ++n1) {
+        uint2 bin2 = make_uint2(0, 0);      // ReLU sign bits of this thread's row, columns of (chunk c, slice cq)
+        if (OP1 == TEPI_BITS_IN && row_ok)
+          bin2 = *reinterpret_cast<const uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 8 + cq * 2);
+        if (OP1 == TEPI_BIAS_RELU_BITS) {
+          const float* bsrc = g.bias1 ? g.bias1 + g.b1_row0[seg] + c * 256 + cq * 64 : nullptr;
+          __syncwarp();
+          bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
+          bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
+          __syncwarp();
+        }
+        mbar_wait(bar(&ctrl->acc1_full), n1 & 1);
+        tc_fence_after();
+        const uint32_t tacc = acc1 + cq * 64 + ((uint32_t)(q * 32) << 16);
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tacc, r0);
+        tmem_ld32_nowait(tacc + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&ctrl->acc1_empty);      // acc1 may be overwritten by GEMM1(c+1)
+        // F is free once GEMM2 of the previous chunk retired and this warp's previous TMA store has read it
+        mbar_wait(bar(&ctrl->f_empty), (n1 & 1) ^ 1);
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        uint32_t wout0 = 0, wout1 = 0;
+        epi_chunk<OP1>(r0, bias_s, 1.f, bin2.x, wout0, zrow, f_row, 0, lane);
+        epi_chunk<OP1>(r1, bias_s + 32, 1.f, bin2.y, wout1, zrow, f_row, 4, lane);
+        fence_async_smem();               // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          arrive_leader(&ctrl->f_full);
+          tma_store_2d(&tmMid, f_box, c * 256 + cq * 64, m0 + q * 32);
+          tma_store_commit();
+        }
+        if (OP1 == TEPI_BIAS_RELU_BITS && row_ok)
+          *reinterpret_cast<uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 8 + cq * 2) = make_uint2(wout0, wout1);
+      }
+      // ---- final epilogue: out = epi2(acc2); F (idle now) is the staging block
+      if (OP2 == TEPI_BIAS) {
+        const float* bsrc = g.bias2 ? g.bias2 + g.b2_row0[seg] + cq * 64 : nullptr;
+        __syncwarp();
+        bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
+        bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
+        __syncwarp();
+      }
+      mbar_wait(bar(&ctrl->acc2_full), ti & 1);
+      tc_fence_after();
+      {
+        const uint32_t tacc = acc2 + cq * 64 + ((uint32_t)(q * 32) << 16);
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tacc, r0);
+        tmem_ld32_nowait(tacc + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          arrive_leader(&ctrl->acc2_empty);
+          tma_store_wait_read();          // this warp's store of the last intermediate chunk has left F
+        }
+        __syncwarp();
+        uint32_t dummy;
+        epi_chunk<OP2>(r0, bias_s, rmask, 0u, dummy, zrow, f_row, 0, lane);
+        epi_chunk<OP2>(r1, bias_s + 32, rmask, 0u, dummy, zrow, f_row, 4, lane);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, f_box, cq * 64, m0 + q * 32);
+          tma_store_commit();
+        }
+      }
+    }
+  }
+  if (warp >= 2 && lane == 0) tma_store_wait_all();
+  tc_fence_before();
+  if (CL == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (CL == 2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -762,6 +1048,58 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
   if (pair_ok) return launch_gemm_tc_cl<OP, 2>(g, e, a_rows_total, b_rows_total, sm_count, st);
   return launch_gemm_tc_cl<OP, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
+}
+
+// mid: bf16 [rows, 1024], out: bf16 [rows, 256]; A bf16 [rows, 256]; B1 stacked [*, 256]; B2 stacked [*, 1024]
+template <int OP1, int OP2, int CL>
+static cudaError_t launch_chain_tc_cl(const ChainProblem& g, const void* A, const void* B1, int b1_rows, const void* B2,
+                                      int b2_rows, void* mid, void* out, int sm_count, cudaStream_t st) {
+  static int stages_cfg = env_int("MMR_CHAIN_STAGES", CL == 2 ? 5 : 2);
+  const int max_stages = CL == 2 ? 5 : 2;
+  const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
+  const int rows = g.segs.row0[g.segs.n];
+  CUtensorMap tmA, tmB1, tmB2, tmMid, tmOut;
+  if (!make_tmap(&tmA, A, CH_K, (uint64_t)rows, CH_K, BK, BM)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB1, B1, CH_K, (uint64_t)b1_rows, CH_K, BK, 256 / CL)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB2, B2, CH_MID, (uint64_t)b2_rows, CH_MID, BK, 256 / CL)) return cudaErrorUnknown;
+  if (!make_tmap(&tmMid, mid, CH_MID, (uint64_t)rows, CH_MID, 64, 32)) return cudaErrorUnknown;
+  if (!make_tmap(&tmOut, out, CH_N, (uint64_t)rows, CH_N, 64, 32)) return cudaErrorUnknown;
+  auto kern = chain_tc_kernel<OP1, OP2, CL>;
+  const int smem = chain_smem_bytes<CL>(stages);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  const int nwork = (rows + CL * BM - 1) / (CL * BM);
+  int grid = nwork * CL < sm_count ? nwork * CL : sm_count;
+  grid -= grid % CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CHAIN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB1, tmB2, tmMid, tmOut, g, stages);
+}
+
+template <int OP1, int OP2>
+static cudaError_t launch_chain_tc(const ChainProblem& g, const void* A, const void* B1, int b1_rows, const void* B2,
+                                   int b2_rows, void* mid, void* out, cudaStream_t st) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  static int pair_cfg = env_int("MMR_CHAIN_PAIR", 1);
+  bool pair_ok = pair_cfg != 0;
+  for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
+  if (pair_ok) return launch_chain_tc_cl<OP1, OP2, 2>(g, A, B1, b1_rows, B2, b2_rows, mid, out, sm_count, st);
+  return launch_chain_tc_cl<OP1, OP2, 1>(g, A, B1, b1_rows, B2, b2_rows, mid, out, sm_count, st);
 }
 
 template <int MT>

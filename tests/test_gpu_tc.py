@@ -38,3 +38,11 @@ def test_tc_gemm_wgrad(Kr, M, N):
                                   "mort_nomask", "pheno_rm1d", "pheno_odd"])
 def test_bf16_tc_engine(name):
     _bf16_case(name, "tc")
+
+
+@pytest.mark.parametrize("name", ["pheno_sharp4", "mort_missing", "pheno_odd"])
+def test_bf16_chained_ffn_kernel(name, monkeypatch):
+    """Opt-in chained FFN kernel (fc1 + ReLU + fc2 and its data-gradient pair in one tcgen05 launch each,
+    CTA pairs, intermediate consumed from shared memory): same bf16 parity bar as the default path."""
+    monkeypatch.setenv("MMR_CHAIN", "1")
+    _bf16_case(name, "tc")

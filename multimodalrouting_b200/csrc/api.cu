@@ -142,6 +142,13 @@ template <> bool mma_attention<bf16>() {
   return !(e && !strcmp(e, "simt"));
 }
 
+// launches a kernel that implements the pdl_trigger / pdl_wait protocol (programmatic dependent launch)
+template <class K, class A>
+static void launch_k(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A& a) {
+  if (tc::pdl_enabled()) launch_pdl(kern, grid, block, smem, st, a);
+  else kern<<<grid, block, smem, st>>>(a);
+}
+
 static Segs single_seg(int rows, int T) {
   Segs s;
   memset(&s, 0, sizeof(s));
@@ -163,6 +170,15 @@ static int fp32_linear(const float* A, int lda, const float* W, int ldw, const f
   launch_gemm_simt<float, float, EPI_BIAS_F32, float, TRANSB>(g, e, st);
   LAUNCH_OK(what);
   return MMR_OK;
+}
+
+static void fp32_problem(GemmProblem* g, EpiParams* e, const float* A, int lda, const float* W, int ldw, const float* bias,
+                         float* C, int ldc, int M, int N, int K) {
+  memset(g, 0, sizeof(*g));
+  g->segs = single_seg(M, 1);
+  g->N = N; g->K = K; g->A = A; g->lda = lda; g->B = W; g->ldb = ldw;
+  memset(e, 0, sizeof(*e));
+  e->bias = bias; e->out = C; e->ldo = ldc;
 }
 
 static int fp32_wgrad(const float* dY, int ldy, const float* X, int ldx, float* out, int ldo, int rows, int M, int N,
@@ -371,7 +387,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
         ProfScope ps(PC_ATTN_FWD, st);
         if (mma_attention<CT>()) {
           dim3 grid(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
-          amma::attn_fwd_kernel<AHG><<<grid, amma::Cfg<AHG>::THREADS, amma::fwd_smem<AHG>(), st>>>(a);
+          launch_k(amma::attn_fwd_kernel<AHG>, grid, dim3(amma::Cfg<AHG>::THREADS), amma::fwd_smem<AHG>(), st, a);
         } else {
           dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
           attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
@@ -392,7 +408,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       LnFwdArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.x = xin(l); a.delta = delta; a.x_out = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l, 10)); a.beta[d] = f(ix.layer(d, l, 11)); }
-      ln_rows_fwd_kernel<CT, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      launch_k(ln_rows_fwd_kernel<CT, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
       LAUNCH_OK("ln1_fwd");
     }
     if (use_chain(P)) {  // fc1 + ReLU + fc2 as one chained kernel: the 1024-wide activation is consumed on chip
@@ -428,7 +444,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       LnFwdArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.x = x1(l); a.delta = delta; a.x_out = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l + 1, 8)); a.beta[d] = f(ix.layer(d, l + 1, 9)); }
-      ln_rows_fwd_kernel<CT, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+      launch_k(ln_rows_fwd_kernel<CT, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
       LAUNCH_OK("ln0_fwd");
     }
   }
@@ -437,7 +453,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     a.q = P.q; a.x = x1(L - 1); a.delta = delta; a.x_out = xin(L); a.maskq = maskq; a.out = fy;
     a.stat = reinterpret_cast<float*>(saved + P.s_statf);
     for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.enc_ln(d, 0)); a.beta[d] = f(ix.enc_ln(d, 1)); }
-    ln_rows_fwd_kernel<float, CT><<<P.MQ / ROWS_PER_BLOCK, 256, 0, st>>>(a);
+    launch_k(ln_rows_fwd_kernel<float, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
     LAUNCH_OK("lnf_fwd");
   }
   {  // masked-mean pooling of the 9 uni/bi-modal routes
@@ -448,10 +464,13 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     LAUNCH_OK("pool_fwd");
   }
   // pair projections and the trimodal composition (mult_model.py:174-178)
-  for (int p = 0; p < 3; ++p) {
-    rc = fp32_linear<false>(zcat + (size_t)p * B * 512, 512, f(ix.pair(p, 0)), 512, f(ix.pair(p, 1)), ecat + p * D, 3 * D,
-                            B, D, 512, st, "pair_proj");
-    if (rc) return rc;
+  {
+    MultiGemm mg; mg.n = 3;     // the three pair projections in one launch
+    for (int p = 0; p < 3; ++p)
+      fp32_problem(&mg.g[p], &mg.e[p], zcat + (size_t)p * B * 512, 512, f(ix.pair(p, 0)), 512, f(ix.pair(p, 1)), ecat + p * D,
+                   3 * D, B, D, 512);
+    launch_gemm_simt_multi<float, float, EPI_BIAS_F32, float, false>(mg, st);
+    LAUNCH_OK("pair_proj");
   }
   rc = fp32_linear<false>(ecat, 3 * D, f(ix.final_lni(0)), 3 * D, f(ix.final_lni(1)), routes + (size_t)9 * B * D, D, B, D,
                           3 * D, st, "final_lni");
@@ -516,15 +535,33 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     float* o1[6] = {gr(ix.final_lni(1)), nullptr, nullptr, nullptr, nullptr, nullptr};
     rc = run_colsum<float>(sb, dz_lni, D, 0, D, o1, 1.0f, st, "b_final_lni");
     if (rc) return rc;
-    for (int p = 0; p < 3; ++p) {
-      rc = fp32_linear<true>(decat + p * D, 3 * D, f(ix.pair(p, 0)), 512, nullptr, dzcat + (size_t)p * B * 512, 512, B, 512, D,
-                             st, "d_pair");
-      if (rc) return rc;
-      rc = fp32_wgrad(decat + p * D, 3 * D, zcat + (size_t)p * B * 512, 512, gr(ix.pair(p, 0)), 512, B, D, 512, st, "w_pair");
-      if (rc) return rc;
-      float* o2[6] = {gr(ix.pair(p, 1)), nullptr, nullptr, nullptr, nullptr, nullptr};
-      rc = run_colsum<float>(sb, decat, 3 * D, p * D, D, o2, 1.0f, st, "b_pair");
-      if (rc) return rc;
+    {
+      MultiGemm mg; mg.n = 3;   // d(zcat_p) = d(e_p) W_p for the three pairs in one launch
+      for (int p = 0; p < 3; ++p)
+        fp32_problem(&mg.g[p], &mg.e[p], decat + p * D, 3 * D, f(ix.pair(p, 0)), 512, nullptr, dzcat + (size_t)p * B * 512, 512, B,
+                     512, D);
+      launch_gemm_simt_multi<float, float, EPI_BIAS_F32, float, true>(mg, st);
+      LAUNCH_OK("d_pair");
+    }
+    {
+      WgradBatch w; memset(&w, 0, sizeof(w));   // dW_p = d(e_p)^T zcat_p
+      w.nbatch = 3; w.rows = B; w.M = D; w.N = 512; w.ldy = 3 * D; w.ldx = 512; w.ldo = 512;
+      bool any = false;
+      for (int p = 0; p < 3; ++p) {
+        w.dY[p] = decat + p * D; w.X[p] = zcat + (size_t)p * B * 512; w.out[p] = gr(ix.pair(p, 0));
+        any = any || w.out[p] != nullptr;
+      }
+      if (any) { launch_wgrad_batched(w, st); LAUNCH_OK("w_pair"); }
+    }
+    {
+      ColsumArgs c; memset(&c, 0, sizeof(c));   // the three pair biases: column sums of d(ecat) [B, 768]
+      c.segs = sb; c.src = decat; c.ld = 3 * D; c.col0 = 0; c.ncols = 3 * D; c.scale = 1.0f; c.colblock = D;
+      bool any = false;
+      for (int p = 0; p < 3; ++p) { c.out[p] = gr(ix.pair(p, 1)); any = any || c.out[p] != nullptr; }
+      if (any) {
+        colsum_kernel<float><<<dim3((3 * D + 255) / 256, (B + 127) / 128), 256, 0, st>>>(c);
+        LAUNCH_OK("b_pair");
+      }
     }
   }
   // ---- pooled gradient through the encoder-final LayerNorm ----
@@ -540,7 +577,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       a.dgamma[d] = gr(ix.enc_ln(d, 0)); a.dbeta[d] = gr(ix.enc_ln(d, 1));
       a.dbias[d] = gr(ix.layer(d, L - 1, 7));
     }
-    ln_rows_bwd_kernel<CT, true><<<P.MQ / 64, 256, 0, st>>>(a);
+    launch_k(ln_rows_bwd_kernel<CT, true>, dim3(P.MQ / 64), dim3(256), 0, st, a);
     LAUNCH_OK("lnf_bwd");
   }
   const float* kmask[NDIR];
@@ -622,7 +659,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         a.dgamma[d] = gr(ix.layer(d, l, 10)); a.dbeta[d] = gr(ix.layer(d, l, 11));
         a.dbias[d] = gr(ix.layer(d, l, 3));
       }
-      ln_rows_bwd_kernel<CT, false><<<P.MQ / 64, 256, 0, st>>>(a);
+      launch_k(ln_rows_bwd_kernel<CT, false>, dim3(P.MQ / 64), dim3(256), 0, st, a);
       LAUNCH_OK("ln1_bwd");
     }
     {  // dO = G1 Wo
@@ -649,8 +686,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         if (mma_attention<CT>()) {
           if (maxTq <= amma::RC && maxTk <= amma::RC && !getenv("MMR_ATTN_BWD_SPLIT")) {
             // one chunk per sequence: fused dQ + dK/dV kernel (operands staged once, no O / D round trip)
-            amma::attn_bwd_fused_kernel<AHG><<<dim3(amma::Cfg<AHG>::NHG, B, NDIR), amma::Cfg<AHG>::THREADS,
-                                               amma::bwd_fused_smem<AHG>(), st>>>(a);
+            launch_k(amma::attn_bwd_fused_kernel<AHG>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(amma::Cfg<AHG>::THREADS),
+                     amma::bwd_fused_smem<AHG>(), st, a);
           } else {
           dim3 g1(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
           dim3 g2(amma::Cfg<AHG>::NHG * ((maxTk + amma::RC - 1) / amma::RC), B, NDIR);
@@ -694,7 +731,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         a.dgamma[d] = gr(ix.layer(d, l, 8)); a.dbeta[d] = gr(ix.layer(d, l, 9));
         a.dbias[d] = l > 0 ? gr(ix.layer(d, l - 1, 7)) : nullptr;
       }
-      ln_rows_bwd_kernel<CT, false><<<P.MQ / 64, 256, 0, st>>>(a);
+      launch_k(ln_rows_bwd_kernel<CT, false>, dim3(P.MQ / 64), dim3(256), 0, st, a);
       LAUNCH_OK("ln0_bwd");
     }
   }

@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Ks = Qs + RC * LDS;
   bf16* Vs = Ks + RC * LDS;
-  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] 1 keep / 0 padded / -1 beyond Tk
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
+  pdl_trigger();
+  pdl_wait();
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
   const int Tq = a.q.T[d], Tk = a.kv.T[d];
   const int q0 = qc * RC;
@@ -536,6 +538,8 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   float* Bs = reinterpret_cast<float*>(Ds + RC * LDS);   // [64] additive key bias
   float* Kp = Bs + RC;                                   // [64] 1 for kept keys else 0
   float4* St = reinterpret_cast<float4*>(Kp + RC);       // [64 queries][HG]: m, 1/l, D, -
+  pdl_trigger();
+  pdl_wait();
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x;
   const int nq = a.q.T[d], nk = a.kv.T[d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -11,13 +11,13 @@ namespace mmr {
 // is what the small (M = batch) pair / trimodal projections are bound by.
 // TRANSB: B is a single row-major [K, N] matrix (B(n,k) = B[k*ldb + b_row0 + n]).
 template <class TA, class TB, int OP, class CT, bool TRANSB, int BK>
-__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams e) {
+__device__ __forceinline__ void gemm_simt_body(const GemmProblem& g, const EpiParams& e, int bx, int by) {
   constexpr int NL = BK / 16;     // 16-wide k slabs per step
   __shared__ __align__(16) float As[BK][68];
   __shared__ __align__(16) float Bs[BK][68];
   const int t = threadIdx.x;
-  const int m0 = blockIdx.y * 64;
-  const int n0 = blockIdx.x * 64;
+  const int m0 = by * 64;
+  const int n0 = bx * 64;
   const int seg = seg_of_row(g.segs, m0);
   const int local0 = m0 - g.segs.row0[seg];
   const int rows_valid = g.segs.rows[seg] - local0;  // may be <= 0 for pure padding tiles
@@ -82,6 +82,30 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams
                           make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
   }
+}
+
+template <class TA, class TB, int OP, class CT, bool TRANSB, int BK>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem g, EpiParams e) {
+  gemm_simt_body<TA, TB, OP, CT, TRANSB, BK>(g, e, blockIdx.x, blockIdx.y);
+}
+
+// Up to 3 independent small GEMMs of identical shape in one launch (blockIdx.z = problem): the pair
+// projections of the trimodal composition (mult_model.py:174-177) and their data gradients.
+struct MultiGemm {
+  int n;
+  GemmProblem g[3];
+  EpiParams e[3];
+};
+template <class TA, class TB, int OP, class CT, bool TRANSB, int BK>
+__global__ void __launch_bounds__(256) gemm_simt_multi_kernel(MultiGemm m) {
+  gemm_simt_body<TA, TB, OP, CT, TRANSB, BK>(m.g[blockIdx.z], m.e[blockIdx.z], blockIdx.x, blockIdx.y);
+}
+template <class TA, class TB, int OP, class CT, bool TRANSB>
+static void launch_gemm_simt_multi(const MultiGemm& m, cudaStream_t st) {
+  const GemmProblem& g = m.g[0];
+  dim3 grid((g.N + 63) / 64, (g.segs.row0[g.segs.n] + 63) / 64, m.n);
+  if (g.K % 64 == 0) gemm_simt_multi_kernel<TA, TB, OP, CT, TRANSB, 64><<<grid, 256, 0, st>>>(m);
+  else gemm_simt_multi_kernel<TA, TB, OP, CT, TRANSB, 16><<<grid, 256, 0, st>>>(m);
 }
 
 template <class TA, class TB, int OP, class CT, bool TRANSB = false>

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmProblem g, TcEpi e, int stages) {
   constexpr int STAGE = gemm_stage_bytes<BN, CL>();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -361,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CL == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  pdl_wait();      // barriers / TMEM are set up; operands of the previous kernel are complete from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -811,6 +813,7 @@ __global__ void __launch_bounds__(NTHREADS, MT == 1 ? 2 : 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                 WgradProblem w, WgradSplits sp_tab, int stages) {
   constexpr int STAGE = wgrad_stage_bytes<MT, BN>();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -843,6 +846,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = ctrl->tmem_base;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -993,6 +997,11 @@ inline int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
 }
+// programmatic dependent launch of the per-layer kernels (MMR_PDL=0 disables)
+inline bool pdl_enabled() {
+  static int on = env_int("MMR_PDL", 0);   // measured: -2.5 % at B=512 (early CTAs compete with the tail), so opt-in
+  return on != 0;
+}
 
 template <int OP, int CL>
 static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
@@ -1021,11 +1030,13 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e, stages);
 }
 
@@ -1133,6 +1144,7 @@ static cudaError_t launch_wgrad_tc_mt(const WgradProblem& w, const CUtensorMap& 
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   dim3 grid((w.N + BN - 1) / BN, (w.M + MT * BM - 1) / (MT * BM), tab.first[w.segs.n]);
+  if (pdl_enabled()) return launch_pdl(kern, grid, dim3(NTHREADS), (size_t)smem, st, tmY, tmX, w, tab, stages);
   kern<<<grid, NTHREADS, smem, st>>>(tmY, tmX, w, tab, stages);
   return cudaGetLastError();
 }

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/mmr_b200.h"
 
@@ -102,6 +103,27 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __flo
 
 // round-trip through the compute type (identity for fp32): mimics autocast rounding points
 template <class T> __device__ __forceinline__ float round_ct(float v) { return to_f<T>(from_f<T>(v)); }
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining; pdl_trigger() (first statement) lets the NEXT kernel do the same, pdl_wait() blocks
+// until the predecessor grid has completed and its writes are visible -- nothing produced by an earlier kernel
+// may be read, and nothing an earlier kernel reads may be written, before it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

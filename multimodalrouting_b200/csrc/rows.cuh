@@ -109,6 +109,8 @@ struct LnFwdArgs {
 
 template <class OT, class CT>
 __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(LnFwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= a.q.row0[a.q.n]) return;
@@ -154,6 +156,8 @@ template <class CT, bool POOLED>
 __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(LnBwdArgs a) {
   constexpr int RPB = 64;   // rows per block (never straddles a 128-aligned segment)
   __shared__ float red[8][3][256];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = blockIdx.x * RPB;
   const int d = seg_of_row(a.q, r0);
@@ -361,6 +365,7 @@ struct ColsumArgs {
   const void* src; int ld; int col0; int ncols;
   float* out[6];
   float scale;
+  int colblock;     // > 0: single segment, column c accumulates into out[c / colblock][c % colblock]
 };
 template <class T>
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
@@ -368,12 +373,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
   const int r0 = blockIdx.y * 128;
   if (r0 >= a.segs.row0[a.segs.n]) return;
   const int seg = seg_of_row(a.segs, r0);
-  if (c >= a.ncols || a.out[seg] == nullptr) return;
+  if (c >= a.ncols) return;
+  float* dst = a.colblock > 0 ? a.out[c / a.colblock] : a.out[seg];
+  if (dst == nullptr) return;
+  dst += a.colblock > 0 ? c % a.colblock : c;
   const int r_end = min(r0 + 128, a.segs.row0[seg] + a.segs.rows[seg]);
   const T* p = reinterpret_cast<const T*>(a.src) + a.col0 + c;
   float s = 0.f;
   for (int r = r0; r < r_end; ++r) s += to_f<T>(p[(size_t)r * a.ld]);
-  atomicAdd(a.out[seg] + c, s * a.scale);
+  atomicAdd(dst, s * a.scale);
 }
 
 // Zero the padding rows [rows, pad_seg(rows)) of every segment of a [*, ld_bytes] buffer.

@@ -121,33 +121,33 @@ static void launch_gemm_simt(const GemmProblem& g, const EpiParams& e, cudaStrea
 template <class TY, class TX>
 __device__ __forceinline__ void wgrad_tile(const TY* dY, int ldy, const TX* X, int ldx, int r_begin, int r_end,
                                            int M, int N, int m0, int n0, float* out, int ldo) {
-  __shared__ float Ys[16][65];
-  __shared__ float Xs[16][65];
+  constexpr int RB = 64;            // reduction rows staged per barrier-separated step (16 loads in flight per thread)
+  __shared__ float Ys[RB][65];
+  __shared__ float Xs[RB][65];
   const int t = threadIdx.x;
   const int ty = t >> 4, tx = t & 15;
+  const int c = t & 63, k0 = t >> 6;          // staging: thread covers column c, rows k0, k0+4, ...
+  const bool y_ok = m0 + c < M, x_ok = n0 + c < N;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int r0 = r_begin; r0 < r_end; r0 += 16) {
-    __syncthreads();
+  for (int r0 = r_begin; r0 < r_end; r0 += RB) {
+    float yv[RB / 4], xv[RB / 4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = t + i * 256;  // 0..1023
-      const int k = idx >> 6, c = idx & 63;
-      const int r = r0 + k;
-      float yv = 0.f, xv = 0.f;
-      if (r < r_end) {
-        if (m0 + c < M) yv = to_f<TY>(dY[(size_t)r * ldy + m0 + c]);
-        if (n0 + c < N) xv = to_f<TX>(X[(size_t)r * ldx + n0 + c]);
-      }
-      Ys[k][c] = yv;
-      Xs[k][c] = xv;
+    for (int i = 0; i < RB / 4; ++i) {
+      const int r = r0 + k0 + 4 * i;
+      yv[i] = (r < r_end && y_ok) ? to_f<TY>(dY[(size_t)r * ldy + m0 + c]) : 0.f;
+      xv[i] = (r < r_end && x_ok) ? to_f<TX>(X[(size_t)r * ldx + n0 + c]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int i = 0; i < RB / 4; ++i) { Ys[k0 + 4 * i][c] = yv[i]; Xs[k0 + 4 * i][c] = xv[i]; }
+    __syncthreads();
+    const int kmax = min(RB, r_end - r0);
+#pragma unroll 8
+    for (int k = 0; k < kmax; ++k) {
       float a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = Ys[k][ty * 4 + i]; b[i] = Xs[k][tx * 4 + i]; }

@@ -140,3 +140,31 @@ def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
 def synth_routes():
     from oracle import synth
     return synth.ROUTES
+
+
+def test_full_size_invariants_and_bf16_vs_fp32():
+    """BASELINE configs[1] at full size (B=512, K=25, L48/N16/I49) with missing modalities: size-independent
+    properties the reference's runtime guards pin (M/main.py:319-338: R sums to 1 over routes; masked routes
+    contribute exactly nothing) plus bf16-vs-fp32 kernel agreement within the north-star bf16 budget."""
+    c = dict(variant="pheno", K=25, orig_d_n=256, B=512, seed=4242, sharp=1.0, temp=1.0, detach=False,
+             missing=True, mask_mode="full")
+    sdm, sdp, sdh, inp = rebuild_case(c)
+    o32 = run_case(c, sdm, sdp, sdh, inp, autocast=False)
+    o16 = run_case(c, sdm, sdp, sdh, inp, autocast=True)
+    rm = inp["route_mask"]
+    for o in (o32, o16):
+        R, alpha = o["R"].float().cpu(), o["alpha"].float().cpu()
+        assert bool(torch.isfinite(o["logits"]).all())
+        kept = rm.sum(1) > 0
+        assert float((R.sum(1)[kept] - 1).abs().max()) < 1e-3
+        assert float(R[rm == 0].abs().max()) == 0.0          # masked routes: R exactly 0
+        assert float(alpha[rm == 0].abs().max()) == 0.0      # ... and alpha exactly 0
+        for g in o["grads"].values():
+            assert g is None or bool(torch.isfinite(g).all())
+    assert max_rel(o16["routes"], o32["routes"]) < 2e-2
+    assert max_rel(o16["alpha"], o32["alpha"]) < 2e-2
+    assert max_rel(o16["logits"], o32["logits"]) < 2e-2
+    assert max_rel(o16["R"], o32["R"]) < 2e-2
+    lg32, lg16 = o32["logits"].float().cpu(), o16["logits"].float().cpu()
+    margin = lg32.abs() > 2e-2 * lg32.abs().max()
+    assert torch.equal((lg16 > 0)[margin], (lg32 > 0)[margin])

@@ -383,7 +383,10 @@ def main():
     achieved = fl_tn / t_tn / 1e12 if t_tn > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 TN GEMM, all six directions per launch)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                "traffic": None, "peak_source": f"{src} sustained bf16 (MEASURED_PEAKS.json)",
+                # dram__bytes_read.sum + dram__bytes_write.sum averaged over the 34 gemm_tc launches of one step,
+                # ncu --set full (profiles/r1_gemm_step.md); algorithmic bytes are 231 MB per launch
+                "traffic": 192.5e6, "traffic_unit": "bytes per launch (ncu dram read+write, mean of the 34 launches of a step)",
+                "peak_source": f"{src} sustained bf16 (MEASURED_PEAKS.json)",
                 "avg_launch_ms": 1e3 * t_tn / n_tn, "launches_per_step": n_tn,
                 "flops_per_launch": fl_tn / n_tn,
                 "wgrad_tc_tflops": (fl_wg / (prof["wgrad_tc"]["ms_per_step"] / 1e3) / 1e12) if prof["wgrad_tc"]["ms_per_step"] > 0 else None,

@@ -116,23 +116,57 @@ def _(x_l, x_n, x_i, mL, mN, mI, pos, params, layers, dtype, engine):
             x_l.new_empty(1, dtype=torch.uint8))
 
 
+_GRAD_LAYOUTS = {}
+
+
+def grad_layout(shapes: Sequence[Tuple[int, ...]], layers: int):
+    """Placement of the parameter gradients inside the flat buffer returned by route_fusion_bwd.
+
+    Per-layer tensors of the six cross-modal encoders are stacked by kind ([24, 768, 256] for all
+    in_proj_weight gradients, ...), so the autograd side can hand them out with one ``unbind`` per kind
+    (13 tensor ops instead of two per parameter); everything else sits in 16-byte aligned slots.
+    Returns (offsets per parameter, total floats, groups = [(offset, [param indices], shape)])."""
+    key = (tuple(shapes), layers)
+    hit = _GRAD_LAYOUTS.get(key)
+    if hit is not None:
+        return hit
+    n = len(shapes)
+    numel = [int(torch.Size(sh).numel()) for sh in shapes]
+    offs = [-1] * n
+    groups = []
+    o = 0
+    per_enc = layers * 12 + 2
+    if n == 9 + 6 * per_enc + 8:        # MULTModel state_dict order (include/mmr_b200.h)
+        for slot in range(12):
+            idx = [9 + d * per_enc + l * 12 + slot for d in range(6) for l in range(layers)]
+            sh = shapes[idx[0]]
+            if any(shapes[i] != sh for i in idx) or numel[idx[0]] % 4:
+                continue
+            groups.append((o, idx, tuple(sh)))
+            for i in idx:
+                offs[i] = o
+                o += numel[i]
+    for i in range(n):
+        if offs[i] < 0:
+            offs[i] = o
+            o += (numel[i] + 3) // 4 * 4
+    out = (offs, o, groups)
+    _GRAD_LAYOUTS[key] = out
+    return out
+
+
 @torch.library.custom_op("mmr_b200::route_fusion_bwd", mutates_args=())
 def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
                      mI: Optional[Tensor], params: Sequence[Tensor], packed: Tensor, saved: Tensor,
                      d_routes: Tensor, need: Sequence[bool], layers: int, dtype: int,
                      engine: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Returns (dx_l, dx_n, dx_i, flat parameter gradients in `params` order)."""
+    """Returns (dx_l, dx_n, dx_i, flat parameter gradients laid out by `grad_layout`)."""
     lib = _lib.load()
     dims = _fusion_dims(x_l, x_n, x_i, layers, dtype, engine)
     _, _, _, sb_b = fusion_sizes(dims)
     dev = x_l.device
     scratch = torch.empty(sb_b, dtype=torch.uint8, device=dev)
-    sizes = [p.numel() for p in params]
-    # 16-byte aligned slots so vectorised accesses in the kernels stay legal
-    offs, o = [], 0
-    for n in sizes:
-        offs.append(o)
-        o += (n + 3) // 4 * 4
+    offs, o, _ = grad_layout([tuple(p.shape) for p in params], layers)   # 16-byte aligned slots
     flat = torch.zeros(o, dtype=torch.float32, device=dev)
     base = flat.data_ptr()
     grads = (c_fp * len(params))()
@@ -148,7 +182,7 @@ def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor]
 
 @route_fusion_bwd.register_fake
 def _(x_l, x_n, x_i, mL, mN, mI, params, packed, saved, d_routes, need, layers, dtype, engine):
-    n = sum((p.numel() + 3) // 4 * 4 for p in params)
+    _, n, _ = grad_layout([tuple(p.shape) for p in params], layers)
     return (torch.empty_like(x_l), torch.empty_like(x_n), torch.empty_like(x_i),
             x_l.new_empty(n, dtype=torch.float32))
 
@@ -216,11 +250,19 @@ class RouteFusionFn(torch.autograd.Function):
         need = [bool(n) for n in ctx.needs_input_grad[10:]]
         dxl, dxn, dxi, flat = route_fusion_bwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], ps, packed, saved, d_all,
                                                need, layers, dtype, engine)
-        grads, o = [], 0
-        for p, nd in zip(ps, need):
-            n = p.numel()
-            grads.append(flat[o:o + n].view(p.shape) if nd else None)
-            o += (n + 3) // 4 * 4
+        offs, _, groups = grad_layout([tuple(p.shape) for p in ps], layers)
+        grads = [None] * len(ps)
+        grouped = set()
+        for start, idx, sh in groups:           # one unbind per parameter kind
+            cnt, numel = len(idx), ps[idx[0]].numel()
+            views = flat[start:start + cnt * numel].view(cnt, *sh).unbind(0)
+            for i, v in zip(idx, views):
+                grouped.add(i)
+                if need[i]:
+                    grads[i] = v
+        for i, p in enumerate(ps):
+            if i not in grouped and need[i]:
+                grads[i] = flat[offs[i]:offs[i] + p.numel()].view(p.shape)
         gi = ctx.needs_input_grad
         return (dxl if gi[0] else None, dxn if gi[1] else None, dxi if gi[2] else None,
                 None, None, None, None, None, None, None, *grads)

@@ -361,6 +361,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   for (int d = 0; d < NDIR; ++d) maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d];
   CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_single_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -387,7 +388,12 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
         ProfScope ps(PC_ATTN_FWD, st);
         if (mma_attention<CT>()) {
           dim3 grid(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
-          launch_k(amma::attn_fwd_kernel<AHG>, grid, dim3(amma::Cfg<AHG>::THREADS), amma::fwd_smem<AHG>(), st, a);
+          int maxTk = 0;
+          for (int d = 0; d < NDIR; ++d) maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d];
+          if (maxTk <= amma::RC && !getenv("MMR_ATTN_FWD_GENERAL"))
+            amma::attn_fwd_single_kernel<AHG><<<grid, amma::Cfg<AHG>::THREADS, amma::fwd_smem<AHG>(), st>>>(a);
+          else
+            launch_k(amma::attn_fwd_kernel<AHG>, grid, dim3(amma::Cfg<AHG>::THREADS), amma::fwd_smem<AHG>(), st, a);
         } else {
           dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
           attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);

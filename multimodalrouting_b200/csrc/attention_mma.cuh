@@ -266,6 +266,110 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
 }
 
 // ------------------------------------------------------------------------------------------
+// Forward specialised for Tk <= 64 (one key chunk: every MIMIC-IV shape).  No running max / sum / output
+// state survives an m-tile, so the tiles are walked in a rolled loop and the kernel fits 6 CTAs (24 warps)
+// per SM -- the general kernel above is bound by dependent-instruction latency at 16 warps per SM.
+// grid: (NHG * ceil(maxTq/64), B, 6)
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn_fwd_single_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Ks = Qs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
+  const int Tq = a.q.T[d], nk = a.kv.T[d];
+  const int q0 = qc * RC;
+  if (q0 >= Tq) return;
+  const int nq = min(RC, Tq - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
+  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
+  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  if (threadIdx.x < RC)
+    Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
+  cp_async_wait_all();
+  __syncthreads();
+  const int NT = (nk + 7) >> 3;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nq) break;
+    uint32_t qa[2][4];
+    frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
+    frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
+    float s[8][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt < NT) {
+        uint32_t kb[4];
+        frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
+        mma16816(s[nt], qa[0], kb[0], kb[1]);
+        mma16816(s[nt], qa[1], kb[2], kb[3]);
+        const float2 kbias = *reinterpret_cast<const float2*>(Ms + nt * 8 + 2 * t);
+        s[nt][0] = rbf(s[nt][0]) + kbias.x; s[nt][1] = rbf(s[nt][1]) + kbias.y;
+        s[nt][2] = rbf(s[nt][2]) + kbias.x; s[nt][3] = rbf(s[nt][3]) + kbias.y;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    }
+    mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < NT) {
+        s[nt][0] = ex2((s[nt][0] - mx0) * L2E); s[nt][1] = ex2((s[nt][1] - mx0) * L2E);
+        s[nt][2] = ex2((s[nt][2] - mx1) * L2E); s[nt][3] = ex2((s[nt][3] - mx1) * L2E);
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+    }
+    sum0 = quad_sum(sum0); sum1 = quad_sum(sum1);
+    const float il0 = 1.0f / sum0, il1 = 1.0f / sum1;      // reference order: normalise, then round P to bf16
+    float o[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (2 * kk < NT) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk][0] * il0, s[2 * kk][1] * il0);
+        pa[1] = pack_bf16(s[2 * kk][2] * il1, s[2 * kk][3] * il1);
+        pa[2] = pack_bf16(s[2 * kk + 1][0] * il0, s[2 * kk + 1][1] * il0);
+        pa[3] = pack_bf16(s[2 * kk + 1][2] * il1, s[2 * kk + 1][3] * il1);
+#pragma unroll
+        for (int nc = 0; nc < 2; ++nc) {
+          uint32_t vb[4];
+          frag_b_kn<LDS>(Vs, kk * 16, hl * 32 + nc * 16, lane, vb);
+          mma16816(o[2 * nc], pa, vb[0], vb[1]);
+          mma16816(o[2 * nc + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    // this warp is the only reader of its (m-tile, head) slot of Qs: reuse it as the output staging tile
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < 4; ++n) put_c<LDS>(Qs, mt * 16, hl * 32 + n * 8, lane, o[n]);
+    if (t == 0) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (r0 < nq) { float* p = a.ml + ((qrow0 + r0) * H + h) * 2; p[0] = mx0; p[1] = il0; }
+      if (r1 < nq) { float* p = a.ml + ((qrow0 + r1) * H + h) * 2; p[0] = mx1; p[1] = il1; }
+    }
+  }
+  __syncthreads();
+  unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
+}
+
+// ------------------------------------------------------------------------------------------
 // dQ pass.  CTA = (direction, patient, head group, 64-query chunk); loops over key chunks.
 //   P = exp(S - m) / l ; dP = dO V^T ; dS = P .* (dP - D) on kept keys ; dQ = dS K
 // Also writes D = rowsum(dO .* O) to a.dvec for the dK/dV pass.
@@ -527,18 +631,26 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
 // CTA = (direction, patient, head group): Q, dO, K, V are staged ONCE; pass A (rows = queries) produces dQ
 // and the softmax-backward row term D_i = sum_j P_ij dP_ij (== rowsum(dO .* O), so O is never re-read);
 // pass B (rows = keys, transposed tiles) produces dK and dV.  grid: (NHG, B, 6)
-template <int HG> constexpr int bwd_fused_smem() { return 5 * RC * Cfg<HG>::LDS * 2 + 2 * RC * 4 + RC * HG * 4 * 4; }
+template <int HG> constexpr int bwd_fused_smem() { return 4 * RC * Cfg<HG>::LDS * 2 + 2 * RC * 4 + RC * HG * 4 * 4; }
 
+// write a 16x8 fp32 C fragment tile as bf16 straight to global memory (row stride ld), rows < nrows only
+__device__ __forceinline__ void put_c_global(bf16* dst, size_t ld, int row0, int col0, int lane, const float (&c)[4], int nrows) {
+  const int g = lane >> 2, t = lane & 3;
+  if (row0 + g < nrows) *reinterpret_cast<uint32_t*>(dst + (size_t)(row0 + g) * ld + col0 + 2 * t) = pack_bf16(c[0], c[1]);
+  if (row0 + g + 8 < nrows) *reinterpret_cast<uint32_t*>(dst + (size_t)(row0 + g + 8) * ld + col0 + 2 * t) = pack_bf16(c[2], c[3]);
+}
+
+// The m-tile loops are rolled and P is held packed (bf16x2) between the row-sum and the dS product, so the kernel
+// fits 5 CTAs (20 warps) per SM: like the forward it is bound by dependent-instruction latency, not by bytes.
 template <int HG>
-__global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn_bwd_fused_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 640 / Cfg<HG>::THREADS) attn_bwd_fused_kernel(AttnArgs a) {
   constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, COLS = Cfg<HG>::COLS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Gs = Qs + RC * LDS;      // dO
   bf16* Ks = Gs + RC * LDS;
   bf16* Vs = Ks + RC * LDS;
-  bf16* Ds = Vs + RC * LDS;      // dQ staging
-  float* Bs = reinterpret_cast<float*>(Ds + RC * LDS);   // [64] additive key bias
+  float* Bs = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
   float* Kp = Bs + RC;                                   // [64] 1 for kept keys else 0
   float4* St = reinterpret_cast<float4*>(Kp + RC);       // [64 queries][HG]: m, 1/l, D, -
   pdl_trigger();
@@ -571,12 +683,13 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   cp_async_wait_all();
   __syncthreads();
   const int NTK = (nk + 7) >> 3, NTQ = (nq + 7) >> 3;
+  bf16* dq_out = reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * COLS;
 
   // ---- pass A: rows = queries ------------------------------------------------------------
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 2; ++i) {
     const int mt = half * 2 + i;
-    if (mt * 16 >= nq) continue;
+    if (mt * 16 >= nq) break;
     uint32_t qa[2][4], ga[2][4];
     frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
     frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
@@ -584,27 +697,32 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
     frag_a<LDS>(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
     const int r0 = mt * 16 + g, r1 = r0 + 8;
     const float4 st0 = St[r0 * HG + hl], st1 = St[r1 * HG + hl];
-    float s[8][4], dp[8][4];
+    uint32_t pp[8][2];          // P of this m-tile, packed bf16x2: [nt][0] = row g, [nt][1] = row g+8
+    float dp[8][4];
     float D0 = 0.f, D1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      pp[nt][0] = pp[nt][1] = 0u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) dp[nt][j] = 0.f;
       if (nt < NTK) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t kb[4], vb[4];
         frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
         frag_b_nk<LDS>(Vs, nt * 8, hl * 32, lane, vb);
-        mma16816(s[nt], qa[0], kb[0], kb[1]);
-        mma16816(s[nt], qa[1], kb[2], kb[3]);
+        mma16816(s, qa[0], kb[0], kb[1]);
+        mma16816(s, qa[1], kb[2], kb[3]);
         mma16816(dp[nt], ga[0], vb[0], vb[1]);
         mma16816(dp[nt], ga[1], vb[2], vb[3]);
         const float2 kbias = *reinterpret_cast<const float2*>(Bs + nt * 8 + 2 * t);
-        s[nt][0] = ex2((rbf(s[nt][0]) + kbias.x - st0.x) * L2E) * st0.y;
-        s[nt][1] = ex2((rbf(s[nt][1]) + kbias.y - st0.x) * L2E) * st0.y;
-        s[nt][2] = ex2((rbf(s[nt][2]) + kbias.x - st1.x) * L2E) * st1.y;
-        s[nt][3] = ex2((rbf(s[nt][3]) + kbias.y - st1.x) * L2E) * st1.y;
-        D0 = fmaf(s[nt][0], dp[nt][0], fmaf(s[nt][1], dp[nt][1], D0));
-        D1 = fmaf(s[nt][2], dp[nt][2], fmaf(s[nt][3], dp[nt][3], D1));
+        const float p0 = ex2((rbf(s[0]) + kbias.x - st0.x) * L2E) * st0.y;
+        const float p1 = ex2((rbf(s[1]) + kbias.y - st0.x) * L2E) * st0.y;
+        const float p2 = ex2((rbf(s[2]) + kbias.x - st1.x) * L2E) * st1.y;
+        const float p3 = ex2((rbf(s[3]) + kbias.y - st1.x) * L2E) * st1.y;
+        D0 = fmaf(p0, dp[nt][0], fmaf(p1, dp[nt][1], D0));
+        D1 = fmaf(p2, dp[nt][2], fmaf(p3, dp[nt][3], D1));
+        pp[nt][0] = pack_bf16(p0, p1);
+        pp[nt][1] = pack_bf16(p2, p3);
       }
     }
     D0 = quad_sum(D0); D1 = quad_sum(D1);
@@ -620,8 +738,10 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
       for (int e = 0; e < 2; ++e) {
         const int nt = 2 * kk + e;
         const float2 keep = *reinterpret_cast<const float2*>(Kp + nt * 8 + 2 * t);   // tiles >= NTK: P = 0 already
-        dsa[e * 2] = pack_bf16(s[nt][0] * (dp[nt][0] - D0) * keep.x, s[nt][1] * (dp[nt][1] - D0) * keep.y);
-        dsa[e * 2 + 1] = pack_bf16(s[nt][2] * (dp[nt][2] - D1) * keep.x, s[nt][3] * (dp[nt][3] - D1) * keep.y);
+        const float p0 = __uint_as_float(pp[nt][0] << 16), p1 = __uint_as_float(pp[nt][0] & 0xffff0000u);
+        const float p2 = __uint_as_float(pp[nt][1] << 16), p3 = __uint_as_float(pp[nt][1] & 0xffff0000u);
+        dsa[e * 2] = pack_bf16(p0 * (dp[nt][0] - D0) * keep.x, p1 * (dp[nt][1] - D0) * keep.y);
+        dsa[e * 2 + 1] = pack_bf16(p2 * (dp[nt][2] - D1) * keep.x, p3 * (dp[nt][3] - D1) * keep.y);
       }
 #pragma unroll
       for (int nc = 0; nc < 2; ++nc) {
@@ -632,22 +752,21 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
       }
     }
 #pragma unroll
-    for (int n = 0; n < 4; ++n) put_c<LDS>(Ds, mt * 16, hl * 32 + n * 8, lane, dq[n]);
+    for (int n = 0; n < 4; ++n) put_c_global(dq_out, D, mt * 16, hl * 32 + n * 8, lane, dq[n], nq);
   }
-  __syncthreads();   // D of every (query, head) visible; dQ staged
+  __syncthreads();   // D of every (query, head) visible
 
   // ---- pass B: rows = keys (transposed tiles) ---------------------------------------------
-  float dk[2][4][4], dv[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
+  bf16* dkv_out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * COLS;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int mt = half * 2 + i;
+    if (mt * 16 >= nk) break;
+    float dk[4][4], dv[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { dk[i][n][j] = 0.f; dv[i][n][j] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int mt = half * 2 + i;
-    if (mt * 16 >= nk) continue;
+      for (int j = 0; j < 4; ++j) { dk[n][j] = 0.f; dv[n][j] = 0.f; }
     uint32_t ka[2][4], va[2][4];
     frag_a<LDS>(Ks, mt * 16, hl * 32, lane, ka[0]);
     frag_a<LDS>(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
@@ -683,29 +802,18 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
         uint32_t gb[4], qb[4];
         frag_b_kn<LDS>(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
         frag_b_kn<LDS>(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
-        mma16816(dv[i][2 * nc], pa, gb[0], gb[1]);
-        mma16816(dv[i][2 * nc + 1], pa, gb[2], gb[3]);
-        mma16816(dk[i][2 * nc], dsa, qb[0], qb[1]);
-        mma16816(dk[i][2 * nc + 1], dsa, qb[2], qb[3]);
+        mma16816(dv[2 * nc], pa, gb[0], gb[1]);
+        mma16816(dv[2 * nc + 1], pa, gb[2], gb[3]);
+        mma16816(dk[2 * nc], dsa, qb[0], qb[1]);
+        mma16816(dk[2 * nc + 1], dsa, qb[2], qb[3]);
       }
     }
-  }
-  __syncthreads();   // every warp is done reading K / V before they become the dK / dV staging tiles
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int mt = half * 2 + i;
-    if (mt * 16 >= nk) continue;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      put_c<LDS>(Ks, mt * 16, hl * 32 + n * 8, lane, dk[i][n]);
-      put_c<LDS>(Vs, mt * 16, hl * 32 + n * 8, lane, dv[i][n]);
+      put_c_global(dkv_out, a.ldkv, mt * 16, hl * 32 + n * 8, lane, dk[n], nk);
+      put_c_global(dkv_out + D, a.ldkv, mt * 16, hl * 32 + n * 8, lane, dv[n], nk);
     }
   }
-  __syncthreads();
-  unstage<HG>(reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * COLS, D, Ds, nq);
-  bf16* out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * COLS;
-  unstage<HG>(out, a.ldkv, Ks, nk);
-  unstage<HG>(out + D, a.ldkv, Vs, nk);
 }
 
 }  // namespace amma

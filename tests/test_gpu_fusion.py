@@ -168,3 +168,74 @@ def test_full_size_invariants_and_bf16_vs_fp32():
     lg32, lg16 = o32["logits"].float().cpu(), o16["logits"].float().cpu()
     margin = lg32.abs() > 2e-2 * lg32.abs().max()
     assert torch.equal((lg16 > 0)[margin], (lg32 > 0)[margin])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=1, TL=1, TN=1, TI=1, K=1, layers=1, d_l=256, d_n=256, d_i=256),
+    dict(B=2, TL=7, TN=3, TI=66, K=32, layers=2, d_l=64, d_n=768, d_i=32),
+    dict(B=3, TL=65, TN=2, TI=5, K=4, layers=3, d_l=256, d_n=256, d_i=256),
+])
+def test_fp32_edge_shapes_vs_oracle(cfg):
+    """Edge shapes the golden cases do not reach (single patient / single token, 1 and 32 labels, 1-3 layers,
+    Conv1d input projections on every modality, a sequence one longer than the attention chunk): fp32 kernels
+    against the oracle, outputs and every gradient."""
+    from oracle import route_fusion_oracle as orc
+    from oracle import synth
+    import multimodalrouting_b200 as mmr
+    from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    L, K, B = cfg["layers"], cfg["K"], cfg["B"]
+    g = torch.Generator().manual_seed(77)
+    sdm = {n: synth._fill(s, k, g) for n, s, k in synth.mult_param_spec(cfg["d_l"], cfg["d_n"], cfg["d_i"], 256, L)}
+    _, sdp, sdh = synth.make_state(K=K, seed=78, sharp=2.0)
+    inp = synth.make_inputs(B=B, TL=cfg["TL"], TN=cfg["TN"], TI=cfg["TI"], d_l=cfg["d_l"], d_n=cfg["d_n"],
+                            d_i=cfg["d_i"], K=K, seed=79, missing=(B > 1))
+    mult = mmr.MULTModel(cfg["d_l"], cfg["d_n"], cfg["d_i"], 256, 256, 256, True, True, True, 8, L, 0,
+                         0., 0., 0., 0., 0., 0., 0., False)
+    proj = rh.RoutePrimaryProjector(256, 32)
+    head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=K)
+    mult.load_state_dict(sdm); proj.load_state_dict(sdp); head.load_state_dict(sdh)
+    mult, proj, head = mult.cuda(), proj.cuda(), head.cuda()
+    d = {k: v.cuda() for k, v in inp.items()}
+    xs = {k: d[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+    logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
+        mult, xs["x_l"], xs["x_n"], xs["x_i"], proj, head, mL=d["mL"], mN=d["mN"], mI=d["mI"],
+        route_adapter=rh.RouteDimAdapter(256, 256, 256, 256), route_mask=d["route_mask"])
+    synth.loss_fn(logits, d["y"], "pheno").backward()
+    # oracle (fp32 and fp64)
+    def run(dt):
+        a, b, h = [{k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()} for sd in (sdm, sdp, sdh)]
+        x = {k: inp[k].to(dt).clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+        lo, al, ro, Ro = orc.full_forward(a, b, h, x["x_l"], x["x_n"], x["x_i"], inp["mL"].to(dt), inp["mN"].to(dt),
+                                          inp["mI"].to(dt), variant="pheno", route_mask=inp["route_mask"].to(dt), layers=L)
+        synth.loss_fn(lo, inp["y"].to(dt), "pheno").backward()
+        gr = {k: v.grad for sd in (a, b, h) for k, v in sd.items()}
+        gr.update({k: v.grad for k, v in x.items()})
+        return lo, al, Ro, gr
+    lo, al, Ro, g32 = run(torch.float32)
+    lt, at, Rt, g64 = run(torch.float64)
+    for mine, r32, r64, what in ((logits, lo, lt, "logits"), (alpha, al, at, "alpha"), (R, Ro, Rt, "R")):
+        e = max_rel(mine, r32)
+        assert e < 1e-4 or max_rel(mine, r64) <= max(1e-4, 3 * max_rel(r32, r64)), f"{what} {e:.2e}"
+    mine = {n: p.grad for m in (mult, proj, head) for n, p in m.named_parameters()}
+    mine.update({k: v.grad for k, v in xs.items()})
+    for k, t in g64.items():
+        if t is None:
+            assert mine[k] is None, k
+            continue
+        e = max_rel(mine[k], g32[k])
+        assert e < 5e-4 or max_rel(mine[k], t) <= max(5e-4, 3 * max_rel(g32[k], t)), f"grad {k}: {e:.2e}"
+    # the same shapes through the bf16 tensor-core path: route embeddings within the bf16 budget, finite gradients
+    for m in (mult, proj, head):
+        m.zero_grad(set_to_none=True)
+    xb = {k: d[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lb, ab, rb, Rb = rh.forward_capsule_from_multmodel(
+            mult, xb["x_l"], xb["x_n"], xb["x_i"], proj, head, mL=d["mL"], mN=d["mN"], mI=d["mI"],
+            route_adapter=rh.RouteDimAdapter(256, 256, 256, 256), route_mask=d["route_mask"])
+    synth.loss_fn(lb, d["y"], "pheno").backward()
+    for r in synth.ROUTES:
+        assert max_rel(rb[r], routes[r]) < 2e-2, f"bf16 route {r}"
+    assert max_rel(ab, alpha) < 2e-2
+    for n, p in [(n, p) for m in (mult, proj, head) for n, p in m.named_parameters()] + list(xb.items()):
+        gg = p.grad
+        assert gg is None or bool(torch.isfinite(gg).all()), n

@@ -53,7 +53,11 @@ def allreduce_gradients(modules: Iterable[torch.nn.Module], world_size: int = No
         return 0
     params = [p for m in modules for p in m.parameters()]
     flats = _flat_groups(params)
+    nccl = dist.get_backend(group) == "nccl"
     for f in flats:
-        dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
-        f.mul_(1.0 / world)
+        if nccl:                   # averaged inside the collective: no extra pass over the 79 MB buffer
+            dist.all_reduce(f, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
+            f.mul_(1.0 / world)
     return len(flats)

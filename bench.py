@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patients per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: all-reduce the gradients after the backward instead of overlapping it, layer by layer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,7 +236,7 @@ def main():
     os.dup2(2, 1)                 # library banners (e.g. NCCL's version line) must not pollute the one JSON line
     import torch.distributed as dist
     from multimodalrouting_b200 import _lib
-    from multimodalrouting_b200.dist import allreduce_gradients
+    from multimodalrouting_b200.dist import OverlappedGradReducer, allreduce_gradients
     from oracle import synth
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -267,19 +269,45 @@ def main():
         loss.backward()
         return loss
 
+    # N>1: the gradient all-reduce is part of the step.  By default it is OVERLAPPED with the backward: the library
+    # records an event when the gradients of a layer are final and the reducer all-reduces that block on a side
+    # stream (NCCL over NVLink) while the earlier layers are still being differentiated; the tail of the buffer is
+    # reduced after the backward.  The collectives are captured into the same CUDA graph as the kernels.
+    reducer = None
+    if world > 1 and not args.no_overlap:
+        reducer = OverlappedGradReducer(mult, (proj, head), LAYERS)
+
+    def train_step():
+        loss = fwd_bwd()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
     # The step is ~130 launches of static shape: capture it once (CUDA graph) so the host cost of issuing it
     # (Python + autograd + launches, about as long as the GPU work at B=512) disappears from the step.
     graphed = None
     launches_per_replay = 0
     if not args.no_graph:
+        from multimodalrouting_b200.graphs import GraphedStep
         try:
-            from multimodalrouting_b200.graphs import GraphedStep
             lc0 = lib.mmr_launch_count()
-            graphed = GraphedStep(fwd_bwd, warmup=2)
+            graphed = GraphedStep(train_step, warmup=2)
             launches_per_replay = (lib.mmr_launch_count() - lc0) // 3     # 2 warm-up calls + 1 capture
-        except Exception as exc:            # noqa: BLE001  -- fall back to eager launches, and say so
-            print(f"[bench] CUDA graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
+        except Exception as exc:            # noqa: BLE001  -- fall back, and say so
+            print(f"[bench] CUDA graph capture failed ({exc!r})", file=sys.stderr)
             graphed = None
+            if reducer is not None:         # retry with the collectives outside the graph
+                reducer.close()
+                reducer = None
+                torch.cuda.synchronize()
+                try:
+                    lc0 = lib.mmr_launch_count()
+                    graphed = GraphedStep(train_step, warmup=2)
+                    launches_per_replay = (lib.mmr_launch_count() - lc0) // 3
+                    print("[bench] captured without the overlapped all-reduce", file=sys.stderr)
+                except Exception as exc2:   # noqa: BLE001
+                    print(f"[bench] CUDA graph capture failed again ({exc2!r}); running eagerly", file=sys.stderr)
+                    graphed = None
 
     # End-to-end input pipeline: the NEXT step's host batch is copied (pinned host -> device staging buffer) on a
     # side stream while the current step computes; at the start of a step the staged batch is moved into the
@@ -311,8 +339,8 @@ def main():
             pipe["primed"] = False
             if not last:
                 prefetch_host_batch()
-        loss = graphed() if graphed is not None else fwd_bwd()
-        if world > 1:
+        loss = graphed() if graphed is not None else train_step()
+        if world > 1 and reducer is None:
             allreduce_gradients(modules, world)
         if from_host:
             return loss.item()          # D2H read of the step's result
@@ -402,6 +430,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None,
+                       "grad_allreduce": (None if world == 1 else
+                                          "overlapped with the backward, per layer block" if reducer is not None
+                                          else "after the backward"),
                        "l2_policy": "per-step working set (activations saved for backward ~3 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

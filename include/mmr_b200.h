@@ -99,6 +99,17 @@ int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_pa
                          const float* d_routes, void* const* host_param_grads,
                          float* dx_l, float* dx_n, float* dx_i, void* stream);
 
+/* Same as mmr_route_fusion_bwd; additionally records host_layer_events[l] (cudaEvent_t, NULL entries skipped) on
+ * `stream` once the out_proj / fc1 / fc2 weight+bias and layer_norms.1 gradients of layer l (all six encoders) are
+ * final, so a data-parallel caller can all-reduce that part of the gradient buffer while the backward continues. */
+int mmr_route_fusion_bwd_events(const mmr_fusion_dims* dims, const void* const* host_params,
+                                const float* x_l, const float* x_n, const float* x_i,
+                                const float* mL, const float* mN, const float* mI,
+                                const void* packed, const void* saved, void* scratch,
+                                const float* d_routes, void* const* host_param_grads,
+                                float* dx_l, float* dx_n, float* dx_i, void* stream,
+                                void* const* host_layer_events);
+
 typedef struct mmr_routing_dims {
   int32_t B;               /* patients */
   int32_t K;               /* labels: 2 (mortality) / 25 (phenotypes); <= MMR_MAX_LABELS */

@@ -486,7 +486,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
 template <class CT>
 static int fusion_bwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
                       const uint8_t* packed, const uint8_t* saved, uint8_t* scratch, const float* d_routes,
-                      void* const* grads, float* const dx[3], cudaStream_t st) {
+                      void* const* grads, float* const dx[3], cudaStream_t st, void* const* layer_events = nullptr) {
   const ParamIndex ix{P.L};
   const int L = P.L, B = P.B;
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
@@ -681,6 +681,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_out_proj");
       if (rc) return rc;
     }
+    // out_proj / fc1 / fc2 weights+biases and LayerNorm-1 gradients of layer l (all six directions) are final
+    // from here on: data-parallel callers may start reducing them while the rest of the backward runs
+    if (layer_events && layer_events[l]) CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(layer_events[l]), st));
     {  // attention backward
       AttnArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.kv = P.kv;
@@ -886,10 +889,11 @@ int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_pa
                            routes_out, st);
 }
 
-int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
-                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
-                         const void* packed, const void* saved, void* scratch, const float* d_routes,
-                         void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream) {
+int mmr_route_fusion_bwd_events(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                                const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                                const void* packed, const void* saved, void* scratch, const float* d_routes,
+                                void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream,
+                                void* const* host_layer_events) {
   Plan P;
   const char* why = "";
   if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
@@ -902,9 +906,17 @@ int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_pa
   ProfScope ps(PC_FUSION_BWD, st);
   if (P.bf16)
     return fusion_bwd<bf16>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
-                            d_routes, host_param_grads, dx, st);
+                            d_routes, host_param_grads, dx, st, host_layer_events);
   return fusion_bwd<float>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
-                           d_routes, host_param_grads, dx, st);
+                           d_routes, host_param_grads, dx, st, host_layer_events);
+}
+
+int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                         const void* packed, const void* saved, void* scratch, const float* d_routes,
+                         void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream) {
+  return mmr_route_fusion_bwd_events(dims, host_params, x_l, x_n, x_i, mL, mN, mI, packed, saved, scratch, d_routes,
+                                     host_param_grads, dx_l, dx_n, dx_i, stream, nullptr);
 }
 
 // ------------------------------------------------------------------------------- routing ---

@@ -61,3 +61,64 @@ def allreduce_gradients(modules: Iterable[torch.nn.Module], world_size: int = No
             dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
             f.mul_(1.0 / world)
     return len(flats)
+
+
+class OverlappedGradReducer:
+    """Gradient all-reduce overlapped with the backward of the route-fusion op.
+
+    The fused backward lays the gradients out in completion order (ops.grad_layout): the block of layer l
+    (out_proj / fc1 / fc2 / LayerNorm-1 of all six encoders, ~3.5 M floats) is final long before the backward
+    ends.  The C library records a CUDA event after each block; this class waits for it on a side stream and
+    all-reduces the block there (NCCL over NVLink) while layers l-1 .. 0 are still being differentiated.  Only
+    the late gradients (in_proj / LayerNorm-0 / small tensors, ~25 %) and the other modules are reduced after
+    the backward (`finish`).  Works eagerly and inside CUDA-graph capture (the side stream is forked from and
+    joined back into the capturing stream)."""
+
+    def __init__(self, mult_module: torch.nn.Module, other_modules: Iterable[torch.nn.Module], layers: int,
+                 group=None):
+        from . import ops
+        self.mult, self.others = mult_module, list(other_modules)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.comm = torch.cuda.Stream()
+        self.events = [torch.cuda.Event() for _ in range(layers)]
+        for e in self.events:          # CUDA events are created lazily: force the handles to exist
+            e.record()
+        torch.cuda.synchronize()
+        self._flat = None
+        self._rest = None
+        ops.set_grad_overlap(self._on_fusion_grads, self.events)
+
+    def close(self):
+        from . import ops
+        ops.set_grad_overlap(None, None)
+
+    def _reduce(self, t: torch.Tensor):
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _on_fusion_grads(self, flat: torch.Tensor, buckets):
+        """Called by the autograd node right after the backward kernels were enqueued."""
+        early, rest = buckets[:-1], buckets[-1]
+        # bucket i holds layer (layers-1-i): completion order
+        n = len(early)
+        for i, (lo, hi) in enumerate(early):
+            ev = self.events[n - 1 - i]
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                self._reduce(flat[lo:hi])
+        self._flat, self._rest = flat, rest
+
+    def finish(self):
+        """Reduces what is left (late fusion gradients, projector, head) and joins the side stream."""
+        cur = torch.cuda.current_stream()
+        if self._flat is not None:
+            lo, hi = self._rest
+            if hi > lo:
+                self._reduce(self._flat[lo:hi])
+            self._flat = None
+        else:                          # the fusion op did not run under the hook: plain path
+            for f in _flat_groups(list(self.mult.parameters())):
+                self._reduce(f)
+        for f in _flat_groups([p for m in self.others for p in m.parameters()]):
+            self._reduce(f)
+        cur.wait_stream(self.comm)

@@ -117,15 +117,23 @@ def _(x_l, x_n, x_i, mL, mN, mI, pos, params, layers, dtype, engine):
 
 
 _GRAD_LAYOUTS = {}
+# per-layer parameter slots (include/mmr_b200.h order) whose gradients are final as soon as the backward of
+# their layer has run: out_proj.{weight,bias}, fc1.{weight,bias}, fc2.{weight,bias}, layer_norms.1.{weight,bias}
+_EARLY_SLOTS = (2, 3, 4, 5, 6, 7, 10, 11)
+_LATE_SLOTS = (0, 1, 8, 9)          # in_proj_{weight,bias}, layer_norms.0.*: finalised by the last kernels
 
 
 def grad_layout(shapes: Sequence[Tuple[int, ...]], layers: int):
     """Placement of the parameter gradients inside the flat buffer returned by route_fusion_bwd.
 
-    Per-layer tensors of the six cross-modal encoders are stacked by kind ([24, 768, 256] for all
-    in_proj_weight gradients, ...), so the autograd side can hand them out with one ``unbind`` per kind
-    (13 tensor ops instead of two per parameter); everything else sits in 16-byte aligned slots.
-    Returns (offsets per parameter, total floats, groups = [(offset, [param indices], shape)])."""
+    * gradients that are final once layer l's backward has run are stacked per (layer, kind) over the six
+      encoders and laid out layer by layer in COMPLETION order (last layer first): a data-parallel caller can
+      all-reduce block l while layers l-1 .. 0 are still being differentiated (`buckets`);
+    * the late kinds are stacked over all 6 x layers instances; everything else sits in 16-byte aligned slots;
+    * stacking lets the autograd side hand the views out with one ``unbind`` per stack instead of two tensor
+      ops per parameter.
+    Returns (offsets per parameter, total floats, groups = [(offset, [param indices], shape)],
+             buckets = [(start, end)] * layers in completion order + [(start of the rest, total)])."""
     key = (tuple(shapes), layers)
     hit = _GRAD_LAYOUTS.get(key)
     if hit is not None:
@@ -133,56 +141,80 @@ def grad_layout(shapes: Sequence[Tuple[int, ...]], layers: int):
     n = len(shapes)
     numel = [int(torch.Size(sh).numel()) for sh in shapes]
     offs = [-1] * n
-    groups = []
-    o = 0
+    groups, buckets = [], []
+    o = rest = 0
     per_enc = layers * 12 + 2
     if n == 9 + 6 * per_enc + 8:        # MULTModel state_dict order (include/mmr_b200.h)
-        for slot in range(12):
-            idx = [9 + d * per_enc + l * 12 + slot for d in range(6) for l in range(layers)]
-            sh = shapes[idx[0]]
-            if any(shapes[i] != sh for i in idx) or numel[idx[0]] % 4:
-                continue
-            groups.append((o, idx, tuple(sh)))
-            for i in idx:
-                offs[i] = o
-                o += numel[i]
+        stackable = all(numel[9 + s] % 4 == 0 for s in range(12))
+        if stackable:
+            for l in range(layers - 1, -1, -1):
+                start = o
+                for slot in _EARLY_SLOTS:
+                    idx = [9 + d * per_enc + l * 12 + slot for d in range(6)]
+                    groups.append((o, idx, tuple(shapes[idx[0]])))
+                    for i in idx:
+                        offs[i] = o
+                        o += numel[i]
+                buckets.append((start, o))
+            rest = o                    # everything from here on is final only when the backward ends
+            for slot in _LATE_SLOTS:
+                idx = [9 + d * per_enc + l * 12 + slot for d in range(6) for l in range(layers)]
+                groups.append((o, idx, tuple(shapes[idx[0]])))
+                for i in idx:
+                    offs[i] = o
+                    o += numel[i]
     for i in range(n):
         if offs[i] < 0:
             offs[i] = o
             o += (numel[i] + 3) // 4 * 4
-    out = (offs, o, groups)
+    buckets.append((rest, o))
+    out = (offs, o, groups, buckets)
     _GRAD_LAYOUTS[key] = out
     return out
+
+
+# Data-parallel overlap (multimodalrouting_b200.dist.OverlappedGradReducer): when set, the backward asks the
+# library to record `events[l]` after layer l's early gradients and then calls hook(flat, buckets).
+_OVERLAP = {"hook": None, "events": None}
+
+
+def set_grad_overlap(hook, events) -> None:
+    _OVERLAP["hook"], _OVERLAP["events"] = hook, events
 
 
 @torch.library.custom_op("mmr_b200::route_fusion_bwd", mutates_args=())
 def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
                      mI: Optional[Tensor], params: Sequence[Tensor], packed: Tensor, saved: Tensor,
                      d_routes: Tensor, need: Sequence[bool], layers: int, dtype: int,
-                     engine: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                     engine: int, events: Sequence[int]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Returns (dx_l, dx_n, dx_i, flat parameter gradients laid out by `grad_layout`)."""
     lib = _lib.load()
     dims = _fusion_dims(x_l, x_n, x_i, layers, dtype, engine)
     _, _, _, sb_b = fusion_sizes(dims)
     dev = x_l.device
     scratch = torch.empty(sb_b, dtype=torch.uint8, device=dev)
-    offs, o, _ = grad_layout([tuple(p.shape) for p in params], layers)   # 16-byte aligned slots
+    offs, o, _, _ = grad_layout([tuple(p.shape) for p in params], layers)   # 16-byte aligned slots
     flat = torch.zeros(o, dtype=torch.float32, device=dev)
     base = flat.data_ptr()
     grads = (c_fp * len(params))()
     for i, p in enumerate(params):
         grads[i] = (base + 4 * offs[i]) if need[i] else None
     dx = [torch.empty_like(x) for x in (x_l, x_n, x_i)]
-    rc = lib.mmr_route_fusion_bwd(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
-                                  _ptr(mN), _ptr(mI), _ptr(packed), _ptr(saved), _ptr(scratch), _ptr(d_routes),
-                                  grads, _ptr(dx[0]), _ptr(dx[1]), _ptr(dx[2]), _stream())
+    evs = None
+    if len(events) > 0:
+        evs = (c_fp * layers)()
+        for l in range(layers):
+            evs[l] = events[l] if l < len(events) and events[l] else None
+    rc = lib.mmr_route_fusion_bwd_events(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
+                                         _ptr(mN), _ptr(mI), _ptr(packed), _ptr(saved), _ptr(scratch), _ptr(d_routes),
+                                         grads, _ptr(dx[0]), _ptr(dx[1]), _ptr(dx[2]), _stream(), evs)
     _lib.check(rc, "mmr_route_fusion_bwd")
     return dx[0], dx[1], dx[2], flat
 
 
 @route_fusion_bwd.register_fake
-def _(x_l, x_n, x_i, mL, mN, mI, params, packed, saved, d_routes, need, layers, dtype, engine):
-    _, n, _ = grad_layout([tuple(p.shape) for p in params], layers)
+def _(x_l, x_n, x_i, mL, mN, mI, params, packed, saved, d_routes, need, layers, dtype, engine, events):
+    _, n, _, _ = grad_layout([tuple(p.shape) for p in params], layers)
     return (torch.empty_like(x_l), torch.empty_like(x_n), torch.empty_like(x_i),
             x_l.new_empty(n, dtype=torch.float32))
 
@@ -248,9 +280,13 @@ class RouteFusionFn(torch.autograd.Function):
             d_all = torch.stack([g.float() if g is not None else torch.zeros(B, 256, device=xs[0].device)
                                  for g in d_routes], dim=0).contiguous()
         need = [bool(n) for n in ctx.needs_input_grad[10:]]
+        hook, events = _OVERLAP["hook"], _OVERLAP["events"]
+        handles = [int(e.cuda_event) for e in events[:layers]] if (hook is not None and events) else []
         dxl, dxn, dxi, flat = route_fusion_bwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], ps, packed, saved, d_all,
-                                               need, layers, dtype, engine)
-        offs, _, groups = grad_layout([tuple(p.shape) for p in ps], layers)
+                                               need, layers, dtype, engine, handles)
+        offs, _, groups, buckets = grad_layout([tuple(p.shape) for p in ps], layers)
+        if hook is not None:
+            hook(flat, buckets)
         grads = [None] * len(ps)
         grouped = set()
         for start, idx, sh in groups:           # one unbind per parameter kind

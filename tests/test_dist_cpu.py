@@ -113,3 +113,35 @@ def test_gloo_world2_gradient_allreduce_matches_single_process():
         assert p.exitcode == 0
     worst = out.get()
     assert worst < 1e-4, worst
+
+
+def test_grad_layout_buckets_follow_backward_completion_order():
+    """ops.grad_layout: the per-layer blocks that OverlappedGradReducer all-reduces during the backward are
+    contiguous, disjoint, ordered last layer first, and hold exactly the 'early' parameter kinds."""
+    from multimodalrouting_b200 import MULTModel
+    from multimodalrouting_b200 import ops
+    layers = 4
+    mult = MULTModel(256, 256, 256, 256, 256, 256, True, True, True, 8, layers, 0, 0., 0., 0., 0., 0., 0., 0., False)
+    names = [n for n, _ in mult.named_parameters()]
+    shapes = [tuple(p.shape) for _, p in mult.named_parameters()]
+    offs, total, groups, buckets = ops.grad_layout(shapes, layers)
+    numel = [int(torch.Size(s).numel()) for s in shapes]
+    # every parameter has its own 16-byte aligned, non-overlapping slot
+    spans = sorted((o, o + n) for o, n in zip(offs, numel))
+    assert all(o % 4 == 0 for o, _ in spans)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= total
+    assert len(buckets) == layers + 1
+    assert buckets[0][0] == 0 and buckets[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+    early = (".self_attn.out_proj.", ".fc1.", ".fc2.", ".layer_norms.1.")
+    for i, (lo, hi) in enumerate(buckets[:-1]):
+        layer = layers - 1 - i                      # completion order of the backward
+        inside = [names[j] for j in range(len(names)) if lo <= offs[j] < hi]
+        assert len(inside) == 6 * 8
+        assert all(f".layers.{layer}." in n and any(e in n for e in early) for n in inside), inside[:3]
+    lo, hi = buckets[-1]
+    late = [names[j] for j in range(len(names)) if lo <= offs[j] < hi]
+    assert all(("in_proj" in n or "layer_norms.0" in n or ".layers." not in n) for n in late)
+    # stacked groups are dense: cnt * numel floats from their start
+    for start, idx, sh in groups:
+        assert [offs[j] for j in idx] == [start + k * numel[idx[0]] for k in range(len(idx))]

@@ -168,6 +168,50 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
                             const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
                             float* d_acts, void* stream);
 
+/* ---- the steps either side of the hot path ---------------------------
+ *
+ * Producer epilogue: replaces _clamp_norm + _safe_tensor + .float() of the encoder outputs
+ * (MortModel/Paired_Cross_Attention/main.py:1772-1796, mode 0) or the nan_to_num-only variant of
+ * PhenoModel/Paired_Cross_Attention/main.py:1445-1460 (mode 1).  x: [rows, D] of in_dtype (MMR_DTYPE_F32 /
+ * MMR_DTYPE_BF16 / MMR_DTYPE_F16), y: fp32 [rows, D]; D % 4 == 0, D <= 1024.
+ *   mode 0: y = nan_to_num(x * min(1, max_norm / (||x||_2 + 1e-6)), nan=0, posinf=1e4, neginf=-1e4)
+ *   mode 1: y = nan_to_num(x, 0, 0, 0)
+ * nonfinite (device, may be NULL) is incremented by the number of entries nan_to_num replaced. */
+#define MMR_DTYPE_F16 2
+int mmr_sanitize_rows_fwd(const void* x, int in_dtype, float* y, int64_t rows, int D, int mode, float max_norm,
+                          unsigned long long* nonfinite, void* stream);
+/* dx = d(y)/d(x)^T dy for rows of finite inputs; rows holding NaN/Inf get dx = 0 (the reference produces NaN there
+ * and skips the optimizer step). */
+int mmr_sanitize_rows_bwd(const void* x, int in_dtype, const float* dy, float* dx, int64_t rows, int D, int mode,
+                          float max_norm, void* stream);
+
+/* Training tail: replaces torch.nn.utils.clip_grad_norm_ + grads_are_finite + torch.optim.AdamW.step + EMA.update
+ * (MortModel/Paired_Cross_Attention/main.py:3143-3165, 2886-2890, 58-108) with three device-side stages that
+ * never synchronise the host: (1) mmr_grad_sqnorm accumulates sum g^2 of any number of tensor tables into
+ * state->sumsq; (2) mmr_opt_prepare turns it into total norm, clip coefficient min(1, max_norm/(norm+1e-6)), a skip
+ * flag (non-finite norm: nothing is updated and the step counter does not advance) and the AdamW bias corrections
+ * of step+1; (3) mmr_opt_apply updates p, exp_avg, exp_avg_sq (and the EMA shadow when has_ema) of a table. */
+typedef struct mmr_opt_tensor {   /* device pointers, fp32, n elements each; ema may be NULL */
+  float* p; const float* g; float* m; float* v; float* ema; int64_t n;
+} mmr_opt_tensor;
+typedef struct mmr_opt_hyper {
+  double lr, beta1, beta2, eps, weight_decay;   /* torch.optim.AdamW arguments (amsgrad=False, maximize=False) */
+  double max_norm;                              /* clip_grad_norm_ max_norm; <= 0 disables clipping */
+  double ema_decay;                             /* EMA.decay */
+  int32_t has_ema, reserved;
+} mmr_opt_hyper;
+typedef struct mmr_opt_state {    /* DEVICE resident, caller-owned, zero-initialised once; persists across steps */
+  double sumsq, bc1, bc2_sqrt;
+  float norm, clip;
+  int32_t step, skip;
+} mmr_opt_state;
+int mmr_grad_sqnorm(const mmr_opt_tensor* host_tensors, int n_tensors, mmr_opt_state* state, void* stream);
+int mmr_opt_prepare(const mmr_opt_hyper* hp, mmr_opt_state* state, void* stream);
+int mmr_opt_apply(const mmr_opt_tensor* host_tensors, int n_tensors, const mmr_opt_hyper* hp,
+                  const mmr_opt_state* state, void* stream);
+/* EMA.update alone: ema = decay * ema + (1 - decay) * p for every table entry (g, m, v ignored). */
+int mmr_ema_update(const mmr_opt_tensor* host_tensors, int n_tensors, double decay, void* stream);
+
 /* Unit-test hook for the GEMM engines: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) with bf16 (dtype 1)
  * or fp32 (dtype 0) operands, fp32 output.  trans=1 computes C[M,N] = A[Kr,M]^T * B[Kr,N]
  * (the weight-gradient form, reduction over rows). */

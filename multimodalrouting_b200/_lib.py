@@ -35,10 +35,24 @@ class RoutingGrads(C.Structure):
                 ("embedding", c_fp), ("bias", c_fp)]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("p", c_fp), ("g", c_fp), ("m", c_fp), ("v", c_fp), ("ema", c_fp), ("n", C.c_int64)]
+
+
+class OptHyper(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("max_norm", C.c_double), ("ema_decay", C.c_double),
+                ("has_ema", C.c_int32), ("reserved", C.c_int32)]
+
+
+OPT_STATE_BYTES = 40     # sizeof(mmr_opt_state): 3 doubles, 2 floats, 2 int32
+
+
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
-           "mmr_prof_enable", "mmr_prof_collect"]
+           "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
+           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update"]
 
 
 def lib_path() -> str:
@@ -86,6 +100,18 @@ def load():
     lib.mmr_launch_count.restype = C.c_longlong
     lib.mmr_prof_enable.argtypes = [C.c_int]
     lib.mmr_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.mmr_sanitize_rows_fwd.argtypes = [c_fp, C.c_int, c_fp, C.c_int64, C.c_int, C.c_int, C.c_float, c_fp, c_fp]
+    lib.mmr_sanitize_rows_fwd.restype = C.c_int
+    lib.mmr_sanitize_rows_bwd.argtypes = [c_fp, C.c_int, c_fp, c_fp, C.c_int64, C.c_int, C.c_int, C.c_float, c_fp]
+    lib.mmr_sanitize_rows_bwd.restype = C.c_int
+    lib.mmr_grad_sqnorm.argtypes = [C.POINTER(OptTensor), C.c_int, c_fp, c_fp]
+    lib.mmr_grad_sqnorm.restype = C.c_int
+    lib.mmr_opt_prepare.argtypes = [C.POINTER(OptHyper), c_fp, c_fp]
+    lib.mmr_opt_prepare.restype = C.c_int
+    lib.mmr_opt_apply.argtypes = [C.POINTER(OptTensor), C.c_int, C.POINTER(OptHyper), c_fp, c_fp]
+    lib.mmr_opt_apply.restype = C.c_int
+    lib.mmr_ema_update.argtypes = [C.POINTER(OptTensor), C.c_int, C.c_double, c_fp]
+    lib.mmr_ema_update.restype = C.c_int
     _LIB = lib
     return lib
 

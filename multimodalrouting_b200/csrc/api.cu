@@ -13,6 +13,7 @@
 #include "plan.cuh"
 #include "routing.cuh"
 #include "rows.cuh"
+#include "tail.cuh"
 
 using namespace mmr;
 
@@ -818,8 +819,122 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   return MMR_OK;
 }
 
+// ------------------------------------------------------- producer epilogue / training tail ---
+template <class T>
+static int sanitize_launch(bool bwd, const SanitizeArgs& a, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((a.rows + SAN_WARPS - 1) / SAN_WARPS);
+  if (bwd) sanitize_bwd_kernel<T><<<blocks, SAN_WARPS * 32, 0, st>>>(a);
+  else sanitize_fwd_kernel<T><<<blocks, SAN_WARPS * 32, 0, st>>>(a);
+  LAUNCH_OK((bwd ? "sanitize_bwd" : "sanitize_fwd"));
+  return MMR_OK;
+}
+
+static int sanitize_dispatch(bool bwd, const void* x, int in_dtype, float* y, const float* dy, float* dx,
+                             int64_t rows, int Dw, int mode, float max_norm, unsigned long long* nonfinite,
+                             void* stream) {
+  if (rows < 0 || Dw <= 0 || Dw % 4 || Dw > SAN_MAX_D)
+    return fail(MMR_ERR_INVALID_ARG, "sanitize: row width must be a positive multiple of 4 and <= 1024");
+  if (mode != 0 && mode != 1) return fail(MMR_ERR_INVALID_ARG, "sanitize: mode must be 0 (clamp-norm) or 1 (nan_to_num)");
+  if (!x || (bwd ? (!dy || !dx) : !y)) return fail(MMR_ERR_INVALID_ARG, "sanitize: null pointer");
+  if (rows == 0) return MMR_OK;
+  if ((rows + SAN_WARPS - 1) / SAN_WARPS > 0x7fffffffLL) return fail(MMR_ERR_INVALID_ARG, "sanitize: too many rows");
+  SanitizeArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.y = y; a.dy = dy; a.dx = dx; a.rows = rows; a.D = Dw; a.mode = mode; a.max_norm = max_norm;
+  a.nonfinite = nonfinite;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (in_dtype) {
+    case MMR_DTYPE_F32: return sanitize_launch<float>(bwd, a, st);
+    case MMR_DTYPE_BF16: return sanitize_launch<bf16>(bwd, a, st);
+    case MMR_DTYPE_F16: return sanitize_launch<__half>(bwd, a, st);
+  }
+  return fail(MMR_ERR_INVALID_ARG, "sanitize: in_dtype must be MMR_DTYPE_F32 / BF16 / F16");
+}
+
+// Walks a host table of tensors in groups of OPT_NT and calls `launch(table, blocks)` for every group.
+template <class F>
+static int opt_for_tables(const mmr_opt_tensor* ts, int n, bool need_g, bool need_mv, bool need_ema, F&& launch) {
+  if (n < 0 || (n > 0 && !ts)) return fail(MMR_ERR_INVALID_ARG, "optimizer table: null");
+  OptTable t;
+  int i = 0;
+  while (i < n) {
+    memset(&t, 0, sizeof(t));
+    long long blocks = 0;
+    while (i < n && t.nt < OPT_NT) {
+      const mmr_opt_tensor& e = ts[i++];
+      if (e.n < 0) return fail(MMR_ERR_INVALID_ARG, "optimizer table: negative size");
+      if (e.n == 0) continue;
+      if (!e.p || (need_g && !e.g) || (need_mv && (!e.m || !e.v)) || (need_ema && !e.ema))
+        return fail(MMR_ERR_INVALID_ARG, "optimizer table: null tensor pointer");
+      const int k = t.nt++;
+      t.p[k] = e.p; t.g[k] = e.g; t.m[k] = e.m; t.v[k] = e.v; t.ema[k] = e.ema; t.n[k] = e.n;
+      t.blk0[k] = (int)blocks;
+      blocks += (e.n + OPT_CHUNK - 1) / OPT_CHUNK;
+      if (blocks > 0x7fffffffLL) return fail(MMR_ERR_INVALID_ARG, "optimizer table: too many elements");
+    }
+    t.blk0[t.nt] = (int)blocks;
+    if (t.nt == 0) continue;
+    int rc = launch(t, (unsigned)blocks);
+    if (rc) return rc;
+  }
+  return MMR_OK;
+}
+
+
 // ================================================================================ C ABI ===
 extern "C" {
+
+int mmr_sanitize_rows_fwd(const void* x, int in_dtype, float* y, int64_t rows, int Dw, int mode, float max_norm,
+                          unsigned long long* nonfinite, void* stream) {
+  return sanitize_dispatch(false, x, in_dtype, y, nullptr, nullptr, rows, Dw, mode, max_norm, nonfinite, stream);
+}
+
+int mmr_sanitize_rows_bwd(const void* x, int in_dtype, const float* dy, float* dx, int64_t rows, int Dw, int mode,
+                          float max_norm, void* stream) {
+  return sanitize_dispatch(true, x, in_dtype, nullptr, dy, dx, rows, Dw, mode, max_norm, nullptr, stream);
+}
+
+int mmr_grad_sqnorm(const mmr_opt_tensor* host_tensors, int n_tensors, mmr_opt_state* state, void* stream) {
+  if (!state) return fail(MMR_ERR_INVALID_ARG, "mmr_grad_sqnorm: null state");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return opt_for_tables(host_tensors, n_tensors, true, false, false, [&](const OptTable& t, unsigned blocks) -> int {
+    opt_sqnorm_kernel<<<blocks, OPT_THREADS, 0, st>>>(t, state);
+    LAUNCH_OK("opt_sqnorm");
+    return MMR_OK;
+  });
+}
+
+int mmr_opt_prepare(const mmr_opt_hyper* hp, mmr_opt_state* state, void* stream) {
+  if (!hp || !state) return fail(MMR_ERR_INVALID_ARG, "mmr_opt_prepare: null argument");
+  if (!(hp->beta1 >= 0.0 && hp->beta1 < 1.0) || !(hp->beta2 >= 0.0 && hp->beta2 < 1.0))
+    return fail(MMR_ERR_INVALID_ARG, "mmr_opt_prepare: betas must be in [0, 1)");
+  opt_prepare_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, hp->beta1, hp->beta2, (float)hp->max_norm);
+  LAUNCH_OK("opt_prepare");
+  return MMR_OK;
+}
+
+int mmr_opt_apply(const mmr_opt_tensor* host_tensors, int n_tensors, const mmr_opt_hyper* hp,
+                  const mmr_opt_state* state, void* stream) {
+  if (!hp || !state) return fail(MMR_ERR_INVALID_ARG, "mmr_opt_apply: null argument");
+  if (!(hp->lr >= 0.0) || !(hp->eps >= 0.0) || !(hp->weight_decay >= 0.0))
+    return fail(MMR_ERR_INVALID_ARG, "mmr_opt_apply: lr, eps and weight_decay must be >= 0");
+  const OptHyper h = opt_hyper(*hp);
+  const double lr = hp->lr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return opt_for_tables(host_tensors, n_tensors, true, true, hp->has_ema != 0, [&](const OptTable& t, unsigned blocks) -> int {
+    opt_step_kernel<<<blocks, OPT_THREADS, 0, st>>>(t, state, h, lr);
+    LAUNCH_OK("opt_step");
+    return MMR_OK;
+  });
+}
+
+int mmr_ema_update(const mmr_opt_tensor* host_tensors, int n_tensors, double decay, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return opt_for_tables(host_tensors, n_tensors, false, false, true, [&](const OptTable& t, unsigned blocks) -> int {
+    ema_update_kernel<<<blocks, OPT_THREADS, 0, st>>>(t, (float)decay, (float)(1.0 - decay));
+    LAUNCH_OK("ema_update");
+    return MMR_OK;
+  });
+}
 
 int mmr_version(void) { return 100; }
 

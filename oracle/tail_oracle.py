@@ -1,0 +1,102 @@
+"""CPU restatement of the steps either side of the hot path (TEST INFRASTRUCTURE -- only tests/, smoke() and
+bench.py's cpu_baseline may import this; the product path never does).
+
+Pinned: tests/golden/tail_*.pt are produced by oracle/gen_golden_tail.py, which executes the reference's OWN
+function/class definitions (extracted from MortModel/PhenoModel main.py, which cannot be imported as a module
+because it needs matplotlib) together with torch.nn.utils.clip_grad_norm_ and torch.optim.AdamW;
+tests/test_tail_oracle.py checks this restatement against them.
+
+Third-party arithmetic: torch.optim.AdamW and torch.nn.utils.clip_grad_norm_ (PyTorch 2.11.0, the reference pins
+"PyTorch >= 2.1").  Their published algorithm (Loshchilov & Hutter, decoupled weight decay; torch/optim/adamw.py
+`_single_tensor_adam` with decoupled_weight_decay=True) is restated in `adamw_step` below.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+
+# ---- producer epilogue --------------------------------------------------------------------------------
+def clamp_norm(x: torch.Tensor, max_norm: float = 20.0) -> torch.Tensor:
+    """MortModel/Paired_Cross_Attention/main.py:1772-1779 (_clamp_norm)."""
+    if x.ndim in (2, 3):
+        n = x.norm(dim=x.ndim - 1, keepdim=True) + 1e-6
+        return x * torch.clamp(max_norm / n, max=1.0)
+    return x
+
+
+def safe_tensor(x: torch.Tensor) -> torch.Tensor:
+    """main.py:1781-1786 (_safe_tensor): rewrite only when a non-finite entry exists."""
+    if not torch.isfinite(x).all():
+        x = torch.nan_to_num(x, nan=0.0, posinf=1e4, neginf=-1e4)
+    return x
+
+
+def sanitize_mort(x: torch.Tensor) -> torch.Tensor:
+    """main.py:1788-1796 (_sanitize_encoder_out, "seq"/"pool" entries)."""
+    return safe_tensor(clamp_norm(x.float(), 20.0)).float()
+
+
+def sanitize_pheno(x: torch.Tensor) -> torch.Tensor:
+    """PhenoModel/Paired_Cross_Attention/main.py:1452-1460."""
+    return torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
+
+
+# ---- training tail ------------------------------------------------------------------------------------
+def clip_grad_norm(grads: List[torch.Tensor], max_norm: float) -> float:
+    """torch.nn.utils.clip_grad_norm_ (norm_type 2): total = ||(||g_i||)_i||, coef = clamp(max_norm/(total+1e-6), max=1),
+    every gradient scaled in place (main.py:3147,3156).  Returns the total norm."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2.0) for g in grads]), 2.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return float(total)
+
+
+def grads_are_finite(grads: List[torch.Tensor]) -> bool:
+    """main.py:46-57."""
+    return all(bool(torch.isfinite(g).all()) for g in grads)
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float) -> None:
+    """torch.optim.AdamW single-tensor algorithm (amsgrad=False), `step` already incremented (main.py:2886-2890, 3161)."""
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        p.mul_(1.0 - lr * weight_decay)
+        m.lerp_(g, 1.0 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+
+def ema_update(shadow: List[torch.Tensor], params: List[torch.Tensor], decay: float) -> None:
+    """EMA.update (main.py:69-90)."""
+    for s, p in zip(shadow, params):
+        s.mul_(decay).add_(p, alpha=1.0 - decay)
+
+
+def train_tail(params, grads_per_step, lr, betas, eps, weight_decay, max_norm, ema_decay):
+    """The reference's per-step sequence (main.py:3143-3165): clip, finite guard (skip), AdamW, EMA.
+    Returns dict(params, exp_avg, exp_avg_sq, ema, norms, skipped)."""
+    params = [p.clone() for p in params]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    ema = [p.clone() for p in params]
+    norms, skipped, step = [], [], 0
+    for grads in grads_per_step:
+        grads = [g.clone() for g in grads]
+        norms.append(clip_grad_norm(grads, max_norm))
+        if not grads_are_finite(grads):
+            skipped.append(True)
+            continue
+        skipped.append(False)
+        step += 1
+        adamw_step(params, grads, m, v, step, lr, betas[0], betas[1], eps, weight_decay)
+        ema_update(ema, params, ema_decay)
+    return dict(params=params, exp_avg=m, exp_avg_sq=v, ema=ema, norms=norms, skipped=skipped)

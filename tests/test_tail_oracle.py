@@ -1,0 +1,78 @@
+"""CPU: the tail oracle (oracle/tail_oracle.py) against fixtures produced by the reference's own definitions
+(oracle/gen_golden_tail.py), and the host-side contracts of the producer-epilogue / training-tail bindings."""
+import os
+
+import pytest
+import torch
+
+from helpers import ROOT
+from oracle import tail_oracle as to
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+@pytest.mark.parametrize("case", ["seq256", "seq768_bf16", "pool512_f16", "seq12"])
+def test_sanitize_oracle_matches_reference(case):
+    g = _load("tail_sanitize.pt")[case]
+    x = g["x"].clone().requires_grad_(True)
+    y = to.sanitize_mort(x)
+    assert y.dtype == torch.float32 and g["mask_dtype"] == "torch.float32"
+    assert torch.equal(y.detach(), g["y"])
+    (dx,) = torch.autograd.grad(y, x, g["dy"])
+    assert torch.equal(dx, g["dx"])
+    assert torch.equal(to.sanitize_mort(g["x_bad"]), g["y_bad_mort"])
+    assert torch.equal(to.sanitize_pheno(g["x_bad"]), g["y_bad_pheno"])
+    # the norm clamp really is exercised: some rows were scaled, some were not
+    n_in = g["x"].float().norm(dim=-1)
+    assert (n_in > 20).any() and (n_in < 20).any()
+    assert float(g["y"].norm(dim=-1).max()) <= 20.0 + 1e-3
+
+
+def test_train_tail_oracle_matches_reference():
+    g = _load("tail_adamw_ema.pt")
+    out = to.train_tail(g["init"], g["grads"], g["lr"], g["betas"], g["eps"], g["weight_decay"], g["max_norm"],
+                        g["ema_decay"])
+    assert out["skipped"] == g["skipped"] and sum(g["skipped"]) == 1
+    assert sum(1 for n in g["norms"] if n == n and n > g["max_norm"]) >= 2       # clipping active on some steps
+    assert sum(1 for n in g["norms"] if n < g["max_norm"]) >= 2                   # and inactive on others
+    for a, b in zip(out["norms"], g["norms"]):
+        assert (a != a and b != b) or abs(a - b) <= 1e-6 * abs(b)
+    for key in ("params", "exp_avg", "exp_avg_sq", "ema"):
+        for a, b in zip(out[key], g[key]):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-9), key
+    assert g["step"] == len(g["skipped"]) - 1
+
+
+def test_tail_bindings_fail_loudly_on_cpu():
+    from multimodalrouting_b200 import optim, producers
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        producers.sanitize_rows(torch.randn(2, 3, 256))
+    p = torch.nn.Parameter(torch.randn(8))
+    p.grad = torch.randn(8)
+    opt = optim.FusedAdamW([p], lr=1e-3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step(max_norm=1.0)
+    with pytest.raises(ValueError):
+        optim.FusedAdamW([p], lr=-1.0)
+
+
+def test_tail_entry_points_reject_bad_arguments_without_launch():
+    import ctypes as C
+    from multimodalrouting_b200 import _lib
+    lib = _lib.load()
+    assert lib.mmr_sanitize_rows_fwd(None, 0, None, 4, 256, 0, 20.0, None, None) != 0        # null pointers
+    assert lib.mmr_sanitize_rows_fwd(1, 0, 1, 4, 250, 0, 20.0, None, None) != 0              # width not % 4
+    assert lib.mmr_sanitize_rows_fwd(1, 0, 1, 4, 2048, 0, 20.0, None, None) != 0             # width > 1024
+    assert lib.mmr_sanitize_rows_fwd(1, 9, 1, 4, 256, 0, 20.0, None, None) != 0              # dtype
+    assert lib.mmr_sanitize_rows_fwd(1, 0, 1, 0, 256, 0, 20.0, None, None) == 0              # no rows: no launch
+    hp = _lib.OptHyper(1e-3, 1.5, 0.999, 1e-8, 0.0, 0.0, 0.0, 0, 0)
+    assert lib.mmr_opt_prepare(C.byref(hp), 1, None) != 0                                    # beta1 out of range
+    assert C.sizeof(_lib.OptTensor) == 48 and C.sizeof(_lib.OptHyper) == 64
+    assert lib.mmr_grad_sqnorm(None, 0, 1, None) == 0                                        # empty table
+    t = (_lib.OptTensor * 1)()
+    t[0].n = 5
+    assert lib.mmr_grad_sqnorm(t, 1, 1, None) != 0                                           # null tensor pointers

@@ -212,6 +212,18 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _teardown(dist, reducer):
+    """Leaves the process group.  With collectives captured inside a CUDA graph the communicator cannot be
+    destroyed while the graph is alive (destroy_process_group then waits forever), so that configuration skips the
+    explicit destroy: the work is complete and synchronised, the process simply exits."""
+    torch.cuda.synchronize()
+    if reducer is not None:
+        reducer.close()
+        sys.stderr.flush()
+        os._exit(0)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,8 +233,10 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patients per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N>1: all-reduce the gradients after the backward instead of overlapping it, layer by layer")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N>1: all-reduce the gradients layer block by layer block on a side stream during the backward "
+                         "(captured into the step graph) instead of after it; measured equal at N=2 (5.91 vs 5.89 ms), "
+                         "so the simpler after-the-backward reduction is the default")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,12 +283,11 @@ def main():
         loss.backward()
         return loss
 
-    # N>1: the gradient all-reduce is part of the step.  By default it is OVERLAPPED with the backward: the library
-    # records an event when the gradients of a layer are final and the reducer all-reduces that block on a side
-    # stream (NCCL over NVLink) while the earlier layers are still being differentiated; the tail of the buffer is
-    # reduced after the backward.  The collectives are captured into the same CUDA graph as the kernels.
+    # N>1: the gradient all-reduce is part of the step: a handful of NCCL AVG all-reduces over the flat gradient
+    # buffers right after the (graph-replayed) backward.  --overlap instead reduces each layer's block on a side
+    # stream as soon as the library signals that it is final (collectives captured into the same CUDA graph).
     reducer = None
-    if world > 1 and not args.no_overlap:
+    if world > 1 and args.overlap:
         reducer = OverlappedGradReducer(mult, (proj, head), LAYERS)
 
     def train_step():
@@ -402,7 +415,7 @@ def main():
         dist.barrier()
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _teardown(dist, reducer)
         return
     tf_peak, hbm_peak, src = peaks()
     fl_tn, fl_wg = gemm_flops_per_step(B)
@@ -440,7 +453,7 @@ def main():
             "kernel_time_ms_per_step": prof}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist, reducer)
 
 
 if __name__ == "__main__":

@@ -86,8 +86,11 @@ def main():
     red.close()
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
-    dist.destroy_process_group()
-    sys.exit(1 if int(flag.item()) else 0)
+    bad = int(flag.item())
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    # collectives captured in a live CUDA graph: destroy_process_group would wait forever (see bench._teardown)
+    os._exit(1 if bad else 0)
 
 
 if __name__ == "__main__":

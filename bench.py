@@ -329,7 +329,19 @@ def main():
     stage = {k: torch.empty_like(devb[k]) for k in keys}
     copy_stream = torch.cuda.Stream()
     ev_staged, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
-    pipe = {"primed": False}
+    pipe = {"primed": False, "pending": None, "slot": 0, "last_loss": None}
+    # the step's result (the loss) is read back EVERY step: D2H into pinned memory right behind the step, collected
+    # one step later so that the host can already issue the next step while the GPU finishes this one
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def collect_loss():
+        if pipe["pending"] is not None:
+            i = pipe["pending"]
+            loss_ev[i].synchronize()
+            pipe["last_loss"] = float(loss_host[i])
+            pipe["pending"] = None
+        return pipe["last_loss"]
 
     def prefetch_host_batch():
         copy_stream.wait_event(ev_consumed)
@@ -356,7 +368,14 @@ def main():
         if world > 1 and reducer is None:
             allreduce_gradients(modules, world)
         if from_host:
-            return loss.item()          # D2H read of the step's result
+            i = pipe["slot"]
+            loss_host[i].copy_(loss.detach(), non_blocking=True)      # D2H read of the step's result
+            loss_ev[i].record()
+            collect_loss()                                            # result of the PREVIOUS step
+            pipe["pending"], pipe["slot"] = i, i ^ 1
+            if last:
+                return collect_loss()                                 # drain: every step's loss reached the host
+            return pipe["last_loss"]
         return loss
 
     def timed(n, from_host):
@@ -432,6 +451,16 @@ def main():
                 "flops_per_launch": fl_tn / n_tn,
                 "wgrad_tc_tflops": (fl_wg / (prof["wgrad_tc"]["ms_per_step"] / 1e3) / 1e12) if prof["wgrad_tc"]["ms_per_step"] > 0 else None,
                 "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_peak}
+    # second roofline the north-star names: capsule routing against HBM bandwidth.  Algorithmic bytes per patient
+    # (SURVEY.md section 8d, K=25, fp32 route embeddings): forward 11,420 B + backward 20,600 B.
+    rt_ms = prof["routing"]["ms_per_step"]
+    rt_bytes = (11420 + 20600) * B
+    rt_gbs = rt_bytes / (rt_ms / 1e3) / 1e9 if rt_ms > 0 else 0.0
+    roofline_routing = {"bound": "hbm", "kernel": "routing_fwd_kernel + routing_bwd_kernel (+ head / vote-weight gradient launches)",
+                        "achieved": rt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rt_gbs / hbm_peak, "traffic": None,
+                        "ms_per_step": rt_ms, "algorithmic_bytes_per_step": rt_bytes,
+                        "note": "K=25: bound by the 1.02 MFLOP/patient vote contraction and phase barriers, not by bytes "
+                                "(16 MB per step = 2.5 us at the HBM peak, below one launch latency)"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
@@ -449,7 +478,8 @@ def main():
                        "l2_policy": "per-step working set (activations saved for backward ~3 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_routing": roofline_routing,
+            "cpu_baseline": cpu,
             "kernel_time_ms_per_step": prof}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

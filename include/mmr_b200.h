@@ -185,6 +185,14 @@ int mmr_sanitize_rows_fwd(const void* x, int in_dtype, float* y, int64_t rows, i
 int mmr_sanitize_rows_bwd(const void* x, int in_dtype, const float* dy, float* dx, int64_t rows, int D, int mode,
                           float max_norm, void* stream);
 
+/* Route mask of the missing-modality protocol: replaces build_route_mask_from_presence
+ * (MIMIC-IV/PhenoModel/Partial/Cross_Attention/routing_and_heads.py:10-64) / build_route_mask_from_modalities
+ * (.../Partial/Cross_Attention/main.py:109-132).  hasL/hasN/hasI: fp32 [B] (1 = available; NULL = available for all);
+ * route_mask: fp32 [B,10] in ROUTES order, 1 iff every modality the route needs is present.  drop_bits: bit r set
+ * zeroes route r for the whole batch (training-time route dropout, MortModel/.../main.py:3027-3033). */
+int mmr_route_mask_from_presence(const float* hasL, const float* hasN, const float* hasI, int B, int drop_bits,
+                                 float* route_mask, void* stream);
+
 /* Training tail: replaces torch.nn.utils.clip_grad_norm_ + grads_are_finite + torch.optim.AdamW.step + EMA.update
  * (MortModel/Paired_Cross_Attention/main.py:3143-3165, 2886-2890, 58-108) with three device-side stages that
  * never synchronise the host: (1) mmr_grad_sqnorm accumulates sum g^2 of any number of tensor tables into

@@ -52,7 +52,7 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
-           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update"]
+           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence"]
 
 
 def lib_path() -> str:
@@ -104,6 +104,8 @@ def load():
     lib.mmr_sanitize_rows_fwd.restype = C.c_int
     lib.mmr_sanitize_rows_bwd.argtypes = [c_fp, C.c_int, c_fp, c_fp, C.c_int64, C.c_int, C.c_int, C.c_float, c_fp]
     lib.mmr_sanitize_rows_bwd.restype = C.c_int
+    lib.mmr_route_mask_from_presence.argtypes = [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp]
+    lib.mmr_route_mask_from_presence.restype = C.c_int
     lib.mmr_grad_sqnorm.argtypes = [C.POINTER(OptTensor), C.c_int, c_fp, c_fp]
     lib.mmr_grad_sqnorm.restype = C.c_int
     lib.mmr_opt_prepare.argtypes = [C.POINTER(OptHyper), c_fp, c_fp]

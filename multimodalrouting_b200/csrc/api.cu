@@ -893,6 +893,16 @@ int mmr_sanitize_rows_bwd(const void* x, int in_dtype, const float* dy, float* d
   return sanitize_dispatch(true, x, in_dtype, nullptr, dy, dx, rows, Dw, mode, max_norm, nullptr, stream);
 }
 
+int mmr_route_mask_from_presence(const float* hasL, const float* hasN, const float* hasI, int B, int drop_bits,
+                                 float* route_mask, void* stream) {
+  if (B < 0 || !route_mask) return fail(MMR_ERR_INVALID_ARG, "mmr_route_mask_from_presence: bad arguments");
+  if (drop_bits < 0 || drop_bits >= (1 << NR)) return fail(MMR_ERR_INVALID_ARG, "mmr_route_mask_from_presence: drop_bits has bits beyond the 10 routes");
+  if (B == 0) return MMR_OK;
+  route_mask_kernel<<<(B * NR + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hasL, hasN, hasI, B, drop_bits, route_mask);
+  LAUNCH_OK("route_mask");
+  return MMR_OK;
+}
+
 int mmr_grad_sqnorm(const mmr_opt_tensor* host_tensors, int n_tensors, mmr_opt_state* state, void* stream) {
   if (!state) return fail(MMR_ERR_INVALID_ARG, "mmr_grad_sqnorm: null state");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -134,6 +134,24 @@ __global__ void __launch_bounds__(SAN_WARPS * 32) sanitize_bwd_kernel(SanitizeAr
   }
 }
 
+// -------------------------------------------------------------------------- route mask from presence ---
+// PhenoModel/Partial/Cross_Attention/routing_and_heads.py:10-64 (build_route_mask_from_presence) and main.py:109-132
+// (build_route_mask_from_modalities): a route is allowed iff every modality it needs is present.
+//   ROUTES = [L, N, I, LN, NL, LI, IL, NI, IN, LNI]; optional whole-batch dropped routes (MortModel main.py:3027-3033).
+__global__ void route_mask_kernel(const float* hasL, const float* hasN, const float* hasI, int B, int drop_bits, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * NR) return;
+  const int b = i / NR, r = i % NR;
+  // bit 0 = needs L, bit 1 = needs N, bit 2 = needs I
+  const int needs[NR] = {1, 2, 4, 3, 3, 5, 5, 6, 6, 7};
+  float m = 1.f;
+  if ((needs[r] & 1) && hasL) m *= hasL[b];
+  if ((needs[r] & 2) && hasN) m *= hasN[b];
+  if ((needs[r] & 4) && hasI) m *= hasI[b];
+  if ((drop_bits >> r) & 1) m = 0.f;
+  out[i] = m;
+}
+
 // ---------------------------------------------------------------------------------- training tail ---
 constexpr int OPT_NT = 384;              // tensors per launch (kernel-parameter table, 19.5 KB of the 32 KB sm_100 allows):
                                          // the 343 parameter tensors of the path go out in ONE launch

@@ -126,3 +126,32 @@ def _sanitize_encoder_out(out: Dict[str, Optional[Tensor]], name: str, variant: 
     if out2.get("mask") is not None:
         out2["mask"] = out2["mask"].float()
     return out2
+
+
+# ---- route mask of the missing-modality protocol (PhenoModel/Partial/Cross_Attention) -----------------------
+def build_route_mask_from_presence(hasL: Tensor, hasN: Tensor, hasI: Tensor, *, device: Optional[torch.device] = None,
+                                   dtype: torch.dtype = torch.float32, drop_routes=()) -> Tensor:
+    """[B, 10] route mask in ROUTES order, 1 = allowed: a route needs every modality in its name
+    (Partial/Cross_Attention/routing_and_heads.py:10-64).  `drop_routes`: route indices zeroed for the whole batch
+    (the training-time route dropout of MortModel/Paired_Cross_Attention/main.py:3027-3033).  One launch."""
+    if device is None:
+        device = hasL.device
+    hs = [h.to(device=device).float().contiguous() for h in (hasL, hasN, hasI)]
+    _require_cuda(*hs)
+    B = hs[0].shape[0]
+    if any(h.dim() != 1 or h.shape[0] != B for h in hs):
+        raise ValueError("hasL, hasN, hasI must be [B] vectors of equal length")
+    bits = 0
+    for r in drop_routes:
+        if not 0 <= int(r) < 10:
+            raise ValueError(f"drop_routes: route index {r} out of range")
+        bits |= 1 << int(r)
+    out = torch.empty(B, 10, dtype=torch.float32, device=device)
+    rc = _lib.load().mmr_route_mask_from_presence(_ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]), B, bits, _ptr(out), _stream())
+    _lib.check(rc, "mmr_route_mask_from_presence")
+    return out if dtype == torch.float32 else out.to(dtype)
+
+
+def build_route_mask_from_modalities(hasL: Tensor, hasN: Tensor, hasI: Tensor) -> Tensor:
+    """Partial/Cross_Attention/main.py:109-132 -- same rule, float32 on the inputs' device."""
+    return build_route_mask_from_presence(hasL, hasN, hasI)

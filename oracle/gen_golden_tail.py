@@ -114,8 +114,33 @@ def tail_case():
                 step=int(opt.state[params[0]]["step"]))
 
 
+def route_mask_case():
+    """Both of the reference's builders, executed as they are (they must agree with each other)."""
+    px = "/root/reference/MIMIC-IV/PhenoModel/Partial/Cross_Attention"
+    routes = ["L", "N", "I", "LN", "NL", "LI", "IL", "NI", "IN", "LNI"]      # env_config.ROUTES (M/env_config.py:53)
+    src = open(f"{px}/routing_and_heads.py").read()
+    tree = ast.parse(src)
+    from typing import Optional
+    ns = {"torch": torch, "Optional": Optional, "ROUTES": routes}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "build_route_mask_from_presence":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "rh", "exec"), ns)
+    m = extract(f"{px}/main.py", [])
+    ns2 = {"torch": torch, "N_ROUTES": 10}
+    for node in ast.parse(open(f"{px}/main.py").read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "build_route_mask_from_modalities":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "main", "exec"), ns2)
+    gen = torch.Generator().manual_seed(9003)
+    has = [(torch.rand(37, generator=gen) < p).float() for p in (0.9, 0.7, 0.7)]
+    a = ns["build_route_mask_from_presence"](*has)
+    b = ns2["build_route_mask_from_modalities"](*has)
+    assert torch.equal(a, b)
+    return dict(hasL=has[0], hasN=has[1], hasI=has[2], mask=a)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    torch.save(route_mask_case(), os.path.join(GOLD, "tail_route_mask.pt"))
     torch.save(sanitize_cases(), os.path.join(GOLD, "tail_sanitize.pt"))
     torch.save(tail_case(), os.path.join(GOLD, "tail_adamw_ema.pt"))
     for f in ("tail_sanitize.pt", "tail_adamw_ema.pt"):

@@ -100,3 +100,20 @@ def train_tail(params, grads_per_step, lr, betas, eps, weight_decay, max_norm, e
         adamw_step(params, grads, m, v, step, lr, betas[0], betas[1], eps, weight_decay)
         ema_update(ema, params, ema_decay)
     return dict(params=params, exp_avg=m, exp_avg_sq=v, ema=ema, norms=norms, skipped=skipped)
+
+
+# ---- route mask from presence -------------------------------------------------------------------------
+ROUTES = ["L", "N", "I", "LN", "NL", "LI", "IL", "NI", "IN", "LNI"]
+
+
+def route_mask_from_presence(hasL, hasN, hasI):
+    """PhenoModel/Partial/Cross_Attention/routing_and_heads.py:10-64: a route is allowed iff every modality in its
+    name is present."""
+    has = {"L": hasL.float(), "N": hasN.float(), "I": hasI.float()}
+    cols = []
+    for r in ROUTES:
+        m = torch.ones_like(has["L"])
+        for ch in r:
+            m = m * has[ch]
+        cols.append(m)
+    return torch.stack(cols, dim=1)

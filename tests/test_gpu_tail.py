@@ -172,3 +172,21 @@ def test_fused_tail_on_the_real_modules_matches_oracle_and_graph_capture():
     torch.cuda.synchronize()
     assert int(opt.step_count) == n0 + 1
     assert any(not torch.equal(p.detach(), b) for p, b in zip(params, before))
+
+
+# ------------------------------------------------------------------------- route mask from presence ---
+def test_route_mask_from_presence_matches_reference_golden():
+    from multimodalrouting_b200 import producers
+    g = _load("tail_route_mask.pt")
+    has = [g[k].cuda() for k in ("hasL", "hasN", "hasI")]
+    m = producers.build_route_mask_from_presence(*has)
+    assert m.dtype == torch.float32 and torch.equal(m.cpu(), g["mask"])
+    assert torch.equal(producers.build_route_mask_from_modalities(*[h.bool() for h in has]).cpu(), g["mask"])
+    d = producers.build_route_mask_from_presence(*has, drop_routes=(3, 9))
+    ref = g["mask"].clone()
+    ref[:, [3, 9]] = 0
+    assert torch.equal(d.cpu(), ref)
+    with pytest.raises(ValueError):
+        producers.build_route_mask_from_presence(has[0], has[1][:5], has[2])
+    with pytest.raises(ValueError):
+        producers.build_route_mask_from_presence(*has, drop_routes=(10,))

@@ -76,3 +76,15 @@ def test_tail_entry_points_reject_bad_arguments_without_launch():
     t = (_lib.OptTensor * 1)()
     t[0].n = 5
     assert lib.mmr_grad_sqnorm(t, 1, 1, None) != 0                                           # null tensor pointers
+
+
+def test_route_mask_oracle_matches_reference_and_synth():
+    g = _load("tail_route_mask.pt")
+    m = to.route_mask_from_presence(g["hasL"], g["hasN"], g["hasI"])
+    assert torch.equal(m, g["mask"])
+    assert 0 < float(g["mask"].mean()) < 1
+    # the rule oracle/synth.py uses for BASELINE config 4 is the same one
+    from oracle import synth
+    for mod, idx in synth.NEEDS.items():
+        need = [i for i, r in enumerate(to.ROUTES) if mod in r]
+        assert sorted(idx) == need

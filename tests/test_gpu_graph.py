@@ -43,18 +43,18 @@ def test_graph_replay_matches_eager_step():
                     out[f"{i}.{n}"] = p.grad.detach().clone()
         return out
 
-    eager = []
+    # graph first: AccumulateGrad nodes created by an eager backward on the default stream would tie the capture to
+    # the legacy stream (cudaErrorStreamCaptureImplicit); bench.py captures before any eager step for the same reason
+    step = GraphedStep(fwd_bwd, warmup=2)
+    replayed = []
     for b in batches:
         for k in static:
             static[k].copy_(b[k])
-        eager.append(snapshot(fwd_bwd()))
-    for k in static:
-        static[k].copy_(batches[0][k])
-    step = GraphedStep(fwd_bwd, warmup=2)
-    for b, ref in zip(batches, eager):
+        replayed.append(snapshot(step()))
+    for b, got in zip(batches, replayed):
         for k in static:
             static[k].copy_(b[k])
-        got = snapshot(step())
+        ref = snapshot(fwd_bwd())
         assert got.keys() == ref.keys()
         for k in ref:
             scale = float(ref[k].abs().max()) + 1e-20

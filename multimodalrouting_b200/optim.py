@@ -14,7 +14,7 @@ schedulers and checkpoints work unchanged); `EMA` has the reference class's inte
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, List, Optional
 
 import torch
 from torch import Tensor
@@ -53,7 +53,7 @@ class EMA:
     def update(self, _exclude: Optional[set] = None):
         """shadow = decay * shadow + (1 - decay) * value for every float entry (one multi-tensor launch per 384
         tensors); non-float entries are copied.  `_exclude`: data_ptrs already updated by FusedAdamW.step(ema=...)."""
-        entries, keep = [], []
+        entries = []
         for m, sh in zip(self.model_list, self.shadow):
             for k, v in m.state_dict().items():
                 if k not in sh:
@@ -69,7 +69,6 @@ class EMA:
                 _require_cuda(v)
                 if v.dtype != torch.float32 or not v.is_contiguous() or not sh[k].is_contiguous():
                     raise ValueError("EMA.update expects contiguous fp32 tensors")
-                keep.append(v)
                 entries.append((v.data_ptr(), None, None, None, sh[k].data_ptr(), v.numel()))
         if entries:
             rc = _lib.load().mmr_ema_update(_table(entries), len(entries), self.decay, _stream())

@@ -264,10 +264,26 @@ def main():
     B = args.batch
     inp = synth.make_inputs(B=B, K=K_LABELS, seed=43 + rank)
     keys = ("x_l", "x_n", "x_i", "mL", "mN", "mI", "route_mask", "y")
-    host = {k: inp[k].contiguous().pin_memory() for k in keys}
-    devb = {k: torch.empty_like(host[k], device=dev) for k in keys}
+    # The batch travels as ONE contiguous arena (256-byte aligned slots): one pinned host buffer, one device staging
+    # buffer, one set of static device inputs -- so a step's H2D copy and its move into the static inputs are one
+    # copy each instead of eight (the eight small device-to-device copies cost 0.15 ms per step, measured).
+    def arena(device=None, pin=False):
+        offs, o = {}, 0
+        for k in keys:
+            offs[k] = o
+            o += (inp[k].numel() * inp[k].element_size() + 255) // 256 * 256
+        buf = torch.empty(o, dtype=torch.uint8, device=device)
+        if pin:
+            buf = buf.pin_memory()
+        views = {k: buf[offs[k]:offs[k] + inp[k].numel() * inp[k].element_size()].view(inp[k].dtype).view(inp[k].shape)
+                 for k in keys}
+        return buf, views
+
+    host_buf, host = arena(pin=True)
     for k in keys:
-        devb[k].copy_(host[k])
+        host[k].copy_(inp[k])
+    dev_buf, devb = arena(device=dev)
+    dev_buf.copy_(host_buf)
     adapter = rh.RouteDimAdapter(256, 256, 256, 256)
     lossf = torch.nn.BCEWithLogitsLoss()
 
@@ -326,7 +342,8 @@ def main():
     # side stream while the current step computes; at the start of a step the staged batch is moved into the
     # static input tensors (device-to-device).  Every step still pays for its own H2D copy inside the timed
     # region -- it is just overlapped, as a prefetching data loader would do.
-    stage = {k: torch.empty_like(devb[k]) for k in keys}
+    stage_buf, stage = arena(device=dev)
+    stage_i32, dev_i32 = stage_buf.view(torch.int32), dev_buf.view(torch.int32)
     copy_stream = torch.cuda.Stream()
     ev_staged, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
     pipe = {"primed": False, "pending": None, "slot": 0, "last_loss": None}
@@ -346,20 +363,23 @@ def main():
     def prefetch_host_batch():
         copy_stream.wait_event(ev_consumed)
         with torch.cuda.stream(copy_stream):
-            for k in keys:
-                stage[k].copy_(host[k], non_blocking=True)
+            stage_buf.copy_(host_buf, non_blocking=True)
             ev_staged.record(copy_stream)
         pipe["primed"] = True
 
+    parts = set(os.environ.get("MMR_E2E_PARTS", "h2d,d2d,loss").split(","))   # diagnostic: drop parts of the e2e path
+
     def step(from_host: bool, last: bool = False):
-        if from_host:
+        if from_host and "h2d" in parts:
             cur = torch.cuda.current_stream()
             if not pipe["primed"]:
                 ev_consumed.record(cur)
                 prefetch_host_batch()
             cur.wait_event(ev_staged)
-            for k in keys:
-                devb[k].copy_(stage[k], non_blocking=True)
+            if "d2d" in parts:
+                # SM copy kernel (one pass at HBM speed, ~20 us for 60 MB); cudaMemcpyAsync D2D runs on a copy engine
+                # at ~1.2 TB/s and cost 0.1 ms per step here
+                torch.bitwise_or(stage_i32, 0, out=dev_i32)
             ev_consumed.record(cur)
             pipe["primed"] = False
             if not last:
@@ -367,6 +387,8 @@ def main():
         loss = graphed() if graphed is not None else train_step()
         if world > 1 and reducer is None:
             allreduce_gradients(modules, world)
+        if from_host and "loss" not in parts:
+            return loss
         if from_host:
             i = pipe["slot"]
             loss_host[i].copy_(loss.detach(), non_blocking=True)      # D2H read of the step's result
@@ -412,7 +434,7 @@ def main():
         step(True, last=True)
     ms_e2e = timed(args.steps, True)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
-    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    h2d = host_buf.numel()
 
     # per-class device time of OUR kernels (CUDA events on the launching stream), separate pass
     prof = None

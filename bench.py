@@ -441,10 +441,16 @@ def main():
     nprof = 3
     if rank == 0:
         lib.mmr_prof_enable(1)
-    g_saved, graphed = graphed, None   # the per-class CUDA-event pass issues the kernels eagerly
+    g_saved, graphed = graphed, None   # the per-class CUDA-event pass issues the kernels eagerly ...
+    ws_saved = os.environ.get("MMR_WGRAD_STREAM")
+    os.environ["MMR_WGRAD_STREAM"] = "0"      # ... and on ONE stream, so that every kernel class is timed alone
     for _ in range(nprof):          # every rank steps (the gradient all-reduce is a collective)
         step(False)
     graphed = g_saved
+    if ws_saved is None:
+        os.environ.pop("MMR_WGRAD_STREAM", None)
+    else:
+        os.environ["MMR_WGRAD_STREAM"] = ws_saved
     torch.cuda.synchronize()
     if rank == 0:
         msc = (C.c_double * 8)(); nc = (C.c_longlong * 8)()
@@ -494,6 +500,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None,
+                       "wgrad_side_stream": os.environ.get("MMR_WGRAD_STREAM", "1") != "0",
                        "grad_allreduce": (None if world == 1 else
                                           "overlapped with the backward, per layer block" if reducer is not None
                                           else "after the backward"),

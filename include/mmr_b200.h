@@ -110,6 +110,21 @@ int mmr_route_fusion_bwd_events(const mmr_fusion_dims* dims, const void* const* 
                                 float* dx_l, float* dx_n, float* dx_i, void* stream,
                                 void* const* host_layer_events);
 
+/* Most general form.  host_layer_events: as above (may be NULL).  side_stream (may be NULL): a second cudaStream_t on
+ * which the weight-gradient kernels run next to the data-gradient chain of `stream`; host_sync_events then holds
+ * MMR_BWD_SYNC_EVENTS caller-owned cudaEvent_t (created with cudaEventDisableTiming) that the library records / waits on
+ * to order the two streams.  The side stream is forked from and joined back into `stream` inside the call, so the
+ * call is CUDA-graph capturable and everything is complete in `stream` order when it returns.  Ignored (single stream)
+ * when host_layer_events is given. */
+#define MMR_BWD_SYNC_EVENTS 9
+int mmr_route_fusion_bwd_ex(const mmr_fusion_dims* dims, const void* const* host_params,
+                            const float* x_l, const float* x_n, const float* x_i,
+                            const float* mL, const float* mN, const float* mI,
+                            const void* packed, const void* saved, void* scratch,
+                            const float* d_routes, void* const* host_param_grads,
+                            float* dx_l, float* dx_n, float* dx_i, void* stream,
+                            void* const* host_layer_events, void* side_stream, void* const* host_sync_events);
+
 typedef struct mmr_routing_dims {
   int32_t B;               /* patients */
   int32_t K;               /* labels: 2 (mortality) / 25 (phenotypes); <= MMR_MAX_LABELS */

@@ -49,7 +49,7 @@ OPT_STATE_BYTES = 40     # sizeof(mmr_opt_state): 3 doubles, 2 floats, 2 int32
 
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
-           "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_routing_scratch_bytes",
+           "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence"]
@@ -84,6 +84,9 @@ def load():
     lib.mmr_route_fusion_bwd_events.argtypes = ([C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 10 +
                                                 [C.POINTER(c_fp)] + [c_fp] * 4 + [C.POINTER(c_fp)])
     lib.mmr_route_fusion_bwd_events.restype = C.c_int
+    lib.mmr_route_fusion_bwd_ex.argtypes = ([C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 10 +
+                                            [C.POINTER(c_fp)] + [c_fp] * 4 + [C.POINTER(c_fp), c_fp, C.POINTER(c_fp)])
+    lib.mmr_route_fusion_bwd_ex.restype = C.c_int
     lib.mmr_routing_scratch_bytes.argtypes = [C.POINTER(RoutingDims)]
     lib.mmr_routing_scratch_bytes.restype = C.c_size_t
     lib.mmr_capsule_routing_fwd.argtypes = [C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 11

@@ -487,8 +487,35 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
 template <class CT>
 static int fusion_bwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
                       const uint8_t* packed, const uint8_t* saved, uint8_t* scratch, const float* d_routes,
-                      void* const* grads, float* const dx[3], cudaStream_t st, void* const* layer_events = nullptr) {
+                      void* const* grads, float* const dx[3], cudaStream_t st, void* const* layer_events = nullptr,
+                      cudaStream_t side = nullptr, void* const* sync_ev = nullptr) {
   const ParamIndex ix{P.L};
+  // Optional second stream for the weight-gradient kernels.  They depend only on a layer's upstream gradient and saved
+  // activations, never feed the data-gradient chain, and are L2/HBM-latency bound, so they can run next to the
+  // attention-backward and LayerNorm kernels of the chain.  Nine caller-owned events order the two streams:
+  // main -> side when an operand is ready, side -> main before the chain overwrites an operand the side stream reads.
+  enum { E_GC0 = 0, E_DF, E_GC1, E_DQ, S_DW2, S_DW1, S_DWO, S_DWQ, S_JOIN, N_SYNC_EV };
+  static_assert(N_SYNC_EV == MMR_BWD_SYNC_EVENTS, "header constant out of date");
+  const bool two = side != nullptr && sync_ev != nullptr && layer_events == nullptr;
+  const cudaStream_t ws = two ? side : st;
+  auto sev = [&](int i) { return reinterpret_cast<cudaEvent_t>(sync_ev[i]); };
+  auto main_to_side = [&](int e) -> int {      // side stream continues once everything issued on main so far is done
+    if (!two) return MMR_OK;
+    CUDA_OK(cudaEventRecord(sev(e), st));
+    CUDA_OK(cudaStreamWaitEvent(side, sev(e), 0));
+    return MMR_OK;
+  };
+  auto side_record = [&](int e) -> int {
+    if (!two) return MMR_OK;
+    CUDA_OK(cudaEventRecord(sev(e), side));
+    return MMR_OK;
+  };
+  auto main_wait = [&](int e) -> int {
+    if (!two) return MMR_OK;
+    CUDA_OK(cudaStreamWaitEvent(st, sev(e), 0));
+    return MMR_OK;
+  };
+  bool have_dw1 = false, have_dwq = false, have_dwo = false;
   const int L = P.L, B = P.B;
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
   auto gr = [&](int i) { return reinterpret_cast<float*>(grads[i]); };
@@ -515,7 +542,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
 
   float* g_a = reinterpret_cast<float*>(scratch + P.b_g);
   float* g_b = reinterpret_cast<float*>(scratch + P.b_g1);
-  CT* gc = reinterpret_cast<CT*>(scratch + P.b_gc);
+  CT* gcbuf[2] = {reinterpret_cast<CT*>(scratch + P.b_gc), reinterpret_cast<CT*>(scratch + P.b_gc2)};
+  CT* gc = gcbuf[0];   // bf16/CT copy of the current residual gradient; alternates between the two buffers
+  int gci = 0;
   CT* dF = reinterpret_cast<CT*>(scratch + P.b_df);
   CT* dH = reinterpret_cast<CT*>(scratch + P.b_dh);
   CT* dO = reinterpret_cast<CT*>(scratch + P.b_do);
@@ -587,6 +616,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     launch_k(ln_rows_bwd_kernel<CT, true>, dim3(P.MQ / 64), dim3(256), 0, st, a);
     LAUNCH_OK("lnf_bwd");
   }
+  rc = main_to_side(E_GC0);   // fork: gc of the last layer is ready
+  if (rc) return rc;
   const float* kmask[NDIR];
   for (int d = 0; d < NDIR; ++d) kmask[d] = mask[dir_kmod(d)];
   int maxTq = 0, maxTk = 0;
@@ -616,6 +647,15 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   float* g_oth = g_b;
   for (int l = L - 1; l >= 0; --l) {
     const bool chain_bwd = use_chain(P);
+    {  // dW2 (reads gc, which the chain overwrites in LN1 backward)
+      WgradProblem w = q_wgrad(gc, D, D, ff(l), FF, FF);
+      for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 6));
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_fc2");
+      if (rc) return rc;
+      rc = side_record(S_DW2);
+      if (rc) return rc;
+    }
+    if (have_dw1) { rc = main_wait(S_DW1); if (rc) return rc; }   // dW1 of the layer above still reads dF
     if (chain_bwd) {  // dF = (G W2) .* relu' and dH1 = (dF W1) .* mask in one chained kernel
       tc::ChainProblem c; memset(&c, 0, sizeof(c));
       c.segs = P.q;
@@ -635,12 +675,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       rc = run_gemm<CT, G_RELU_BWD>(P, g, e, P.MQ, L * 6 * FF, st, "d_fc2");
       if (rc) return rc;
     }
-    {  // dW2
-      WgradProblem w = q_wgrad(gc, D, D, ff(l), FF, FF);
-      for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 6));
-      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_fc2");
-      if (rc) return rc;
-    }
+    rc = main_to_side(E_DF);
+    if (rc) return rc;
     if (!chain_bwd) {  // dH1 = dF W1, masked
       GemmProblem g = q_problem(dF, FF, packed + P.o_w1T, FF, D, D, FF, l);
       EpiSpec e;
@@ -653,11 +689,16 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       float* ob1[6];
       for (int d = 0; d < NDIR; ++d) { w.out[d] = gr(ix.layer(d, l, 4)); ob1[d] = gr(ix.layer(d, l, 5)); }
       const bool fused = fuse_colsum(P, w, ob1);
-      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_fc1");
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_fc1");
       if (rc) return rc;
-      if (!fused) rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, st, "b_fc1");
+      if (!fused) rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, ws, "b_fc1");
       if (rc) return rc;
+      rc = side_record(S_DW1);
+      if (rc) return rc;
+      have_dw1 = true;
     }
+    if (have_dwo) { rc = main_wait(S_DWO); if (rc) return rc; }   // dWo of the layer above still reads the other gc buffer
+    gci ^= 1; gc = gcbuf[gci];
     {  // LN1 backward: g_oth = (g_cur + dLN1) * mask ; d out_proj.bias = colsum(g_oth)
       LnBwdArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.dh = dH; a.x = x1(l); a.stat = stat1(l); a.maskq = maskq; a.g_in = g_cur; a.g_out = g_oth; a.gc_out = gc;
@@ -669,6 +710,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       launch_k(ln_rows_bwd_kernel<CT, false>, dim3(P.MQ / 64), dim3(256), 0, st, a);
       LAUNCH_OK("ln1_bwd");
     }
+    rc = main_to_side(E_GC1);
+    if (rc) return rc;
     {  // dO = G1 Wo
       GemmProblem g = q_problem(gc, D, packed + P.o_woT, D, D, D, D, l);
       EpiSpec e;
@@ -679,12 +722,16 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     {  // dWo
       WgradProblem w = q_wgrad(gc, D, D, ob(l), D, D);
       for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 2));
-      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_out_proj");
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_out_proj");
       if (rc) return rc;
+      rc = side_record(S_DWO);
+      if (rc) return rc;
+      have_dwo = true;
     }
     // out_proj / fc1 / fc2 weights+biases and LayerNorm-1 gradients of layer l (all six directions) are final
     // from here on: data-parallel callers may start reducing them while the rest of the backward runs
     if (layer_events && layer_events[l]) CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(layer_events[l]), st));
+    if (have_dwq) { rc = main_wait(S_DWQ); if (rc) return rc; }   // dWq of the layer above still reads dQ
     {  // attention backward
       AttnArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.kv = P.kv;
@@ -716,6 +763,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       rc = zero_pad(P.q, dQ, (size_t)D * sizeof(CT), st);
       if (rc) return rc;
     }
+    rc = main_to_side(E_DQ);
+    if (rc) return rc;
     {  // dH0 = dQ Wq', masked
       GemmProblem g = q_problem(dQ, D, packed + P.o_wqT, D, D, D, D, l);
       EpiSpec e;
@@ -728,11 +777,17 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       float* obq[6];
       for (int d = 0; d < NDIR; ++d) { w.out[d] = dwq + ((size_t)l * 6 + d) * D * D; obq[d] = dbq + ((size_t)l * 6 + d) * D; }
       const bool fused = fuse_colsum(P, w, obq);
-      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, st, "w_q_proj");
+      rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_q_proj");
       if (rc) return rc;
-      if (!fused) rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, st, "b_q_proj");
+      if (!fused) rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, ws, "b_q_proj");
       if (rc) return rc;
+      rc = side_record(S_DWQ);
+      if (rc) return rc;
+      have_dwq = true;
     }
+    rc = main_wait(S_DW2);   // LN0 backward overwrites the gc buffer dW2 of this layer reads
+    if (rc) return rc;
+    gci ^= 1; gc = gcbuf[gci];
     {  // LN0 backward: g_cur = (g_oth + dLN0) * mask ; d fc2.bias of the previous layer = colsum(g_cur)
       LnBwdArgs a; memset(&a, 0, sizeof(a));
       a.q = P.q; a.dh = dH; a.x = xin(l); a.stat = stat0(l); a.maskq = maskq; a.g_in = g_oth; a.g_out = g_cur; a.gc_out = gc;
@@ -744,6 +799,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       launch_k(ln_rows_bwd_kernel<CT, false>, dim3(P.MQ / 64), dim3(256), 0, st, a);
       LAUNCH_OK("ln0_bwd");
     }
+    rc = main_to_side(E_GC0);
+    if (rc) return rc;
   }
   // ---- K/V stream ----
   rc = zero_pad(P.kv, dKV, (size_t)ldkv * sizeof(CT), st);
@@ -773,6 +830,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     if (rc) return rc;
   }
   // ---- unfold packed-weight gradients into in_proj_{weight,bias} and LN0 ----
+  rc = side_record(S_JOIN);   // join: every weight gradient issued on the side stream is complete
+  if (rc) return rc;
+  rc = main_wait(S_JOIN);
+  if (rc) return rc;
   {
     UnfoldJobs uj; memset(&uj, 0, sizeof(uj));
     uj.scaling = 1.0f / sqrtf((float)HD);
@@ -1014,34 +1075,49 @@ int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_pa
                            routes_out, st);
 }
 
+int mmr_route_fusion_bwd_ex(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                            const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                            const void* packed, const void* saved, void* scratch, const float* d_routes,
+                            void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream,
+                            void* const* host_layer_events, void* side_stream, void* const* host_sync_events) {
+  Plan P;
+  const char* why = "";
+  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
+  if (!host_params || !x_l || !x_n || !x_i || !packed || !saved || !scratch || !d_routes || !host_param_grads)
+    return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (side_stream && !host_sync_events) return fail(MMR_ERR_INVALID_ARG, "side_stream needs MMR_BWD_SYNC_EVENTS events");
+  if (side_stream && side_stream == stream) return fail(MMR_ERR_INVALID_ARG, "side_stream must differ from stream");
+  if (side_stream)
+    for (int i = 0; i < MMR_BWD_SYNC_EVENTS; ++i)
+      if (!host_sync_events[i]) return fail(MMR_ERR_INVALID_ARG, "null entry in host_sync_events");
+  const float* x[3] = {x_l, x_n, x_i};
+  const float* mask[3] = {mL, mN, mI};
+  float* dx[3] = {dx_l, dx_n, dx_i};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
+  ProfScope ps(PC_FUSION_BWD, st);
+  if (P.bf16)
+    return fusion_bwd<bf16>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
+                            d_routes, host_param_grads, dx, st, host_layer_events, side, host_sync_events);
+  return fusion_bwd<float>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
+                           d_routes, host_param_grads, dx, st, host_layer_events, side, host_sync_events);
+}
+
 int mmr_route_fusion_bwd_events(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
                                 const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
                                 const void* packed, const void* saved, void* scratch, const float* d_routes,
                                 void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream,
                                 void* const* host_layer_events) {
-  Plan P;
-  const char* why = "";
-  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
-  if (!host_params || !packed || !saved || !scratch || !d_routes || !host_param_grads || !x_l || !x_n || !x_i)
-    return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
-  const float* x[3] = {x_l, x_n, x_i};
-  const float* mask[3] = {mL, mN, mI};
-  float* dx[3] = {dx_l, dx_n, dx_i};
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  ProfScope ps(PC_FUSION_BWD, st);
-  if (P.bf16)
-    return fusion_bwd<bf16>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
-                            d_routes, host_param_grads, dx, st, host_layer_events);
-  return fusion_bwd<float>(P, host_params, x, mask, (const uint8_t*)packed, (const uint8_t*)saved, (uint8_t*)scratch,
-                           d_routes, host_param_grads, dx, st, host_layer_events);
+  return mmr_route_fusion_bwd_ex(dims, host_params, x_l, x_n, x_i, mL, mN, mI, packed, saved, scratch, d_routes,
+                                 host_param_grads, dx_l, dx_n, dx_i, stream, host_layer_events, nullptr, nullptr);
 }
 
 int mmr_route_fusion_bwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
                          const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
                          const void* packed, const void* saved, void* scratch, const float* d_routes,
                          void* const* host_param_grads, float* dx_l, float* dx_n, float* dx_i, void* stream) {
-  return mmr_route_fusion_bwd_events(dims, host_params, x_l, x_n, x_i, mL, mN, mI, packed, saved, scratch, d_routes,
-                                     host_param_grads, dx_l, dx_n, dx_i, stream, nullptr);
+  return mmr_route_fusion_bwd_ex(dims, host_params, x_l, x_n, x_i, mL, mN, mI, packed, saved, scratch, d_routes,
+                                 host_param_grads, dx_l, dx_n, dx_i, stream, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------- routing ---

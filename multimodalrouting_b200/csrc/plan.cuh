@@ -69,7 +69,8 @@ struct Plan {
 
   // ---- backward scratch ---------------------------------------------------------------------
   size_t b_g, b_g1;                       // fp32 [MQ,256] residual-stream gradients (ping/pong)
-  size_t b_gc;                            // CT [MQ,256] copy of the current gradient
+  size_t b_gc, b_gc2;                     // CT [MQ,256] copy of the current gradient (ping/pong: the weight-gradient
+                                          // stream may still read one while the chain writes the other)
   size_t b_df;                            // CT [MQ,1024]
   size_t b_dh;                            // CT [MQ,256]   (dH1 / dH0)
   size_t b_do, b_dq;                      // CT [MQ,256]
@@ -147,7 +148,7 @@ inline bool build_plan(const mmr_fusion_dims* d, Plan* p, const char** why) {
   p->scratch_fwd_bytes = o;
 
   o = 0;
-  p->b_g = take(MQ * D * 4); p->b_g1 = take(MQ * D * 4); p->b_gc = take(MQ * D * ct);
+  p->b_g = take(MQ * D * 4); p->b_g1 = take(MQ * D * 4); p->b_gc = take(MQ * D * ct); p->b_gc2 = take(MQ * D * ct);
   p->b_df = take(MQ * FF * ct); p->b_dh = take(MQ * D * ct); p->b_do = take(MQ * D * ct); p->b_dq = take(MQ * D * ct);
   p->b_dkv = take(MK * L * 2 * D * ct);
   p->b_dp = take(MM * D * 4); p->b_dvec = take(MQ * H * 4);

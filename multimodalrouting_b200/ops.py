@@ -182,6 +182,31 @@ def set_grad_overlap(hook, events) -> None:
     _OVERLAP["hook"], _OVERLAP["events"] = hook, events
 
 
+# Second stream for the weight-gradient kernels of the backward (mmr_route_fusion_bwd_ex): one side stream and nine
+# ordering events per device, created once (outside any CUDA-graph capture) and owned here, not by the library.
+N_BWD_SYNC_EVENTS = 9
+_WGRAD_SIDE = {}
+
+
+def wgrad_side_stream(device):
+    """(side stream, ctypes event table) for `device`, or (None, None) when MMR_WGRAD_STREAM=0."""
+    if os.environ.get("MMR_WGRAD_STREAM", "1") == "0":
+        return None, None
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ent = _WGRAD_SIDE.get(key)
+    if ent is None:
+        with torch.cuda.device(key):
+            stream = torch.cuda.Stream()
+            events = [torch.cuda.Event() for _ in range(N_BWD_SYNC_EVENTS)]
+            for e in events:           # CUDA events are created lazily: force the handles to exist
+                e.record(stream)
+            stream.synchronize()
+        table = (c_fp * N_BWD_SYNC_EVENTS)(*[int(e.cuda_event) for e in events])
+        ent = (stream, events, table)
+        _WGRAD_SIDE[key] = ent
+    return ent[0], ent[2]
+
+
 @torch.library.custom_op("mmr_b200::route_fusion_bwd", mutates_args=())
 def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
                      mI: Optional[Tensor], params: Sequence[Tensor], packed: Tensor, saved: Tensor,
@@ -205,9 +230,13 @@ def route_fusion_bwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor]
         evs = (c_fp * layers)()
         for l in range(layers):
             evs[l] = events[l] if l < len(events) and events[l] else None
-    rc = lib.mmr_route_fusion_bwd_events(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
-                                         _ptr(mN), _ptr(mI), _ptr(packed), _ptr(saved), _ptr(scratch), _ptr(d_routes),
-                                         grads, _ptr(dx[0]), _ptr(dx[1]), _ptr(dx[2]), _stream(), evs)
+    side, sync = (None, None) if evs is not None else wgrad_side_stream(dev)
+    # (the side stream is forked from and joined back into the current stream inside the call, so every buffer is
+    # released in current-stream order: no record_stream needed, and the call stays CUDA-graph capturable)
+    rc = lib.mmr_route_fusion_bwd_ex(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
+                                     _ptr(mN), _ptr(mI), _ptr(packed), _ptr(saved), _ptr(scratch), _ptr(d_routes),
+                                     grads, _ptr(dx[0]), _ptr(dx[1]), _ptr(dx[2]), _stream(), evs,
+                                     side.cuda_stream if side is not None else None, sync)
     _lib.check(rc, "mmr_route_fusion_bwd")
     return dx[0], dx[1], dx[2], flat
 

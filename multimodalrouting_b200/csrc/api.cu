@@ -805,6 +805,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   // ---- K/V stream ----
   rc = zero_pad(P.kv, dKV, (size_t)ldkv * sizeof(CT), st);
   if (rc) return rc;
+  rc = main_to_side(E_DQ);   // dKV is complete
+  if (rc) return rc;
   {
     GemmProblem g; memset(&g, 0, sizeof(g));
     g.segs = P.kv;
@@ -824,9 +826,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     }
     w.dY = dKV; w.ldy = ldkv; w.X = xh; w.ldx = D; w.M = ldkv; w.N = D; w.ldo = D;
     const bool fused = fuse_colsum(P, w, obkv);
-    rc = run_wgrad<CT>(P, w, P.MK, P.MM, st, "w_kv_proj");
+    rc = run_wgrad<CT>(P, w, P.MK, P.MM, ws, "w_kv_proj");    // side stream: runs next to the dKV data-gradient GEMM
     if (rc) return rc;
-    if (!fused) rc = run_colsum<CT>(P.kv, dKV, ldkv, 0, ldkv, obkv, 1.0f, st, "b_kv_proj");
+    if (!fused) rc = run_colsum<CT>(P.kv, dKV, ldkv, 0, ldkv, obkv, 1.0f, ws, "b_kv_proj");
     if (rc) return rc;
   }
   // ---- unfold packed-weight gradients into in_proj_{weight,bias} and LN0 ----

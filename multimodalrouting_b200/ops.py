@@ -195,6 +195,8 @@ def wgrad_side_stream(device):
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     ent = _WGRAD_SIDE.get(key)
     if ent is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None, None          # cannot create / synchronise during a capture: this call stays single-stream
         with torch.cuda.device(key):
             stream = torch.cuda.Stream()
             events = [torch.cuda.Event() for _ in range(N_BWD_SYNC_EVENTS)]

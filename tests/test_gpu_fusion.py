@@ -103,7 +103,8 @@ def test_bf16_simt_engine(name):
     _bf16_case(name, "simt")
 
 
-@pytest.mark.parametrize("TL,TN,TI,missing", [(150, 70, 33, True), (48, 16, 49, True), (64, 65, 17, False)])
+@pytest.mark.parametrize("TL,TN,TI,missing", [(150, 70, 33, True), (48, 16, 49, True), (64, 65, 17, False),
+                                                 (512, 128, 196, True)])   # INSPECT token counts (BASELINE configs[4])
 def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
     """Tensor-core attention (mma.sync tiles, 64-row chunks with online softmax) against the SIMT
     attention kernels on the same bf16 path, including sequences longer than one chunk, plus the fp32

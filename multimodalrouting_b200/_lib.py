@@ -56,7 +56,8 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """csrc/libmmr_b200.so; MMR_B200_LIB points at another build of the same sources (tuning experiments)."""
+    return os.environ.get("MMR_B200_LIB") or _build.LIB
 
 
 def load():

@@ -1151,8 +1151,11 @@ static RtLaunch routing_launch_cfg(const mmr_routing_dims* d, bool bwd) {
   const size_t ut = L.bf16 ? 2 : 4;
   const int cand[4] = {8, 4, 2, 1};
   L.PB = 1;
+  const char* force = getenv("MMR_RT_PB");   // tuning override: largest tile size to consider
+  const int pb_max = force ? atoi(force) : 8;
   for (int i = 0; i < 4; ++i) {
     const int pb = cand[i];
+    if (pb > pb_max) continue;
     const size_t smem = rt_smem_bytes(d->K, d->num_routing, bwd, pb, ut, d->from_poses != 0);
     if (smem > (size_t)227 * 1024) continue;
     if (pb > 1 && (d->B + pb - 1) / pb < 100) continue;

@@ -14,7 +14,13 @@
 
 namespace mmr {
 
-constexpr int RT_THREADS = 512;    // 16 warps: one CTA per SM, latency hidden by warps rather than by CTAs
+#ifndef MMR_RT_THREADS
+#define MMR_RT_THREADS 512
+#endif
+#ifndef MMR_RT_MINB
+#define MMR_RT_MINB 1
+#endif
+constexpr int RT_THREADS = MMR_RT_THREADS;    // 16 warps: one CTA per SM, latency hidden by warps rather than by CTAs
 constexpr int RT_GSLOTS = 1024 / RT_THREADS;   // K*32 <= 1024 head-gradient accumulators spread over the CTA
 constexpr int RT_MAXIT = 4;
 
@@ -333,7 +339,7 @@ __device__ inline void rt_iterate(const RoutingArgs& a, const RtScratch& s, cons
 }
 
 template <int PB, class UT>
-__global__ void __launch_bounds__(RT_THREADS, 1) routing_fwd_kernel(RoutingArgs a) {
+__global__ void __launch_bounds__(RT_THREADS, MMR_RT_MINB) routing_fwd_kernel(RoutingArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int K = a.d.K, nit = a.d.num_routing;
   float* sf = reinterpret_cast<float*>(smem_raw);
@@ -367,7 +373,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) routing_fwd_kernel(RoutingArgs 
 }
 
 template <int PB, class UT>
-__global__ void __launch_bounds__(RT_THREADS, 1) routing_bwd_kernel(RoutingArgs a) {
+__global__ void __launch_bounds__(RT_THREADS, MMR_RT_MINB) routing_bwd_kernel(RoutingArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int K = a.d.K, KD = K * 64, nit = a.d.num_routing;
   float* sf = reinterpret_cast<float*>(smem_raw);

@@ -27,7 +27,7 @@ class RoutingDims(C.Structure):
 
 class RoutingParams(C.Structure):
     _fields_ = [("proj_w", c_fp * 10), ("proj_b", c_fp * 10), ("caps_w", c_fp), ("pose_to_mc", c_fp),
-                ("embedding", c_fp), ("bias", c_fp)]
+                ("embedding", c_fp), ("bias", c_fp), ("caps_wt_bf16", c_fp), ("proj_w_bf16", c_fp)]
 
 
 class RoutingGrads(C.Structure):
@@ -52,7 +52,7 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
-           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence"]
+           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights"]
 
 
 def lib_path() -> str:
@@ -90,6 +90,8 @@ def load():
     lib.mmr_route_fusion_bwd_ex.restype = C.c_int
     lib.mmr_routing_scratch_bytes.argtypes = [C.POINTER(RoutingDims)]
     lib.mmr_routing_scratch_bytes.restype = C.c_size_t
+    lib.mmr_routing_pack_weights.argtypes = [C.POINTER(RoutingParams), C.c_int, c_fp, c_fp, c_fp]
+    lib.mmr_routing_pack_weights.restype = C.c_int
     lib.mmr_capsule_routing_fwd.argtypes = [C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 11
     lib.mmr_capsule_routing_fwd.restype = C.c_int
     lib.mmr_capsule_routing_bwd.argtypes = ([C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 8 +

@@ -1197,6 +1197,21 @@ static cudaError_t dispatch_routing(const RoutingArgs& a, const RtLaunch& L, boo
 
 extern "C" {
 
+int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_bf16, void* proj_w_bf16,
+                             void* stream) {
+  if (!params || !params->caps_w || !caps_wt_bf16) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: null argument");
+  if (K < 1 || K > MMR_MAX_LABELS) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: K out of range");
+  const bool proj = proj_w_bf16 != nullptr && params->proj_w[0] != nullptr;
+  if (proj)
+    for (int r = 0; r < NR; ++r)
+      if (!params->proj_w[r]) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: missing projector weight");
+  const long long n = 10LL * K * 64 + (proj ? 10LL * 40 * 32 : 0);
+  routing_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *params, K, reinterpret_cast<bf16*>(caps_wt_bf16), proj ? reinterpret_cast<bf16*>(proj_w_bf16) : nullptr);
+  LAUNCH_OK("routing_pack");
+  return MMR_OK;
+}
+
 int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
                             const float* poses_in, const float* acts_in, const float* acts_override,
                             const float* route_mask, float* logits, float* alpha, float* R, float* poses_out,

@@ -10,6 +10,8 @@
 //   CapsuleMortalityHead.forward          Mort :194-268 / Pheno :194-272
 //   CapsuleFC.forward                     capsule_layers.py:75-117
 #pragma once
+#include <type_traits>
+
 #include "mmr_common.cuh"
 
 namespace mmr {
@@ -114,6 +116,106 @@ __device__ inline void rt_build_G(const RoutingArgs& a, float* G) {
   }
 }
 
+// ---- tensor-core forms of the projector and the vote contraction (reduced-precision mode) ------------------
+// Both are small GEMMs whose M dimension is the patient tile (PB <= 8 rows of an m16n8k16 tile; rows >= PB are zero)
+// and whose B operand is a weight matrix pre-packed to bf16 with the reduction index contiguous
+// (mmr_routing_pack_weights): caps_wt[r][c][a] (a = 32) and proj_wb[r][n (40, rows >= 33 zero)][k (256)].
+// The reduction index is permuted so that ONE 16-byte load per lane yields the B fragments of two k-steps:
+// logical k-slot (step s, column 2t+e / 2t+8+e of the fragment) <-> physical index 8t + 4s + e / 8t + 4s + 2 + e
+// inside a group of 32; the A fragments are built from shared memory with the same permutation.
+__device__ __forceinline__ uint32_t rt_pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void rt_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  const uint32_t z = 0u;    // rows 8..15 of the A tile are unused
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+}
+// A fragments (two k-steps) of 8 consecutive fp32 values x[8t .. 8t+7] of this lane's row
+__device__ __forceinline__ void rt_afrag(const float* x8, bool valid, uint32_t (&A)[4]) {
+  A[0] = A[1] = A[2] = A[3] = 0u;
+  if (valid) {
+    const float4 x0 = *reinterpret_cast<const float4*>(x8), x1 = *reinterpret_cast<const float4*>(x8 + 4);
+    A[0] = rt_pack2(x0.x, x0.y); A[1] = rt_pack2(x0.z, x0.w); A[2] = rt_pack2(x1.x, x1.y); A[3] = rt_pack2(x1.z, x1.w);
+  }
+}
+
+// projector: pose[p][r][j] / zl[p][r] = sum_k emb[p][r][k] * W_r[j][k] + b_r[j]   (one warp per route)
+template <int PB>
+__device__ inline void rt_project_mma(const RoutingArgs& a, float* pp, const uint8_t* ureg, size_t ustride, bool bwd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint4* pw = reinterpret_cast<const uint4*>(a.p.proj_w_bf16);
+  for (int r = warp; r < 10; r += RT_THREADS / 32) {
+    float acc[5][4];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    const float* e = reinterpret_cast<const float*>(ureg + (g < PB ? g : 0) * ustride) + r * 256 + 8 * t;
+#pragma unroll 2
+    for (int kk = 0; kk < 8; ++kk) {
+      uint32_t A[4];
+      rt_afrag(e + 32 * kk, g < PB, A);
+#pragma unroll
+      for (int n = 0; n < 5; ++n) {
+        const uint4 q = __ldg(pw + ((size_t)(r * 40 + n * 8 + g) * 32 + kk * 4 + t));
+        rt_mma(acc[n], A[0], A[1], q.x, q.y);
+        rt_mma(acc[n], A[2], A[3], q.z, q.w);
+      }
+    }
+    if (g < PB) {
+      RtPatient s = rt_patient(pp, g, bwd);
+#pragma unroll
+      for (int n = 0; n < 5; ++n)
+#pragma unroll
+        for (int ee = 0; ee < 2; ++ee) {
+          const int j = n * 8 + 2 * t + ee;
+          if (j < 33) {
+            const float v = acc[n][ee] + a.p.proj_b[r][j];
+            if (j < 32) s.pose[r * 32 + j] = v; else s.zl[r] = v;
+          }
+        }
+    }
+  }
+}
+
+// votes: u[p][r][c] = sum_a pose[p][r][a] * w[r][a][c]   (n-tiles of 8 columns round-robin over the warps)
+template <int PB>
+__device__ inline void rt_votes_mma(const RoutingArgs& a, const float* pp, uint8_t* ureg, size_t ustride, bool bwd) {
+  const int KD = a.d.K * 64, NT = KD / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int ppstride = bwd ? RT_PP_BWD : RT_PP_FWD;
+  constexpr int NW = RT_THREADS / 32;
+  __half* urow = reinterpret_cast<__half*>(ureg + (g < PB ? g : 0) * ustride);
+  for (int r = 0; r < 10; ++r) {
+    uint32_t A[4];
+    rt_afrag(pp + (g < PB ? g : 0) * ppstride + r * 32 + 8 * t, g < PB, A);
+    const uint4* wr = reinterpret_cast<const uint4*>(a.p.caps_wt_bf16) + (size_t)r * KD * 4 + (size_t)g * 4 + t;
+    for (int nt0 = warp; nt0 < NT; nt0 += 4 * NW) {
+      uint4 q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nt = nt0 + i * NW;
+        q[i] = nt < NT ? __ldg(wr + (size_t)nt * 32) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nt = nt0 + i * NW;
+        if (nt >= NT) break;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        rt_mma(acc, A[0], A[1], q[i].x, q[i].y);
+        rt_mma(acc, A[2], A[3], q[i].z, q[i].w);
+        if (g < PB) {
+          const float L = 65504.f;
+          *reinterpret_cast<__half2*>(urow + r * KD + nt * 8 + 2 * t) =
+              __floats2half2_rn(fminf(fmaxf(acc[0], -L), L), fminf(fmaxf(acc[1], -L), L));
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // ---- tile phase 1: projector + activation chain for the np patients b0 .. b0+np-1 ---------------
 template <int PB>
 __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg, size_t ustride, bool bwd, int b0, int np) {
@@ -135,24 +237,28 @@ __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(ureg + p * ustride) + r * 256 + c) = v;
     }
     __syncthreads();
-    // 10 x 33 dot products of length 256: one warp per output, the weight row is shared by the tile
-    for (int o = warp; o < 330; o += RT_THREADS / 32) {
-      const int r = o / 33, j = o % 33;
-      const float* w = a.p.proj_w[r] + (size_t)j * 256;
-      float wv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + lane + 32 * i);
-      const float bias = a.p.proj_b[r][j];
-#pragma unroll
-      for (int p = 0; p < PB; ++p) {
-        const float* e = reinterpret_cast<const float*>(ureg + p * ustride) + r * 256;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(wv[i], e[lane + 32 * i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          RtPatient s = rt_patient(pp, p, bwd);
-          if (j < 32) s.pose[r * 32 + j] = acc + bias; else s.zl[r] = acc + bias;
+    if (a.p.proj_w_bf16 != nullptr && a.d.vote_dtype == MMR_DTYPE_BF16 && PB <= 8) {
+      rt_project_mma<PB>(a, pp, ureg, ustride, bwd);   // tensor cores, bf16 operands (as the reference's autocast Linear)
+    } else {
+      // 10 x 33 dot products of length 256: one warp per output, the weight row is shared by the tile
+      for (int o = warp; o < 330; o += RT_THREADS / 32) {
+        const int r = o / 33, j = o % 33;
+        const float* w = a.p.proj_w[r] + (size_t)j * 256;
+        float wv[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + lane + 32 * i);
+        const float bias = a.p.proj_b[r][j];
+  #pragma unroll
+        for (int p = 0; p < PB; ++p) {
+          const float* e = reinterpret_cast<const float*>(ureg + p * ustride) + r * 256;
+          float acc = 0.f;
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(wv[i], e[lane + 32 * i], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            RtPatient s = rt_patient(pp, p, bwd);
+            if (j < 32) s.pose[r * 32 + j] = acc + bias; else s.zl[r] = acc + bias;
+          }
         }
       }
     }
@@ -217,6 +323,12 @@ __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg
 // A thread owns 4 consecutive columns; every 16-byte weight load feeds PB*4 FMAs.
 template <int PB, class UT>
 __device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* ureg, size_t ustride, bool bwd) {
+  if constexpr (std::is_same<UT, __half>::value && PB <= 8) {
+    if (a.p.caps_wt_bf16 != nullptr) {
+      rt_votes_mma<PB>(a, pp, ureg, ustride, bwd);
+      return;
+    }
+  }
   const int KD = a.d.K * 64;
   const int ppstride = bwd ? RT_PP_BWD : RT_PP_FWD;
   for (int cg = threadIdx.x; cg < KD / 4; cg += RT_THREADS) {
@@ -629,6 +741,40 @@ __global__ void routing_head_grads_kernel(const float* dG, const float* pose_to_
     for (int p = 0; p < PC; ++p) acc = fmaf(dG[k * 32 + p], pose_to_mc[m * PC + p], acc);
     d_embedding[j] += acc;
   }
+}
+
+// bf16, reduction-index-contiguous copies of the two weight tensors the tensor-core paths read:
+//   caps_wt[r][c][a] = w[r][a][c]            (10 x K*64 columns of 32)       one thread per column
+//   proj_wb[r][n][k] = proj_w[r][n][k], n<33 (10 x 40 rows of 256, rest 0)   one thread per 8 elements
+__global__ void routing_pack_kernel(mmr_routing_params p, int K, bf16* caps_wt, bf16* proj_wb) {
+  const int KD = K * 64;
+  const long long n_caps = 10LL * KD;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_caps) {
+    const int r = (int)(i / KD), c = (int)(i % KD);
+    const float* w = p.caps_w + (size_t)r * 32 * KD + c;
+    uint4* dst = reinterpret_cast<uint4*>(caps_wt + i * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = rt_pack2(w[(size_t)(8 * q + 0) * KD], w[(size_t)(8 * q + 1) * KD]);
+      o.y = rt_pack2(w[(size_t)(8 * q + 2) * KD], w[(size_t)(8 * q + 3) * KD]);
+      o.z = rt_pack2(w[(size_t)(8 * q + 4) * KD], w[(size_t)(8 * q + 5) * KD]);
+      o.w = rt_pack2(w[(size_t)(8 * q + 6) * KD], w[(size_t)(8 * q + 7) * KD]);
+      dst[q] = o;
+    }
+    return;
+  }
+  const long long j = i - n_caps;
+  if (proj_wb == nullptr || j >= 10LL * 40 * 32) return;
+  const int row = (int)(j / 32), chunk = (int)(j % 32), r = row / 40, n = row % 40;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (n < 33) {
+    const float* w = p.proj_w[r] + (size_t)n * 256 + chunk * 8;
+    const float4 x0 = *reinterpret_cast<const float4*>(w), x1 = *reinterpret_cast<const float4*>(w + 4);
+    o.x = rt_pack2(x0.x, x0.y); o.y = rt_pack2(x0.z, x0.w); o.z = rt_pack2(x1.x, x1.y); o.w = rt_pack2(x1.z, x1.w);
+  }
+  reinterpret_cast<uint4*>(proj_wb)[j] = o;
 }
 
 }  // namespace mmr

@@ -348,8 +348,20 @@ def _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, f
                        float(ceil), int(rs), int(bs), int(vdt), 0)
 
 
-def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias) -> RoutingParams:
+PROJ_PACK_BYTES = 10 * 40 * 256 * 2
+
+
+def routing_pack_bytes(K: int) -> int:
+    """bytes of the bf16 weight copies the tensor-core routing paths read (caps_wt | proj_wb)."""
+    return 10 * K * 64 * 32 * 2 + PROJ_PACK_BYTES
+
+
+def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed=None) -> RoutingParams:
     rp = RoutingParams()
+    if packed is not None and packed.numel() > 0:
+        K = embedding.shape[0]
+        rp.caps_wt_bf16 = packed.data_ptr()
+        rp.proj_w_bf16 = (packed.data_ptr() + 10 * K * 64 * 32 * 2) if proj_w else None
     for r in range(N_ROUTES):
         rp.proj_w[r] = proj_w[r].data_ptr() if proj_w else None
         rp.proj_b[r] = proj_b[r].data_ptr() if proj_b else None
@@ -366,15 +378,21 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                         proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
                         embedding: Tensor, bias: Tensor, B: int, variant: int, num_routing: int,
                         detach_priors: bool, temp: float, floor: float, ceil: float, vdt: int
-                        ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10])."""
+                        ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10], packed bf16 weights | empty)."""
     _require_cuda(caps_w, embs, poses_in)
     lib = _lib.load()
     K = embedding.shape[0]
     from_poses = embs is None
     dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt)
-    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
     dev = caps_w.device
+    # reduced-precision mode: projector and vote contraction run on tensor cores from bf16 weight copies
+    use_tc = vdt == DTYPE_BF16 and os.environ.get("MMR_RT_TC", "1") != "0"
+    packed = torch.empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8, device=dev)
+    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed)
+    if use_tc:
+        rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_bf16, rp.proj_w_bf16, _stream())
+        _lib.check(rc, "mmr_routing_pack_weights")
     logits = torch.empty(B, K, dtype=torch.float32, device=dev)
     alpha = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
     R = torch.empty(B, N_ROUTES, K, dtype=torch.float32, device=dev)
@@ -385,7 +403,7 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                                      None if from_poses else _ptr(poses), None if from_poses else _ptr(acts),
                                      _stream())
     _lib.check(rc, "mmr_capsule_routing_fwd")
-    return logits, alpha, R, poses, acts
+    return logits, alpha, R, poses, acts, packed
 
 
 @capsule_routing_fwd.register_fake
@@ -394,7 +412,7 @@ def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b
     K = embedding.shape[0]
     e = caps_w
     return (e.new_empty(B, K), e.new_empty(B, N_ROUTES), e.new_empty(B, N_ROUTES, K),
-            e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES))
+            e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES), e.new_empty(0, dtype=torch.uint8))
 
 
 @torch.library.custom_op("mmr_b200::capsule_routing_bwd", mutates_args=())
@@ -403,7 +421,7 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                         proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], caps_w: Tensor, pose_to_mc: Tensor,
                         embedding: Tensor, bias: Tensor, d_logits: Tensor, d_R: Optional[Tensor], B: int,
                         variant: int, num_routing: int, detach_priors: bool, temp: float, floor: float,
-                        ceil: float, vdt: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                        ceil: float, vdt: int, packed: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Returns (d_embs [10,B,256] | empty, d_poses [B,10,32] | empty, d_acts [B,10] | empty, flat grads)
     flat grads layout: proj_w[10] (33*256 each) | proj_b[10] (36 each, 33 used) | caps_w | pose_to_mc |
     embedding | bias."""
@@ -411,7 +429,7 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     K = embedding.shape[0]
     from_poses = embs is None
     dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt)
-    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias)
+    rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed)
     dev = caps_w.device
     scratch = torch.empty(int(lib.mmr_routing_scratch_bytes(C.byref(dims))), dtype=torch.uint8, device=dev)
     n_flat = routing_flat_layout(K)["total"]
@@ -447,7 +465,7 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
 
 @capsule_routing_bwd.register_fake
 def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b, caps_w, pose_to_mc, embedding,
-      bias, d_logits, d_R, B, variant, num_routing, detach_priors, temp, floor, ceil, vdt):
+      bias, d_logits, d_R, B, variant, num_routing, detach_priors, temp, floor, ceil, vdt, packed=None):
     K = embedding.shape[0]
     e = caps_w
     n = routing_flat_layout(K)["total"]
@@ -495,7 +513,7 @@ class RoutingFn(torch.autograd.Function):
             poses_c = acts_c = None
         rm = _f32c(route_mask.detach()) if route_mask is not None else None
         ao = _f32c(acts_override.detach()) if acts_override is not None else None
-        logits, alpha, R, poses, acts = capsule_routing_fwd(
+        logits, alpha, R, poses, acts, packed = capsule_routing_fwd(
             embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w.detach(), pose_to_mc.detach(),
             embedding.detach(), bias.detach(), B, variant, num_routing, detach_priors, temp, floor, ceil, vdt)
         ctx.cfg = cfg
@@ -505,7 +523,7 @@ class RoutingFn(torch.autograd.Function):
         tensors = [t for t in (embs_dense, poses_c, acts_c, ao, rm) if t is not None]
         ctx.n_in = len(tensors)
         ctx.save_for_backward(*tensors, caps_w.detach(), pose_to_mc.detach(), embedding.detach(), bias.detach(),
-                              *proj_w, *proj_b)
+                              *proj_w, *proj_b, packed)
         ctx.mark_non_differentiable(alpha, poses, acts)
         return logits, alpha, R, poses, acts
 
@@ -528,6 +546,7 @@ class RoutingFn(torch.autograd.Function):
         k += 4
         proj_w = sv[k:k + N_ROUTES] if has_embs else []
         proj_b = sv[k + N_ROUTES:k + 2 * N_ROUTES] if has_embs else []
+        packed = sv[-1]
         B, K = ctx.B, embedding.shape[0]
         if d_logits is None:
             d_logits = torch.zeros(B, K, device=caps_w.device)
@@ -535,7 +554,7 @@ class RoutingFn(torch.autograd.Function):
         d_embs, d_poses, d_acts, flat = capsule_routing_bwd(
             embs_dense, rs, bs, poses_c, acts_c, ao, rm, proj_w, proj_b, caps_w, pose_to_mc, embedding, bias,
             _f32c(d_logits), _f32c(d_R) if d_R is not None else None, B, variant, num_routing, detach_priors, temp,
-            floor, ceil, ctx.vdt)
+            floor, ceil, ctx.vdt, packed)
         lay = routing_flat_layout(K)
         g_caps = flat[lay["caps_w"]:lay["caps_w"] + caps_w.numel()].view(caps_w.shape)
         g_mc = flat[lay["pose_to_mc"]:lay["pose_to_mc"] + 64 * 32].view(64, 32)

@@ -126,3 +126,58 @@ def test_head_forward_from_poses():
         if variant == "pheno":
             _accurate(a1.grad, o32[4].grad, o64[4].grad, 2e-4, "d act")
         _accurate(head.capsule.w.grad, o32[5]["capsule.w"].grad, o64[5]["capsule.w"].grad, 2e-4, "d w")
+
+
+@pytest.mark.parametrize("variant,K,masked", [("pheno", 25, True), ("mort", 2, True), ("pheno", 32, False), ("pheno", 3, True)])
+def test_routing_reduced_precision_tensor_core_vs_cuda_core(variant, K, masked, monkeypatch):
+    """Reduced-precision routing (what runs under autocast): the tensor-core projector / vote contraction
+    (mma.sync, bf16 weight copies from mmr_routing_pack_weights) against the CUDA-core path of the same mode and the fp32
+    oracle.  Bars: logits / alpha / R within 2e-2 of the oracle (BASELINE.json bf16 tolerance); gradients at least
+    as close to the oracle as the CUDA-core reduced-precision path (x2) or 5e-2."""
+    if variant == "mort":
+        from multimodalrouting_b200.MortModel import routing_and_heads as rh
+    else:
+        from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    B = 45          # 11 full tiles of 4 patients + a ragged one
+    _, sdp, sdh = synth.make_state(K=K, seed=15 + K, sharp=2.0)
+    g = torch.Generator().manual_seed(21)
+    embs = {r: 0.5 * torch.randn(B, 256, generator=g) for r in synth.ROUTES}
+    rm = None
+    if masked:
+        rm = (torch.rand(B, 10, generator=g) < 0.75).float()
+        rm[0] = 0.0
+        rm[1] = 1.0
+    gl = torch.randn(B, K, generator=g)
+    gR = torch.randn(B, 10, K, generator=g)
+    lo, ao, Ro, po, ho, eo = _oracle_routing(torch.float32, sdp, sdh, embs, rm, gl, gR, variant, 1.2, False)
+    res = {}
+    for eng in ("0", "1"):
+        monkeypatch.setenv("MMR_RT_TC", eng)
+        proj = rh.RoutePrimaryProjector(256, 32)
+        head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=K)
+        proj.load_state_dict(sdp); head.load_state_dict(sdh)
+        proj, head = proj.cuda(), head.cuda()
+        ed = {r: v.clone().cuda().requires_grad_(True) for r, v in embs.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            l, a, _, R = rh.forward_capsule_from_route_dict(ed, proj, head, route_mask=None if rm is None else rm.cuda(),
+                                                            act_temperature=1.2)
+        ((l.float() * gl.cuda()).sum() + (R.float() * gR.cuda()).sum()).backward()
+        grads = {f"emb {r}": ed[r].grad for r in synth.ROUTES}
+        grads.update({f"proj_w {r}": proj.proj[r].weight.grad for r in synth.ROUTES})
+        grads.update({"capsule.w": head.capsule.w.grad, "pose_to_mc": head.pose_to_mc.weight.grad,
+                      "embedding": head.embedding.grad, "bias": head.bias.grad})
+        res[eng] = (l.float(), a.float(), R.float(), grads)
+    ref_g = {f"emb {r}": eo[r].grad for r in synth.ROUTES}
+    ref_g.update({f"proj_w {r}": po[f"proj.{r}.weight"].grad for r in synth.ROUTES})
+    ref_g.update({"capsule.w": ho["capsule.w"].grad, "pose_to_mc": ho["pose_to_mc.weight"].grad,
+                  "embedding": ho["embedding"].grad, "bias": ho["bias"].grad})
+    for eng in ("0", "1"):
+        l, a, R, _ = res[eng]
+        assert max_rel(l, lo) < 2e-2 and max_rel(a, ao) < 2e-2 and max_rel(R, Ro) < 2e-2, eng
+        if rm is not None:          # masked routes: exactly zero alpha and R, as in the fp32 path
+            assert float((a.cpu() * (1 - rm)).abs().max()) == 0.0
+            assert float((R.cpu() * (1 - rm).unsqueeze(-1)).abs().max()) == 0.0
+    for k, ref in ref_g.items():
+        e_tc, e_cc = max_rel(res["1"][3][k], ref), max_rel(res["0"][3][k], ref)
+        assert bool(torch.isfinite(res["1"][3][k]).all()), k
+        assert e_tc <= max(5e-2, 2.0 * e_cc), f"grad {k}: tensor-core {e_tc:.2e} cuda-core {e_cc:.2e}"

@@ -149,10 +149,10 @@ typedef struct mmr_routing_params {
   const float* pose_to_mc;           /* [64,32] */
   const float* embedding;            /* [K,64] */
   const float* bias;                 /* [K] */
-  /* optional (NULL: CUDA-core contraction): bf16 copies written by mmr_routing_pack_weights, read by the tensor-core
+  /* optional (NULL: CUDA-core contraction): fp16 copies written by mmr_routing_pack_weights, read by the tensor-core
    * projector / vote contraction of the reduced-precision mode (vote_dtype = MMR_DTYPE_BF16) */
-  const void* caps_wt_bf16;          /* [10, K*64, 32] */
-  const void* proj_w_bf16;           /* [10, 40, 256], rows >= 33 zero */
+  const void* caps_wt_f16;          /* [10, K*64, 32] */
+  const void* proj_w_f16;           /* [10, 40, 256], rows >= 33 zero */
 } mmr_routing_params;
 
 typedef struct mmr_routing_grads {   /* zero-initialised fp32 accumulators; NULL entries skipped */
@@ -166,10 +166,10 @@ typedef struct mmr_routing_grads {   /* zero-initialised fp32 accumulators; NULL
 
 size_t mmr_routing_scratch_bytes(const mmr_routing_dims* dims);
 
-/* Packs capsule.w (and, when params->proj_w[0] != NULL and proj_w_bf16 != NULL, the projector weights) into the bf16
- * layouts above.  caps_wt_bf16 needs 10*K*64*32*2 bytes, proj_w_bf16 10*40*256*2 bytes (16-byte aligned, caller-owned).
+/* Packs capsule.w (and, when params->proj_w[0] != NULL and proj_w_f16 != NULL, the projector weights) into the fp16
+ * layouts above.  caps_wt_f16 needs 10*K*64*32*2 bytes, proj_w_f16 10*40*256*2 bytes (16-byte aligned, caller-owned).
  * Call once per parameter version (the Python op does it per forward and hands the buffers to the backward). */
-int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_bf16, void* proj_w_bf16,
+int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* proj_w_f16,
                              void* stream);
 
 /* Replaces forward_capsule_from_route_dict / CapsuleMortalityHead.forward.

@@ -27,7 +27,7 @@ class RoutingDims(C.Structure):
 
 class RoutingParams(C.Structure):
     _fields_ = [("proj_w", c_fp * 10), ("proj_b", c_fp * 10), ("caps_w", c_fp), ("pose_to_mc", c_fp),
-                ("embedding", c_fp), ("bias", c_fp), ("caps_wt_bf16", c_fp), ("proj_w_bf16", c_fp)]
+                ("embedding", c_fp), ("bias", c_fp), ("caps_wt_f16", c_fp), ("proj_w_f16", c_fp)]
 
 
 class RoutingGrads(C.Structure):

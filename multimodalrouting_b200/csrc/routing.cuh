@@ -118,18 +118,21 @@ __device__ inline void rt_build_G(const RoutingArgs& a, float* G) {
 
 // ---- tensor-core forms of the projector and the vote contraction (reduced-precision mode) ------------------
 // Both are small GEMMs whose M dimension is the patient tile (PB <= 8 rows of an m16n8k16 tile; rows >= PB are zero)
-// and whose B operand is a weight matrix pre-packed to bf16 with the reduction index contiguous
+// and whose B operand is a weight matrix pre-packed to fp16 with the reduction index contiguous
 // (mmr_routing_pack_weights): caps_wt[r][c][a] (a = 32) and proj_wb[r][n (40, rows >= 33 zero)][k (256)].
 // The reduction index is permuted so that ONE 16-byte load per lane yields the B fragments of two k-steps:
 // logical k-slot (step s, column 2t+e / 2t+8+e of the fragment) <-> physical index 8t + 4s + e / 8t + 4s + 2 + e
 // inside a group of 32; the A fragments are built from shared memory with the same permutation.
+// operands are fp16 (11-bit mantissa, saturating), like the votes held in shared memory: 8x tighter than the bf16 the
+// reference's autocast einsums use -- sharpened routing amplifies operand rounding (tests/golden pheno_sharp4)
 __device__ __forceinline__ uint32_t rt_pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  const float L = 65504.f;
+  __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -L), L), fminf(fmaxf(hi, -L), L));
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ void rt_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
   const uint32_t z = 0u;    // rows 8..15 of the A tile are unused
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
 }
@@ -146,7 +149,7 @@ __device__ __forceinline__ void rt_afrag(const float* x8, bool valid, uint32_t (
 template <int PB>
 __device__ inline void rt_project_mma(const RoutingArgs& a, float* pp, const uint8_t* ureg, size_t ustride, bool bwd) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const uint4* pw = reinterpret_cast<const uint4*>(a.p.proj_w_bf16);
+  const uint4* pw = reinterpret_cast<const uint4*>(a.p.proj_w_f16);
   for (int r = warp; r < 10; r += RT_THREADS / 32) {
     float acc[5][4];
 #pragma unroll
@@ -190,7 +193,7 @@ __device__ inline void rt_votes_mma(const RoutingArgs& a, const float* pp, uint8
   for (int r = 0; r < 10; ++r) {
     uint32_t A[4];
     rt_afrag(pp + (g < PB ? g : 0) * ppstride + r * 32 + 8 * t, g < PB, A);
-    const uint4* wr = reinterpret_cast<const uint4*>(a.p.caps_wt_bf16) + (size_t)r * KD * 4 + (size_t)g * 4 + t;
+    const uint4* wr = reinterpret_cast<const uint4*>(a.p.caps_wt_f16) + (size_t)r * KD * 4 + (size_t)g * 4 + t;
     for (int nt0 = warp; nt0 < NT; nt0 += 4 * NW) {
       uint4 q[4];
 #pragma unroll
@@ -237,8 +240,8 @@ __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(ureg + p * ustride) + r * 256 + c) = v;
     }
     __syncthreads();
-    if (a.p.proj_w_bf16 != nullptr && a.d.vote_dtype == MMR_DTYPE_BF16 && PB <= 8) {
-      rt_project_mma<PB>(a, pp, ureg, ustride, bwd);   // tensor cores, bf16 operands (as the reference's autocast Linear)
+    if (a.p.proj_w_f16 != nullptr && a.d.vote_dtype == MMR_DTYPE_BF16 && PB <= 8) {
+      rt_project_mma<PB>(a, pp, ureg, ustride, bwd);   // tensor cores, fp16 operands, fp32 accumulation
     } else {
       // 10 x 33 dot products of length 256: one warp per output, the weight row is shared by the tile
       for (int o = warp; o < 330; o += RT_THREADS / 32) {
@@ -324,7 +327,7 @@ __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg
 template <int PB, class UT>
 __device__ inline void rt_votes(const RoutingArgs& a, const float* pp, uint8_t* ureg, size_t ustride, bool bwd) {
   if constexpr (std::is_same<UT, __half>::value && PB <= 8) {
-    if (a.p.caps_wt_bf16 != nullptr) {
+    if (a.p.caps_wt_f16 != nullptr) {
       rt_votes_mma<PB>(a, pp, ureg, ustride, bwd);
       return;
     }
@@ -743,10 +746,10 @@ __global__ void routing_head_grads_kernel(const float* dG, const float* pose_to_
   }
 }
 
-// bf16, reduction-index-contiguous copies of the two weight tensors the tensor-core paths read:
+// fp16, reduction-index-contiguous copies of the two weight tensors the tensor-core paths read:
 //   caps_wt[r][c][a] = w[r][a][c]            (10 x K*64 columns of 32)       one thread per column
 //   proj_wb[r][n][k] = proj_w[r][n][k], n<33 (10 x 40 rows of 256, rest 0)   one thread per 8 elements
-__global__ void routing_pack_kernel(mmr_routing_params p, int K, bf16* caps_wt, bf16* proj_wb) {
+__global__ void routing_pack_kernel(mmr_routing_params p, int K, __half* caps_wt, __half* proj_wb) {
   const int KD = K * 64;
   const long long n_caps = 10LL * KD;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -352,7 +352,7 @@ PROJ_PACK_BYTES = 10 * 40 * 256 * 2
 
 
 def routing_pack_bytes(K: int) -> int:
-    """bytes of the bf16 weight copies the tensor-core routing paths read (caps_wt | proj_wb)."""
+    """bytes of the fp16 weight copies the tensor-core routing paths read (caps_wt | proj_wb)."""
     return 10 * K * 64 * 32 * 2 + PROJ_PACK_BYTES
 
 
@@ -360,8 +360,8 @@ def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed=
     rp = RoutingParams()
     if packed is not None and packed.numel() > 0:
         K = embedding.shape[0]
-        rp.caps_wt_bf16 = packed.data_ptr()
-        rp.proj_w_bf16 = (packed.data_ptr() + 10 * K * 64 * 32 * 2) if proj_w else None
+        rp.caps_wt_f16 = packed.data_ptr()
+        rp.proj_w_f16 = (packed.data_ptr() + 10 * K * 64 * 32 * 2) if proj_w else None
     for r in range(N_ROUTES):
         rp.proj_w[r] = proj_w[r].data_ptr() if proj_w else None
         rp.proj_b[r] = proj_b[r].data_ptr() if proj_b else None
@@ -379,19 +379,19 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
                         embedding: Tensor, bias: Tensor, B: int, variant: int, num_routing: int,
                         detach_priors: bool, temp: float, floor: float, ceil: float, vdt: int
                         ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10], packed bf16 weights | empty)."""
+    """Returns (logits [B,K], alpha [B,10], R [B,10,K], poses [B,10,32], acts [B,10], packed fp16 weights | empty)."""
     _require_cuda(caps_w, embs, poses_in)
     lib = _lib.load()
     K = embedding.shape[0]
     from_poses = embs is None
     dims = _routing_dims(B, K, variant, num_routing, detach_priors, from_poses, temp, floor, ceil, rs, bs, vdt)
     dev = caps_w.device
-    # reduced-precision mode: projector and vote contraction run on tensor cores from bf16 weight copies
+    # reduced-precision mode: projector and vote contraction run on tensor cores from fp16 weight copies
     use_tc = vdt == DTYPE_BF16 and os.environ.get("MMR_RT_TC", "1") != "0"
     packed = torch.empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8, device=dev)
     rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed)
     if use_tc:
-        rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_bf16, rp.proj_w_bf16, _stream())
+        rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_f16, rp.proj_w_f16, _stream())
         _lib.check(rc, "mmr_routing_pack_weights")
     logits = torch.empty(B, K, dtype=torch.float32, device=dev)
     alpha = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)

@@ -59,6 +59,9 @@ def test_graph_replay_matches_eager_step():
         for k in ref:
             scale = float(ref[k].abs().max()) + 1e-20
             err = float((got[k].float() - ref[k].float()).abs().max()) / scale
-            # forward results are deterministic; split-K weight gradients accumulate with atomics
-            tol = 1e-5 if k in ("loss", "logits", "R") else 2e-3
+            # forward results are deterministic.  Gradients are not, replayed or not: fp32 atomics (split-K weight
+            # gradients, cross-direction sums) feed bf16 roundings, and tools/diag_determinism.py measures up to 7e-3
+            # between two runs of the SAME path at this batch size (1e-7 with the fp32 kernels) -- so the bar here is
+            # the bf16 budget of BASELINE.json, not bit equality.
+            tol = 1e-5 if k in ("loss", "logits", "R") else 2e-2
             assert err <= tol, f"{k}: {err:.3e}"

@@ -131,7 +131,7 @@ def test_head_forward_from_poses():
 @pytest.mark.parametrize("variant,K,masked", [("pheno", 25, True), ("mort", 2, True), ("pheno", 32, False), ("pheno", 3, True)])
 def test_routing_reduced_precision_tensor_core_vs_cuda_core(variant, K, masked, monkeypatch):
     """Reduced-precision routing (what runs under autocast): the tensor-core projector / vote contraction
-    (mma.sync, bf16 weight copies from mmr_routing_pack_weights) against the CUDA-core path of the same mode and the fp32
+    (mma.sync, fp16 weight copies from mmr_routing_pack_weights) against the CUDA-core path of the same mode and the fp32
     oracle.  Bars: logits / alpha / R within 2e-2 of the oracle (BASELINE.json bf16 tolerance); gradients at least
     as close to the oracle as the CUDA-core reduced-precision path (x2) or 5e-2."""
     if variant == "mort":

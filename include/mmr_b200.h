@@ -151,7 +151,8 @@ typedef struct mmr_routing_params {
   const float* bias;                 /* [K] */
   /* optional (NULL: CUDA-core contraction): fp16 copies written by mmr_routing_pack_weights, read by the tensor-core
    * projector / vote contraction of the reduced-precision mode (vote_dtype = MMR_DTYPE_BF16) */
-  const void* caps_wt_f16;          /* [10, K*64, 32] */
+  const void* caps_wt_f16;          /* [10, K*64, 32]  (transposed: forward vote contraction) */
+  const void* caps_w_f16;           /* [10, 32, K*64]  (original layout: backward of the vote contraction) */
   const void* proj_w_f16;           /* [10, 40, 256], rows >= 33 zero */
 } mmr_routing_params;
 
@@ -167,10 +168,10 @@ typedef struct mmr_routing_grads {   /* zero-initialised fp32 accumulators; NULL
 size_t mmr_routing_scratch_bytes(const mmr_routing_dims* dims);
 
 /* Packs capsule.w (and, when params->proj_w[0] != NULL and proj_w_f16 != NULL, the projector weights) into the fp16
- * layouts above.  caps_wt_f16 needs 10*K*64*32*2 bytes, proj_w_f16 10*40*256*2 bytes (16-byte aligned, caller-owned).
+ * layouts above.  caps_wt_f16 and caps_w_f16 need 10*K*64*32*2 bytes each, proj_w_f16 10*40*256*2 bytes (16-byte aligned, caller-owned).
  * Call once per parameter version (the Python op does it per forward and hands the buffers to the backward). */
-int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* proj_w_f16,
-                             void* stream);
+int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* caps_w_f16,
+                             void* proj_w_f16, void* stream);
 
 /* Replaces forward_capsule_from_route_dict / CapsuleMortalityHead.forward.
  * route_embs: fp32, element (r,b,c) at r*emb_route_stride + b*emb_batch_stride + c.

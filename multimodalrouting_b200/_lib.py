@@ -27,7 +27,7 @@ class RoutingDims(C.Structure):
 
 class RoutingParams(C.Structure):
     _fields_ = [("proj_w", c_fp * 10), ("proj_b", c_fp * 10), ("caps_w", c_fp), ("pose_to_mc", c_fp),
-                ("embedding", c_fp), ("bias", c_fp), ("caps_wt_f16", c_fp), ("proj_w_f16", c_fp)]
+                ("embedding", c_fp), ("bias", c_fp), ("caps_wt_f16", c_fp), ("caps_w_f16", c_fp), ("proj_w_f16", c_fp)]
 
 
 class RoutingGrads(C.Structure):
@@ -90,7 +90,7 @@ def load():
     lib.mmr_route_fusion_bwd_ex.restype = C.c_int
     lib.mmr_routing_scratch_bytes.argtypes = [C.POINTER(RoutingDims)]
     lib.mmr_routing_scratch_bytes.restype = C.c_size_t
-    lib.mmr_routing_pack_weights.argtypes = [C.POINTER(RoutingParams), C.c_int, c_fp, c_fp, c_fp]
+    lib.mmr_routing_pack_weights.argtypes = [C.POINTER(RoutingParams), C.c_int, c_fp, c_fp, c_fp, c_fp]
     lib.mmr_routing_pack_weights.restype = C.c_int
     lib.mmr_capsule_routing_fwd.argtypes = [C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 11
     lib.mmr_capsule_routing_fwd.restype = C.c_int

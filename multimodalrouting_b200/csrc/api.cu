@@ -1197,17 +1197,17 @@ static cudaError_t dispatch_routing(const RoutingArgs& a, const RtLaunch& L, boo
 
 extern "C" {
 
-int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* proj_w_f16,
-                             void* stream) {
-  if (!params || !params->caps_w || !caps_wt_f16) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: null argument");
+int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* caps_w_f16,
+                             void* proj_w_f16, void* stream) {
+  if (!params || !params->caps_w || !caps_wt_f16 || !caps_w_f16) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: null argument");
   if (K < 1 || K > MMR_MAX_LABELS) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: K out of range");
   const bool proj = proj_w_f16 != nullptr && params->proj_w[0] != nullptr;
   if (proj)
     for (int r = 0; r < NR; ++r)
       if (!params->proj_w[r]) return fail(MMR_ERR_INVALID_ARG, "mmr_routing_pack_weights: missing projector weight");
-  const long long n = 10LL * K * 64 + (proj ? 10LL * 40 * 32 : 0);
+  const long long n = 10LL * K * 64 + 10LL * 32 * K * 64 / 8 + (proj ? 10LL * 40 * 32 : 0);
   routing_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *params, K, reinterpret_cast<__half*>(caps_wt_f16), proj ? reinterpret_cast<__half*>(proj_w_f16) : nullptr);
+      *params, K, reinterpret_cast<__half*>(caps_wt_f16), reinterpret_cast<__half*>(caps_w_f16), proj ? reinterpret_cast<__half*>(proj_w_f16) : nullptr);
   LAUNCH_OK("routing_pack");
   return MMR_OK;
 }

@@ -219,6 +219,47 @@ __device__ inline void rt_votes_mma(const RoutingArgs& a, const float* pp, uint8
   __syncthreads();
 }
 
+// backward of the vote contraction: dpose[p][r][a] += sum_c du[p][r][c] * w[r][a][c]  (du already fp16 in the vote region;
+// (route, 32-column group) units are split evenly over the warps, partial tiles are flushed with shared-memory atomics)
+template <int PB>
+__device__ inline void rt_dpose_mma(const RoutingArgs& a, float* pp, const uint8_t* ureg, size_t ustride, int np) {
+  const int KD = a.d.K * 64, G = KD / 32, U = 10 * G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  constexpr int NW = RT_THREADS / 32;
+  const int u0 = (int)((long long)U * warp / NW), u1 = (int)((long long)U * (warp + 1) / NW);
+  const __half* urow = reinterpret_cast<const __half*>(ureg + (g < PB ? g : 0) * ustride);
+  const uint4* w16 = reinterpret_cast<const uint4*>(a.p.caps_w_f16);
+  float acc[4][4];
+  int rcur = -1;
+  auto flush = [&]() {
+    if (rcur < 0 || g >= PB || g >= np) return;
+    float* dp = rt_patient(pp, g, true).dpose + rcur * 32;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      atomicAdd(dp + n * 8 + 2 * t, acc[n][0]);
+      atomicAdd(dp + n * 8 + 2 * t + 1, acc[n][1]);
+    }
+  };
+  for (int u = u0; u < u1; ++u) {
+    const int r = u / G, kk = u % G;
+    if (r != rcur) {
+      flush();
+      rcur = r;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    }
+    uint4 A = make_uint4(0u, 0u, 0u, 0u);
+    if (g < PB) A = *reinterpret_cast<const uint4*>(urow + r * KD + 32 * kk + 8 * t);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const uint4 q = __ldg(w16 + ((size_t)(r * 32 + n * 8 + g) * KD + 32 * kk + 8 * t) / 8);
+      rt_mma(acc[n], A.x, A.y, q.x, q.y);
+      rt_mma(acc[n], A.z, A.w, q.z, q.w);
+    }
+  }
+  flush();
+}
+
 // ---- tile phase 1: projector + activation chain for the np patients b0 .. b0+np-1 ---------------
 template <int PB>
 __device__ inline void rt_project(const RoutingArgs& a, float* pp, uint8_t* ureg, size_t ustride, bool bwd, int b0, int np) {
@@ -628,6 +669,14 @@ __global__ void __launch_bounds__(RT_THREADS, MMR_RT_MINB) routing_bwd_kernel(Ro
     }
     // (f') dpose[p][r][a] += sum_c du[p][r][c]*w[r][a][c]: a thread owns (column quarter, r, a); lanes of a
     // warp share r, so the du reads are shared-memory broadcasts and each weight load feeds PB dot products.
+    bool dpose_done = false;
+    if constexpr (std::is_same<UT, __half>::value && PB <= 8) {
+      if (a.p.caps_w_f16 != nullptr) {
+        rt_dpose_mma<PB>(a, pp, ureg, ustride, np);
+        dpose_done = true;
+      }
+    }
+    if (!dpose_done)
     for (int item = tid; item < 4 * 320; item += RT_THREADS) {
       const int cq = item / 320, ra = item % 320, r = ra >> 5;
       const int c4_lo = (KD / 4) * cq / 4, c4_hi = (KD / 4) * (cq + 1) / 4;
@@ -748,8 +797,9 @@ __global__ void routing_head_grads_kernel(const float* dG, const float* pose_to_
 
 // fp16, reduction-index-contiguous copies of the two weight tensors the tensor-core paths read:
 //   caps_wt[r][c][a] = w[r][a][c]            (10 x K*64 columns of 32)       one thread per column
+//   caps_w16[r][a][c] = w[r][a][c]           (original layout, for the backward) one thread per 8 elements
 //   proj_wb[r][n][k] = proj_w[r][n][k], n<33 (10 x 40 rows of 256, rest 0)   one thread per 8 elements
-__global__ void routing_pack_kernel(mmr_routing_params p, int K, __half* caps_wt, __half* proj_wb) {
+__global__ void routing_pack_kernel(mmr_routing_params p, int K, __half* caps_wt, __half* caps_w16, __half* proj_wb) {
   const int KD = K * 64;
   const long long n_caps = 10LL * KD;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -768,7 +818,16 @@ __global__ void routing_pack_kernel(mmr_routing_params p, int K, __half* caps_wt
     }
     return;
   }
-  const long long j = i - n_caps;
+  const long long n_w16 = 10LL * 32 * KD / 8;       // caps_w16[r][a][c] = w[r][a][c]: one thread per 8 elements
+  if (i < n_caps + n_w16) {
+    const long long e = (i - n_caps) * 8;
+    const float4 x0 = *reinterpret_cast<const float4*>(p.caps_w + e), x1 = *reinterpret_cast<const float4*>(p.caps_w + e + 4);
+    uint4 o;
+    o.x = rt_pack2(x0.x, x0.y); o.y = rt_pack2(x0.z, x0.w); o.z = rt_pack2(x1.x, x1.y); o.w = rt_pack2(x1.z, x1.w);
+    reinterpret_cast<uint4*>(caps_w16)[i - n_caps] = o;
+    return;
+  }
+  const long long j = i - n_caps - n_w16;
   if (proj_wb == nullptr || j >= 10LL * 40 * 32) return;
   const int row = (int)(j / 32), chunk = (int)(j % 32), r = row / 40, n = row % 40;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);

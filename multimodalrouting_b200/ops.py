@@ -352,16 +352,18 @@ PROJ_PACK_BYTES = 10 * 40 * 256 * 2
 
 
 def routing_pack_bytes(K: int) -> int:
-    """bytes of the fp16 weight copies the tensor-core routing paths read (caps_wt | proj_wb)."""
-    return 10 * K * 64 * 32 * 2 + PROJ_PACK_BYTES
+    """bytes of the fp16 weight copies the tensor-core routing paths read (caps_wt | caps_w16 | proj_wb)."""
+    return 2 * (10 * K * 64 * 32 * 2) + PROJ_PACK_BYTES
 
 
 def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed=None) -> RoutingParams:
     rp = RoutingParams()
     if packed is not None and packed.numel() > 0:
         K = embedding.shape[0]
+        caps = 10 * K * 64 * 32 * 2
         rp.caps_wt_f16 = packed.data_ptr()
-        rp.proj_w_f16 = (packed.data_ptr() + 10 * K * 64 * 32 * 2) if proj_w else None
+        rp.caps_w_f16 = packed.data_ptr() + caps
+        rp.proj_w_f16 = (packed.data_ptr() + 2 * caps) if proj_w else None
     for r in range(N_ROUTES):
         rp.proj_w[r] = proj_w[r].data_ptr() if proj_w else None
         rp.proj_b[r] = proj_b[r].data_ptr() if proj_b else None
@@ -391,7 +393,7 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     packed = torch.empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8, device=dev)
     rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed)
     if use_tc:
-        rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_f16, rp.proj_w_f16, _stream())
+        rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_f16, rp.caps_w_f16, rp.proj_w_f16, _stream())
         _lib.check(rc, "mmr_routing_pack_weights")
     logits = torch.empty(B, K, dtype=torch.float32, device=dev)
     alpha = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)

@@ -273,6 +273,11 @@ long long mmr_launch_count(void);
 int mmr_prof_enable(int on);
 int mmr_prof_collect(double* ms_by_class, long long* n_by_class);
 
+/* sizeof() of the public structs, in declaration order: mmr_fusion_dims, mmr_routing_dims, mmr_routing_params,
+ * mmr_routing_grads, mmr_opt_tensor, mmr_opt_hyper, mmr_opt_state.  Lets a foreign-language binding assert that its
+ * mirror of the structs matches this build (returns the number of entries written, at most n). */
+int mmr_abi_struct_sizes(size_t* out, int n);
+
 int mmr_version(void);
 const char* mmr_last_error_string(void);
 

@@ -52,7 +52,7 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
-           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights"]
+           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes"]
 
 
 def lib_path() -> str:
@@ -120,6 +120,18 @@ def load():
     lib.mmr_opt_apply.restype = C.c_int
     lib.mmr_ema_update.argtypes = [C.POINTER(OptTensor), C.c_int, C.c_double, c_fp]
     lib.mmr_ema_update.restype = C.c_int
+    lib.mmr_abi_struct_sizes.argtypes = [C.POINTER(C.c_size_t), C.c_int]
+    lib.mmr_abi_struct_sizes.restype = C.c_int
+    # the ctypes mirrors above must match the structs this build was compiled with
+    sizes = (C.c_size_t * 7)()
+    n = lib.mmr_abi_struct_sizes(sizes, 7)
+    mirrors = (FusionDims, RoutingDims, RoutingParams, RoutingGrads, OptTensor, OptHyper)
+    for i, cls in enumerate(mirrors[:n]):
+        if C.sizeof(cls) != sizes[i]:
+            raise RuntimeError(f"ABI mismatch: ctypes {cls.__name__} is {C.sizeof(cls)} bytes, {path} has {sizes[i]} "
+                               "(stale libmmr_b200.so? rebuild with python -m multimodalrouting_b200.build)")
+    if n >= 7 and sizes[6] != OPT_STATE_BYTES:
+        raise RuntimeError(f"ABI mismatch: mmr_opt_state is {sizes[6]} bytes, binding expects {OPT_STATE_BYTES}")
     _LIB = lib
     return lib
 

@@ -1009,6 +1009,15 @@ int mmr_ema_update(const mmr_opt_tensor* host_tensors, int n_tensors, double dec
   });
 }
 
+int mmr_abi_struct_sizes(size_t* out, int n) {
+  const size_t sz[] = {sizeof(mmr_fusion_dims), sizeof(mmr_routing_dims), sizeof(mmr_routing_params),
+                       sizeof(mmr_routing_grads), sizeof(mmr_opt_tensor), sizeof(mmr_opt_hyper), sizeof(mmr_opt_state)};
+  const int m = (int)(sizeof(sz) / sizeof(sz[0]));
+  int i = 0;
+  for (; out && i < n && i < m; ++i) out[i] = sz[i];
+  return i;
+}
+
 int mmr_version(void) { return 100; }
 
 long long mmr_launch_count(void) { return g_launches.load(); }

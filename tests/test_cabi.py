@@ -84,3 +84,25 @@ def test_state_dict_keys_match_reference_layout():
                                       "pose_to_mc.weight"}
     proj = rh.RoutePrimaryProjector(256, 32)
     assert set(proj.state_dict()) == {f"proj.{r}.{k}" for r in synth.ROUTES for k in ("weight", "bias")}
+
+
+def test_ctypes_mirrors_match_the_compiled_structs():
+    """mmr_abi_struct_sizes: the binding refuses to load a library whose public structs differ from its mirrors."""
+    lib, L = _lib()
+    sizes = (C.c_size_t * 7)()
+    assert lib.mmr_abi_struct_sizes(sizes, 7) == 7
+    mirrors = (L.FusionDims, L.RoutingDims, L.RoutingParams, L.RoutingGrads, L.OptTensor, L.OptHyper)
+    assert [C.sizeof(m) for m in mirrors] == list(sizes)[:6]
+    assert sizes[6] == L.OPT_STATE_BYTES
+    assert lib.mmr_abi_struct_sizes(sizes, 2) == 2 and lib.mmr_abi_struct_sizes(None, 7) == 0
+
+
+def test_routing_pack_rejects_bad_arguments_without_launch():
+    lib, L = _lib()
+    p = L.RoutingParams()
+    assert lib.mmr_routing_pack_weights(C.byref(p), 25, 16, 32, None, None) != 0      # caps_w missing
+    p.caps_w = 64
+    assert lib.mmr_routing_pack_weights(C.byref(p), 0, 16, 32, None, None) != 0       # K out of range
+    assert lib.mmr_routing_pack_weights(C.byref(p), 25, None, 32, None, None) != 0    # output missing
+    from multimodalrouting_b200 import ops
+    assert ops.routing_pack_bytes(25) == 2 * 10 * 25 * 64 * 32 * 2 + 10 * 40 * 256 * 2

@@ -106,3 +106,26 @@ def test_routing_pack_rejects_bad_arguments_without_launch():
     assert lib.mmr_routing_pack_weights(C.byref(p), 25, None, 32, None, None) != 0    # output missing
     from multimodalrouting_b200 import ops
     assert ops.routing_pack_bytes(25) == 2 * 10 * 25 * 64 * 32 * 2 + 10 * 40 * 256 * 2
+
+
+def test_header_is_plain_c99_and_a_c_host_links():
+    """include/mmr_b200.h compiles as C99 (-pedantic -Werror) and examples/c_host.c links against the library and runs
+    its host-only entry points."""
+    import shutil
+    import subprocess
+    import tempfile
+    _lib()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    from multimodalrouting_b200 import build
+    csrc = os.path.dirname(build.LIB)
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "c_host")
+        cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "examples", "c_host.c"), "-L", csrc, "-lmmr_b200", f"-Wl,-rpath,{csrc}", "-o", exe]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert run.returncode == 0, run.stdout + run.stderr
+        assert "params=317" in run.stdout and "packed=" in run.stdout

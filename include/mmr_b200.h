@@ -246,6 +246,47 @@ int mmr_opt_apply(const mmr_opt_tensor* host_tensors, int n_tensors, const mmr_o
 /* EMA.update alone: ema = decay * ema + (1 - decay) * p for every table entry (g, m, v ignored). */
 int mmr_ema_update(const mmr_opt_tensor* host_tensors, int n_tensors, double decay, void* stream);
 
+/* ---- loss tail: what consumes logits / alpha / R right after capsule routing ----------
+ * Replaces, without any host synchronisation (the reference's coerce_rc_to_report calls .item() twice per step),
+ *   MORT   death_logit_from_logits2 + label smoothing + BCEWithLogitsLoss + route-entropy bonus + route-uniformity
+ *          penalty on alpha                               MortModel/Paired_Cross_Attention/main.py:1753-1755, 3084-3126
+ *   PHENO  coerce_rc_to_report + assert_routing_over_routes + BCEWithLogitsLoss(pos_weight) + batch-mean routing
+ *          entropy / uniformity terms      PhenoModel/Paired_Cross_Attention/main.py:1472-1564, 261-276, 2755-2812
+ * loss = base - ent + uni.  Only `base` carries gradient in the reference (alpha is returned detached,
+ * routing_and_heads.py:363, and coerce_rc_to_report detaches R, main.py:1483), so `dlogits` = d loss / d logits is
+ * the whole backward of this step; logits rewritten by _safe_tensor (NaN/Inf) get zero gradient like nan_to_num.
+ * Lambdas of 0 disable a term (the epoch warm-up gates are host logic).  Everything is fp32 except rc_raw. */
+typedef struct mmr_loss_state {   /* DEVICE resident, caller-owned, zero-initialised once */
+  float loss, base, ent, uni;     /* ent / uni already multiplied by their lambdas */
+  float err_routes, err_k;        /* max |sum_r R - 1|, max |sum_k R - 1| of the sanitised input (coerce case selection) */
+  float max_route_sum_err;        /* max |sum_r rc_report - 1|: assert_routing_over_routes fails when > atol */
+  int32_t info;                   /* 0 no routing coefficients; 1 already p(route|phenotype); 2 sums to one over labels
+                                     (the reference raises TypeError there, main.py:1519); 3 forced normalisation */
+  int32_t nonfinite_logits;       /* entries _safe_tensor rewrote */
+  uint32_t ticket;                /* internal */
+  int32_t reserved[2];
+} mmr_loss_state;
+typedef struct mmr_loss_args {
+  int32_t variant;                /* MMR_VARIANT_MORT (logits [B,2], y [B]) / MMR_VARIANT_PHENO (logits, y [B,K]) */
+  int32_t B, K;
+  int32_t rc_dtype;               /* MMR_DTYPE_F32 / MMR_DTYPE_BF16 of rc_raw */
+  const float* logits;
+  const float* y;
+  const float* pos_weight;        /* [K] or NULL (PHENO) */
+  const float* prim_acts;         /* [B,10] or NULL: alpha (MORT regularisers) */
+  const void* rc_raw;             /* [B,10,K] or NULL: R as returned by the capsule head (PHENO) */
+  const float* route_mask;        /* [B,10] or NULL */
+  float label_smoothing;          /* MORT */
+  float route_entropy_lambda, route_uniform_lambda;
+  float atol;                     /* coerce_rc_to_report / assert_routing_over_routes tolerance (reference: 1e-3) */
+  float* dlogits;                 /* [B,K] out or NULL (evaluation) */
+  float* rc_report;               /* [B,10,K] fp32 out or NULL */
+  mmr_loss_state* state;
+  void* scratch;                  /* mmr_loss_scratch_bytes(B) bytes, 8-byte aligned */
+} mmr_loss_args;
+size_t mmr_loss_scratch_bytes(int B);
+int mmr_loss_fwd_bwd(const mmr_loss_args* args, void* stream);
+
 /* Unit-test hook for the GEMM engines: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) with bf16 (dtype 1)
  * or fp32 (dtype 0) operands, fp32 output.  trans=1 computes C[M,N] = A[Kr,M]^T * B[Kr,N]
  * (the weight-gradient form, reduction over rows). */
@@ -274,7 +315,7 @@ int mmr_prof_enable(int on);
 int mmr_prof_collect(double* ms_by_class, long long* n_by_class);
 
 /* sizeof() of the public structs, in declaration order: mmr_fusion_dims, mmr_routing_dims, mmr_routing_params,
- * mmr_routing_grads, mmr_opt_tensor, mmr_opt_hyper, mmr_opt_state.  Lets a foreign-language binding assert that its
+ * mmr_routing_grads, mmr_opt_tensor, mmr_opt_hyper, mmr_opt_state, mmr_loss_state, mmr_loss_args.  Lets a foreign-language binding assert that its
  * mirror of the structs matches this build (returns the number of entries written, at most n). */
 int mmr_abi_struct_sizes(size_t* out, int n);
 

@@ -46,13 +46,23 @@ class OptHyper(C.Structure):
 
 
 OPT_STATE_BYTES = 40     # sizeof(mmr_opt_state): 3 doubles, 2 floats, 2 int32
+LOSS_STATE_BYTES = 48    # sizeof(mmr_loss_state): 7 floats, 2 int32, ticket, 2 reserved
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("B", C.c_int32), ("K", C.c_int32), ("rc_dtype", C.c_int32),
+                ("logits", c_fp), ("y", c_fp), ("pos_weight", c_fp), ("prim_acts", c_fp), ("rc_raw", c_fp),
+                ("route_mask", c_fp), ("label_smoothing", C.c_float), ("route_entropy_lambda", C.c_float),
+                ("route_uniform_lambda", C.c_float), ("atol", C.c_float), ("dlogits", c_fp), ("rc_report", c_fp),
+                ("state", c_fp), ("scratch", c_fp)]
 
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
-           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes"]
+           "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
+           "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd"]
 
 
 def lib_path() -> str:
@@ -123,8 +133,12 @@ def load():
     lib.mmr_abi_struct_sizes.argtypes = [C.POINTER(C.c_size_t), C.c_int]
     lib.mmr_abi_struct_sizes.restype = C.c_int
     # the ctypes mirrors above must match the structs this build was compiled with
-    sizes = (C.c_size_t * 7)()
-    n = lib.mmr_abi_struct_sizes(sizes, 7)
+    lib.mmr_loss_scratch_bytes.argtypes = [C.c_int]
+    lib.mmr_loss_scratch_bytes.restype = C.c_size_t
+    lib.mmr_loss_fwd_bwd.argtypes = [C.POINTER(LossArgs), c_fp]
+    lib.mmr_loss_fwd_bwd.restype = C.c_int
+    sizes = (C.c_size_t * 9)()
+    n = lib.mmr_abi_struct_sizes(sizes, 9)
     mirrors = (FusionDims, RoutingDims, RoutingParams, RoutingGrads, OptTensor, OptHyper)
     for i, cls in enumerate(mirrors[:n]):
         if C.sizeof(cls) != sizes[i]:
@@ -132,6 +146,9 @@ def load():
                                "(stale libmmr_b200.so? rebuild with python -m multimodalrouting_b200.build)")
     if n >= 7 and sizes[6] != OPT_STATE_BYTES:
         raise RuntimeError(f"ABI mismatch: mmr_opt_state is {sizes[6]} bytes, binding expects {OPT_STATE_BYTES}")
+    if n < 9 or sizes[7] != LOSS_STATE_BYTES or sizes[8] != C.sizeof(LossArgs):
+        raise RuntimeError(f"ABI mismatch: loss structs are {list(sizes[7:n])} bytes, binding expects "
+                           f"[{LOSS_STATE_BYTES}, {C.sizeof(LossArgs)}] (stale libmmr_b200.so?)")
     _LIB = lib
     return lib
 

@@ -14,6 +14,7 @@
 #include "routing.cuh"
 #include "rows.cuh"
 #include "tail.cuh"
+#include "loss.cuh"
 
 using namespace mmr;
 
@@ -1009,9 +1010,52 @@ int mmr_ema_update(const mmr_opt_tensor* host_tensors, int n_tensors, double dec
   });
 }
 
+// ------------------------------------------------------------------------------- loss tail ---
+size_t mmr_loss_scratch_bytes(int B) {
+  const size_t nblk = B > 0 ? (size_t)(B + LOSS_PB - 1) / LOSS_PB : 1;
+  return nblk * LOSS_SLOTS * sizeof(double);
+}
+
+int mmr_loss_fwd_bwd(const mmr_loss_args* g, void* stream) {
+  if (!g) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: null args");
+  if (g->variant != MMR_VARIANT_MORT && g->variant != MMR_VARIANT_PHENO)
+    return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: variant must be MMR_VARIANT_MORT or MMR_VARIANT_PHENO");
+  if (g->B < 1) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: B must be >= 1");
+  if (g->variant == MMR_VARIANT_MORT && g->K != 2)
+    return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: the mortality head has 2 logits (death_logit_from_logits2 expects [B,2])");
+  if (g->K < 1 || g->K > MMR_MAX_LABELS) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: K must be in [1, 32]");
+  if (!g->logits || !g->y || !g->state || !g->scratch) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: null pointer");
+  if ((reinterpret_cast<uintptr_t>(g->scratch) & 7) != 0) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: scratch must be 8-byte aligned");
+  if (g->rc_dtype != MMR_DTYPE_F32 && g->rc_dtype != MMR_DTYPE_BF16)
+    return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: rc_dtype must be MMR_DTYPE_F32 or MMR_DTYPE_BF16");
+  if (g->variant == MMR_VARIANT_MORT && (g->rc_raw || g->rc_report || g->pos_weight))
+    return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: rc_raw / rc_report / pos_weight belong to the PHENO variant");
+  if (g->rc_report && !g->rc_raw) return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: rc_report needs rc_raw");
+  if (!(g->label_smoothing >= 0.f && g->label_smoothing <= 1.f) || !(g->route_entropy_lambda >= 0.f) ||
+      !(g->route_uniform_lambda >= 0.f) || !(g->atol > 0.f))
+    return fail(MMR_ERR_INVALID_ARG, "mmr_loss_fwd_bwd: label_smoothing in [0,1], lambdas >= 0, atol > 0");
+  LossArgs a;
+  a.variant = g->variant; a.B = g->B; a.K = g->K;
+  a.logits = g->logits; a.y = g->y; a.pos_weight = g->pos_weight; a.prim_acts = g->prim_acts;
+  a.rc_raw = g->rc_raw; a.rc_bf16 = g->rc_dtype == MMR_DTYPE_BF16; a.route_mask = g->route_mask;
+  a.label_smoothing = g->label_smoothing; a.lam_ent = g->route_entropy_lambda; a.lam_uni = g->route_uniform_lambda;
+  a.atol = g->atol; a.dlogits = g->dlogits; a.rc_report = g->rc_report; a.state = g->state;
+  a.scratch = reinterpret_cast<double*>(g->scratch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((g->B + LOSS_PB - 1) / LOSS_PB);
+  loss_stage1_kernel<<<blocks, LOSS_WARPS * 32, 0, st>>>(a);
+  LAUNCH_OK("loss_stage1");
+  if (g->variant == MMR_VARIANT_PHENO && g->rc_raw) {
+    loss_stage2_kernel<<<blocks, LOSS_WARPS * 32, 0, st>>>(a);
+    LAUNCH_OK("loss_stage2");
+  }
+  return MMR_OK;
+}
+
 int mmr_abi_struct_sizes(size_t* out, int n) {
   const size_t sz[] = {sizeof(mmr_fusion_dims), sizeof(mmr_routing_dims), sizeof(mmr_routing_params),
-                       sizeof(mmr_routing_grads), sizeof(mmr_opt_tensor), sizeof(mmr_opt_hyper), sizeof(mmr_opt_state)};
+                       sizeof(mmr_routing_grads), sizeof(mmr_opt_tensor), sizeof(mmr_opt_hyper), sizeof(mmr_opt_state),
+                       sizeof(mmr_loss_state), sizeof(mmr_loss_args)};
   const int m = (int)(sizeof(sz) / sizeof(sz[0]));
   int i = 0;
   for (; out && i < n && i < m; ++i) out[i] = sz[i];

@@ -138,12 +138,132 @@ def route_mask_case():
     return dict(hasL=has[0], hasN=has[1], hasI=has[2], mask=a)
 
 
+def _inline(path, first, last, ns):
+    """Execute the reference's own statements `first`..`last` (1-based, inclusive; they sit inside the training loop of
+    main(), so they are dedented, not imported) in namespace `ns`."""
+    import textwrap
+    lines = open(path).read().splitlines()[first - 1:last]
+    exec(compile(textwrap.dedent("\n".join(lines)), f"{path}:{first}-{last}", "exec"), ns)
+    return ns
+
+
+def _anchor(path, text):
+    for i, ln in enumerate(open(path).read().splitlines(), 1):
+        if ln.strip().startswith(text):
+            return i
+    raise AssertionError(f"{text!r} not found in {path}")
+
+
+def loss_cases():
+    """Mort: main.py `y_f = y.float().view(-1, 1)` .. `loss = base_loss - ent_bonus + uniform_pen` (3092-3126) executed
+    as they are; Pheno: coerce_rc_to_report / assert_routing_over_routes / _safe_tensor definitions executed as they
+    are, then `loss = bce(logits, y.float())` .. the uniform term (2793-2812) executed as they are."""
+    from typing import Optional
+    gen = torch.Generator().manual_seed(9004)
+    out = {"mort": [], "pheno": []}
+    # ---- Mort
+    m = extract(M_MAIN, ["death_logit_from_logits2", "_safe_tensor"])
+    a0, a1 = _anchor(M_MAIN, "y_f = y.float().view(-1, 1)"), _anchor(M_MAIN, "loss = base_loss - ent_bonus + uniform_pen")
+    assert (a0, a1) == (3092, 3126), (a0, a1)
+    B = 37
+    for name, ls, le, we, lu, wu, cur, bad in (("plain", 0.02, 0.0, 0, 0.0, 0, 1, False), ("regs", 0.0, 0.01, 0, 0.1, 0, 1, False),
+                                               ("gated", 0.05, 0.02, 3, 0.1, 2, 2, False), ("nonfinite", 0.02, 0.01, 0, 0.1, 0, 1, True)):
+        logits = (torch.randn(B, 2, generator=gen) * 2.0)
+        if bad:
+            logits[3, 1] = float("nan"); logits[5, 0] = float("inf"); logits[7, 1] = float("-inf")
+        y = (torch.rand(B, generator=gen) < 0.15).long()
+        pa = torch.sigmoid(torch.randn(B, 10, generator=gen)) * (torch.rand(B, 10, generator=gen) < 0.8).float()
+        lg = logits.clone().requires_grad_(True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ns = dict(torch=torch, y=y, death_logit_from_logits2=m["death_logit_from_logits2"], epoch=cur - 1, start_epoch=-5,
+                      step=1, label_smoothing=ls, loss_fn_train=torch.nn.BCEWithLogitsLoss(), rc_raw=None,
+                      logits=m["_safe_tensor"](lg.float(), "logits(fp32)"), prim_acts=m["_safe_tensor"](pa.float(), "prim_acts(fp32)"),
+                      route_entropy_lambda=le, route_entropy_warmup_epochs=we, route_uniform_lambda=lu, route_uniform_warmup_epochs=wu)
+            _inline(M_MAIN, a0, a1, ns)
+        (dl,) = torch.autograd.grad(ns["loss"], lg)
+        out["mort"].append(dict(name=name, logits=logits, y=y, prim_acts=pa, label_smoothing=ls, lam_ent=le, warm_ent=we,
+                                lam_uni=lu, warm_uni=wu, cur_epoch=cur, loss=ns["loss"].detach(), base=ns["base_loss"].detach(),
+                                ent=ns["ent_bonus"].detach(), uni=ns["uniform_pen"].detach(), dlogits=dl))
+    # ---- Pheno
+    rh = {}
+    for node in ast.parse(open("/root/reference/MIMIC-IV/PhenoModel/Paired_Cross_Attention/routing_and_heads.py").read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "route_given_pheno":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "rh", "exec"), rh)
+    p = extract(P_MAIN, ["_safe_tensor", "assert_routing_over_routes"])
+    pc = {"torch": torch, "Optional": Optional, "route_given_pheno": rh["route_given_pheno"]}
+    for node in ast.parse(open(P_MAIN).read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "coerce_rc_to_report":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), P_MAIN, "exec"), pc)
+    b0, b1 = _anchor(P_MAIN, "loss = bce(logits, y.float())"), _anchor(P_MAIN, "loss = loss + route_uniform_lambda * uniform_loss")
+    assert (b0, b1) == (2793, 2812), (b0, b1)
+
+    def rc_routes(B, K, mask):
+        q = torch.rand(B, 10, K, generator=gen) ** 2 + 1e-3
+        if mask is not None:
+            q = q * mask.unsqueeze(-1)
+        return q / q.sum(dim=1, keepdim=True).clamp_min(1e-10)
+
+    for name, B, K, kind, use_mask, le, we, lu, wu, cur in (
+            ("routes_mask", 37, 25, "routes", True, 0.01, 0, 0.1, 0, 1.0), ("routes_nomask", 16, 25, "routes", False, 0.01, 0, 0.1, 0, 1.0),
+            ("routes_bf16", 37, 25, "routes_bf16", True, 0.01, 0, 0.1, 0, 1.0), ("forced", 21, 3, "raw", True, 0.01, 0, 0.0, 0, 1.0),
+            ("forced_nomask", 9, 25, "raw", False, 0.0, 0, 0.1, 0, 1.0), ("gated", 12, 25, "routes", True, 0.01, 1, 0.1, 2, 1.0),
+            ("over_labels", 8, 25, "labels", True, 0.01, 0, 0.1, 0, 1.0), ("all_masked", 8, 25, "routes_dead", True, 0.01, 0, 0.1, 0, 1.0)):
+        mask = None
+        if use_mask:
+            mask = (torch.rand(B, 10, generator=gen) < 0.7).float()
+            mask[:, 0] = 1.0
+            if kind == "routes_dead":
+                mask[2] = 0.0
+        if kind in ("routes", "routes_dead"):
+            rc = rc_routes(B, K, mask)
+        elif kind == "routes_bf16":
+            rc = rc_routes(B, K, mask).to(torch.bfloat16)
+        elif kind == "labels":
+            rc = torch.softmax(torch.randn(B, 10, K, generator=gen), dim=2)
+        else:
+            rc = torch.randn(B, 10, K, generator=gen) * 0.3 + 0.2
+            rc[1, 2, 0] = float("nan"); rc[2, 3, 1] = float("inf")
+            if mask is not None:
+                rc[4] = -1.0                                   # every route clamps to 0: denominators < 1e-8 -> uniform over kept routes
+        logits = torch.randn(B, K, generator=gen) * 2.0
+        if name == "forced":
+            logits[0, 1] = float("nan"); logits[1, 2] = float("inf")
+        y = (torch.rand(B, K, generator=gen) < 0.2).float()
+        pw = torch.clamp(torch.rand(K, generator=gen) * 6.0, 0.1, 5.0)
+        pa = torch.sigmoid(torch.randn(B, 10, generator=gen))
+        rec = dict(name=name, logits=logits, y=y, pos_weight=pw, rc_raw=rc, prim_acts=pa, route_mask=mask, lam_ent=le, warm_ent=we,
+                   lam_uni=lu, warm_uni=wu, cur_epoch=cur, raises=None)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                rc_report, info = pc["coerce_rc_to_report"](rc, pa, mask, split_name="TRAIN")
+        except TypeError as e:
+            rec["raises"] = ("TypeError", str(e))
+            out["pheno"].append(rec)
+            continue
+        rec.update(rc_report=rc_report, info=info)
+        try:
+            p["assert_routing_over_routes"](rc_report, routes_dim=1, atol=1e-3, name="TRAIN.rc_report")
+        except AssertionError as e:
+            rec["raises"] = ("AssertionError", str(e)[:80])
+        lg = logits.clone().requires_grad_(True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ns = dict(torch=torch, y=y, epoch=0, bce=torch.nn.BCEWithLogitsLoss(pos_weight=pw, reduction="mean"),
+                      logits=p["_safe_tensor"](lg.float(), "logits(fp32)"), routing_coef=rc_report, cur_epoch=cur,
+                      route_entropy_lambda=le, route_entropy_warmup_epochs=we, route_uniform_lambda=lu, route_uniform_warmup_epochs=wu)
+            _inline(P_MAIN, b0, b1, ns)
+        (dl,) = torch.autograd.grad(ns["loss"], lg)
+        rec.update(loss=ns["loss"].detach(), dlogits=dl)
+        out["pheno"].append(rec)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.save(route_mask_case(), os.path.join(GOLD, "tail_route_mask.pt"))
     torch.save(sanitize_cases(), os.path.join(GOLD, "tail_sanitize.pt"))
     torch.save(tail_case(), os.path.join(GOLD, "tail_adamw_ema.pt"))
-    for f in ("tail_sanitize.pt", "tail_adamw_ema.pt"):
+    torch.save(loss_cases(), os.path.join(GOLD, "tail_loss.pt"))
+    for f in ("tail_sanitize.pt", "tail_adamw_ema.pt", "tail_loss.pt"):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
 

@@ -117,3 +117,88 @@ def route_mask_from_presence(hasL, hasN, hasI):
             m = m * has[ch]
         cols.append(m)
     return torch.stack(cols, dim=1)
+
+
+# ---- loss tail ----------------------------------------------------------------------------------------
+# Third-party arithmetic: torch.nn.functional.binary_cross_entropy_with_logits (ATen; the reference builds
+# nn.BCEWithLogitsLoss objects, MortModel main.py:2717, PhenoModel main.py:2467).  Its published formula,
+# loss = (1 - y) x - (1 + (pos_weight - 1) y) log(sigmoid(x)), mean-reduced, is what `bce_with_logits` restates.
+def bce_with_logits(x: torch.Tensor, y: torch.Tensor, pos_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lw = 1.0 if pos_weight is None else (pos_weight - 1.0) * y + 1.0
+    return ((1.0 - y) * x - lw * torch.nn.functional.logsigmoid(x)).mean()
+
+
+def mort_train_loss(logits, y, prim_acts, label_smoothing=0.02, route_entropy_lambda=0.0,
+                    route_entropy_warmup_epochs=0, route_uniform_lambda=0.0, route_uniform_warmup_epochs=0, cur_epoch=1):
+    """MortModel/Paired_Cross_Attention/main.py:3084-3126.  Returns dict(loss, base, ent, uni)."""
+    logits = safe_tensor(logits.float())                                   # :3084
+    prim_acts = safe_tensor(prim_acts.float())                             # :3085
+    y_f = y.float().view(-1, 1)                                            # :3092
+    death_logit = (logits[:, 1] - logits[:, 0]).unsqueeze(1)               # :1753-1755
+    if label_smoothing > 0.0:
+        y_f = y_f * (1.0 - label_smoothing) + 0.5 * label_smoothing        # :3104-3105
+    base = bce_with_logits(death_logit, y_f)                               # :3107
+    ent = base.new_zeros(())
+    uni = base.new_zeros(())
+    pa = prim_acts.clamp_min(1e-6)
+    pa = pa / pa.sum(dim=1, keepdim=True).clamp_min(1e-6)                  # :3113-3114
+    if route_entropy_lambda > 0.0 and (route_entropy_warmup_epochs <= 0 or cur_epoch >= route_entropy_warmup_epochs):
+        p = pa.clamp_min(1e-12)
+        ent = -(p * p.log()).sum(dim=1).mean() * route_entropy_lambda       # :3116-3119
+    if route_uniform_lambda > 0.0 and (route_uniform_warmup_epochs <= 0 or cur_epoch >= route_uniform_warmup_epochs):
+        p_mean = pa.mean(dim=0)
+        uni = ((p_mean - 1.0 / p_mean.numel()).pow(2)).sum() * route_uniform_lambda   # :3120-3123
+    return dict(loss=base - ent + uni, base=base, ent=ent, uni=uni)
+
+
+def coerce_rc_to_report(rc_raw, prim_acts, route_mask, atol=1e-3):
+    """PhenoModel/Paired_Cross_Attention/main.py:1472-1564.  Returns (rc_report, info code 1 | 3); info 2 (the
+    coefficients sum to one over labels) raises TypeError exactly as the reference's call at :1519 does
+    (`route_given_pheno(rc_raw_f, pa_f, route_mask=rm_f)` binds route_mask twice)."""
+    rc = torch.nan_to_num(rc_raw.detach().float(), nan=0.0, posinf=0.0, neginf=0.0)
+    rm = None if route_mask is None else torch.nan_to_num(route_mask.detach().float(), nan=0.0, posinf=0.0, neginf=0.0)
+    err_routes = float((rc.sum(dim=1) - 1.0).abs().max())
+    err_k = float((rc.sum(dim=2) - 1.0).abs().max())
+    if err_routes < atol:
+        info = 1
+    elif err_k < atol:
+        raise TypeError("route_given_pheno() got multiple values for argument 'route_mask'")
+    else:
+        info = 3
+        rc = rc.clamp(min=0.0)
+    if rm is not None:
+        rc = rc * rm.unsqueeze(-1)
+    denom = rc.sum(dim=1, keepdim=True)
+    bad = (~torch.isfinite(denom)) | (denom < 1e-8)
+    if bad.any():
+        if rm is not None:
+            avail = rm.unsqueeze(-1)
+            uniform = avail / avail.sum(dim=1, keepdim=True).clamp(min=1.0)
+            rc = torch.where(bad, uniform.expand_as(rc), rc)
+        else:
+            rc = torch.where(bad, torch.full_like(rc, 1.0 / float(rc.shape[1])), rc)
+    rc = rc / rc.sum(dim=1, keepdim=True).clamp(min=1e-8)
+    return rc, info
+
+
+def pheno_train_loss(logits, y, routing_coef, prim_acts, route_mask, pos_weight=None, route_entropy_lambda=0.0,
+                     route_entropy_warmup_epochs=0, route_uniform_lambda=0.0, route_uniform_warmup_epochs=0,
+                     cur_epoch=1.0, atol=1e-3):
+    """PhenoModel/Paired_Cross_Attention/main.py:2755-2812.  Returns dict(loss, base, ent, uni, rc_report, info)."""
+    rc_report, info = (None, 0)
+    if routing_coef is not None:
+        rc_report, info = coerce_rc_to_report(routing_coef, prim_acts, route_mask, atol)        # :2764
+    logits = safe_tensor(logits.float())                                                        # :2784
+    base = bce_with_logits(logits, y.float(), pos_weight)                                       # :2793
+    ent = base.new_zeros(())
+    uni = base.new_zeros(())
+    if rc_report is not None:
+        rc = rc_report.float().clamp(1e-6, 1.0)                                                 # :2797
+        R = rc.shape[1]
+        if route_entropy_lambda > 0.0 and (route_entropy_warmup_epochs <= 0 or cur_epoch > route_entropy_warmup_epochs):
+            m = rc.mean(dim=0)
+            ent = route_entropy_lambda * (-(m * m.log()).sum(dim=0)).mean()                     # :2800-2804
+        if route_uniform_lambda > 0.0 and (route_uniform_warmup_epochs <= 0 or cur_epoch > route_uniform_warmup_epochs):
+            m = rc.mean(dim=0)
+            uni = route_uniform_lambda * (((m.transpose(0, 1) - 1.0 / R) ** 2).sum(dim=1)).mean()   # :2806-2812
+    return dict(loss=base - ent + uni, base=base, ent=ent, uni=uni, rc_report=rc_report, info=info)

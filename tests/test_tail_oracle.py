@@ -88,3 +88,81 @@ def test_route_mask_oracle_matches_reference_and_synth():
     for mod, idx in synth.NEEDS.items():
         need = [i for i, r in enumerate(to.ROUTES) if mod in r]
         assert sorted(idx) == need
+
+
+# ------------------------------------------------------------------------------------- loss tail ---
+def _close(a, b, tol=1e-6):
+    a, b = float(torch.as_tensor(a).detach()), float(torch.as_tensor(b).detach())
+    return abs(a - b) <= tol * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_mort_loss_oracle_matches_reference(idx):
+    """Fixtures: the reference's own statements main.py:3092-3126 executed by oracle/gen_golden_tail.py."""
+    g = _load("tail_loss.pt")["mort"][idx]
+    lg = g["logits"].clone().requires_grad_(True)
+    o = to.mort_train_loss(lg, g["y"], g["prim_acts"], g["label_smoothing"], g["lam_ent"], g["warm_ent"], g["lam_uni"],
+                           g["warm_uni"], g["cur_epoch"])
+    for k in ("loss", "base", "ent", "uni"):
+        assert _close(o[k], g[k]), (g["name"], k)
+    (dl,) = torch.autograd.grad(o["loss"], lg)
+    assert torch.allclose(dl, g["dlogits"], rtol=1e-5, atol=1e-9)
+    if g["name"] == "gated":
+        assert float(g["ent"]) == 0.0 and float(g["uni"]) > 0.0        # `>=` gate: warm-up 3 off, warm-up 2 on at epoch 2
+    if g["name"] == "nonfinite":
+        bad = ~torch.isfinite(g["logits"])
+        assert bad.sum() == 3 and bool((g["dlogits"][bad] == 0).all())   # nan_to_num blocks the gradient there
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_pheno_loss_oracle_matches_reference(idx):
+    """Fixtures: coerce_rc_to_report / assert_routing_over_routes definitions and the statements main.py:2793-2812 of
+    the reference executed as they are."""
+    g = _load("tail_loss.pt")["pheno"][idx]
+    args = (g["y"], g["rc_raw"], g["prim_acts"], g["route_mask"], g["pos_weight"], g["lam_ent"], g["warm_ent"],
+            g["lam_uni"], g["warm_uni"], g["cur_epoch"])
+    if g["raises"] and g["raises"][0] == "TypeError":
+        with pytest.raises(TypeError, match="multiple values"):
+            to.pheno_train_loss(g["logits"], *args)
+        return
+    lg = g["logits"].clone().requires_grad_(True)
+    o = to.pheno_train_loss(lg, *args)
+    assert to_info(o["info"]) == g["info"]
+    assert torch.allclose(o["rc_report"], g["rc_report"], rtol=1e-6, atol=1e-9)
+    assert _close(o["loss"], g["loss"])
+    (dl,) = torch.autograd.grad(o["loss"], lg)
+    assert torch.allclose(dl, g["dlogits"], rtol=1e-5, atol=1e-9)
+    s = o["rc_report"].sum(dim=1)
+    ok = bool(torch.allclose(s, torch.ones_like(s), atol=1e-3, rtol=0.0))
+    assert ok == (g["raises"] is None)                                  # all_masked: the reference's assertion fires
+    if g["name"] == "gated":
+        assert _close(o["ent"], 0.0) and _close(o["uni"], 0.0)          # strict `>` gate at cur_epoch == 1.0
+
+
+def to_info(code):
+    from multimodalrouting_b200.losses import INFO_TEXT
+    return INFO_TEXT[code]
+
+
+def test_loss_bindings_fail_loudly_on_cpu_and_validate():
+    import ctypes as C
+    from multimodalrouting_b200 import _lib, losses
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.mort_train_loss(torch.randn(4, 2), torch.zeros(4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.coerce_rc_to_report(torch.rand(2, 10, 3), None, None)
+    lib = _lib.load()
+    assert lib.mmr_loss_scratch_bytes(512) == 16 * 336 * 8 and lib.mmr_loss_scratch_bytes(1) == 336 * 8
+    a = _lib.LossArgs()
+    a.variant, a.B, a.K, a.atol = 0, 4, 3, 1e-3                          # Mort needs [B,2]
+    assert lib.mmr_loss_fwd_bwd(C.byref(a), None) == 1
+    assert b"2 logits" in lib.mmr_last_error_string()
+    a.K = 2                                                              # null pointers: rejected before any launch
+    assert lib.mmr_loss_fwd_bwd(C.byref(a), None) == 1
+    assert b"null pointer" in lib.mmr_last_error_string()
+    a.variant, a.K = 1, 33
+    assert lib.mmr_loss_fwd_bwd(C.byref(a), None) == 1
+    assert lib.mmr_loss_fwd_bwd(None, None) == 1
+    # warm-up gates: Mort `>=`, Pheno `>`  (main.py:3116 vs PhenoModel main.py:2799)
+    assert losses._gate(0.1, 2, 2, False) == 0.1 and losses._gate(0.1, 2, 2.0, True) == 0.0
+    assert losses._gate(0.1, 0, 1, True) == 0.1 and losses._gate(0.0, 0, 5, False) == 0.0

@@ -13,6 +13,7 @@
 #include "plan.cuh"
 #include "routing.cuh"
 #include "rows.cuh"
+#include "attention_tc.cuh"
 #include "tail.cuh"
 #include "loss.cuh"
 
@@ -142,6 +143,14 @@ template <class CT> static bool mma_attention() { return false; }
 template <> bool mma_attention<bf16>() {
   const char* e = getenv("MMR_ATTN");   // read per call so tests can switch engines inside one process
   return !(e && !strcmp(e, "simt"));
+}
+
+// MMR_ATTN=tc: tcgen05 / TMEM / TMA attention forward (attention_tc.cuh), the long-sequence engine; the backward stays on
+// the mma.sync kernels, which consume the same (o, ml) outputs
+template <class CT> static bool tc_attention() { return false; }
+template <> bool tc_attention<bf16>() {
+  const char* e = getenv("MMR_ATTN");
+  return e && !strcmp(e, "tc");
 }
 
 // launches a kernel that implements the pdl_trigger / pdl_wait protocol (programmatic dependent launch)
@@ -388,7 +397,10 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
       {
         ProfScope ps(PC_ATTN_FWD, st);
-        if (mma_attention<CT>()) {
+        if (tc_attention<CT>()) {
+          cudaError_t ce = atc::launch_attn_fwd_tc(a, B, maxTq, st);
+          if (ce != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("launch attn_fwd_tc: ") + cudaGetErrorString(ce));
+        } else if (mma_attention<CT>()) {
           dim3 grid(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
           int maxTk = 0;
           for (int d = 0; d < NDIR; ++d) maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d];

@@ -1,0 +1,221 @@
+// tcgen05 / TMEM / TMA cross-attention forward for the bf16 path (multihead_attention.py:93-143), all six directions in
+// one launch -- the long-sequence engine (INSPECT token counts, BASELINE configs[4]: 512 / 128 / 196 tokens), selected
+// with MMR_ATTN=tc.  The mma.sync kernels of attention_mma.cuh stay the default for the 16-49-token MIMIC shapes, where a
+// 128-row UMMA tile would be mostly padding ("Attention").
+//
+// CTA = (direction, patient, head PAIR, 128-query block), 9 warps:
+//   warp 8, lane 0   TMA producer + tcgen05.mma issuer
+//                      S_h  = Q_h K_h^T     M=128 queries x N=128 keys x K=32   (two K=16 steps per head, both operands
+//                                            K-major slices of one 128B-swizzled [128 x 64] tile that holds both heads)
+//                      O_h  = P_h V_pair    M=128 x N=64 x K=128 keys           (A = P_h, K-major, written by the softmax
+//                                            warps; B = the [keys x 64] V tile as it lies in memory = MN-major; the 32
+//                                            columns of the other head are computed and ignored)
+//   warps 0-3 / 4-7  softmax + epilogue of head 0 / 1: thread = query row (TMEM lane), scores read with tcgen05.ld,
+//                    rounded to bf16 like the reference's bmm output, key bias added (finfo(bf16).min for padded keys,
+//                    -inf for tile padding), online softmax over 128-key chunks with the running output in registers
+// TMEM: S 2 x 128 columns, O 2 x 64 columns.  Output and statistics are identical in meaning to amma::attn_fwd_kernel
+// (unnormalised bf16 P per chunk, final 1/l scaling, ml = (row max, 1/row sum)), so the mma.sync backward consumes them.
+#pragma once
+#include "attention_mma.cuh"
+#include "gemm_tc.cuh"
+
+namespace mmr {
+namespace atc {
+
+using namespace tc;
+
+constexpr int QB = 128;                 // queries per CTA
+constexpr int KC = 128;                 // keys per chunk
+constexpr int THREADS = 288;
+constexpr int TILE = 128 * 64 * 2;      // one 128B-swizzled [128 rows x 64 bf16] tile
+constexpr int SMEM_BYTES = 7 * TILE + 2 * KC * 4 + 256 + 1024;   // Q, K, V, P[2 heads][2 key blocks], key bias, ctrl, alignment
+
+struct Ctrl {
+  uint64_t kv_full;      // TMA: (Q +) K + V of the chunk landed
+  uint64_t s_full;       // both heads' score tiles are in TMEM
+  uint64_t p_full[2];    // head's P tile is in shared memory (4 warps arrive)
+  uint64_t o_full[2];    // head's P V product is in TMEM
+  uint32_t tmem_base;
+};
+
+// every legitimate wait in this kernel is far below a millisecond: trap early instead of spinning for minutes
+__device__ __forceinline__ void mbar_wait_short(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int d = blockIdx.z, b = blockIdx.y, hp = blockIdx.x & 3, qblk = blockIdx.x >> 2;
+  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  const int q0 = qblk * QB;
+  if (q0 >= Tq) return;
+  const int nq = min(QB, Tq - q0);
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t sQ = sbase, sK = sQ + TILE, sV = sK + TILE, sP = sV + TILE;
+  float* Ms = reinterpret_cast<float*>(sgen + 7 * TILE);          // [2][KC] additive key bias, double buffered
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(Ms + 2 * KC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&ctrl->kv_full), 1);
+    mbar_init(smem_u32(&ctrl->s_full), 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(&ctrl->p_full[h]), 4);
+      mbar_init(smem_u32(&ctrl->o_full[h]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctrl->tmem_base;
+  const uint32_t tS = tmem, tO = tmem + 256;
+  const int qrow0 = a.q.row0[d] + b * Tq + q0;
+  const int kvrow0 = a.kv.row0[d] + b * Tk;
+  const int nchunks = (Tk + KC - 1) / KC;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+      constexpr uint32_t idesc_s = make_idesc(KC, 0, 0);          // N = 128 keys, both operands K-major
+      constexpr uint32_t idesc_o = make_idesc(64, 0, 1);          // N = 64 value columns, B (= V) MN-major
+      const uint32_t kv_full = smem_u32(&ctrl->kv_full);
+      for (int c = 0; c < nchunks; ++c) {
+        // every MMA that read K, V and P of the previous chunk has retired (the second head's commit covers all)
+        if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[1]), (uint32_t)(c - 1) & 1u);
+        mbar_expect_tx(kv_full, (c == 0 ? 3u : 2u) * TILE);
+        if (c == 0) tma_load_2d(sQ, &tmQ, hp * 64, qrow0, kv_full);
+        tma_load_2d(sK, &tmKV, a.col0 + hp * 64, kvrow0 + c * KC, kv_full);
+        tma_load_2d(sV, &tmKV, a.col0 + D + hp * 64, kvrow0 + c * KC, kv_full);
+        mbar_wait_short(kv_full, (uint32_t)c & 1u);
+        tc_fence_after();
+        const uint64_t qdesc = make_smem_desc(sQ, 16, 1024), kdesc = make_smem_desc(sK, 16, 1024);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)     // head h = columns [32h, 32h+32) of the tile: K=16 steps 2h, 2h+1 (+32 B each)
+            umma_bf16(tS + h * KC, qdesc + 2 * (2 * h + k), kdesc + 2 * (2 * h + k), idesc_s, k != 0);
+        umma_commit(smem_u32(&ctrl->s_full));
+        const uint64_t vdesc = make_smem_desc(sV, 8192, 1024);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_short(smem_u32(&ctrl->p_full[h]), (uint32_t)c & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < KC / 16; ++j) {   // 16 keys per step: +32 B inside P's swizzle row, +16 rows (2048 B) of V
+            const uint64_t pdesc = make_smem_desc(sP + (2 * h + (j >> 2)) * TILE, 16, 1024) + 2 * (j & 3);
+            umma_bf16(tO + h * 64, pdesc, vdesc + 128 * j, idesc_o, j != 0);
+          }
+          umma_commit(smem_u32(&ctrl->o_full[h]));
+        }
+      }
+    }
+  } else {
+    const int hl = warp >> 2, q = warp & 3, r = q * 32 + lane, h = hp * 2 + hl;
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    const uint32_t tS_h = tS + hl * KC + lane_bits;
+    const uint32_t tO_h = tO + hl * 64 + hl * 32 + lane_bits;     // this head's 32 columns of its 64-column product
+    const uint32_t p_row = sP + (uint32_t)(2 * hl) * TILE + (uint32_t)r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
+    float o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int k0 = c * KC;
+      float* ms = Ms + (c & 1) * KC;
+      if (threadIdx.x < KC) {
+        const int idx = k0 + (int)threadIdx.x;
+        ms[threadIdx.x] = amma::key_bias(idx < Tk ? (km ? (km[idx] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
+      }
+      softmax_bar();
+      mbar_wait_short(smem_u32(&ctrl->s_full), (uint32_t)c & 1u);
+      tc_fence_after();
+      float v[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KC / 32; ++j) {
+        tmem_ld32(tS_h + j * 32, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, amma::rbf(v[e]) + ms[j * 32 + e]);
+      }
+      const float mn = fmaxf(m_run, mx);                           // finite: every chunk holds at least one real key
+      const float corr = amma::ex2((m_run - mn) * amma::L2E);      // 0 on the first chunk
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < KC / 32; ++j) {
+        tmem_ld32(tS_h + j * 32, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          v[e] = amma::ex2((amma::rbf(v[e]) + ms[j * 32 + e] - mn) * amma::L2E);
+          sum += v[e];
+        }
+        // keys [32j, 32j+32) of row r: key block j >> 1, 16-byte units 4 (j & 1) .. +3, XOR-swizzled by r & 7
+        const uint32_t blk = p_row + (uint32_t)(j >> 1) * TILE;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t addr = blk + ((((uint32_t)(j & 1) * 4 + u) ^ sw) << 4);
+          const uint32_t w0 = pack2_bf16(v[8 * u], v[8 * u + 1]), w1 = pack2_bf16(v[8 * u + 2], v[8 * u + 3]);
+          const uint32_t w2 = pack2_bf16(v[8 * u + 4], v[8 * u + 5]), w3 = pack2_bf16(v[8 * u + 6], v[8 * u + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        }
+      }
+      l_run = l_run * corr + sum;
+      m_run = mn;
+      tc_fence_before();
+      fence_async_smem();                // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctrl->p_full[hl]));
+      mbar_wait_short(smem_u32(&ctrl->o_full[hl]), (uint32_t)c & 1u);
+      tc_fence_after();
+      tmem_ld32(tO_h, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * corr + v[i];
+      tc_fence_before();
+    }
+    if (r < nq) {
+      const float il = 1.0f / l_run;
+      bf16* dst = reinterpret_cast<bf16*>(a.o) + (size_t)(qrow0 + r) * D + h * HD;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = pack2_bf16(o[8 * u] * il, o[8 * u + 1] * il); w.y = pack2_bf16(o[8 * u + 2] * il, o[8 * u + 3] * il);
+        w.z = pack2_bf16(o[8 * u + 4] * il, o[8 * u + 5] * il); w.w = pack2_bf16(o[8 * u + 6] * il, o[8 * u + 7] * il);
+        *reinterpret_cast<uint4*>(dst + 8 * u) = w;
+      }
+      float* p = a.ml + ((size_t)(qrow0 + r) * H + h) * 2;
+      p[0] = m_run; p[1] = il;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// host: one launch for all six directions of a layer
+static cudaError_t launch_attn_fwd_tc(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmKV;
+  if (!make_tmap(&tmQ, a.qb, (uint64_t)D, (uint64_t)a.q.row0[a.q.n], (uint64_t)D, 64, QB)) return cudaErrorUnknown;
+  if (!make_tmap(&tmKV, a.kvbuf, (uint64_t)a.ldkv, (uint64_t)a.kv.row0[a.kv.n], (uint64_t)a.ldkv, 64, KC)) return cudaErrorUnknown;
+  dim3 grid(4 * ((maxTq + QB - 1) / QB), B, NDIR);
+  attn_fwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmQ, tmKV, a);
+  return cudaGetLastError();
+}
+
+}  // namespace atc
+}  // namespace mmr

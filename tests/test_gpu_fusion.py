@@ -140,14 +140,12 @@ def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
     assert max_rel(a["routes"], ref) < 2e-2
 
 
-@pytest.mark.skipif(os.environ.get("MMR_TEST_ATTN_TC") != "1",
-                    reason="tcgen05 attention forward (MMR_ATTN=tc) is opt-in until it has been verified on a B200; "
-                           "set MMR_TEST_ATTN_TC=1 to run")
 @pytest.mark.parametrize("TL,TN,TI,missing", [(48, 16, 49, False), (150, 70, 33, True), (512, 128, 196, True)])
 def test_bf16_tcgen05_attention_forward_matches_mma(TL, TN, TI, missing):
     """tcgen05 / TMEM / TMA attention forward (csrc/attention_tc.cuh, MMR_ATTN=tc) against the mma.sync engine on the same
-    bf16 path: same rounding points (bf16 scores, bf16 P per 128-key chunk), so route embeddings agree to bf16 noise, and
-    the mma.sync backward consumes its (o, ml) outputs."""
+    bf16 path: same rounding points (bf16 scores, bf16 P per key chunk), so the forward agrees far inside the bf16 budget
+    (measured 2e-4 on the route embeddings); the mma.sync backward consumes its (o, ml) outputs, so the gradients are
+    anchored on the fp32 oracle exactly like the mma-vs-SIMT test above."""
     c = dict(variant="pheno", K=5, orig_d_n=256, B=3, seed=911, sharp=1.0, temp=1.0, detach=False,
              missing=missing, mask_mode="full", TL=TL, TN=TN, TI=TI)
     sdm, sdp, sdh, inp = rebuild_case(c)
@@ -161,13 +159,17 @@ def test_bf16_tcgen05_attention_forward_matches_mma(TL, TN, TI, missing):
         torch.cuda.synchronize()
     a, b = outs["tc"], outs["mma"]
     assert bool(torch.isfinite(a["routes"]).all())
-    print("tc-vs-mma routes", max_rel(a["routes"], b["routes"]), "logits", max_rel(a["logits"], b["logits"]))
-    assert max_rel(a["routes"], b["routes"]) < 1e-2
-    assert max_rel(a["logits"], b["logits"]) < 2e-2
+    assert max_rel(a["routes"], b["routes"]) < 2e-3
+    assert max_rel(a["logits"], b["logits"]) < 2e-3
+    assert max_rel(a["R"], b["R"]) < 1e-2            # R is a bf16 output: one ulp near 1 is 4e-3
+    g32 = oracle_grads(c, sdm, sdp, sdh, inp, None, torch.float32)
     for k, g in b["grads"].items():
-        if g is not None:
-            assert bool(torch.isfinite(a["grads"][k]).all()), k
-            assert max_rel(a["grads"][k], g) < 1e-1, k
+        if g is None:
+            assert a["grads"][k] is None
+            continue
+        assert bool(torch.isfinite(a["grads"][k]).all()), k
+        e_tc, e_mma = max_rel(a["grads"][k], g32[k]), max_rel(g, g32[k])
+        assert e_tc <= max(8e-2, 2.0 * e_mma), f"grad {k}: tc {e_tc:.2e} mma {e_mma:.2e}"
 
 
 def synth_routes():

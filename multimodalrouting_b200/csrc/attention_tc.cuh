@@ -13,7 +13,10 @@
 //   warps 0-3 / 4-7  softmax + epilogue of head 0 / 1: thread = query row (TMEM lane), scores read with tcgen05.ld,
 //                    rounded to bf16 like the reference's bmm output, key bias added (finfo(bf16).min for padded keys,
 //                    -inf for tile padding), online softmax over 128-key chunks with the running output in registers
-// TMEM: S 2 x 128 columns, O 2 x 64 columns.  Output and statistics are identical in meaning to amma::attn_fwd_kernel
+// NH = 1 variant (MMR_ATTN_TC_HEADS=1): one head per CTA (5 warps, 80 KB of shared memory, 256 TMEM columns), so two CTAs
+// share an SM and one CTA's TMA / MMA / barrier latencies hide behind the other's softmax; the head pair's Q / K / V tiles
+// are then fetched by both CTAs of the pair (L2 hits).
+// TMEM: S NH x 128 columns, O NH x 64 columns.  Output and statistics are identical in meaning to amma::attn_fwd_kernel
 // (unnormalised bf16 P per chunk, final 1/l scaling, ml = (row max, 1/row sum)), so the mma.sync backward consumes them.
 #pragma once
 #include "attention_mma.cuh"
@@ -26,9 +29,10 @@ using namespace tc;
 
 constexpr int QB = 128;                 // queries per CTA
 constexpr int KC = 128;                 // keys per chunk
-constexpr int THREADS = 288;
 constexpr int TILE = 128 * 64 * 2;      // one 128B-swizzled [128 rows x 64 bf16] tile
-constexpr int SMEM_BYTES = 7 * TILE + 2 * KC * 4 + 256 + 1024;   // Q, K, V, P[2 heads][2 key blocks], key bias, ctrl, alignment
+template <int NH> constexpr int threads() { return NH * 128 + 32; }
+// Q, K, V, P[NH heads][2 key blocks], key bias, ctrl, alignment
+template <int NH> constexpr int smem_bytes() { return (3 + 2 * NH) * TILE + 2 * KC * 4 + 256 + 1024; }
 
 struct Ctrl {
   uint64_t kv_full;      // TMA: (Q +) K + V of the chunk landed
@@ -45,12 +49,18 @@ __device__ __forceinline__ void mbar_wait_short(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NH>
+__global__ void __launch_bounds__(threads<NH>(), 3 - NH)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
+  constexpr int CW = NH * 4;            // control warp
+  constexpr int HX = 8 / NH;            // CTAs per (patient, query block)
+  constexpr uint32_t TMEM_COLS = NH == 2 ? 512 : 256;
   extern __shared__ uint8_t smem_raw[];
-  const int d = blockIdx.z, b = blockIdx.y, hp = blockIdx.x & 3, qblk = blockIdx.x >> 2;
+  const int d = blockIdx.z, b = blockIdx.y, hx = blockIdx.x % HX, qblk = blockIdx.x / HX;
+  const int hp = NH == 2 ? hx : hx >> 1;          // head pair: 64-column slice of Q / K / V
+  const int hsel = hx & 1;                        // NH == 1: which head of the pair this CTA owns
   const int Tq = a.q.T[d], Tk = a.kv.T[d];
   const int q0 = qblk * QB;
   if (q0 >= Tq) return;
@@ -58,30 +68,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t sQ = sbase, sK = sQ + TILE, sV = sK + TILE, sP = sV + TILE;
-  float* Ms = reinterpret_cast<float*>(sgen + 7 * TILE);          // [2][KC] additive key bias, double buffered
+  float* Ms = reinterpret_cast<float*>(sgen + (3 + 2 * NH) * TILE);          // [2][KC] additive key bias, double buffered
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(Ms + 2 * KC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&ctrl->kv_full), 1);
     mbar_init(smem_u32(&ctrl->s_full), 1);
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NH; ++h) {
       mbar_init(smem_u32(&ctrl->p_full[h]), 4);
       mbar_init(smem_u32(&ctrl->o_full[h]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
+  if (warp == CW) tmem_alloc(smem_u32(&ctrl->tmem_base), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctrl->tmem_base;
-  const uint32_t tS = tmem, tO = tmem + 256;
+  const uint32_t tS = tmem, tO = tmem + NH * KC;
   const int qrow0 = a.q.row0[d] + b * Tq + q0;
   const int kvrow0 = a.kv.row0[d] + b * Tk;
   const int nchunks = (Tk + KC - 1) / KC;
 
-  if (warp == 8) {
+  if (warp == CW) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
@@ -90,7 +100,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t kv_full = smem_u32(&ctrl->kv_full);
       for (int c = 0; c < nchunks; ++c) {
         // every MMA that read K, V and P of the previous chunk has retired (the second head's commit covers all)
-        if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[1]), (uint32_t)(c - 1) & 1u);
+        if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[NH - 1]), (uint32_t)(c - 1) & 1u);
         mbar_expect_tx(kv_full, (c == 0 ? 3u : 2u) * TILE);
         if (c == 0) tma_load_2d(sQ, &tmQ, hp * 64, qrow0, kv_full);
         tma_load_2d(sK, &tmKV, a.col0 + hp * 64, kvrow0 + c * KC, kv_full);
@@ -99,14 +109,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc(sQ, 16, 1024), kdesc = make_smem_desc(sK, 16, 1024);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < NH; ++h) {
+          const int hc = NH == 2 ? h : hsel;   // head hc = columns [32hc, 32hc+32) of the tile: K=16 steps 2hc, 2hc+1 (+32 B each)
 #pragma unroll
-          for (int k = 0; k < 2; ++k)     // head h = columns [32h, 32h+32) of the tile: K=16 steps 2h, 2h+1 (+32 B each)
-            umma_bf16(tS + h * KC, qdesc + 2 * (2 * h + k), kdesc + 2 * (2 * h + k), idesc_s, k != 0);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(tS + h * KC, qdesc + 2 * (2 * hc + k), kdesc + 2 * (2 * hc + k), idesc_s, k != 0);
+        }
         umma_commit(smem_u32(&ctrl->s_full));
         const uint64_t vdesc = make_smem_desc(sV, 8192, 1024);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NH; ++h) {
           mbar_wait_short(smem_u32(&ctrl->p_full[h]), (uint32_t)c & 1u);
           tc_fence_after();
 #pragma unroll
@@ -119,10 +131,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    const int hl = warp >> 2, q = warp & 3, r = q * 32 + lane, h = hp * 2 + hl;
+    const int hl = NH == 2 ? warp >> 2 : 0;        // local head slot: barriers, TMEM accumulators, P tiles
+    const int hc = NH == 2 ? hl : hsel;            // which half of the 64-column pair slice
+    const int q = warp & 3, r = q * 32 + lane, h = hp * 2 + hc;
     const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
     const uint32_t tS_h = tS + hl * KC + lane_bits;
-    const uint32_t tO_h = tO + hl * 64 + hl * 32 + lane_bits;     // this head's 32 columns of its 64-column product
+    const uint32_t tO_h = tO + hl * 64 + hc * 32 + lane_bits;     // this head's 32 columns of its 64-column product
     const uint32_t p_row = sP + (uint32_t)(2 * hl) * TILE + (uint32_t)r * 128;
     const uint32_t sw = (uint32_t)(r & 7);
     const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
@@ -137,7 +151,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int idx = k0 + (int)threadIdx.x;
         ms[threadIdx.x] = amma::key_bias(idx < Tk ? (km ? (km[idx] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
       }
-      softmax_bar();
+      softmax_bar<NH * 128>();
       mbar_wait_short(smem_u32(&ctrl->s_full), (uint32_t)c & 1u);
       tc_fence_after();
       float v[32];
@@ -198,23 +212,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == CW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // host: one launch for all six directions of a layer
-static cudaError_t launch_attn_fwd_tc(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
+template <int NH>
+static cudaError_t launch_attn_fwd_tc_nh(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnArgs& a, int B, int maxTq,
+                                         cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NH>());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  dim3 grid((8 / NH) * ((maxTq + QB - 1) / QB), B, NDIR);
+  attn_fwd_tc_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH>(), st>>>(tmQ, tmKV, a);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_attn_fwd_tc(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
   CUtensorMap tmQ, tmKV;
   if (!make_tmap(&tmQ, a.qb, (uint64_t)D, (uint64_t)a.q.row0[a.q.n], (uint64_t)D, 64, QB)) return cudaErrorUnknown;
   if (!make_tmap(&tmKV, a.kvbuf, (uint64_t)a.ldkv, (uint64_t)a.kv.row0[a.kv.n], (uint64_t)a.ldkv, 64, KC)) return cudaErrorUnknown;
-  dim3 grid(4 * ((maxTq + QB - 1) / QB), B, NDIR);
-  attn_fwd_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmQ, tmKV, a);
-  return cudaGetLastError();
+  const char* e = getenv("MMR_ATTN_TC_HEADS");      // heads per CTA: 2 (default) or 1 (two CTAs per SM)
+  if (e && atoi(e) == 1) return launch_attn_fwd_tc_nh<1>(tmQ, tmKV, a, B, maxTq, st);
+  return launch_attn_fwd_tc_nh<2>(tmQ, tmKV, a, B, maxTq, st);
 }
 
 }  // namespace atc

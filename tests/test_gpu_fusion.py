@@ -140,8 +140,10 @@ def test_bf16_mma_attention_matches_simt_attention(TL, TN, TI, missing):
     assert max_rel(a["routes"], ref) < 2e-2
 
 
-@pytest.mark.parametrize("TL,TN,TI,missing", [(48, 16, 49, False), (150, 70, 33, True), (512, 128, 196, True)])
-def test_bf16_tcgen05_attention_forward_matches_mma(TL, TN, TI, missing):
+@pytest.mark.parametrize("TL,TN,TI,missing,heads", [(48, 16, 49, False, 2), (150, 70, 33, True, 2), (512, 128, 196, True, 2),
+                                                       (150, 70, 33, True, 1), (512, 128, 196, True, 1)],
+                         ids=["mimic-heads2", "mid-heads2", "inspect-heads2", "mid-heads1", "inspect-heads1"])
+def test_bf16_tcgen05_attention_forward_matches_mma(TL, TN, TI, missing, heads):
     """tcgen05 / TMEM / TMA attention forward (csrc/attention_tc.cuh, MMR_ATTN=tc) against the mma.sync engine on the same
     bf16 path: same rounding points (bf16 scores, bf16 P per key chunk), so the forward agrees far inside the bf16 budget
     (measured 2e-4 on the route embeddings); the mma.sync backward consumes its (o, ml) outputs, so the gradients are
@@ -152,10 +154,12 @@ def test_bf16_tcgen05_attention_forward_matches_mma(TL, TN, TI, missing):
     outs = {}
     for eng in ("mma", "tc"):
         os.environ["MMR_ATTN"] = eng
+        os.environ["MMR_ATTN_TC_HEADS"] = str(heads)      # heads per CTA: 2 = one CTA per SM, 1 = two CTAs per SM
         try:
             outs[eng] = run_case(c, sdm, sdp, sdh, inp, autocast=True)
         finally:
             os.environ.pop("MMR_ATTN", None)
+            os.environ.pop("MMR_ATTN_TC_HEADS", None)
         torch.cuda.synchronize()
     a, b = outs["tc"], outs["mma"]
     assert bool(torch.isfinite(a["routes"]).all())

@@ -51,8 +51,9 @@ def run(K, B, TL, TN, TI, iters):
 
     os.environ["MMR_WGRAD_STREAM"] = "0"
     ref = None
-    for eng in ("mma", "tc"):
-        os.environ["MMR_ATTN"] = eng
+    for eng in ("mma", "tc2", "tc1"):      # tcN: tcgen05 engine with N heads per CTA (MMR_ATTN_TC_HEADS)
+        os.environ["MMR_ATTN"] = "tc" if eng.startswith("tc") else eng
+        os.environ["MMR_ATTN_TC_HEADS"] = eng[2:] if eng.startswith("tc") else "2"
         for _ in range(3):
             logits = step()
         torch.cuda.synchronize()
@@ -80,6 +81,7 @@ def run(K, B, TL, TN, TI, iters):
                           "attn_bwd_ms_per_step": round(msc[3] / iters, 4), "step_ms_eager": round(step_ms, 3),
                           "logits_max_rel_vs_mma": err}), flush=True)
     os.environ.pop("MMR_ATTN", None)
+    os.environ.pop("MMR_ATTN_TC_HEADS", None)
 
 
 if __name__ == "__main__":

@@ -187,7 +187,7 @@ def pheno_train_loss(logits, y, routing_coef, prim_acts, route_mask, pos_weight=
     """PhenoModel/Paired_Cross_Attention/main.py:2755-2812.  Returns dict(loss, base, ent, uni, rc_report, info)."""
     rc_report, info = (None, 0)
     if routing_coef is not None:
-        rc_report, info = coerce_rc_to_report(routing_coef, prim_acts, route_mask, atol)        # :2764
+        rc_report, info = coerce_rc_to_report(routing_coef, prim_acts, route_mask, atol)        # :2765
     logits = safe_tensor(logits.float())                                                        # :2784
     base = bce_with_logits(logits, y.float(), pos_weight)                                       # :2793
     ent = base.new_zeros(())

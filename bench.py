@@ -133,7 +133,7 @@ class ClockSampler:
 
 
 def build_models(device, seed=42):
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     from multimodalrouting_b200 import MULTModel
     from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
     sdm, sdp, sdh = synth.make_state(K=K_LABELS, seed=seed, sharp=1.0)
@@ -147,7 +147,7 @@ def build_models(device, seed=42):
 def cpu_oracle_rate(budget_s, batch, threads, sds=None, min_iters=2):
     """Times the CPU port of the reference path (oracle, fp32) fwd+bwd on `threads` host threads."""
     from oracle import route_fusion_oracle as orc
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     torch.set_num_threads(threads)
     if sds is None:
         sds = synth.make_state(K=K_LABELS, seed=42)
@@ -176,7 +176,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import route_fusion_oracle as orc
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     batch = 64     # bounded sample of the 512-patient workload per step
@@ -251,7 +251,7 @@ def main():
     import torch.distributed as dist
     from multimodalrouting_b200 import _lib
     from multimodalrouting_b200.dist import OverlappedGradReducer, allreduce_gradients
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from oracle import synth  # noqa: E402
+from multimodalrouting_b200 import synth  # noqa: E402
 from multimodalrouting_b200 import MULTModel, _lib  # noqa: E402
 from multimodalrouting_b200.PhenoModel import routing_and_heads as rh  # noqa: E402
 

@@ -21,7 +21,7 @@ def main():
     from multimodalrouting_b200 import MULTModel
     from multimodalrouting_b200.MortModel import routing_and_heads as rh
     from multimodalrouting_b200.dist import allreduce_gradients, shard_range
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)

@@ -20,7 +20,7 @@ def main():
     import bench
     from multimodalrouting_b200.dist import OverlappedGradReducer, allreduce_gradients
     from multimodalrouting_b200.graphs import GraphedStep
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)

@@ -18,7 +18,7 @@ import torch  # noqa: E402
 def main():
     from gpu_common import build_modules, to_dev
     from multimodalrouting_b200.graphs import GraphedStep
-    from oracle import synth
+    from multimodalrouting_b200 import synth
     B = int(os.environ.get("B", "16"))
     c = dict(variant="pheno", K=25, orig_d_n=256, temp=1.0, detach=False)
     sdm, sdp, sdh = synth.make_state(K=25, seed=31, sharp=2.0)

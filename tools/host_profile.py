@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import bench  # noqa: E402
-from oracle import synth  # noqa: E402
+from multimodalrouting_b200 import synth  # noqa: E402
 
 dev = torch.device("cuda", 0)
 rh, mult, proj, head, _ = bench.build_models(dev)

@@ -7,7 +7,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from oracle import synth  # noqa: E402
+from multimodalrouting_b200 import synth  # noqa: E402
 from multimodalrouting_b200 import MULTModel  # noqa: E402
 
 

@@ -132,6 +132,12 @@ class MULTModel(nn.Module):
         mL = self._ensure_float_mask(mL, B, TL, device)
         mN = self._ensure_float_mask(mN, B, TN, device)
         mI = self._ensure_float_mask(mI, B, TI, device)
+        for m, T in ((mL, TL), (mN, TN), (mI, TI)):
+            # the reference fails in the broadcast `x * mask` (transformer.py:77-79) with a RuntimeError; the kernels
+            # index the mask as [B, T], so a wrong shape must never reach them
+            if m is not None and tuple(m.shape) != (B, T):
+                raise RuntimeError(f"The size of the mask {tuple(m.shape)} must match the size of the token axis "
+                                   f"[B, T] = [{B}, {T}]")
         pos = truncated_sinusoid_table(max(TL, TN, TI), self.d_l, device)
         params = self._param_list()
         # parameters that never take part (proj_* when orig_d == d) get no gradient, as in the reference

@@ -48,3 +48,30 @@ def test_signature_matches_reference(variant, name):
     assert [p[0] for p in ours] == [p[0] for p in ref], f"{name}: parameter names / order"
     assert [p[1] for p in ours] == [p[1] for p in ref], f"{name}: parameter kinds"
     assert [p[2] for p in ours] == [p[2] for p in ref], f"{name}: defaults"
+
+
+@pytest.mark.parametrize("variant", ["mort", "pheno"])
+def test_default_init_matches_reference(variant):
+    """SURVEY.md section 8b "Init semantics": constructed under the same seed, the drop-in modules consume the RNG in the
+    reference's order and hold the same tensors (fixture: oracle/gen_golden_init.py run on the unmodified reference)."""
+    import torch
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "init_checksums.json")))
+    c = g["configs"][variant]
+    import multimodalrouting_b200 as mmr
+    _, rh = _mods(variant)
+    torch.manual_seed(g["seed"])
+    mult = mmr.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True, 8, 4, 0, 0., 0., 0., 0., 0., 0., 0., False)
+    proj = rh.RoutePrimaryProjector(256, 32)
+    head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=c["K"])
+    seen = set()
+    for tag, m in (("mult", mult), ("proj", proj), ("head", head)):
+        for k, t in m.state_dict().items():
+            ref = g[variant][f"{tag}.{k}"]
+            d = t.detach().double()
+            assert list(t.shape) == ref[0], k
+            for got, want in ((float(d.sum()), ref[1]), (float(d.norm()), ref[2]), (float(d.flatten()[0]), ref[3])):
+                assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), f"{tag}.{k}"
+            seen.add(f"{tag}.{k}")
+    assert seen == set(g[variant]) and len(seen) > 300
+    # the quirks of the reference's init the tests elsewhere have to perturb: zero decision embedding / biases
+    assert float(head.embedding.detach().abs().max()) == 0.0 and float(head.bias.detach().abs().max()) == 0.0

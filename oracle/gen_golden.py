@@ -56,6 +56,13 @@ CASES = {
     # short odd shapes + 3 labels (INSPECT-like head), exercises ragged tiles
     "pheno_odd": dict(variant="pheno", K=3, orig_d_n=256, B=5, seed=808, sharp=4.0, temp=1.0,
                       detach=False, missing=True, mask_mode="full", TL=21, TN=5, TI=9),
+    # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
+    # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
+    # BASELINE configs[4] with a 3-label head
+    "pheno_tl256": dict(variant="pheno", K=25, orig_d_n=256, B=2, seed=909, sharp=2.0, temp=1.0,
+                        detach=False, missing=True, mask_mode="full", TL=256, TN=16, TI=49, long=True),
+    "pheno_inspect": dict(variant="pheno", K=3, orig_d_n=256, B=2, seed=1010, sharp=8.0, temp=1.0,
+                          detach=False, missing=False, mask_mode="full", TL=512, TN=128, TI=196, long=True),
 }
 
 FULL_GRADS = ["embedding", "bias", "pose_to_mc.weight", "x_n",
@@ -106,8 +113,9 @@ def run_variant(variant: str):
     from oracle import synth
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = [n for n in os.environ.get("MMR_GOLDEN_ONLY", "").split(",") if n]   # regenerate a subset, leave the rest untouched
     for name, c in CASES.items():
-        if c["variant"] != variant:
+        if c["variant"] != variant or (only and name not in only):
             continue
         sdm, sdp, sdh, inp = build_case_inputs(c)
         with contextlib.redirect_stdout(io.StringIO()):

@@ -14,6 +14,9 @@ from oracle import synth  # noqa: E402
 
 GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "pheno_missing",
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
+# long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
+# reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect"]
 
 
 def load_golden(name):

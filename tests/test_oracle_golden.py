@@ -2,12 +2,12 @@
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, check_grad_checksums, load_golden, max_rel, r_grad_probe, rebuild_case
+from helpers import GOLDEN_CASES, GOLDEN_LONG, check_grad_checksums, load_golden, max_rel, r_grad_probe, rebuild_case
 from oracle import route_fusion_oracle as orc
 from oracle import synth
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_LONG)
 def test_oracle_matches_reference_golden(name):
     gold = load_golden(name)
     c = gold["case"]

@@ -199,8 +199,6 @@ struct TcEpi {
   int ld_bits;
   void* out;
   int ldo;
-  int bias_cache;             // opt-in (MMR_TC_BIAS_CACHE=1, not yet measured): keep the bias slice of the previous tile when
-                              // the next tile uses the same one, instead of re-fetching it from global memory per tile
 };
 
 constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -434,7 +432,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int HC = BN / 2;            // columns per epilogue warp
     float* bias_s = bias_all + (warp - 2) * HC;
     const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
-    const float* bias_src_prev = nullptr;
     uint32_t i = 0;
     for (int t = w0; t < nwork; t += wstep, ++i) {
       const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN + ch * HC;
@@ -457,15 +454,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (OP == TEPI_BIAS || OP == TEPI_BIAS_RELU_BITS || OP == TEPI_BIAS_F32) {
         const float* bsrc = e.bias ? e.bias + g.b_row0[seg] + n0 : nullptr;
-        // with N = BN every tile of a segment uses the same 128 bias values: the fetch (an L2 round trip that sits in
-        // front of the accumulator wait when the MMA warp runs ahead) is only repeated when the slice changes
-        if (!e.bias_cache || i == 0 || bsrc != bias_src_prev) {
-          __syncwarp();
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < HC / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
-          __syncwarp();
-          bias_src_prev = bsrc;
-        }
+        for (int j = 0; j < HC / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
+        __syncwarp();
       }
       const uint32_t buf = i & 1;
       mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
@@ -1016,7 +1008,6 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
                                      int sm_count, cudaStream_t st) {
   constexpr int BN = 256;
   static int stages_cfg = env_int("MMR_TC_STAGES", CL == 2 ? 4 : 3);
-  static int bias_cache_cfg = env_int("MMR_TC_BIAS_CACHE", 0);
   const int max_stages = CL == 2 ? 4 : 3;      // 32 KB (pair) / 48 KB operand stages + 64 KB of TMA-store staging
   const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
   constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
@@ -1046,9 +1037,7 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  TcEpi e2 = e;
-  e2.bias_cache = bias_cache_cfg;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e2, stages);
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e, stages);
 }
 
 // a_rows_total / b_rows_total: number of rows physically present in A / B (TMA bounds).

@@ -79,7 +79,7 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
 def _launch(variant: int, logits: Tensor, y: Tensor, *, pos_weight=None, prim_acts=None, rc_raw=None, route_mask=None,
             label_smoothing=0.0, lam_ent=0.0, lam_uni=0.0, atol=1e-3, want_grad=True, want_report=True,
             state: Optional[LossState] = None):
-    _require_cuda(logits, y, pos_weight, prim_acts, rc_raw, route_mask)
+    # shape checks first (they mirror the reference's assertions / torch's BCE error and need no device), then the device check
     if logits.ndim != 2:
         raise ValueError(f"logits must be [B,K], got {tuple(logits.shape)}")
     B, K = logits.shape
@@ -88,7 +88,7 @@ def _launch(variant: int, logits: Tensor, y: Tensor, *, pos_weight=None, prim_ac
         if y.numel() != B:
             raise ValueError(f"y must hold one label per patient, got {tuple(y.shape)}")
     elif tuple(y.shape) != (B, K):
-        raise ValueError(f"Target size ({tuple(y.shape)}) must be the same as input size ({tuple(logits.shape)})")
+        raise ValueError(f"Target size ({y.size()}) must be the same as input size ({logits.size()})")   # torch's BCE text
     lg, yf = _f32(logits), _f32(y)
     pw, pa = _f32(pos_weight), _f32(prim_acts)
     if pw is not None and pw.numel() != K:
@@ -110,6 +110,7 @@ def _launch(variant: int, logits: Tensor, y: Tensor, *, pos_weight=None, prim_ac
             rm = rm.view(1, -1).expand(B, -1).contiguous()
         if tuple(rm.shape) != (B, 10):
             raise ValueError(f"route_mask must be [B,10] or [10], got {tuple(route_mask.shape)}")
+    _require_cuda(logits, y, pos_weight, prim_acts, rc_raw, route_mask)
     dev = logits.device
     st = state if state is not None else LossState(dev)
     lib = _lib.load()
@@ -171,7 +172,6 @@ def mort_train_loss(logits: Tensor, y: Tensor, prim_acts: Optional[Tensor] = Non
                     route_uniform_lambda: float = 0.0, route_uniform_warmup_epochs: int = 0, cur_epoch: int = 1,
                     state: Optional[LossState] = None) -> LossParts:
     """loss = BCEWithLogits(logits[:,1]-logits[:,0], smooth(y)) - ent_bonus + uniform_pen    (main.py:3092-3126)."""
-    _require_cuda(logits)
     st = state if state is not None else LossState(logits.device)
     kw = dict(prim_acts=prim_acts, label_smoothing=float(label_smoothing),
               lam_ent=_gate(route_entropy_lambda, route_entropy_warmup_epochs, cur_epoch, False),
@@ -188,7 +188,6 @@ def pheno_train_loss(logits: Tensor, y: Tensor, routing_coef: Optional[Tensor] =
     """rc_report = coerce_rc_to_report(routing_coef, prim_acts, route_mask); loss = BCEWithLogits(logits, y, pos_weight)
     - lambda_e * H(mean_b rc) + lambda_u * U(mean_b rc)                                          (main.py:2755-2812).
     `state.check()` performs the reference's host-side assertions when the caller wants them."""
-    _require_cuda(logits)
     st = state if state is not None else LossState(logits.device)
     kw = dict(pos_weight=pos_weight, prim_acts=prim_acts, rc_raw=routing_coef, route_mask=route_mask, atol=float(atol),
               lam_ent=_gate(route_entropy_lambda, route_entropy_warmup_epochs, cur_epoch, True),
@@ -212,7 +211,6 @@ def coerce_rc_to_report(rc_raw: Tensor, prim_acts: Optional[Tensor], route_mask:
 def coerce_rc_to_report_async(rc_raw: Tensor, prim_acts: Optional[Tensor], route_mask: Optional[Tensor], *,
                               atol: float = 1e-3, state: Optional[LossState] = None) -> Tuple[Tensor, LossState]:
     assert rc_raw.ndim == 3, f"rc_raw must be [B,R,K], got {tuple(rc_raw.shape)}"
-    _require_cuda(rc_raw)
     B, _, K = rc_raw.shape
     zeros = torch.zeros(B, K, dtype=torch.float32, device=rc_raw.device)
     st, _, rep = _launch(PHENO, zeros, zeros, prim_acts=None, rc_raw=rc_raw, route_mask=route_mask, atol=float(atol),

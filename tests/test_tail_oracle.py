@@ -166,3 +166,34 @@ def test_loss_bindings_fail_loudly_on_cpu_and_validate():
     # warm-up gates: Mort `>=`, Pheno `>`  (main.py:3116 vs PhenoModel main.py:2799)
     assert losses._gate(0.1, 2, 2, False) == 0.1 and losses._gate(0.1, 2, 2.0, True) == 0.0
     assert losses._gate(0.1, 0, 1, True) == 0.1 and losses._gate(0.0, 0, 5, False) == 0.0
+
+
+def test_loss_argument_errors_match_the_reference_drivers():
+    """Host-side checks of losses.py fire before any device work and raise what the reference's statements raise:
+    torch's BCE shape error (ValueError, same text), the drivers' asserts on routing_coef (PhenoModel main.py:2761-2762),
+    death_logit_from_logits2's assert (MortModel main.py:1754)."""
+    from multimodalrouting_b200 import losses
+    lg, y = torch.randn(4, 25), torch.zeros(4, 25)
+    with pytest.raises(ValueError) as ours:
+        losses.pheno_train_loss(lg, torch.zeros(4, 24))
+    with pytest.raises(ValueError) as ref:
+        torch.nn.BCEWithLogitsLoss()(lg, torch.zeros(4, 24))
+    assert str(ours.value) == str(ref.value)
+    with pytest.raises(AssertionError, match=r"routing_coef must be \[B,R,K\]"):
+        losses.pheno_train_loss(lg, y, torch.rand(4, 250))
+    with pytest.raises(AssertionError, match="Expected R=10"):
+        losses.pheno_train_loss(lg, y, torch.rand(4, 9, 25))
+    with pytest.raises(ValueError, match="pos_weight"):
+        losses.pheno_train_loss(lg, y, pos_weight=torch.ones(3))
+    with pytest.raises(ValueError, match="route_mask"):
+        losses.pheno_train_loss(lg, y, torch.rand(4, 10, 25), None, torch.ones(4, 9))
+    with pytest.raises(AssertionError, match=r"expected \[B,2\]"):
+        losses.mort_train_loss(torch.randn(4, 3), torch.zeros(4))
+    with pytest.raises(AssertionError, match=r"expected \[B,2\]"):
+        losses.death_logit_from_logits2(torch.randn(4, 3))
+    assert torch.equal(losses.death_logit_from_logits2(torch.tensor([[1.0, 3.0]])), torch.tensor([[2.0]]))
+    with pytest.raises(AssertionError):
+        losses.coerce_rc_to_report(torch.rand(4, 250), None, None)
+    # well-formed CPU arguments pass validation and are refused by the device check
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.pheno_train_loss(lg, y, torch.rand(4, 10, 25), torch.rand(4, 10), torch.ones(10))

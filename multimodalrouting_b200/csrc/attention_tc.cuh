@@ -18,6 +18,12 @@
 // are then fetched by both CTAs of the pair (L2 hits).
 // TMEM: S NH x 128 columns, O NH x 64 columns.  Output and statistics are identical in meaning to amma::attn_fwd_kernel
 // (unnormalised bf16 P per chunk, final 1/l scaling, ml = (row max, 1/row sum)), so the mma.sync backward consumes them.
+//
+// Known gap (why it is opt-in besides speed): the K / V boxes of the last chunk extend past the patient's Tk rows into
+// the next patient's rows of the same 2-D row space.  Their scores get a -inf bias and their P is exactly 0, but 0 x NaN
+// is NaN inside the MMA, so a non-finite K / V row of patient b+1 would leak into patient b (the mma.sync kernels zero-fill
+// the rows they stage).  Fix planned with the pipeline work: per-direction 3-D tensor maps [patient][token][column] whose
+// token extent is Tk, so that the TMA unit zero-fills everything past a patient's last key.
 #pragma once
 #include "attention_mma.cuh"
 #include "gemm_tc.cuh"

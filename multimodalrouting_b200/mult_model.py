@@ -125,6 +125,10 @@ class MULTModel(nn.Module):
         BN, TN, _ = x_n.shape
         BI, TI, _ = x_i.shape
         assert B == BN == BI
+        if 0 in (B, TL, TN, TI):
+            # the reference fails in MultiheadAttention's head reshape (multihead_attention.py:93-97) with this error
+            raise RuntimeError(f"cannot reshape tensor of 0 elements: empty batch / modality (B={B}, TL={TL}, TN={TN}, TI={TI}) "
+                               "is not a valid input of the cross-modal encoders")
         if x_l.shape[2] != self.orig_d_l or x_n.shape[2] != self.orig_d_n or x_i.shape[2] != self.orig_d_i:
             raise ValueError("input feature dims do not match orig_d_l / orig_d_n / orig_d_i")
         self._check_dropout()

@@ -49,6 +49,9 @@ CASES = {
     # MULTModel.forward (mult_model.py:117-121)
     "mult_rank2_input": lambda ns: ns["mult"](ns["ok"]["x_l"][:, 0], ns["ok"]["x_n"], ns["ok"]["x_i"]),
     "mult_batch_mismatch": lambda ns: ns["mult"](ns["ok"]["x_l"], ns["ok"]["x_n"][:1], ns["ok"]["x_i"]),
+    # empty batch / empty modality: the reference fails in MultiheadAttention's head reshape (RuntimeError)
+    "mult_empty_batch": lambda ns: ns["mult"](torch.zeros(0, 6, 256), torch.zeros(0, 4, 256), torch.zeros(0, 5, 256)),
+    "mult_empty_modality": lambda ns: ns["mult"](ns["ok"]["x_l"], torch.zeros(B, 0, 256), ns["ok"]["x_i"]),
     # masks whose shape does not match the token axis (multihead_attention.py:121-124 for key masks)
     "mult_key_mask_too_long": lambda ns: ns["mult"](ns["ok"]["x_l"], ns["ok"]["x_n"], ns["ok"]["x_i"],
                                                     mL=ns["ok"]["mL"], mN=torch.ones(B, 7), mI=ns["ok"]["mI"]),

@@ -56,6 +56,9 @@ CASES = {
     # short odd shapes + 3 labels (INSPECT-like head), exercises ragged tiles
     "pheno_odd": dict(variant="pheno", K=3, orig_d_n=256, B=5, seed=808, sharp=4.0, temp=1.0,
                       detach=False, missing=True, mask_mode="full", TL=21, TN=5, TI=9),
+    # acts_override: externally supplied route priors replace the projector's sigmoid activations (routing_and_heads.py:314)
+    "pheno_override": dict(variant="pheno", K=25, orig_d_n=256, B=4, seed=1111, sharp=3.0, temp=1.2,
+                           detach=False, missing=True, mask_mode="full", override=True, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
     # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
     # BASELINE configs[4] with a 3-label head
@@ -98,6 +101,8 @@ def build_case_inputs(c):
         rm = torch.ones(10)
         rm[[1, 4, 8]] = 0.0
         inp["route_mask"] = rm
+    if c.get("override"):
+        inp["acts_override"] = torch.rand(c["B"], 10, 1, generator=torch.Generator().manual_seed(c["seed"] + 3))
     return sdm, sdp, sdh, inp
 
 
@@ -132,7 +137,8 @@ def run_variant(variant: str):
                 mult, xs["x_l"], xs["x_n"], xs["x_i"], proj, head,
                 mL=inp["mL"], mN=inp["mN"], mI=inp["mI"],
                 route_adapter=rh.RouteDimAdapter(256, 256, 256, 256),
-                route_mask=inp["route_mask"], act_temperature=c["temp"], detach_priors=c["detach"])
+                route_mask=inp["route_mask"], act_temperature=c["temp"], detach_priors=c["detach"],
+                acts_override=inp.get("acts_override"))
         loss = synth.loss_fn(logits, inp["y"], variant)
         # also push a gradient through R so the routing-coefficient path is pinned
         gR = torch.randn(R.shape, generator=torch.Generator().manual_seed(c["seed"] + 7))

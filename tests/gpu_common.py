@@ -35,7 +35,7 @@ def run_case(c, sdm, sdp, sdh, inp, *, autocast=False, backward=True, r_probe=No
         logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
             mult, xs["x_l"], xs["x_n"], xs["x_i"], proj, head, mL=d["mL"], mN=d["mN"], mI=d["mI"],
             route_adapter=rh.RouteDimAdapter(256, 256, 256, 256), route_mask=d["route_mask"],
-            act_temperature=c["temp"], detach_priors=c["detach"])
+            act_temperature=c["temp"], detach_priors=c["detach"], acts_override=d.get("acts_override"))
     out = {"logits": logits, "alpha": alpha, "R": R,
            "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
     if backward:

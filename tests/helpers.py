@@ -16,7 +16,7 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
-GOLDEN_LONG = ["pheno_tl256", "pheno_inspect"]
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override"]     # + acts_override (added late, same gating on the GPU)
 
 
 def load_golden(name):
@@ -35,6 +35,8 @@ def rebuild_case(c):
         rm = torch.ones(10)
         rm[[1, 4, 8]] = 0.0
         inp["route_mask"] = rm
+    if c.get("override"):
+        inp["acts_override"] = torch.rand(c["B"], 10, 1, generator=torch.Generator().manual_seed(c["seed"] + 3))
     return sdm, sdp, sdh, inp
 
 
@@ -91,7 +93,7 @@ def fp64_truth(c, sdm, sdp, sdh, inp):
     logits, alpha, routes, R = orc.full_forward(
         d(sdm), d(sdp), d(sdh), inp["x_l"].double(), inp["x_n"].double(), inp["x_i"].double(),
         f(inp["mL"]), f(inp["mN"]), f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
-        act_temperature=c["temp"], detach_priors=c["detach"])
+        act_temperature=c["temp"], detach_priors=c["detach"], acts_override=f(inp.get("acts_override")))
     return {"logits": logits, "alpha": alpha, "R": R,
             "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
 
@@ -105,8 +107,11 @@ def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
     base = {r: routes_bt[:, i].double() for i, r in enumerate(synth.ROUTES)}
     g = torch.Generator().manual_seed(1234)
     pert = {r: v * (1 + eps * torch.randn(v.shape, generator=g, dtype=torch.float64)) for r, v in base.items()}
-    l0, _, R0 = orc.routing_forward(d(sdp), d(sdh), base, variant=c["variant"], route_mask=rm, act_temperature=c["temp"])
-    l1, _, R1 = orc.routing_forward(d(sdp), d(sdh), pert, variant=c["variant"], route_mask=rm, act_temperature=c["temp"])
+    ao = None if inp.get("acts_override") is None else inp["acts_override"].double()
+    l0, _, R0 = orc.routing_forward(d(sdp), d(sdh), base, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
+                                    acts_override=ao)
+    l1, _, R1 = orc.routing_forward(d(sdp), d(sdh), pert, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
+                                    acts_override=ao)
     dl = (l1 - l0).abs().amax(dim=1) / l0.abs().max().clamp_min(1e-12)
     dR = (R1 - R0).abs().amax(dim=(1, 2)) / R0.abs().max().clamp_min(1e-12)
     return torch.maximum(dl, dR) / eps
@@ -122,7 +127,8 @@ def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
     xs = {k: inp[k].to(dtype).clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
     logits, _, _, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
                                        f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
-                                       act_temperature=c["temp"], detach_priors=c["detach"])
+                                       act_temperature=c["temp"], detach_priors=c["detach"],
+                                       acts_override=f(inp.get("acts_override")))
     total = synth.loss_fn(logits, inp["y"].to(dtype), c["variant"])
     if r_probe is not None:
         total = total + 0.05 * (R * r_probe.to(dtype)).sum()

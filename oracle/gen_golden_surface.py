@@ -55,7 +55,26 @@ def run_variant(variant):
     for name in CALLABLES:
         mod = mult_model if name.startswith("MULTModel") else rh
         sigs[name] = sig_of(resolve(mod, name))
-    print(json.dumps({"driver_imports": imports, "signatures": sigs}))
+    # small helpers that stay plain tensor / dict code in the drop-in: pin their behaviour too
+    import torch
+    g = torch.Generator().manual_seed(5)
+    q = torch.rand(2, 10, 3, generator=g)
+    m2 = (torch.rand(2, 10, generator=g) < 0.7).float()
+    m1 = torch.tensor([1., 0, 1, 1, 0, 1, 1, 1, 0, 1])
+    rgp = {"q": q.tolist(), "m1": m1.tolist(), "m2": m2.tolist(),
+           "none": rh.route_given_pheno(q).tolist(), "mask1d": rh.route_given_pheno(q, m1).tolist(),
+           "mask2d": rh.route_given_pheno(q, route_mask=m2).tolist()}
+
+    class Stub(torch.nn.Module):
+        def forward(self, *a, **kw):
+            self.seen = {"n_positional": len(a), "kwargs": sorted(kw), "mask_is_none": sorted(k for k, v in kw.items() if v is None)}
+            return {r: torch.zeros(1, 4) for r in rh.ROUTES}
+    stub = Stub()
+    z = {"L": {"seq": torch.zeros(1, 2, 4), "mask": torch.ones(1, 2)}, "N": {"seq": torch.zeros(1, 3, 4)},
+         "I": {"seq": torch.zeros(1, 2, 4), "mask": None}}
+    out = rh.make_route_inputs_mult(z, stub)
+    mri = {"call": stub.seen, "returns_keys": sorted(out)}
+    print(json.dumps({"driver_imports": imports, "signatures": sigs, "route_given_pheno": rgp, "make_route_inputs_mult": mri}))
 
 
 def main():

@@ -75,3 +75,27 @@ def test_default_init_matches_reference(variant):
     assert seen == set(g[variant]) and len(seen) > 300
     # the quirks of the reference's init the tests elsewhere have to perturb: zero decision embedding / biases
     assert float(head.embedding.detach().abs().max()) == 0.0 and float(head.bias.detach().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("variant", ["mort", "pheno"])
+def test_small_helpers_behave_like_the_reference(variant):
+    """route_given_pheno (plain tensor code in the drop-in too) and make_route_inputs_mult's call convention, against outputs
+    recorded from the unmodified reference (oracle/gen_golden_surface.py)."""
+    import torch
+    _, rh = _mods(variant)
+    g = GOLD[variant]["route_given_pheno"]
+    q, m1, m2 = torch.tensor(g["q"]), torch.tensor(g["m1"]), torch.tensor(g["m2"])
+    assert torch.equal(rh.route_given_pheno(q), torch.tensor(g["none"]))
+    assert torch.equal(rh.route_given_pheno(q, m1), torch.tensor(g["mask1d"]))
+    assert torch.equal(rh.route_given_pheno(q, route_mask=m2), torch.tensor(g["mask2d"]))
+
+    class Stub(torch.nn.Module):
+        def forward(self, *a, **kw):
+            self.seen = {"n_positional": len(a), "kwargs": sorted(kw), "mask_is_none": sorted(k for k, v in kw.items() if v is None)}
+            return {r: torch.zeros(1, 4) for r in rh.ROUTES}
+    stub = Stub()
+    z = {"L": {"seq": torch.zeros(1, 2, 4), "mask": torch.ones(1, 2)}, "N": {"seq": torch.zeros(1, 3, 4)},
+         "I": {"seq": torch.zeros(1, 2, 4), "mask": None}}
+    out = rh.make_route_inputs_mult(z, stub)
+    ref = GOLD[variant]["make_route_inputs_mult"]
+    assert stub.seen == ref["call"] and sorted(out) == ref["returns_keys"]

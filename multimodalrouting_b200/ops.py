@@ -112,8 +112,10 @@ def route_fusion_fwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor]
 @route_fusion_fwd.register_fake
 def _(x_l, x_n, x_i, mL, mN, mI, pos, params, layers, dtype, engine):
     B = x_l.shape[0]
-    return (x_l.new_empty(N_ROUTES, B, 256, dtype=torch.float32), x_l.new_empty(1, dtype=torch.uint8),
-            x_l.new_empty(1, dtype=torch.uint8))
+    # same metadata as the real op: the byte counts come from the (host-only) planner of the C ABI
+    packed_b, saved_b, _, _ = fusion_sizes(_fusion_dims(x_l, x_n, x_i, layers, dtype, engine))
+    return (x_l.new_empty(N_ROUTES, B, 256, dtype=torch.float32), x_l.new_empty(packed_b, dtype=torch.uint8),
+            x_l.new_empty(saved_b, dtype=torch.uint8))
 
 
 _GRAD_LAYOUTS = {}
@@ -413,8 +415,10 @@ def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b
       bias, B, variant, num_routing, detach_priors, temp, floor, ceil, vdt):
     K = embedding.shape[0]
     e = caps_w
+    use_tc = vdt == DTYPE_BF16 and os.environ.get("MMR_RT_TC", "1") != "0"
     return (e.new_empty(B, K), e.new_empty(B, N_ROUTES), e.new_empty(B, N_ROUTES, K),
-            e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES), e.new_empty(0, dtype=torch.uint8))
+            e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES),
+            e.new_empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8))
 
 
 @torch.library.custom_op("mmr_b200::capsule_routing_bwd", mutates_args=())

@@ -12,6 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
+from torch._subclasses.fake_tensor import FakeTensor
 
 from . import _lib
 from ._lib import FusionDims, RoutingDims, RoutingGrads, RoutingParams, c_fp
@@ -258,6 +259,8 @@ def _common_base(ts: Sequence[Optional[Tensor]], shape) -> Optional[Tuple[int, i
     t0 = ts[0]
     if any(t is None or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) for t in ts):
         return None
+    if any(isinstance(t, FakeTensor) for t in ts):
+        return None     # tracing: fake tensors have no addresses; the caller falls back to the dense copy
     if t0.stride(1) != 1 or any(t.stride() != t0.stride() for t in ts):
         return None
     st0 = t0.untyped_storage().data_ptr()

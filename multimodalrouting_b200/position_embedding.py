@@ -11,6 +11,7 @@ import math
 from typing import Dict, Tuple
 
 import torch
+from torch._subclasses.fake_tensor import FakeTensor
 
 _CACHE: Dict[Tuple[int, int, str], torch.Tensor] = {}
 
@@ -28,7 +29,8 @@ def truncated_sinusoid_table(T: int, dim: int, device) -> torch.Tensor:
             full = torch.cat([full, torch.zeros(T + 1, 1)], dim=1)
         full[0, :] = 0.0
         tab = full.to(torch.int64)[1:T + 1].to(torch.float32).contiguous().to(device)
-        _CACHE[key] = tab
+        if not isinstance(tab, FakeTensor):     # never let a tracing-time (fake) table leak into later real calls
+            _CACHE[key] = tab
     return tab
 
 

@@ -68,3 +68,35 @@ def test_sanitize_fakes():
         assert y.shape == x.shape and y.dtype == torch.float32
         dx = producers.sanitize_rows_bwd(x, torch.empty(5, 7, 768, device="cuda"), 0, 20.0)
         assert dx.shape == x.shape and dx.dtype == torch.float32
+
+
+@pytest.mark.parametrize("variant,K,d_n,masks", [("pheno", 25, 256, "full"), ("mort", 2, 768, "full"), ("pheno", 3, 256, "none"),
+                                                   ("mort", 2, 256, "rm1d")])
+def test_full_forward_runs_on_fake_cuda_tensors(variant, K, d_n, masks):
+    """The whole host side of the drop-in path -- module forward, mask plumbing, autograd.Function forward, custom ops with
+    their fake kernels -- executes on fake CUDA tensors (no GPU, no arithmetic): what torch.compile / export trace, and a CPU
+    check of every output's shape, dtype and device."""
+    import multimodalrouting_b200 as mmr
+    if variant == "mort":
+        from multimodalrouting_b200.MortModel import routing_and_heads as rh
+    else:
+        from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    B, TL, TN, TI = 5, 48, 16, 49
+    with FakeTensorMode(), torch.device("cuda"):
+        mult = mmr.MULTModel(256, d_n, 256, 256, 256, 256, True, True, True, 8, 4, 0, 0., 0., 0., 0., 0., 0., 0., False)
+        proj, head = rh.RoutePrimaryProjector(256, 32), rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=K)
+        x = [torch.randn(B, T, d, requires_grad=True) for T, d in ((TL, 256), (TN, d_n), (TI, 256))]
+        m = [None, None, None] if masks == "none" else [torch.ones(B, T) for T in (TL, TN, TI)]
+        rm = None if masks == "none" else (torch.ones(10) if masks == "rm1d" else torch.ones(B, 10))
+        for autocast in (False, True):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
+                    mult, x[0], x[1], x[2], proj, head, mL=m[0], mN=m[1], mI=m[2],
+                    route_adapter=rh.RouteDimAdapter(256, 256, 256, 256), route_mask=rm, act_temperature=1.2)
+            assert tuple(logits.shape) == (B, K) and logits.dtype == torch.float32 and logits.device.type == "cuda"
+            assert tuple(alpha.shape) == (B, 10) and not alpha.requires_grad            # prim_acts come back detached
+            assert tuple(R.shape) == (B, 10, K) and R.requires_grad and logits.requires_grad
+            assert sorted(routes) == sorted(rh.ROUTES) and all(tuple(v.shape) == (B, 256) for v in routes.values())
+            assert all(v.dtype == mult.final_lni.weight.dtype for v in routes.values())
+        out = rh.forward_capsule_from_route_dict(routes, proj, head, route_mask=rm, return_routing=False)
+        assert out[3] is None and tuple(out[0].shape) == (B, K)

@@ -232,6 +232,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patients per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-loss", action="store_true",
+                    help="opt-in: compute the loss with the device-side loss tail (losses.pheno_train_loss) instead of torch BCE")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--overlap", action="store_true",
                     help="N>1: all-reduce the gradients layer block by layer block on a side stream during the backward "
@@ -286,6 +288,11 @@ def main():
     dev_buf.copy_(host_buf)
     adapter = rh.RouteDimAdapter(256, 256, 256, 256)
     lossf = torch.nn.BCEWithLogitsLoss()
+    if args.fused_loss:
+        # opt-in: the reference's Pheno training loss through the device-side loss tail (csrc/loss.cuh; same BCE, plus
+        # coerce_rc_to_report on R) instead of torch's BCE kernels -- not part of the default measurement
+        from multimodalrouting_b200 import losses as _losses
+        _loss_state = _losses.LossState(dev)
 
     def fwd_bwd():
         for m in modules:
@@ -295,7 +302,10 @@ def main():
             logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
                 mult, xs[0], xs[1], xs[2], proj, head, mL=devb["mL"], mN=devb["mN"], mI=devb["mI"],
                 route_adapter=adapter, route_mask=devb["route_mask"])
-        loss = lossf(logits.float(), devb["y"])
+        if args.fused_loss:
+            loss = _losses.pheno_train_loss(logits, devb["y"], R, alpha, devb["route_mask"], state=_loss_state).loss
+        else:
+            loss = lossf(logits.float(), devb["y"])
         loss.backward()
         return loss
 

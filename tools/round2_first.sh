@@ -18,5 +18,7 @@ MMR_TC_WS=1 timeout 60 python tools/bench_gemm.py > gpurun_out/r2_first_gemm_ws.
 echo "== step, default vs WS"
 timeout 120 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_first_bench_default.json 2> gpurun_out/r2_first_bench_default.err; cut -c1-260 gpurun_out/r2_first_bench_default.json
 MMR_TC_WS=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_first_bench_ws.json 2> gpurun_out/r2_first_bench_ws.err; cut -c1-260 gpurun_out/r2_first_bench_ws.json
+echo "== step with the device-side loss tail"
+timeout 120 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --fused-loss > gpurun_out/r2_first_bench_fusedloss.json 2> gpurun_out/r2_first_bench_fusedloss.err; cut -c1-260 gpurun_out/r2_first_bench_fusedloss.json
 echo "== long-sequence goldens on the GPU"
 MMR_TEST_LONG_GOLDEN=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k long > gpurun_out/r2_first_long.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/r2_first_long.log

@@ -1074,7 +1074,7 @@ int mmr_abi_struct_sizes(size_t* out, int n) {
   return i;
 }
 
-int mmr_version(void) { return 100; }
+int mmr_version(void) { return 101; }   // 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd)
 
 long long mmr_launch_count(void) { return g_launches.load(); }
 

@@ -56,6 +56,19 @@ def gemm_flops_per_step(B):
     return fwd_tn + bwd_tn, wgrad
 
 
+def gemm_bytes_per_step(B):
+    """Algorithmic HBM bytes of the tensor-core GEMM launches of one step (operands once + outputs once, valid rows;
+    weights excluded: 13 MB): per layer q / out projection 2 x (512 + 512) B per query row, fc1 512 + 2048 + 128 (ReLU bits),
+    fc2 2048 + 512, the same again for the four data gradients; K/V of all layers 512 + 4096 B per key row forward and
+    4096 + 1024 (fp32) backward.  profiles/r1_step_bytes.md."""
+    T = {"l": TL, "n": TN, "i": TI}
+    dirs = [("l", "n"), ("l", "i"), ("n", "l"), ("n", "i"), ("i", "l"), ("i", "n")]
+    mq = sum(B * T[q] for q, _ in dirs)
+    mk = sum(B * T[k] for _, k in dirs)
+    per_layer = 1024 + 1024 + 2688 + 2560
+    return 2 * LAYERS * mq * per_layer + mk * (4608 + 5120)
+
+
 def total_flops_per_patient():
     d, L = 256, LAYERS
     T = {"l": TL, "n": TN, "i": TI}
@@ -488,7 +501,12 @@ def main():
                 "avg_launch_ms": 1e3 * t_tn / n_tn, "launches_per_step": n_tn,
                 "flops_per_launch": fl_tn / n_tn,
                 "wgrad_tc_tflops": (fl_wg / (prof["wgrad_tc"]["ms_per_step"] / 1e3) / 1e12) if prof["wgrad_tc"]["ms_per_step"] > 0 else None,
-                "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_peak}
+                "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_peak,
+                # the same launches seen from the HBM side: they are HBM-shaped (128-230 FLOP/B against a machine balance
+                # of ~214), so this fraction explains the tensor fraction above (profiles/r1_step_bytes.md)
+                "hbm_view": {"algorithmic_bytes_per_step": gemm_bytes_per_step(B),
+                             "achieved_GBps": (gemm_bytes_per_step(B) / t_tn / 1e9) if t_tn > 0 else 0.0,
+                             "frac_of_hbm_peak": (gemm_bytes_per_step(B) / t_tn / 1e9 / hbm_peak) if t_tn > 0 else 0.0}}
     # second roofline the north-star names: capsule routing against HBM bandwidth.  Algorithmic bytes per patient
     # (SURVEY.md section 8d, K=25, fp32 route embeddings): forward 11,420 B + backward 20,600 B.
     rt_ms = prof["routing"]["ms_per_step"]

@@ -22,8 +22,10 @@
 // Known gap (why it is opt-in besides speed): the K / V boxes of the last chunk extend past the patient's Tk rows into
 // the next patient's rows of the same 2-D row space.  Their scores get a -inf bias and their P is exactly 0, but 0 x NaN
 // is NaN inside the MMA, so a non-finite K / V row of patient b+1 would leak into patient b (the mma.sync kernels zero-fill
-// the rows they stage).  Fix planned with the pipeline work: per-direction 3-D tensor maps [patient][token][column] whose
-// token extent is Tk, so that the TMA unit zero-fills everything past a patient's last key.
+// the rows they stage).  Fix: per-direction 3-D tensor maps [patient][token][column] whose token extent is Tk, so that the
+// TMA unit zero-fills everything past a patient's last key -- implemented as attn_fwd_tc3_kernel (MMR_ATTN_TC_MAP3D=1), same
+// body with a different loader; written after the round's GPU budget was spent, so it still has to see a GPU
+// (tools/round2_first.sh).  The 2-D kernels' SASS is unchanged by that refactor up to one don't-care mask bit.
 #pragma once
 #include "attention_mma.cuh"
 #include "gemm_tc.cuh"
@@ -57,9 +59,48 @@ __device__ __forceinline__ void mbar_wait_short(uint32_t bar, uint32_t parity) {
 }
 template <int N> __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-template <int NH>
-__global__ void __launch_bounds__(threads<NH>(), 3 - NH)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+
+// Where the Q / K / V boxes come from.
+//  Load2D: the [rows, columns] row spaces as they are; a box that starts at a patient's row runs on into the next patient's
+//          rows (masked by the key bias; see "Known gap" above).
+//  Load3D: per-direction [patient][token][column] views whose token extent is the direction's T, so that the TMA unit
+//          zero-fills every row past a patient's last token (opt-in MMR_ATTN_TC_MAP3D=1; not yet run on a GPU).
+struct Load2D {
+  const CUtensorMap* q; const CUtensorMap* kv;
+  __device__ __forceinline__ void prefetch(int) const {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(kv)) : "memory");
+  }
+  __device__ __forceinline__ void load_q(uint32_t dst, int col, int, int row_abs, int, int, uint32_t bar) const {
+    tma_load_2d(dst, q, col, row_abs, bar);
+  }
+  __device__ __forceinline__ void load_kv(uint32_t dst, int col, int, int row_abs, int, int, uint32_t bar) const {
+    tma_load_2d(dst, kv, col, row_abs, bar);
+  }
+};
+struct Maps3D { CUtensorMap q[NDIR]; CUtensorMap kv[NDIR]; };
+struct Load3D {
+  const Maps3D* m;
+  __device__ __forceinline__ void prefetch(int d) const {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&m->q[d])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&m->kv[d])) : "memory");
+  }
+  __device__ __forceinline__ void load_q(uint32_t dst, int col, int tok, int, int b, int d, uint32_t bar) const {
+    tma_load_3d(dst, &m->q[d], col, tok, b, bar);
+  }
+  __device__ __forceinline__ void load_kv(uint32_t dst, int col, int tok, int, int b, int d, uint32_t bar) const {
+    tma_load_3d(dst, &m->kv[d], col, tok, b, bar);
+  }
+};
+
+template <int NH, class Loader>
+__device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnArgs& a) {
   constexpr int CW = NH * 4;            // control warp
   constexpr int HX = 8 / NH;            // CTAs per (patient, query block)
   constexpr uint32_t TMEM_COLS = NH == 2 ? 512 : 256;
@@ -99,8 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == CW) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+      ldr.prefetch(d);
       constexpr uint32_t idesc_s = make_idesc(KC, 0, 0);          // N = 128 keys, both operands K-major
       constexpr uint32_t idesc_o = make_idesc(64, 0, 1);          // N = 64 value columns, B (= V) MN-major
       const uint32_t kv_full = smem_u32(&ctrl->kv_full);
@@ -108,9 +148,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // every MMA that read K, V and P of the previous chunk has retired (the second head's commit covers all)
         if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[NH - 1]), (uint32_t)(c - 1) & 1u);
         mbar_expect_tx(kv_full, (c == 0 ? 3u : 2u) * TILE);
-        if (c == 0) tma_load_2d(sQ, &tmQ, hp * 64, qrow0, kv_full);
-        tma_load_2d(sK, &tmKV, a.col0 + hp * 64, kvrow0 + c * KC, kv_full);
-        tma_load_2d(sV, &tmKV, a.col0 + D + hp * 64, kvrow0 + c * KC, kv_full);
+        if (c == 0) ldr.load_q(sQ, hp * 64, q0, qrow0, b, d, kv_full);
+        ldr.load_kv(sK, a.col0 + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
+        ldr.load_kv(sV, a.col0 + D + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
         mbar_wait_short(kv_full, (uint32_t)c & 1u);
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc(sQ, 16, 1024), kdesc = make_smem_desc(sK, 16, 1024);
@@ -221,6 +261,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == CW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+template <int NH>
+__global__ void __launch_bounds__(threads<NH>(), 3 - NH)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
+  attn_fwd_tc_body<NH>(Load2D{&tmQ, &tmKV}, a);
+}
+template <int NH>
+__global__ void __launch_bounds__(threads<NH>(), 3 - NH)
+attn_fwd_tc3_kernel(const __grid_constant__ Maps3D maps, AttnArgs a) {
+  attn_fwd_tc_body<NH>(Load3D{&maps}, a);
+}
+
 // host: one launch for all six directions of a layer
 template <int NH>
 static cudaError_t launch_attn_fwd_tc_nh(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnArgs& a, int B, int maxTq,
@@ -236,7 +287,47 @@ static cudaError_t launch_attn_fwd_tc_nh(const CUtensorMap& tmQ, const CUtensorM
   return cudaGetLastError();
 }
 
+// [patient][token][column] view of one direction's rows inside a [rows, ld] bf16 matrix: box = 64 columns x 128 tokens x 1 patient
+static bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t tokens, uint64_t patients, uint64_t ld,
+                         uint32_t box_tokens) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {cols, tokens, patients};
+  cuuint64_t strides[2] = {ld * 2, tokens * ld * 2};
+  cuuint32_t box[3] = {64, box_tokens, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NH>
+static cudaError_t launch_attn_fwd_tc3_nh(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc3_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NH>());
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  Maps3D maps;
+  for (int d = 0; d < NDIR; ++d) {
+    const bf16* qbase = reinterpret_cast<const bf16*>(a.qb) + (size_t)a.q.row0[d] * D;
+    const bf16* kbase = reinterpret_cast<const bf16*>(a.kvbuf) + (size_t)a.kv.row0[d] * a.ldkv;
+    if (!make_tmap_3d(&maps.q[d], qbase, (uint64_t)D, (uint64_t)a.q.T[d], (uint64_t)B, (uint64_t)D, QB)) return cudaErrorUnknown;
+    if (!make_tmap_3d(&maps.kv[d], kbase, (uint64_t)a.ldkv, (uint64_t)a.kv.T[d], (uint64_t)B, (uint64_t)a.ldkv, KC)) return cudaErrorUnknown;
+  }
+  dim3 grid((8 / NH) * ((maxTq + QB - 1) / QB), B, NDIR);
+  attn_fwd_tc3_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH>(), st>>>(maps, a);
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_attn_fwd_tc(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
+  const char* e3 = getenv("MMR_ATTN_TC_MAP3D");     // per-patient 3-D tensor maps (zero fill past a patient's last token)
+  if (e3 && atoi(e3) == 1) {
+    const char* eh = getenv("MMR_ATTN_TC_HEADS");
+    if (eh && atoi(eh) == 1) return launch_attn_fwd_tc3_nh<1>(a, B, maxTq, st);
+    return launch_attn_fwd_tc3_nh<2>(a, B, maxTq, st);
+  }
   CUtensorMap tmQ, tmKV;
   if (!make_tmap(&tmQ, a.qb, (uint64_t)D, (uint64_t)a.q.row0[a.q.n], (uint64_t)D, 64, QB)) return cudaErrorUnknown;
   if (!make_tmap(&tmKV, a.kvbuf, (uint64_t)a.ldkv, (uint64_t)a.kv.row0[a.kv.n], (uint64_t)a.ldkv, 64, KC)) return cudaErrorUnknown;

@@ -40,7 +40,7 @@ constexpr int KC = 128;                 // keys per chunk
 constexpr int TILE = 128 * 64 * 2;      // one 128B-swizzled [128 rows x 64 bf16] tile
 template <int NH> constexpr int threads() { return NH * 128 + 32; }
 // Q, K, V, P[NH heads][2 key blocks], key bias, ctrl, alignment
-template <int NH> constexpr int smem_bytes() { return (3 + 2 * NH) * TILE + 2 * KC * 4 + 256 + 1024; }
+template <int NH, int ST = 1> constexpr int smem_bytes() { return (1 + 2 * ST + 2 * NH) * TILE + 2 * KC * 4 + 256 + 1024; }
 
 struct Ctrl {
   uint64_t kv_full;      // TMA: (Q +) K + V of the chunk landed
@@ -48,6 +48,8 @@ struct Ctrl {
   uint64_t p_full[2];    // head's P tile is in shared memory (4 warps arrive)
   uint64_t o_full[2];    // head's P V product is in TMEM
   uint32_t tmem_base;
+  uint32_t pad_;
+  uint64_t kv_full2;     // ST = 2: the second K / V stage
 };
 
 // every legitimate wait in this kernel is far below a millisecond: trap early instead of spinning for minutes
@@ -99,7 +101,9 @@ struct Load3D {
   }
 };
 
-template <int NH, class Loader>
+// ST = 2 (opt-in MMR_ATTN_TC_PREFETCH=1, not yet run on a GPU): two K / V stages; the TMA loads of chunk c+1 are issued before
+// chunk c is computed, as soon as the MMAs of chunk c-1 -- the last readers of that stage -- have retired.
+template <int NH, class Loader, int ST = 1>
 __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnArgs& a) {
   constexpr int CW = NH * 4;            // control warp
   constexpr int HX = 8 / NH;            // CTAs per (patient, query block)
@@ -114,13 +118,14 @@ __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnAr
   const int nq = min(QB, Tq - q0);
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sQ = sbase, sK = sQ + TILE, sV = sK + TILE, sP = sV + TILE;
-  float* Ms = reinterpret_cast<float*>(sgen + (3 + 2 * NH) * TILE);          // [2][KC] additive key bias, double buffered
+  const uint32_t sQ = sbase, sK = sQ + TILE, sV = sK + TILE, sP = sQ + (1 + 2 * ST) * TILE;   // ST = 2: second K, V after the first
+  float* Ms = reinterpret_cast<float*>(sgen + (1 + 2 * ST + 2 * NH) * TILE);   // [2][KC] additive key bias, double buffered
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(Ms + 2 * KC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&ctrl->kv_full), 1);
+    if (ST == 2) mbar_init(smem_u32(&ctrl->kv_full2), 1);
     mbar_init(smem_u32(&ctrl->s_full), 1);
     for (int h = 0; h < NH; ++h) {
       mbar_init(smem_u32(&ctrl->p_full[h]), 4);
@@ -144,16 +149,35 @@ __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnAr
       constexpr uint32_t idesc_s = make_idesc(KC, 0, 0);          // N = 128 keys, both operands K-major
       constexpr uint32_t idesc_o = make_idesc(64, 0, 1);          // N = 64 value columns, B (= V) MN-major
       const uint32_t kv_full = smem_u32(&ctrl->kv_full);
+      auto issue_kv = [&](int c, uint32_t bar, uint32_t dk, uint32_t dv) {
+        mbar_expect_tx(bar, (c == 0 ? 3u : 2u) * TILE);
+        if (c == 0) ldr.load_q(sQ, hp * 64, q0, qrow0, b, d, bar);
+        ldr.load_kv(dk, a.col0 + hp * 64, c * KC, kvrow0 + c * KC, b, d, bar);
+        ldr.load_kv(dv, a.col0 + D + hp * 64, c * KC, kvrow0 + c * KC, b, d, bar);
+      };
+      if (ST == 2) issue_kv(0, kv_full, sK, sV);
       for (int c = 0; c < nchunks; ++c) {
-        // every MMA that read K, V and P of the previous chunk has retired (the second head's commit covers all)
-        if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[NH - 1]), (uint32_t)(c - 1) & 1u);
-        mbar_expect_tx(kv_full, (c == 0 ? 3u : 2u) * TILE);
-        if (c == 0) ldr.load_q(sQ, hp * 64, q0, qrow0, b, d, kv_full);
-        ldr.load_kv(sK, a.col0 + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
-        ldr.load_kv(sV, a.col0 + D + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
-        mbar_wait_short(kv_full, (uint32_t)c & 1u);
+        uint32_t sKc = sK, sVc = sV;
+        if (ST == 1) {
+          // every MMA that read K, V and P of the previous chunk has retired (the second head's commit covers all)
+          if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[NH - 1]), (uint32_t)(c - 1) & 1u);
+          mbar_expect_tx(kv_full, (c == 0 ? 3u : 2u) * TILE);
+          if (c == 0) ldr.load_q(sQ, hp * 64, q0, qrow0, b, d, kv_full);
+          ldr.load_kv(sK, a.col0 + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
+          ldr.load_kv(sV, a.col0 + D + hp * 64, c * KC, kvrow0 + c * KC, b, d, kv_full);
+          mbar_wait_short(kv_full, (uint32_t)c & 1u);
+        } else {
+          const uint32_t st = (uint32_t)c & 1u;
+          if (c + 1 < nchunks) {       // stage of chunk c+1 = stage of chunk c-1: free once that chunk's MMAs have retired
+            if (c > 0) mbar_wait_short(smem_u32(&ctrl->o_full[NH - 1]), (uint32_t)(c - 1) & 1u);
+            const uint32_t nst = st ^ 1u;
+            issue_kv(c + 1, nst ? smem_u32(&ctrl->kv_full2) : kv_full, sK + nst * 2 * TILE, sV + nst * 2 * TILE);
+          }
+          sKc = sK + st * 2 * TILE; sVc = sV + st * 2 * TILE;
+          mbar_wait_short(st ? smem_u32(&ctrl->kv_full2) : kv_full, (uint32_t)(c >> 1) & 1u);
+        }
         tc_fence_after();
-        const uint64_t qdesc = make_smem_desc(sQ, 16, 1024), kdesc = make_smem_desc(sK, 16, 1024);
+        const uint64_t qdesc = make_smem_desc(sQ, 16, 1024), kdesc = make_smem_desc(sKc, 16, 1024);
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           const int hc = NH == 2 ? h : hsel;   // head hc = columns [32hc, 32hc+32) of the tile: K=16 steps 2hc, 2hc+1 (+32 B each)
@@ -162,7 +186,7 @@ __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnAr
             umma_bf16(tS + h * KC, qdesc + 2 * (2 * hc + k), kdesc + 2 * (2 * hc + k), idesc_s, k != 0);
         }
         umma_commit(smem_u32(&ctrl->s_full));
-        const uint64_t vdesc = make_smem_desc(sV, 8192, 1024);
+        const uint64_t vdesc = make_smem_desc(sVc, 8192, 1024);
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           mbar_wait_short(smem_u32(&ctrl->p_full[h]), (uint32_t)c & 1u);
@@ -271,6 +295,11 @@ __global__ void __launch_bounds__(threads<NH>(), 3 - NH)
 attn_fwd_tc3_kernel(const __grid_constant__ Maps3D maps, AttnArgs a) {
   attn_fwd_tc_body<NH>(Load3D{&maps}, a);
 }
+template <int NH>
+__global__ void __launch_bounds__(threads<NH>(), 1)
+attn_fwd_tc_pf_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
+  attn_fwd_tc_body<NH, Load2D, 2>(Load2D{&tmQ, &tmKV}, a);
+}
 
 // host: one launch for all six directions of a layer
 template <int NH>
@@ -283,6 +312,17 @@ static cudaError_t launch_attn_fwd_tc_nh(const CUtensorMap& tmQ, const CUtensorM
     attr_set = true;
   }
   dim3 grid((8 / NH) * ((maxTq + QB - 1) / QB), B, NDIR);
+  const char* pf = getenv("MMR_ATTN_TC_PREFETCH");   // two K / V stages (opt-in)
+  if (pf && atoi(pf) == 1) {
+    static bool attr_pf = false;
+    if (!attr_pf) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_pf_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NH, 2>());
+      if (e != cudaSuccess) return e;
+      attr_pf = true;
+    }
+    attn_fwd_tc_pf_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH, 2>(), st>>>(tmQ, tmKV, a);
+    return cudaGetLastError();
+  }
   attn_fwd_tc_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH>(), st>>>(tmQ, tmKV, a);
   return cudaGetLastError();
 }

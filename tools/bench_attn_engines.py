@@ -51,9 +51,14 @@ def run(K, B, TL, TN, TI, iters):
 
     os.environ["MMR_WGRAD_STREAM"] = "0"
     ref = None
-    for eng in ("mma", "tc2", "tc1"):      # tcN: tcgen05 engine with N heads per CTA (MMR_ATTN_TC_HEADS)
+    engines = ["mma", "tc2", "tc1"]        # tcN: tcgen05 engine with N heads per CTA (MMR_ATTN_TC_HEADS)
+    if "--variants" in sys.argv:           # opt-in variants: p = two K / V stages (prefetch), m = per-patient 3-D tensor maps
+        engines += ["tc2p", "tc2m", "tc2pm"]
+    for eng in engines:
         os.environ["MMR_ATTN"] = "tc" if eng.startswith("tc") else eng
-        os.environ["MMR_ATTN_TC_HEADS"] = eng[2:] if eng.startswith("tc") else "2"
+        os.environ["MMR_ATTN_TC_HEADS"] = eng[2] if eng.startswith("tc") else "2"
+        os.environ["MMR_ATTN_TC_PREFETCH"] = "1" if eng.startswith("tc") and "p" in eng[3:] else "0"
+        os.environ["MMR_ATTN_TC_MAP3D"] = "1" if eng.startswith("tc") and "m" in eng[3:] else "0"
         for _ in range(3):
             logits = step()
         torch.cuda.synchronize()
@@ -82,6 +87,8 @@ def run(K, B, TL, TN, TI, iters):
                           "logits_max_rel_vs_mma": err}), flush=True)
     os.environ.pop("MMR_ATTN", None)
     os.environ.pop("MMR_ATTN_TC_HEADS", None)
+    os.environ.pop("MMR_ATTN_TC_PREFETCH", None)
+    os.environ.pop("MMR_ATTN_TC_MAP3D", None)
 
 
 if __name__ == "__main__":

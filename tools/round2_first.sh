@@ -22,5 +22,8 @@ echo "== step with the device-side loss tail"
 timeout 120 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --fused-loss > gpurun_out/r2_first_bench_fusedloss.json 2> gpurun_out/r2_first_bench_fusedloss.err; cut -c1-260 gpurun_out/r2_first_bench_fusedloss.json
 echo "== tcgen05 attention with per-patient 3-D tensor maps (zero fill past a patient's last token)"
 MMR_ATTN_TC_MAP3D=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k tcgen05 > gpurun_out/r2_first_attn_map3d.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/r2_first_attn_map3d.log
+echo "== tcgen05 attention with two K / V stages (prefetch), then the engine comparison incl. the variants"
+MMR_ATTN_TC_PREFETCH=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k tcgen05 > gpurun_out/r2_first_attn_prefetch.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/r2_first_attn_prefetch.log
+timeout 90 python tools/bench_attn_engines.py --quick --variants > gpurun_out/r2_first_attn_engines.jsonl 2> gpurun_out/r2_first_attn_engines.err; cat gpurun_out/r2_first_attn_engines.jsonl
 echo "== long-sequence goldens on the GPU"
 MMR_TEST_LONG_GOLDEN=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k long > gpurun_out/r2_first_long.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/r2_first_long.log

@@ -53,7 +53,7 @@ def run(K, B, TL, TN, TI, iters):
     ref = None
     engines = ["mma", "tc2", "tc1"]        # tcN: tcgen05 engine with N heads per CTA (MMR_ATTN_TC_HEADS)
     if "--variants" in sys.argv:           # opt-in variants: p = two K / V stages (prefetch), m = per-patient 3-D tensor maps
-        engines += ["tc2p", "tc2m", "tc2pm"]
+        engines += ["tc2p", "tc1p", "tc2m"]
     for eng in engines:
         os.environ["MMR_ATTN"] = "tc" if eng.startswith("tc") else eng
         os.environ["MMR_ATTN_TC_HEADS"] = eng[2] if eng.startswith("tc") else "2"

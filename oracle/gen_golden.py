@@ -59,6 +59,9 @@ CASES = {
     # acts_override: externally supplied route priors replace the projector's sigmoid activations (routing_and_heads.py:314)
     "pheno_override": dict(variant="pheno", K=25, orig_d_n=256, B=4, seed=1111, sharp=3.0, temp=1.2,
                            detach=False, missing=True, mask_mode="full", override=True, long=True),
+    # two routing iterations instead of the drivers' three (CapsuleMortalityHead(num_routing=2), routing_and_heads.py:233-247)
+    "mort_iter2": dict(variant="mort", K=2, orig_d_n=256, B=4, seed=1212, sharp=4.0, temp=1.0,
+                       detach=False, missing=True, mask_mode="full", iters=2, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
     # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
     # BASELINE configs[4] with a 3-label head
@@ -127,7 +130,7 @@ def run_variant(variant: str):
             mult = mult_model.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True,
                                         8, 4, 0, 0., 0., 0., 0., 0., 0., 0., False)
             proj = rh.RoutePrimaryProjector(256, 32)
-            head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=c["K"])
+            head = rh.CapsuleMortalityHead(32, 64, c.get("iters", 3), 0.0, "EM", num_classes=c["K"])
         mult.load_state_dict(sdm, strict=True)
         proj.load_state_dict(sdp, strict=True)
         head.load_state_dict(sdh, strict=True)

@@ -331,10 +331,11 @@ def routing_forward(sd_proj, sd_head, route_embs: Dict[str, torch.Tensor], *, va
 
 def full_forward(sd_mult, sd_proj, sd_head, x_l, x_n, x_i, mL, mN, mI, *, variant: str,
                  route_mask=None, act_temperature: float = 1.0, detach_priors: bool = False,
-                 heads: int = 8, layers: int = 4, acts_override=None):
+                 heads: int = 8, layers: int = 4, acts_override=None, num_routing: int = 3):
     """forward_capsule_from_multmodel, M/routing_and_heads.py:372-409 (adapter = Identity)."""
     routes = mult_forward(sd_mult, x_l, x_n, x_i, mL, mN, mI, heads=heads, layers=layers)
     logits, alpha, R = routing_forward(sd_proj, sd_head, routes, variant=variant,
                                        route_mask=route_mask, act_temperature=act_temperature,
-                                       detach_priors=detach_priors, acts_override=acts_override)
+                                       detach_priors=detach_priors, acts_override=acts_override,
+                                       num_routing=num_routing)
     return logits, alpha, routes, R

@@ -14,7 +14,7 @@ def build_modules(c, sdm, sdp, sdh, device="cuda"):
     mult = mmr.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True, 8, 4, 0,
                          0., 0., 0., 0., 0., 0., 0., False)
     proj = rh.RoutePrimaryProjector(256, 32)
-    head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=c["K"])
+    head = rh.CapsuleMortalityHead(32, 64, c.get("iters", 3), 0.0, "EM", num_classes=c["K"])
     mult.load_state_dict(sdm, strict=True)
     proj.load_state_dict(sdp, strict=True)
     head.load_state_dict(sdh, strict=True)

@@ -16,7 +16,7 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
-GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override"]     # + acts_override (added late, same gating on the GPU)
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2"]   # + acts_override, num_routing=2 (added late)
 
 
 def load_golden(name):
@@ -93,7 +93,8 @@ def fp64_truth(c, sdm, sdp, sdh, inp):
     logits, alpha, routes, R = orc.full_forward(
         d(sdm), d(sdp), d(sdh), inp["x_l"].double(), inp["x_n"].double(), inp["x_i"].double(),
         f(inp["mL"]), f(inp["mN"]), f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
-        act_temperature=c["temp"], detach_priors=c["detach"], acts_override=f(inp.get("acts_override")))
+        act_temperature=c["temp"], detach_priors=c["detach"], acts_override=f(inp.get("acts_override")),
+        num_routing=c.get("iters", 3))
     return {"logits": logits, "alpha": alpha, "R": R,
             "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
 
@@ -109,9 +110,9 @@ def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
     pert = {r: v * (1 + eps * torch.randn(v.shape, generator=g, dtype=torch.float64)) for r, v in base.items()}
     ao = None if inp.get("acts_override") is None else inp["acts_override"].double()
     l0, _, R0 = orc.routing_forward(d(sdp), d(sdh), base, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
-                                    acts_override=ao)
+                                    acts_override=ao, num_routing=c.get("iters", 3))
     l1, _, R1 = orc.routing_forward(d(sdp), d(sdh), pert, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
-                                    acts_override=ao)
+                                    acts_override=ao, num_routing=c.get("iters", 3))
     dl = (l1 - l0).abs().amax(dim=1) / l0.abs().max().clamp_min(1e-12)
     dR = (R1 - R0).abs().amax(dim=(1, 2)) / R0.abs().max().clamp_min(1e-12)
     return torch.maximum(dl, dR) / eps
@@ -128,7 +129,7 @@ def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
     logits, _, _, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
                                        f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
                                        act_temperature=c["temp"], detach_priors=c["detach"],
-                                       acts_override=f(inp.get("acts_override")))
+                                       acts_override=f(inp.get("acts_override")), num_routing=c.get("iters", 3))
     total = synth.loss_fn(logits, inp["y"].to(dtype), c["variant"])
     if r_probe is not None:
         total = total + 0.05 * (R * r_probe.to(dtype)).sum()

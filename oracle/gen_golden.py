@@ -62,6 +62,9 @@ CASES = {
     # two routing iterations instead of the drivers' three (CapsuleMortalityHead(num_routing=2), routing_and_heads.py:233-247)
     "mort_iter2": dict(variant="mort", K=2, orig_d_n=256, B=4, seed=1212, sharp=4.0, temp=1.0,
                        detach=False, missing=True, mask_mode="full", iters=2, long=True),
+    # two cross-modal layers instead of four (MULTModel(layers=2), mult_model.py:59-81)
+    "pheno_layers2": dict(variant="pheno", K=25, orig_d_n=256, B=3, seed=1313, sharp=3.0, temp=1.0,
+                          detach=False, missing=True, mask_mode="full", layers=2, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
     # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
     # BASELINE configs[4] with a 3-label head
@@ -94,7 +97,8 @@ def checksum(name: str, t: torch.Tensor):
 def build_case_inputs(c):
     sys.path.insert(0, ROOT)
     from oracle import synth
-    sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"])
+    sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"],
+                                     layers=c.get("layers", 4))
     inp = synth.make_inputs(B=c["B"], d_n=c["orig_d_n"], K=c["K"], seed=c["seed"] + 1, missing=c["missing"],
                             TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49))
     if c["mask_mode"] == "none":
@@ -128,7 +132,7 @@ def run_variant(variant: str):
         sdm, sdp, sdh, inp = build_case_inputs(c)
         with contextlib.redirect_stdout(io.StringIO()):
             mult = mult_model.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True,
-                                        8, 4, 0, 0., 0., 0., 0., 0., 0., 0., False)
+                                        8, c.get("layers", 4), 0, 0., 0., 0., 0., 0., 0., 0., False)
             proj = rh.RoutePrimaryProjector(256, 32)
             head = rh.CapsuleMortalityHead(32, 64, c.get("iters", 3), 0.0, "EM", num_classes=c["K"])
         mult.load_state_dict(sdm, strict=True)

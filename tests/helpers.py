@@ -16,7 +16,7 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
-GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2"]   # + acts_override, num_routing=2 (added late)
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2"]   # + acts_override, num_routing=2, layers=2 (added late)
 
 
 def load_golden(name):
@@ -25,7 +25,8 @@ def load_golden(name):
 
 def rebuild_case(c):
     """Same construction as oracle/gen_golden.py:build_case_inputs (no reference needed)."""
-    sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"])
+    sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"],
+                                     layers=c.get("layers", 4))
     inp = synth.make_inputs(B=c["B"], d_n=c["orig_d_n"], K=c["K"], seed=c["seed"] + 1, missing=c["missing"],
                             TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49))
     if c["mask_mode"] == "none":
@@ -94,7 +95,7 @@ def fp64_truth(c, sdm, sdp, sdh, inp):
         d(sdm), d(sdp), d(sdh), inp["x_l"].double(), inp["x_n"].double(), inp["x_i"].double(),
         f(inp["mL"]), f(inp["mN"]), f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
         act_temperature=c["temp"], detach_priors=c["detach"], acts_override=f(inp.get("acts_override")),
-        num_routing=c.get("iters", 3))
+        num_routing=c.get("iters", 3), layers=c.get("layers", 4))
     return {"logits": logits, "alpha": alpha, "R": R,
             "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
 
@@ -129,7 +130,7 @@ def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
     logits, _, _, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
                                        f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
                                        act_temperature=c["temp"], detach_priors=c["detach"],
-                                       acts_override=f(inp.get("acts_override")), num_routing=c.get("iters", 3))
+                                       acts_override=f(inp.get("acts_override")), num_routing=c.get("iters", 3), layers=c.get("layers", 4))
     total = synth.loss_fn(logits, inp["y"].to(dtype), c["variant"])
     if r_probe is not None:
         total = total + 0.05 * (R * r_probe.to(dtype)).sum()

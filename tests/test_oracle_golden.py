@@ -19,7 +19,7 @@ def test_oracle_matches_reference_golden(name):
     logits, alpha, routes, R = orc.full_forward(
         sdm, sdp, sdh, xs["x_l"], xs["x_n"], xs["x_i"], inp["mL"], inp["mN"], inp["mI"],
         variant=c["variant"], route_mask=inp["route_mask"], act_temperature=c["temp"],
-        detach_priors=c["detach"], acts_override=inp.get("acts_override"), num_routing=c.get("iters", 3))
+        detach_priors=c["detach"], acts_override=inp.get("acts_override"), num_routing=c.get("iters", 3), layers=c.get("layers", 4))
     routes_t = torch.stack([routes[r] for r in synth.ROUTES], dim=1)
     assert max_rel(routes_t, gold["routes"]) < 2e-5
     assert max_rel(logits, gold["logits"]) < 2e-5

@@ -63,10 +63,10 @@ def _fill(shape, kind, g) -> torch.Tensor:
 
 
 def make_state(*, K: int, orig_d_n: int = 256, seed: int = 42, sharp: float = 1.0, d: int = 256,
-               layers: int = 4, pc_dim: int = 32, mc_dim: int = 64):
-    """Returns (sd_mult, sd_proj, sd_head) on CPU fp32."""
+               layers: int = 4, pc_dim: int = 32, mc_dim: int = 64, orig_d_l: int = 0, orig_d_i: int = 0):
+    """Returns (sd_mult, sd_proj, sd_head) on CPU fp32.  orig_d_l / orig_d_i default to d (no input projection)."""
     g = torch.Generator().manual_seed(seed)
-    sd_mult = {n: _fill(s, k, g) for n, s, k in mult_param_spec(d, orig_d_n, d, d, layers)}
+    sd_mult = {n: _fill(s, k, g) for n, s, k in mult_param_spec(orig_d_l or d, orig_d_n, orig_d_i or d, d, layers)}
     sd_proj = {}
     for r in ROUTES:
         sd_proj[f"proj.{r}.weight"] = sharp * _fill((pc_dim + 1, d), "linear", g)

@@ -65,6 +65,9 @@ CASES = {
     # two cross-modal layers instead of four (MULTModel(layers=2), mult_model.py:59-81)
     "pheno_layers2": dict(variant="pheno", K=25, orig_d_n=256, B=3, seed=1313, sharp=3.0, temp=1.0,
                           detach=False, missing=True, mask_mode="full", layers=2, long=True),
+    # Conv1d(k=1) input projections on all three modalities (orig_d_l=64, orig_d_n=768, orig_d_i=32; mult_model.py:30-32,134-136)
+    "mort_proj_all": dict(variant="mort", K=2, orig_d_n=768, B=3, seed=1414, sharp=3.0, temp=1.0,
+                          detach=False, missing=True, mask_mode="full", orig_d_l=64, orig_d_i=32, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
     # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
     # BASELINE configs[4] with a 3-label head
@@ -98,9 +101,10 @@ def build_case_inputs(c):
     sys.path.insert(0, ROOT)
     from oracle import synth
     sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"],
-                                     layers=c.get("layers", 4))
+                                     layers=c.get("layers", 4), orig_d_l=c.get("orig_d_l", 0), orig_d_i=c.get("orig_d_i", 0))
     inp = synth.make_inputs(B=c["B"], d_n=c["orig_d_n"], K=c["K"], seed=c["seed"] + 1, missing=c["missing"],
-                            TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49))
+                            TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49),
+                            d_l=c.get("orig_d_l", 0) or 256, d_i=c.get("orig_d_i", 0) or 256)
     if c["mask_mode"] == "none":
         inp["mL"] = inp["mN"] = inp["mI"] = None
         inp["route_mask"] = None
@@ -131,7 +135,7 @@ def run_variant(variant: str):
             continue
         sdm, sdp, sdh, inp = build_case_inputs(c)
         with contextlib.redirect_stdout(io.StringIO()):
-            mult = mult_model.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True,
+            mult = mult_model.MULTModel(c.get("orig_d_l", 0) or 256, c["orig_d_n"], c.get("orig_d_i", 0) or 256, 256, 256, 256, True, True, True,
                                         8, c.get("layers", 4), 0, 0., 0., 0., 0., 0., 0., 0., False)
             proj = rh.RoutePrimaryProjector(256, 32)
             head = rh.CapsuleMortalityHead(32, 64, c.get("iters", 3), 0.0, "EM", num_classes=c["K"])

@@ -11,7 +11,8 @@ def build_modules(c, sdm, sdp, sdh, device="cuda"):
         from multimodalrouting_b200.MortModel import routing_and_heads as rh
     else:
         from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
-    mult = mmr.MULTModel(256, c["orig_d_n"], 256, 256, 256, 256, True, True, True, 8, c.get("layers", 4), 0,
+    mult = mmr.MULTModel(c.get("orig_d_l", 0) or 256, c["orig_d_n"], c.get("orig_d_i", 0) or 256, 256, 256, 256, True, True, True, 8,
+                         c.get("layers", 4), 0,
                          0., 0., 0., 0., 0., 0., 0., False)
     proj = rh.RoutePrimaryProjector(256, 32)
     head = rh.CapsuleMortalityHead(32, 64, c.get("iters", 3), 0.0, "EM", num_classes=c["K"])

@@ -16,7 +16,7 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
-GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2"]   # + acts_override, num_routing=2, layers=2 (added late)
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2", "mort_proj_all"]   # + acts_override, num_routing=2, layers=2, Conv1d on L/N/I
 
 
 def load_golden(name):
@@ -26,9 +26,10 @@ def load_golden(name):
 def rebuild_case(c):
     """Same construction as oracle/gen_golden.py:build_case_inputs (no reference needed)."""
     sdm, sdp, sdh = synth.make_state(K=c["K"], orig_d_n=c["orig_d_n"], seed=c["seed"], sharp=c["sharp"],
-                                     layers=c.get("layers", 4))
+                                     layers=c.get("layers", 4), orig_d_l=c.get("orig_d_l", 0), orig_d_i=c.get("orig_d_i", 0))
     inp = synth.make_inputs(B=c["B"], d_n=c["orig_d_n"], K=c["K"], seed=c["seed"] + 1, missing=c["missing"],
-                            TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49))
+                            TL=c.get("TL", 48), TN=c.get("TN", 16), TI=c.get("TI", 49),
+                            d_l=c.get("orig_d_l", 0) or 256, d_i=c.get("orig_d_i", 0) or 256)
     if c["mask_mode"] == "none":
         inp["mL"] = inp["mN"] = inp["mI"] = None
         inp["route_mask"] = None

@@ -25,5 +25,7 @@ MMR_ATTN_TC_MAP3D=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m 
 echo "== tcgen05 attention with two K / V stages (prefetch), then the engine comparison incl. the variants"
 MMR_ATTN_TC_PREFETCH=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k tcgen05 > gpurun_out/r2_first_attn_prefetch.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/r2_first_attn_prefetch.log
 timeout 90 python tools/bench_attn_engines.py --quick --variants > gpurun_out/r2_first_attn_engines.jsonl 2> gpurun_out/r2_first_attn_engines.err; cat gpurun_out/r2_first_attn_engines.jsonl
+echo "== the integrated training-step example (graph capture incl. the loss tail)"
+timeout 90 python examples/train_step.py 6 > gpurun_out/r2_first_train_step.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/r2_first_train_step.log
 echo "== long-sequence goldens on the GPU"
 MMR_TEST_LONG_GOLDEN=1 timeout 120 python -m pytest tests/test_gpu_fusion.py -q -m gpu -k long > gpurun_out/r2_first_long.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/r2_first_long.log

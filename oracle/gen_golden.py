@@ -68,6 +68,14 @@ CASES = {
     # Conv1d(k=1) input projections on all three modalities (orig_d_l=64, orig_d_n=768, orig_d_i=32; mult_model.py:30-32,134-136)
     "mort_proj_all": dict(variant="mort", K=2, orig_d_n=768, B=3, seed=1414, sharp=3.0, temp=1.0,
                           detach=False, missing=True, mask_mode="full", orig_d_l=64, orig_d_i=32, long=True),
+    # unsharpened missing-modality pair (sharp=1: routing is well conditioned for every patient, so the bf16 bar of the GPU
+    # tests applies to all of them) and the gradient through an externally supplied acts_override (Mort variant)
+    "pheno_missing1": dict(variant="pheno", K=25, orig_d_n=256, B=8, seed=1515, sharp=1.0, temp=1.0,
+                           detach=False, missing=True, mask_mode="full", long=True),
+    "mort_missing1": dict(variant="mort", K=2, orig_d_n=256, B=8, seed=1616, sharp=1.0, temp=1.0,
+                          detach=False, missing=True, mask_mode="full", long=True),
+    "mort_override": dict(variant="mort", K=2, orig_d_n=256, B=4, seed=1717, sharp=3.0, temp=1.5,
+                          detach=False, missing=True, mask_mode="full", override=True, override_grad=True, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the
     # oracle): PhenoModel's own default structured_seq_len=256 (P/env_config.py:96) and the INSPECT token counts of
     # BASELINE configs[4] with a 3-label head
@@ -143,6 +151,8 @@ def run_variant(variant: str):
         proj.load_state_dict(sdp, strict=True)
         head.load_state_dict(sdh, strict=True)
         xs = {k: inp[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+        if c.get("override_grad"):
+            inp["acts_override"] = inp["acts_override"].clone().requires_grad_(True)
         with contextlib.redirect_stdout(io.StringIO()):
             logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
                 mult, xs["x_l"], xs["x_n"], xs["x_i"], proj, head,
@@ -161,13 +171,15 @@ def run_variant(variant: str):
                 grads[n] = p.grad
         for k, v in xs.items():
             grads[k] = v.grad
+        if c.get("override_grad"):
+            grads["acts_override"] = inp["acts_override"].grad
         out = {
             "case": dict(c), "logits": logits.detach(), "alpha": alpha.detach(), "R": R.detach(),
             "routes": torch.stack([routes[r].detach() for r in synth.ROUTES], dim=1),
             "loss": float(loss), "total": float(total),
             "grad_none": sorted(n for n, g in grads.items() if g is None),
             "grad_checksum": {n: checksum(n, g) for n, g in grads.items() if g is not None},
-            "grad_full": {n: grads[n].detach().clone() for n in FULL_GRADS if grads.get(n) is not None},
+            "grad_full": {n: grads[n].detach().clone() for n in FULL_GRADS + ["acts_override"] if grads.get(n) is not None},
         }
         torch.save(out, os.path.join(GOLD, name + ".pt"))
         print(f"[golden] {name}: loss={float(loss):.6f} |logits|max={float(logits.abs().max()):.4f} "

@@ -31,12 +31,15 @@ def run_case(c, sdm, sdp, sdh, inp, *, autocast=False, backward=True, r_probe=No
     rh, mult, proj, head = build_modules(c, sdm, sdp, sdh)
     d = to_dev(inp)
     xs = {k: d[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+    ao = d.get("acts_override")
+    if ao is not None:
+        ao = ao.detach().clone().requires_grad_(bool(c.get("override_grad")))
     ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else torch.autocast("cuda", enabled=False)
     with ctx:
         logits, alpha, routes, R = rh.forward_capsule_from_multmodel(
             mult, xs["x_l"], xs["x_n"], xs["x_i"], proj, head, mL=d["mL"], mN=d["mN"], mI=d["mI"],
             route_adapter=rh.RouteDimAdapter(256, 256, 256, 256), route_mask=d["route_mask"],
-            act_temperature=c["temp"], detach_priors=c["detach"], acts_override=d.get("acts_override"))
+            act_temperature=c["temp"], detach_priors=c["detach"], acts_override=ao)
     out = {"logits": logits, "alpha": alpha, "R": R,
            "routes": torch.stack([routes[r] for r in synth.ROUTES], dim=1)}
     if backward:
@@ -51,6 +54,8 @@ def run_case(c, sdm, sdp, sdh, inp, *, autocast=False, backward=True, r_probe=No
                 grads[n] = p.grad
         for k, v in xs.items():
             grads[k] = v.grad
+        if ao is not None and ao.requires_grad:
+            grads["acts_override"] = ao.grad
         out["loss"] = float(loss.detach())
         out["grads"] = grads
     return out

@@ -16,7 +16,8 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
                 "mort_nomask", "pheno_rm1d", "pheno_odd"]
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
-GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2", "mort_proj_all"]   # + acts_override, num_routing=2, layers=2, Conv1d on L/N/I
+GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2", "mort_proj_all",   # + acts_override, num_routing=2, layers=2, Conv1d on L/N/I
+               "pheno_missing1", "mort_missing1", "mort_override"]   # sharp=1 missing-modality pair; gradient through acts_override
 
 
 def load_golden(name):
@@ -39,6 +40,8 @@ def rebuild_case(c):
         inp["route_mask"] = rm
     if c.get("override"):
         inp["acts_override"] = torch.rand(c["B"], 10, 1, generator=torch.Generator().manual_seed(c["seed"] + 3))
+        if c.get("override_grad"):
+            inp["acts_override"].requires_grad_(True)
     return sdm, sdp, sdh, inp
 
 
@@ -91,7 +94,7 @@ def fp64_truth(c, sdm, sdp, sdh, inp):
     implementation that is as close to the fp64 truth as the reference's fp32 result is."""
     from oracle import route_fusion_oracle as orc
     d = lambda sd: {k: v.double() for k, v in sd.items()}
-    f = lambda t: None if t is None else t.double()
+    f = lambda t: None if t is None else t.detach().double()
     logits, alpha, routes, R = orc.full_forward(
         d(sdm), d(sdp), d(sdh), inp["x_l"].double(), inp["x_n"].double(), inp["x_i"].double(),
         f(inp["mL"]), f(inp["mN"]), f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
@@ -110,7 +113,7 @@ def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
     base = {r: routes_bt[:, i].double() for i, r in enumerate(synth.ROUTES)}
     g = torch.Generator().manual_seed(1234)
     pert = {r: v * (1 + eps * torch.randn(v.shape, generator=g, dtype=torch.float64)) for r, v in base.items()}
-    ao = None if inp.get("acts_override") is None else inp["acts_override"].double()
+    ao = None if inp.get("acts_override") is None else inp["acts_override"].detach().double()
     l0, _, R0 = orc.routing_forward(d(sdp), d(sdh), base, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
                                     acts_override=ao, num_routing=c.get("iters", 3))
     l1, _, R1 = orc.routing_forward(d(sdp), d(sdh), pert, variant=c["variant"], route_mask=rm, act_temperature=c["temp"],
@@ -120,21 +123,28 @@ def routing_amplification(c, sdp, sdh, inp, routes_bt, eps=1e-4):
     return torch.maximum(dl, dR) / eps
 
 
-def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
-    """All parameter / input gradients of the oracle (same loss + R probe as gpu_common.run_case) in
-    `dtype`; float64 gives the exact-arithmetic gradients used by the conditioning-aware criterion."""
+def oracle_run(c, sdm, sdp, sdh, inp, r_probe, dtype, device="cpu", autocast=False):
+    """Forward + loss (+ R probe) + backward of the oracle in `dtype` on `device`.  float64 on the CPU gives the
+    exact-arithmetic answer used by the conditioning-aware criteria; ``device="cuda", autocast=True`` is the
+    reference's own mixed-precision path (same modules under torch.autocast("cuda", bfloat16), TF32 as the drivers set it,
+    M/main.py:2613-2621,2641) -- the yardstick for the bf16 kernels.  Returns (outputs, gradients)."""
     from oracle import route_fusion_oracle as orc
-    cv = lambda sd: {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
-    f = lambda t: None if t is None else t.to(dtype)
+    cv = lambda sd: {k: v.detach().to(device=device, dtype=dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    f = lambda t: None if t is None else t.detach().to(device=device, dtype=dtype)
     a, b, h = cv(sdm), cv(sdp), cv(sdh)
-    xs = {k: inp[k].to(dtype).clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
-    logits, _, _, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
-                                       f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
-                                       act_temperature=c["temp"], detach_priors=c["detach"],
-                                       acts_override=f(inp.get("acts_override")), num_routing=c.get("iters", 3), layers=c.get("layers", 4))
-    total = synth.loss_fn(logits, inp["y"].to(dtype), c["variant"])
+    xs = {k: inp[k].detach().to(device=device, dtype=dtype).clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")}
+    ao = f(inp.get("acts_override"))
+    if ao is not None and c.get("override_grad"):
+        ao.requires_grad_(True)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else torch.autocast("cuda", enabled=False)
+    with ctx:
+        logits, alpha, routes, R = orc.full_forward(a, b, h, xs["x_l"], xs["x_n"], xs["x_i"], f(inp["mL"]), f(inp["mN"]),
+                                                    f(inp["mI"]), variant=c["variant"], route_mask=f(inp["route_mask"]),
+                                                    act_temperature=c["temp"], detach_priors=c["detach"],
+                                                    acts_override=ao, num_routing=c.get("iters", 3), layers=c.get("layers", 4))
+    total = synth.loss_fn(logits.float() if autocast else logits, inp["y"].to(device=device, dtype=logits.dtype if not autocast else torch.float32), c["variant"])
     if r_probe is not None:
-        total = total + 0.05 * (R * r_probe.to(dtype)).sum()
+        total = total + 0.05 * (R.to(total.dtype) * r_probe.to(device=device, dtype=total.dtype)).sum()
     total.backward()
     g = {}
     for sd in (a, b, h):
@@ -142,4 +152,22 @@ def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
             g[k] = v.grad
     for k, v in xs.items():
         g[k] = v.grad
-    return g
+    if ao is not None and ao.requires_grad:
+        g["acts_override"] = ao.grad
+    out = {"logits": logits.detach(), "alpha": alpha.detach(), "R": R.detach(),
+           "routes": torch.stack([routes[r].detach() for r in synth.ROUTES], dim=1)}
+    return out, g
+
+
+def oracle_grads(c, sdm, sdp, sdh, inp, r_probe, dtype):
+    """All parameter / input gradients of the oracle (same loss + R probe as gpu_common.run_case) in
+    `dtype`; float64 gives the exact-arithmetic gradients used by the conditioning-aware criterion."""
+    return oracle_run(c, sdm, sdp, sdh, inp, r_probe, dtype)[1]
+
+
+def per_patient_err(a, b, floor=1e-6):
+    """[B] max |a-b| over everything but the batch dimension, relative to the whole tensor's scale."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    d = (a - b).abs().reshape(a.shape[0], -1).amax(dim=1)
+    return d / (b.abs().max() + floor)

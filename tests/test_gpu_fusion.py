@@ -8,7 +8,7 @@ import torch
 
 from gpu_common import run_case
 from helpers import (GOLDEN_CASES, GOLDEN_LONG, check_grad_checksums, fp64_truth, load_golden, max_rel, oracle_grads,
-                     r_grad_probe, rebuild_case, routing_amplification)
+                     oracle_run, per_patient_err, r_grad_probe, rebuild_case)
 
 pytestmark = pytest.mark.gpu
 
@@ -60,58 +60,69 @@ def test_fp32_matches_reference_golden(name):
             assert e_mine <= max(5e-4, 3.0 * e_ref), f"grad {k}: vs fp64 mine {e_mine:.2e} ref {e_ref:.2e}"
 
 
-_LONG_OFF = os.environ.get("MMR_TEST_LONG_GOLDEN") != "1"
-_LONG_WHY = ("reference goldens at 256 / 512-token sequences: pinned against the oracle on CPU (tests/test_oracle_golden.py); the "
-             "GPU comparison was added after the round's GPU budget was spent -- set MMR_TEST_LONG_GOLDEN=1 to run it")
-
-
-@pytest.mark.skipif(_LONG_OFF, reason=_LONG_WHY)
 @pytest.mark.parametrize("name", GOLDEN_LONG)
 def test_fp32_matches_reference_golden_long(name):
+    """Reference goldens at 256 / 512-token sequences (INSPECT token counts of BASELINE configs[4]), acts_override (with and
+    without gradient), num_routing=2, layers=2, Conv1d on all three modalities, sharp=1 missing-modality pair."""
     test_fp32_matches_reference_golden(name)
 
 
-@pytest.mark.skipif(_LONG_OFF, reason=_LONG_WHY)
-@pytest.mark.parametrize("name", GOLDEN_LONG)
-def test_bf16_tc_engine_long(name):
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_LONG)
+def test_bf16_tc_engine(name):
     _bf16_case(name, "tc")
 
 
+BF16_TOL, BF16_GRAD_TOL, BF16_SLACK = 2e-2, 8e-2, 3.0
+
+
 def _bf16_case(name, engine):
+    """bf16 budget of the north star: 2e-2 on logits and the route weights alpha / R, identical argmax -- for EVERY patient.
+    Where sharpened routing amplifies bf16 rounding of the route embeddings past any fixed tolerance (it does so in the
+    reference's own autocast path just as much), the yardstick is the reference's mixed-precision path itself: the oracle run
+    on the GPU under torch.autocast("cuda", bfloat16) (SURVEY 8c hygiene (3)).  Per patient the kernels must be within 2e-2 of
+    the reference golden or no further from the exact (fp64) answer than BF16_SLACK x the reference's own bf16 error; every
+    parameter / input gradient likewise (8e-2, the bar the well-conditioned goldens meet)."""
     os.environ["MMR_B200_GEMM"] = engine
     try:
         gold = load_golden(name)
         c = gold["case"]
         sdm, sdp, sdh, inp = rebuild_case(c)
-        out = run_case(c, sdm, sdp, sdh, inp, autocast=True, r_probe=r_grad_probe(c, gold["R"].shape))
+        probe = r_grad_probe(c, gold["R"].shape)
+        out = run_case(c, sdm, sdp, sdh, inp, autocast=True, r_probe=probe)
     finally:
         os.environ.pop("MMR_B200_GEMM", None)
-    # bf16 budget (north_star): 2e-2 on logits and route weights alpha / R, identical argmax.  Patients
-    # whose routing amplifies input noise by more than 10x (fp64 condition estimate) are excluded from
-    # the logits / R comparison: bf16 rounding of the route embeddings (~1e-3) alone moves them past any
-    # fixed tolerance, in the reference's own autocast path as much as here.
-    amp = routing_amplification(c, sdp, sdh, inp, gold["routes"])
-    ok = amp <= 10.0
-    assert int(ok.sum()) >= 2, f"too few well-conditioned patients: {amp}"
-    assert max_rel(out["routes"], gold["routes"]) < 2e-2, "route embeddings"
-    assert max_rel(out["alpha"], gold["alpha"]) < 2e-2, "alpha"
-    assert max_rel(out["logits"].cpu()[ok], gold["logits"][ok]) < 2e-2, f"logits (amp {amp})"
-    assert max_rel(out["R"].cpu()[ok], gold["R"][ok]) < 2e-2, f"R (amp {amp})"
-    lg, lo = out["logits"].cpu()[ok], gold["logits"][ok]
+    t64, g64 = oracle_run(c, sdm, sdp, sdh, inp, probe, torch.float64)
+    r16, g16 = oracle_run(c, sdm, sdp, sdh, inp, probe, torch.float32, device="cuda", autocast=True)
+    assert max_rel(out["routes"], gold["routes"]) < BF16_TOL, "route embeddings"
+    assert max_rel(out["alpha"], gold["alpha"]) < BF16_TOL, "alpha"
+    allow = {}
+    for key in ("logits", "R"):
+        e_gold = per_patient_err(out[key], gold[key])
+        e_mine = per_patient_err(out[key], t64[key])
+        e_ref = per_patient_err(r16[key], t64[key])
+        allow[key] = torch.clamp(BF16_SLACK * e_ref, min=BF16_TOL)
+        bad = (e_gold >= BF16_TOL) & (e_mine > allow[key])
+        assert not bool(bad.any()), (f"{key}: patients {bad.nonzero().flatten().tolist()} vs golden {e_gold.tolist()} "
+                                     f"vs fp64 mine {e_mine.tolist()} reference-bf16 {e_ref.tolist()}")
+    # argmax parity (M/main.py:1753-1758, P/main.py:2847-2848) outside each patient's own error margin
+    lg, lt = out["logits"].float().cpu(), t64["logits"].float()
+    scale = lt.abs().max()
     if c["variant"] == "mort":
-        margin = (lo[:, 1] - lo[:, 0]).abs() > 2e-2 * lo.abs().max()
-        assert torch.equal((lg[:, 1] > lg[:, 0])[margin], (lo[:, 1] > lo[:, 0])[margin])
+        margin = (lt[:, 1] - lt[:, 0]).abs() > 2 * allow["logits"].float() * scale
+        assert torch.equal((lg[:, 1] > lg[:, 0])[margin], (lt[:, 1] > lt[:, 0])[margin])
     else:
-        margin = lo.abs() > 2e-2 * lo.abs().max()
-        assert torch.equal((lg > 0)[margin], (lo > 0)[margin])
-    # gradients mix all patients through the batch-mean loss: compare them only when every patient is
-    # well conditioned, otherwise just require finiteness
-    if bool((amp <= 10.0).all()):
-        for k, g in gold["grad_full"].items():
-            assert max_rel(out["grads"][k], g) < 8e-2, f"grad {k}"
-    else:
-        for k, g in out["grads"].items():
-            assert g is None or bool(torch.isfinite(g).all()), f"grad {k} not finite"
+        margin = lt.abs() > (allow["logits"].float() * scale).unsqueeze(1)
+        assert torch.equal((lg > 0)[margin], (lt > 0)[margin])
+    none = sorted(k for k, g in out["grads"].items() if g is None)
+    assert none == gold["grad_none"], (none, gold["grad_none"])
+    worst = []
+    for k, t in g64.items():
+        if t is None:
+            continue
+        e_mine, e_ref = max_rel(out["grads"][k], t), max_rel(g16[k], t)
+        if e_mine > max(BF16_GRAD_TOL, BF16_SLACK * e_ref):
+            worst.append((k, e_mine, e_ref))
+    assert not worst, f"{len(worst)} gradients further from fp64 than {BF16_SLACK}x the reference's bf16 path: {worst[:5]}"
     return out, gold
 
 
@@ -198,10 +209,12 @@ def synth_routes():
     return synth.ROUTES
 
 
-def test_full_size_invariants_and_bf16_vs_fp32():
-    """BASELINE configs[1] at full size (B=512, K=25, L48/N16/I49) with missing modalities: size-independent
-    properties the reference's runtime guards pin (M/main.py:319-338: R sums to 1 over routes; masked routes
-    contribute exactly nothing) plus bf16-vs-fp32 kernel agreement within the north-star bf16 budget."""
+def test_full_size_vs_oracle():
+    """BASELINE configs[1] at full size (B=512, K=25, L48/N16/I49) with missing modalities -- the benchmark configuration --
+    against the oracle: fp32 kernels vs the fp32 CPU oracle (1e-4, conditioning-aware against fp64 like the goldens), bf16
+    kernels vs the reference's own mixed-precision path (oracle on the GPU under autocast) per patient, plus the
+    size-independent properties the reference's runtime guards pin (M/main.py:319-338: R sums to 1 over routes; masked
+    routes contribute exactly nothing)."""
     c = dict(variant="pheno", K=25, orig_d_n=256, B=512, seed=4242, sharp=1.0, temp=1.0, detach=False,
              missing=True, mask_mode="full")
     sdm, sdp, sdh, inp = rebuild_case(c)
@@ -217,13 +230,35 @@ def test_full_size_invariants_and_bf16_vs_fp32():
         assert float(alpha[rm == 0].abs().max()) == 0.0      # ... and alpha exactly 0
         for g in o["grads"].values():
             assert g is None or bool(torch.isfinite(g).all())
-    assert max_rel(o16["routes"], o32["routes"]) < 2e-2
-    assert max_rel(o16["alpha"], o32["alpha"]) < 2e-2
-    assert max_rel(o16["logits"], o32["logits"]) < 2e-2
-    assert max_rel(o16["R"], o32["R"]) < 2e-2
-    lg32, lg16 = o32["logits"].float().cpu(), o16["logits"].float().cpu()
-    margin = lg32.abs() > 2e-2 * lg32.abs().max()
-    assert torch.equal((lg16 > 0)[margin], (lg32 > 0)[margin])
+    r32, g32 = oracle_run(c, sdm, sdp, sdh, inp, None, torch.float32)
+    t64, g64 = oracle_run(c, sdm, sdp, sdh, inp, None, torch.float64)
+    r16, g16 = oracle_run(c, sdm, sdp, sdh, inp, None, torch.float32, device="cuda", autocast=True)
+    for key in ("routes", "logits", "alpha", "R"):
+        e = max_rel(o32[key], r32[key])
+        assert e < 1e-4 or max_rel(o32[key], t64[key]) <= max(1e-4, 3 * max_rel(r32[key], t64[key])), f"fp32 {key} {e:.2e}"
+    for k, t in g64.items():
+        if t is None:
+            assert o32["grads"][k] is None, k
+            continue
+        e = max_rel(o32["grads"][k], g32[k])
+        assert e < 5e-4 or max_rel(o32["grads"][k], t) <= max(5e-4, 3 * max_rel(g32[k], t)), f"fp32 grad {k}: {e:.2e}"
+    assert max_rel(o16["routes"], r32["routes"]) < BF16_TOL
+    assert max_rel(o16["alpha"], r32["alpha"]) < BF16_TOL
+    for key in ("logits", "R"):
+        e_gold = per_patient_err(o16[key], r32[key])
+        e_mine = per_patient_err(o16[key], t64[key])
+        e_ref = per_patient_err(r16[key], t64[key])
+        bad = (e_gold >= BF16_TOL) & (e_mine > torch.clamp(BF16_SLACK * e_ref, min=BF16_TOL))
+        assert not bool(bad.any()), f"bf16 {key}: patients {bad.nonzero().flatten().tolist()[:8]} worst {float(e_gold.max()):.2e}"
+    lt, lg16 = t64["logits"].float(), o16["logits"].float().cpu()
+    margin = lt.abs() > 2e-2 * lt.abs().max()
+    assert torch.equal((lg16 > 0)[margin], (lt > 0)[margin])
+    assert torch.equal((o32["logits"].cpu() > 0)[margin], (lt > 0)[margin])
+    for k, t in g64.items():
+        if t is None:
+            continue
+        e_mine, e_ref = max_rel(o16["grads"][k], t), max_rel(g16[k], t)
+        assert e_mine <= max(BF16_GRAD_TOL, BF16_SLACK * e_ref), f"bf16 grad {k}: {e_mine:.2e} (reference bf16 {e_ref:.2e})"
 
 
 @pytest.mark.parametrize("cfg", [

@@ -1,7 +1,5 @@
 """-m gpu: the tcgen05/TMEM/TMA GEMM engine -- unit parity against fp64 matmul and end-to-end bf16
 parity of the full path running on it (the default engine for bf16)."""
-import os
-
 import pytest
 import torch
 
@@ -24,15 +22,6 @@ def test_tc_gemm_tn(M, N, K):
     assert max_rel(C, ref) < 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("MMR_TC_WS") != "1",
-                    reason="shapes that engage the weight-stationary GEMM variant; it is opt-in (run the suite with MMR_TC_WS=1)")
-@pytest.mark.parametrize("M,N,K", [(2048, 256, 256), (1536, 512, 128), (4096, 1024, 256), (1024, 2048, 64), (115712, 256, 256)])
-def test_tc_gemm_tn_weight_stationary_shapes(M, N, K):
-    """K <= 256 with 256-row aligned row spaces: one, two, four and eight n-blocks (the grid is trimmed to a multiple of the
-    n-block count so that a CTA pair keeps its weight block), up to the path's own 115,712-row space."""
-    test_tc_gemm_tn(M, N, K)
-
-
 @pytest.mark.parametrize("Kr,M,N", [(64, 128, 256), (128, 128, 256), (1000, 256, 1024), (5000, 1024, 256), (777, 2048, 256)])
 def test_tc_gemm_wgrad(Kr, M, N):
     from multimodalrouting_b200 import ops
@@ -43,12 +32,6 @@ def test_tc_gemm_wgrad(Kr, M, N):
     torch.cuda.synchronize()
     ref = Y.double().t() @ X.double()
     assert max_rel(W, ref) < 1e-5
-
-
-@pytest.mark.parametrize("name", ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "pheno_missing",
-                                  "mort_nomask", "pheno_rm1d", "pheno_odd"])
-def test_bf16_tc_engine(name):
-    _bf16_case(name, "tc")
 
 
 @pytest.mark.parametrize("name", ["pheno_sharp4", "mort_missing", "pheno_odd"])

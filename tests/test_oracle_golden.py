@@ -35,6 +35,8 @@ def test_oracle_matches_reference_golden(name):
             grads[k] = v.grad
     for k, v in xs.items():
         grads[k] = v.grad
+    if c.get("override_grad"):
+        grads["acts_override"] = inp["acts_override"].grad
     none = sorted(k for k, g in grads.items() if g is None)
     assert none == gold["grad_none"], (none, gold["grad_none"])
     check_grad_checksums(grads, gold["grad_checksum"], 1e-4, name)

@@ -27,26 +27,39 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-B_PER_GPU = 512
-TL, TN, TI, K_LABELS, LAYERS = 48, 16, 49, 25, 4
+LAYERS = 4
 METRIC = "patients/sec route-fusion+capsule routing fwd+bwd at 1/2/4/8 B200; % roofline"
 UNIT = "patients/sec"
-WORKLOAD = ("BASELINE configs[1]: MIMIC-IV PhenoModel 25-label, random-init, synthetic batch=512/GPU, "
-            "L48/N16/I49 x 256, fwd+bwd bf16")
+# --config: the default is the configuration BASELINE.json's metric is quoted on (configs[1]); the other two are the
+# remaining multi-GPU configs of BASELINE.json, kept as secondary lines (profiles/), not the headline.
+WORKLOADS = {
+    "pheno512": dict(variant="pheno", K=25, TL=48, TN=16, TI=49, batch=512, scaling="weak",
+                     name="BASELINE configs[1]: MIMIC-IV PhenoModel 25-label, random-init, synthetic batch=512/GPU, "
+                          "L48/N16/I49 x 256, fwd+bwd bf16"),
+    "mort8192": dict(variant="mort", K=2, TL=48, TN=16, TI=49, batch=8192, scaling="strong",
+                     name="BASELINE configs[2]: MIMIC-IV MortModel (K=2), random-init, synthetic GLOBAL batch=8192 split over "
+                          "the GPUs, L48/N16/I49 x 256, fwd+bwd bf16 + gradient all-reduce"),
+    "inspect": dict(variant="pheno", K=3, TL=512, TN=128, TI=196, batch=256, scaling="weak",
+                    name="BASELINE configs[4]: INSPECT token counts L512/N128/I196 x 256, 3-label head, synthetic "
+                         "batch=256/GPU, fwd+bwd bf16"),
+}
+WL = dict(WORKLOADS["pheno512"])          # the selected workload (set in main)
 
 
 def peaks():
+    """(burst bf16 TF/s, sustained bf16 TF/s, HBM GB/s, source).  A kernel class timed alone in a short region is held
+    against the BURST peak, the whole step inside a long run against the SUSTAINED one (MEASURED_PEAKS.json "how")."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1402.1), d.get("hbm_gbs", 6548.5), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops", 1663.5), d.get("bf16_tflops_sustained", 1402.1), d.get("hbm_gbs", 6548.5), "measured"
+    return 1663.5, 1402.1, 6548.5, "fallback (B200_PROFILING.md / the pool's last measured peaks)"
 
 
 def gemm_flops_per_step(B):
     """Algorithmic FLOPs of the tensor-core GEMMs (valid rows only), by class."""
     d, f, L = 256, 1024, LAYERS
-    T = {"l": TL, "n": TN, "i": TI}
+    T = {"l": WL["TL"], "n": WL["TN"], "i": WL["TI"]}
     dirs = [("l", "n"), ("l", "i"), ("n", "l"), ("n", "i"), ("i", "l"), ("i", "n")]
     mq = sum(B * T[q] for q, _ in dirs)
     mk = sum(B * T[k] for _, k in dirs)
@@ -61,7 +74,7 @@ def gemm_bytes_per_step(B):
     weights excluded: 13 MB): per layer q / out projection 2 x (512 + 512) B per query row, fc1 512 + 2048 + 128 (ReLU bits),
     fc2 2048 + 512, the same again for the four data gradients; K/V of all layers 512 + 4096 B per key row forward and
     4096 + 1024 (fp32) backward.  profiles/r1_step_bytes.md."""
-    T = {"l": TL, "n": TN, "i": TI}
+    T = {"l": WL["TL"], "n": WL["TN"], "i": WL["TI"]}
     dirs = [("l", "n"), ("l", "i"), ("n", "l"), ("n", "i"), ("i", "l"), ("i", "n")]
     mq = sum(B * T[q] for q, _ in dirs)
     mk = sum(B * T[k] for _, k in dirs)
@@ -71,7 +84,7 @@ def gemm_bytes_per_step(B):
 
 def total_flops_per_patient():
     d, L = 256, LAYERS
-    T = {"l": TL, "n": TN, "i": TI}
+    T = {"l": WL["TL"], "n": WL["TN"], "i": WL["TI"]}
     dirs = [("l", "n"), ("l", "i"), ("n", "l"), ("n", "i"), ("i", "l"), ("i", "n")]
     fwd = sum(L * (20 * T[q] * d * d + 4 * T[k] * d * d + 4 * T[q] * T[k] * d) for q, k in dirs)
     return 3 * fwd   # fwd+bwd = 3x forward
@@ -145,36 +158,51 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def make_batch(B, seed):
+    from multimodalrouting_b200 import synth
+    return synth.make_inputs(B=B, K=WL["K"], seed=seed, TL=WL["TL"], TN=WL["TN"], TI=WL["TI"])
+
+
 def build_models(device, seed=42):
     from multimodalrouting_b200 import synth
     from multimodalrouting_b200 import MULTModel
-    from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
-    sdm, sdp, sdh = synth.make_state(K=K_LABELS, seed=seed, sharp=1.0)
+    if WL["variant"] == "mort":
+        from multimodalrouting_b200.MortModel import routing_and_heads as rh
+    else:
+        from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    sdm, sdp, sdh = synth.make_state(K=WL["K"], seed=seed, sharp=1.0)
     mult = MULTModel(256, 256, 256, 256, 256, 256, True, True, True, 8, LAYERS, 0, 0., 0., 0., 0., 0., 0., 0., False)
     proj = rh.RoutePrimaryProjector(256, 32)
-    head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=K_LABELS)
+    head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=WL["K"])
     mult.load_state_dict(sdm); proj.load_state_dict(sdp); head.load_state_dict(sdh)
     return rh, mult.to(device), proj.to(device), head.to(device), (sdm, sdp, sdh)
 
 
-def cpu_oracle_rate(budget_s, batch, threads, sds=None, min_iters=2):
-    """Times the CPU port of the reference path (oracle, fp32) fwd+bwd on `threads` host threads."""
+def oracle_stepper(batch, sds, device="cpu", autocast=False, seed=43):
+    """One fwd + loss + bwd step of the oracle restatement of the reference path (eager PyTorch) on `device`."""
     from oracle import route_fusion_oracle as orc
     from multimodalrouting_b200 import synth
-    torch.set_num_threads(threads)
-    if sds is None:
-        sds = synth.make_state(K=K_LABELS, seed=42)
-    sdm, sdp, sdh = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in sds]
-    inp = synth.make_inputs(B=batch, K=K_LABELS, seed=43)
+    sdm, sdp, sdh = [{k: v.detach().to(device).clone().requires_grad_(True) for k, v in sd.items()} for sd in sds]
+    inp = {k: v.to(device) for k, v in make_batch(batch, seed).items()}
 
     def step():
         for sd in (sdm, sdp, sdh):
             for v in sd.values():
                 v.grad = None
         xs = [inp[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")]
-        logits, _, _, _ = orc.full_forward(sdm, sdp, sdh, xs[0], xs[1], xs[2], inp["mL"], inp["mN"], inp["mI"],
-                                           variant="pheno", route_mask=inp["route_mask"])
-        synth.loss_fn(logits, inp["y"], "pheno").backward()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            logits, _, _, _ = orc.full_forward(sdm, sdp, sdh, xs[0], xs[1], xs[2], inp["mL"], inp["mN"], inp["mI"],
+                                               variant=WL["variant"], route_mask=inp["route_mask"])
+        loss = synth.loss_fn(logits, inp["y"], WL["variant"])
+        loss.backward()
+        return loss
+    return step
+
+
+def cpu_oracle_rate(budget_s, batch, threads, sds, min_iters=2):
+    """Times the CPU port of the reference path (oracle, fp32) fwd+bwd on `threads` host threads."""
+    torch.set_num_threads(threads)
+    step = oracle_stepper(batch, sds)
     step()
     times = []
     t_end = time.time() + budget_s
@@ -183,44 +211,66 @@ def cpu_oracle_rate(budget_s, batch, threads, sds=None, min_iters=2):
     return batch / statistics.median(times), len(times)
 
 
+def gpu_eager_reference(batch, sds, device, iters=10, warmup=3):
+    """The reference's eager path ON THIS GPU ("the number to beat"): the oracle restatement of the reference
+    modules (same ATen op families: F.linear / bmm / einsum / layer_norm / fp32 softmax) on CUDA under
+    torch.autocast(bfloat16) with TF32 enabled, exactly the switches the reference drivers set
+    (MIMIC-IV/MortModel/Paired_Cross_Attention/main.py:2613-2621 TF32, :2633-2659 autocast).  Same batch, CUDA events."""
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        step = oracle_stepper(batch, sds, device=device, autocast=True)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return {"value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": batch, "iters": iters,
+            "what": "reference eager path on the same B200: oracle restatement of the reference modules (eager PyTorch/ATen, "
+                    "cuBLAS GEMMs) under torch.autocast(bfloat16), TF32 on (main.py:2613-2621,2633-2659), device-resident "
+                    "inputs, CUDA events; host launch overhead included, as a user of the reference pays it"}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own (CPU, eager PyTorch fp32) implementation of the path,
-    as restated in oracle/ (the reference is Python and does not exist on the GPU box)."""
+    """--impl reference: the reference's own (CPU, eager PyTorch fp32) implementation of the path, as restated in oracle/
+    (the reference is a Python script tree that cannot be installed or shipped to the GPU box), on
+    all host threads, on the SAME per-GPU batch as the product arm."""
     if rank != 0:
         return
-    from oracle import route_fusion_oracle as orc
     from multimodalrouting_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    batch = 64     # bounded sample of the 512-patient workload per step
-    sds = synth.make_state(K=K_LABELS, seed=42)
-    sdm, sdp, sdh = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in sds]
-    inp = synth.make_inputs(B=batch, K=K_LABELS, seed=43)
-
-    def step():
-        for sd in (sdm, sdp, sdh):
-            for v in sd.values():
-                v.grad = None
-        xs = [inp[k].clone().requires_grad_(True) for k in ("x_l", "x_n", "x_i")]
-        logits, _, _, _ = orc.full_forward(sdm, sdp, sdh, xs[0], xs[1], xs[2], inp["mL"], inp["mN"], inp["mI"],
-                                           variant="pheno", route_mask=inp["route_mask"])
-        loss = synth.loss_fn(logits, inp["y"], "pheno")
-        loss.backward()
-        return float(loss.detach())
+    cap = 512 if WL["TL"] <= 64 else 32        # bounded sample: the whole --steps/--warmup run must end within minutes
+    batch = min(args.batch, cap)
+    sds = synth.make_state(K=WL["K"], seed=42)
+    step = oracle_stepper(batch, sds)
     for _ in range(args.warmup):
         step()
     t0 = time.time()
     for _ in range(args.steps):
-        step()
+        float(step().detach())
     dt = time.time() - t0
     value = batch * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * args.gpus,
-                       "parallelism": f"dp{args.gpus}", "reference_sample_per_step": batch},
+            "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WL["name"], "batch_per_gpu": batch, "global_batch": batch * args.gpus,
+                       "parallelism": f"dp{args.gpus}", "reference_sample_per_step": batch,
+                       "torch_num_threads": torch.get_num_threads()},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps x {batch} patients, oracle port of the reference eager path, fp32"},
+                             "torch_num_threads": torch.get_num_threads(),
+                             "sample": f"{args.steps} steps x {batch} patients ("
+                                       + ("the product arm's full per-GPU batch" if batch == args.batch else
+                                          f"bounded sample of the {args.batch}-patient per-GPU batch")
+                                       + "), oracle port of the reference eager path, fp32, rank 0 only"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -233,7 +283,7 @@ def _teardown(dist, reducer):
     if reducer is not None:
         reducer.close()
         sys.stderr.flush()
-        os._exit(0)
+        os._exit(0)       # only with --overlap (opt-in); the default path below leaves the group cleanly
     dist.destroy_process_group()
 
 
@@ -243,7 +293,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patients per GPU")
+    ap.add_argument("--config", default="pheno512", choices=sorted(WORKLOADS),
+                    help="pheno512 = BASELINE configs[1] (the headline); mort8192 = configs[2] (global batch 8192, strong "
+                         "scaling); inspect = configs[4] token counts (256 patients per GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="patients per GPU (default: the workload's)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-eager-on-this-GPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-loss", action="store_true",
                     help="opt-in: compute the loss with the device-side loss tail (losses.pheno_train_loss) instead of torch BCE")
@@ -256,6 +310,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    WL.clear(); WL.update(WORKLOADS[args.config])
+    if args.batch <= 0:
+        args.batch = WL["batch"] // world if WL["scaling"] == "strong" else WL["batch"]
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -277,7 +334,7 @@ def main():
     rh, mult, proj, head, sds = build_models(dev)
     modules = (mult, proj, head)
     B = args.batch
-    inp = synth.make_inputs(B=B, K=K_LABELS, seed=43 + rank)
+    inp = make_batch(B, 43 + rank)
     keys = ("x_l", "x_n", "x_i", "mL", "mN", "mI", "route_mask", "y")
     # The batch travels as ONE contiguous arena (256-byte aligned slots): one pinned host buffer, one device staging
     # buffer, one set of static device inputs -- so a step's H2D copy and its move into the static inputs are one
@@ -300,7 +357,8 @@ def main():
     dev_buf, devb = arena(device=dev)
     dev_buf.copy_(host_buf)
     adapter = rh.RouteDimAdapter(256, 256, 256, 256)
-    lossf = torch.nn.BCEWithLogitsLoss()
+    if args.fused_loss and WL["variant"] != "pheno":
+        raise SystemExit("--fused-loss is wired for the Pheno workloads")
     if args.fused_loss:
         # opt-in: the reference's Pheno training loss through the device-side loss tail (csrc/loss.cuh; same BCE, plus
         # coerce_rc_to_report on R) instead of torch's BCE kernels -- not part of the default measurement
@@ -318,7 +376,7 @@ def main():
         if args.fused_loss:
             loss = _losses.pheno_train_loss(logits, devb["y"], R, alpha, devb["route_mask"], state=_loss_state).loss
         else:
-            loss = lossf(logits.float(), devb["y"])
+            loss = synth.loss_fn(logits, devb["y"], WL["variant"])
         loss.backward()
         return loss
 
@@ -487,21 +545,24 @@ def main():
         if world > 1:
             _teardown(dist, reducer)
         return
-    tf_peak, hbm_peak, src = peaks()
+    tf_burst, tf_sust, hbm_peak, src = peaks()
     fl_tn, fl_wg = gemm_flops_per_step(B)
     t_tn = prof["gemm_tc"]["ms_per_step"] / 1e3
     n_tn = max(prof["gemm_tc"]["launch_groups_per_step"], 1)
     achieved = fl_tn / t_tn / 1e12 if t_tn > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 TN GEMM, all six directions per launch)",
-                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                 # dram__bytes_read.sum + dram__bytes_write.sum averaged over the 34 gemm_tc launches of one step,
                 # ncu --set full (profiles/r1_gemm_step.md); algorithmic bytes are 231 MB per launch
                 "traffic": 192.5e6, "traffic_unit": "bytes per launch (ncu dram read+write, mean of the 34 launches of a step)",
-                "peak_source": f"{src} sustained bf16 (MEASURED_PEAKS.json)",
+                "peak_source": f"{src} BURST bf16 (MEASURED_PEAKS.json bf16_tflops): the class is timed alone, eagerly, in a "
+                               f"~0.1 s region; frac_of_sustained uses bf16_tflops_sustained",
+                "frac_of_sustained": achieved / tf_sust,
                 "avg_launch_ms": 1e3 * t_tn / n_tn, "launches_per_step": n_tn,
                 "flops_per_launch": fl_tn / n_tn,
                 "wgrad_tc_tflops": (fl_wg / (prof["wgrad_tc"]["ms_per_step"] / 1e3) / 1e12) if prof["wgrad_tc"]["ms_per_step"] > 0 else None,
-                "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_peak,
+                "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_sust,
+                "whole_step_peak": tf_sust,
                 # the same launches seen from the HBM side: they are HBM-shaped (128-230 FLOP/B against a machine balance
                 # of ~214), so this fraction explains the tensor fraction above (profiles/r1_step_bytes.md)
                 "hbm_view": {"algorithmic_bytes_per_step": gemm_bytes_per_step(B),
@@ -510,7 +571,8 @@ def main():
     # second roofline the north-star names: capsule routing against HBM bandwidth.  Algorithmic bytes per patient
     # (SURVEY.md section 8d, K=25, fp32 route embeddings): forward 11,420 B + backward 20,600 B.
     rt_ms = prof["routing"]["ms_per_step"]
-    rt_bytes = (11420 + 20600) * B
+    Kl = WL["K"]
+    rt_bytes = ((10240 + 40 + 4 * Kl + 40 + 40 * Kl) + (10240 + 4 * Kl + 40 * Kl + 10240)) * B
     rt_gbs = rt_bytes / (rt_ms / 1e3) / 1e9 if rt_ms > 0 else 0.0
     roofline_routing = {"bound": "hbm", "kernel": "routing_fwd_kernel + routing_bwd_kernel (+ head / vote-weight gradient launches)",
                         "achieved": rt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rt_gbs / hbm_peak, "traffic": None,
@@ -518,15 +580,24 @@ def main():
                         "note": "K=25: bound by the 1.02 MFLOP/patient vote contraction and phase barriers, not by bytes "
                                 "(16 MB per step = 2.5 us at the HBM peak, below one launch latency)"}
     cpu = None
+    gpu_ref = None
+    if not args.no_gpu_reference and world == 1:
+        try:
+            gpu_ref = gpu_eager_reference(B, sds, dev)
+            gpu_ref["speedup_device_resident"] = value / gpu_ref["value"]
+            gpu_ref["speedup_e2e"] = e2e / gpu_ref["value"]
+        except Exception as exc:      # noqa: BLE001 -- a reported baseline must not take the product line down
+            gpu_ref = {"unavailable": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        rate, iters = cpu_oracle_rate(15.0, 32, threads, sds)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{iters} fwd+bwd iterations x 32 patients of the same workload, oracle port (eager PyTorch fp32)"}
+        cb = min(B, 128)
+        rate, iters = cpu_oracle_rate(15.0, cb, threads, sds)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "torch_num_threads": torch.get_num_threads(),
+               "sample": f"{iters} fwd+bwd iterations x {cb} patients of the same workload, oracle port (eager PyTorch fp32)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": WL["scaling"],
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": WL["name"], "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None,
                        "wgrad_side_stream": os.environ.get("MMR_WGRAD_STREAM", "1") != "0",
                        "grad_allreduce": (None if world == 1 else
@@ -536,7 +607,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_routing": roofline_routing,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "reference_gpu_eager": gpu_ref,
             "kernel_time_ms_per_step": prof}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

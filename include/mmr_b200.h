@@ -186,13 +186,27 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
                             float* acts_out, void* stream);
 
 /* Backward: d_logits [B,K], d_R [B,10,K] or NULL.  d_route_embs uses the same strides as
- * route_embs; d_poses [B,10,32] / d_acts [B,10] are written when from_poses=1. */
+ * route_embs; d_poses [B,10,32] / d_acts [B,10] are written when from_poses=1.  With from_poses=0 and acts_override
+ * given, d_acts (may be NULL) receives the gradient wrt acts_override [B,10] (routing_and_heads.py:314: the prior chain
+ * ends at the override instead of the projector's activation logit). */
 int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_params* params,
                             const float* route_embs, const float* poses_in, const float* acts_in,
                             const float* acts_override, const float* route_mask,
                             const float* d_logits, const float* d_R, void* scratch,
                             const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
                             float* d_acts, void* stream);
+
+/* Replaces RoutePrimaryProjector.forward alone (routing_and_heads.py:111-121) for callers that use the projector outside
+ * forward_capsule_from_route_dict: poses [B,10,32] = (W_r e_r + b_r)[:32], acts [B,10] = sigmoid((W_r e_r + b_r)[32]).
+ * route_embs / strides as above; only params->proj_w / proj_b are read.  fp32. */
+int mmr_projector_fwd(const mmr_routing_params* params, const float* route_embs, int64_t emb_route_stride,
+                      int64_t emb_batch_stride, int B, float* poses, float* acts, void* stream);
+/* Backward of the above: d_poses [B,10,32] / d_acts [B,10] (either may be NULL = zero); scratch: B*330*4 bytes;
+ * accumulates into grads->proj_w / proj_b (zero-initialised, NULL entries skipped; other fields ignored) and writes
+ * d_route_embs (same strides as route_embs; may be NULL). */
+int mmr_projector_bwd(const mmr_routing_params* params, const float* route_embs, int64_t emb_route_stride,
+                      int64_t emb_batch_stride, int B, const float* d_poses, const float* d_acts, void* scratch,
+                      const mmr_routing_grads* grads, float* d_route_embs, void* stream);
 
 /* ---- the steps either side of the hot path ---------------------------
  *

@@ -59,21 +59,30 @@ class RoutePrimaryProjector(nn.Module):
         return [self.proj[r].weight for r in ROUTES], [self.proj[r].bias for r in ROUTES]
 
     def forward(self, route_embs):
-        # Standalone projector call: run the routing kernel's projector stage and return its
-        # (poses, acts); gradients flow through a head-less routing node.
-        return _ProjectorOnly.apply(self, *[route_embs[r] for r in ROUTES])
+        """routing_and_heads.py:111-121: (poses [B,10,pc_dim], acts [B,10,1]) of the projector alone.  The hot path
+        (forward_capsule_from_route_dict) runs the same projection inside the routing kernel; this entry serves callers
+        that use the projector by itself (csrc/projector.cuh, fp32)."""
+        embs = [route_embs[r] for r in ROUTES]                 # KeyError on a missing route, like the reference
+        _check_route_embs(embs, self.d_in)
+        pw, pb = self._weights()
+        return ops.ProjectorFn.apply(*embs, *pw, *pb)
 
 
-class _ProjectorOnly(torch.autograd.Function):
-    """poses/acts of the projector alone.  Implemented with the routing kernels by routing a
-    one-label dummy head, so no extra arithmetic path exists; used only when a caller invokes
-    ``projector(route_embs)`` directly (the hot path uses forward_capsule_from_route_dict)."""
-
-    @staticmethod
-    def forward(ctx, projector, *embs):
-        raise NotImplementedError(
-            "standalone RoutePrimaryProjector.forward is not part of the fused B200 path; use "
-            "forward_capsule_from_route_dict (which returns logits, alpha, R) instead")
+def _check_route_embs(embs, d_in):
+    """Shapes must be settled before raw pointers go to the C ABI; the reference fails in F.linear / torch.stack
+    (RuntimeError) for the same inputs."""
+    B = embs[0].shape[0]
+    dev = embs[0].device
+    for r, x in zip(ROUTES, embs):
+        if x.dim() != 2 or x.shape[1] != d_in:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({'x'.join(map(str, x.shape))} and {d_in}x33): "
+                               f"route '{r}' must be [B,{d_in}]")
+        if x.shape[0] != B:
+            raise RuntimeError(f"stack expects each tensor to be equal size, but route '{r}' has batch {x.shape[0]}, "
+                               f"route '{ROUTES[0]}' has {B}")
+        if x.device != dev:
+            raise RuntimeError(f"Expected all tensors to be on the same device, but route '{r}' is on {x.device} and "
+                               f"route '{ROUTES[0]}' on {dev}")
 
 
 class RouteDimAdapter(nn.Module):
@@ -100,6 +109,11 @@ def _expand_route_mask(route_mask, B, device):
         rm = rm.view(1, -1).expand(B, -1)
     elif rm.ndim != 2:
         raise ValueError(f"route_mask must be [R] or [B,R], got {tuple(rm.shape)}")
+    if rm.shape[1] != len(ROUTES) or rm.shape[0] != B:
+        # the kernels index route_mask[b*10 + r]; the reference fails in the broadcast `acts * mask` with this error
+        d = 1 if rm.shape[1] != len(ROUTES) else 0
+        raise RuntimeError(f"The size of tensor a ({(B, len(ROUTES))[d]}) must match the size of tensor b ({rm.shape[d]}) at "
+                           f"non-singleton dimension {d}: route_mask must be [{len(ROUTES)}] or [{B},{len(ROUTES)}]")
     return rm.to(device=device, dtype=torch.float32).contiguous()
 
 
@@ -145,6 +159,14 @@ class _CapsuleHeadBase(nn.Module):
         if route_mask is not None and route_mask.ndim not in (1, 2):
             raise ValueError(f"route_mask must be [R] or [B,R], got {tuple(route_mask.shape)}")
         B = prim_pose.shape[0]
+        # the kernels read poses_in[b*320 + j] and acts_in[b*10 + r]: a wrong shape must never reach them (the reference
+        # fails in CapsuleFC's einsum with a RuntimeError)
+        if prim_pose.dim() != 3 or tuple(prim_pose.shape[1:]) != (len(ROUTES), self.in_d_capsules):
+            raise RuntimeError(f"einsum(): prim_pose must be [B,{len(ROUTES)},{self.in_d_capsules}], got {tuple(prim_pose.shape)}")
+        if tuple(prim_act.shape) != (B, len(ROUTES)):
+            raise RuntimeError(f"einsum(): prim_act must be [{B},{len(ROUTES)}] to broadcast with prim_pose, got {tuple(prim_act.shape)}")
+        if prim_act.device != prim_pose.device:
+            raise RuntimeError("Expected all tensors to be on the same device")
         rm = _expand_route_mask(route_mask, B, prim_pose.device)
         cfg = (ops.VARIANT[self.VARIANT], self.num_routing, False, 1.0, 0.0, 1.0, True)
         logits, alpha, R, _, _ = ops.RoutingFn.apply(cfg, None, rm, self.capsule.w, self.pose_to_mc.weight,
@@ -178,14 +200,16 @@ def forward_capsule_from_route_dict(route_embs_in: Dict[str, torch.Tensor], proj
         route_embs[r] = x
     B = route_embs[ROUTES[0]].shape[0]
     dev = route_embs[ROUTES[0]].device
+    _check_route_embs([route_embs[r] for r in ROUTES], projector.d_in)
     if route_mask is not None and route_mask.ndim not in (1, 2):
         raise ValueError(f"route_mask must be [R] or [B,R], got {tuple(route_mask.shape)}")
     rm = _expand_route_mask(route_mask, B, dev)
     ao = None
     if acts_override is not None:
-        if acts_override.requires_grad:
-            raise NotImplementedError("gradients through acts_override are not implemented")
-        ao = acts_override.reshape(B, len(ROUTES)).to(device=dev, dtype=torch.float32)
+        if acts_override.numel() != B * len(ROUTES) or acts_override.shape[0] != B:
+            raise RuntimeError(f"einsum(): acts_override must be [{B},{len(ROUTES)},1] (or [{B},{len(ROUTES)}]), got "
+                               f"{tuple(acts_override.shape)}")
+        ao = acts_override.to(device=dev, dtype=torch.float32)     # [B,10,1] | [B,10]; gradients flow back (csrc/routing.cuh)
     floor = float(getattr(CFG, "route_prior_floor", 1e-3))
     ceil = float(getattr(CFG, "route_prior_ceiling", 0.999))
     lo = floor if floor > 0.0 else 0.0

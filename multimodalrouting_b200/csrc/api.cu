@@ -16,6 +16,7 @@
 #include "attention_tc.cuh"
 #include "tail.cuh"
 #include "loss.cuh"
+#include "projector.cuh"
 
 using namespace mmr;
 
@@ -1365,6 +1366,58 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
     proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, dims->B, *grads);
     LAUNCH_OK("b_proj");
   }
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------- standalone projector ---
+static int projector_args(ProjectorArgs* a, const mmr_routing_params* params, const float* route_embs, int64_t rs, int64_t bs,
+                          int B) {
+  if (!params || !route_embs) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (B <= 0 || bs < 256 || rs < 0) return fail(MMR_ERR_INVALID_ARG, "bad projector batch / strides");
+  memset(a, 0, sizeof(*a));
+  for (int r = 0; r < MMR_ROUTES; ++r) {
+    if (!params->proj_w[r] || !params->proj_b[r]) return fail(MMR_ERR_INVALID_ARG, "null projector weight");
+    a->w[r] = params->proj_w[r]; a->b[r] = params->proj_b[r];
+  }
+  a->embs = route_embs; a->rs = rs; a->bs = bs; a->B = B;
+  return MMR_OK;
+}
+
+int mmr_projector_fwd(const mmr_routing_params* params, const float* route_embs, int64_t emb_route_stride,
+                      int64_t emb_batch_stride, int B, float* poses, float* acts, void* stream) {
+  ProjectorArgs a;
+  int rc = projector_args(&a, params, route_embs, emb_route_stride, emb_batch_stride, B);
+  if (rc) return rc;
+  if (!poses || !acts) return fail(MMR_ERR_INVALID_ARG, "null output");
+  a.poses = poses; a.acts = acts;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  projector_fwd_kernel<<<dim3((B + PJ_PB - 1) / PJ_PB, MMR_ROUTES), 256, 0, st>>>(a);
+  LAUNCH_OK("projector_fwd");
+  return MMR_OK;
+}
+
+int mmr_projector_bwd(const mmr_routing_params* params, const float* route_embs, int64_t emb_route_stride,
+                      int64_t emb_batch_stride, int B, const float* d_poses, const float* d_acts, void* scratch,
+                      const mmr_routing_grads* grads, float* d_route_embs, void* stream) {
+  ProjectorArgs a;
+  int rc = projector_args(&a, params, route_embs, emb_route_stride, emb_batch_stride, B);
+  if (rc) return rc;
+  if (!scratch || !grads) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  float* dpc = reinterpret_cast<float*>(scratch);     // [B,10,33]
+  a.d_poses = d_poses; a.d_acts = d_acts; a.dpc = dpc; a.d_embs = d_route_embs;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  projector_bwd_kernel<<<dim3((B + PJ_PB - 1) / PJ_PB, MMR_ROUTES), 256, 0, st>>>(a);
+  LAUNCH_OK("projector_bwd");
+  WgradBatch w; memset(&w, 0, sizeof(w));
+  w.nbatch = 10; w.rows = B; w.M = 33; w.N = 256; w.ldy = 330; w.ldx = (int)emb_batch_stride; w.ldo = 256;
+  bool any = false;
+  for (int r = 0; r < 10; ++r) {
+    w.dY[r] = dpc + r * 33; w.X[r] = route_embs + (size_t)r * emb_route_stride; w.out[r] = grads->proj_w[r];
+    any = any || grads->proj_w[r] != nullptr;
+  }
+  if (any) { launch_wgrad_batched(w, st); LAUNCH_OK("w_proj"); }
+  proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, B, *grads);
+  LAUNCH_OK("b_proj");
   return MMR_OK;
 }
 

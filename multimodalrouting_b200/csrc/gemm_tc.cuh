@@ -174,7 +174,6 @@ struct Ctrl {   // lives after the stages
   uint64_t tempty[2];     // persistent GEMM: accumulator buffer drained
   uint32_t tmem_base;
   uint32_t pad_;
-  uint64_t bfull;         // weight-stationary GEMM: the resident B block has landed
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -324,31 +323,17 @@ template <int BN, int CL> __host__ __device__ constexpr int gemm_stage_bytes() {
 template <int BN, int CL> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
   return stages * gemm_stage_bytes<BN, CL>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
 }
-// Weight-stationary variant (WS, K <= 256, opt-in MMR_TC_WS=1; written after the round's GPU budget was spent, NOT yet run
-// on a GPU): the stages hold A only; the segment's B block ([BN / CL rows x K], up to WS_KB k-blocks) stays resident in
-// shared memory and is re-fetched only when the tile's weight block changes.  Why: at K = 256 every 128 x 256 tile re-loads
-// its whole 128 KB weight tile -- 118 of the 179 MB that cross L2 -> SM per q / out projection launch, 463 of 717 MB per fc1
-// launch (profiles/r1_gemm_epilogue.md) -- and those launches run at 0.56-0.67 of the HBM peak in algorithmic bytes.
-constexpr int WS_KB = 4;
-template <int BN, int CL> __host__ __device__ constexpr int gemm_ws_bslab() { return (BN / CL) * BK * 2; }
-template <int BN, int CL> __host__ __device__ constexpr int gemm_ws_smem_bytes(int stages) {
-  return stages * (BM * BK * 2) + WS_KB * gemm_ws_bslab<BN, CL>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
-}
-
-template <int BN, int OP, int CL, bool WS = false>
+template <int BN, int OP, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmProblem g, TcEpi e, int stages) {
-  constexpr int STAGE = WS ? BM * BK * 2 : gemm_stage_bytes<BN, CL>();
-  constexpr int BSLAB = gemm_ws_bslab<BN, CL>();              // one k-block of the resident weights (WS)
-  constexpr int BRES = WS ? WS_KB * BSLAB : 0;
+  constexpr int STAGE = gemm_stage_bytes<BN, CL>();
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sbres = sbase + stages * STAGE;        // resident weights (WS), 1024-byte aligned
-  const uint32_t cstg_base = sbres + BRES;              // 1024-byte aligned (stages are multiples of 1 KB)
-  float* bias_all = reinterpret_cast<float*>(sgen + stages * STAGE + BRES + 8 * CSTG_BYTES);
+  const uint32_t cstg_base = sbase + stages * STAGE;    // 1024-byte aligned (stages are multiples of 1 KB)
+  float* bias_all = reinterpret_cast<float*>(sgen + stages * STAGE + 8 * CSTG_BYTES);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 8 * (BN / 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
@@ -367,7 +352,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&ctrl->tfull[b]), 1);
       mbar_init(smem_u32(&ctrl->tempty[b]), 8 * CL);
     }
-    if (WS) mbar_init(smem_u32(&ctrl->bfull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -386,30 +370,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
-      int b_res = -1;     // WS: first B row of the weight block that is resident
       for (int t = w0; t < nwork; t += wstep) {
         const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN;
         const int seg = seg_of_row(g.segs, m0);
         const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
         const int b_row = g.b_row0[seg] + n0 + (int)rank * (BN / CL);
-        if (WS && b_row != b_res) {
-          // every MMA that read the resident weights has retired once the previous use of every stage slot has been
-          // released (the same waits the next `stages` k-block loads would do anyway)
-          for (int j = 0; j < stages; ++j) {
-            const uint32_t itj = it + (uint32_t)j;
-            mbar_wait(smem_u32(&ctrl->empty[itj % stages]), ((itj / stages) & 1) ^ 1);
-          }
-          if (CL == 2) {
-            const uint32_t bf = mapa_u32(smem_u32(&ctrl->bfull), 0);
-            if (rank == 0) mbar_expect_tx(smem_u32(&ctrl->bfull), 2 * kblocks * BSLAB);
-            for (int kb = 0; kb < kblocks; ++kb) tma_load_2d_pair(sbres + kb * BSLAB, &tmB, kb * BK, b_row, bf);
-          } else {
-            const uint32_t bf = smem_u32(&ctrl->bfull);
-            mbar_expect_tx(bf, kblocks * BSLAB);
-            for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sbres + kb * BSLAB, &tmB, kb * BK, b_row, bf);
-          }
-          b_res = b_row;
-        }
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
@@ -421,12 +386,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t full = mapa_u32(smem_u32(&ctrl->full[s]), 0);
             if (rank == 0) mbar_expect_tx(smem_u32(&ctrl->full[s]), 2 * STAGE);
             tma_load_2d_pair(sa, &tmA, kb * BK, a_row, full);
-            if (!WS) tma_load_2d_pair(sb, &tmB, kb * BK, b_row, full);
+            tma_load_2d_pair(sb, &tmB, kb * BK, b_row, full);
           } else {
             const uint32_t full = smem_u32(&ctrl->full[s]);
             mbar_expect_tx(full, STAGE);
             tma_load_2d(sa, &tmA, kb * BK, a_row, full);
-            if (!WS) tma_load_2d(sb, &tmB, kb * BK, b_row, full);
+            tma_load_2d(sb, &tmB, kb * BK, b_row, full);
           }
         }
       }
@@ -435,30 +400,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       uint32_t it = 0, i = 0;
-      int b_res = -1;
-      uint32_t nb = 0;    // WS: resident weight blocks consumed so far (phase of bfull)
       for (int t = w0; t < nwork; t += wstep, ++i) {
         const uint32_t buf = i & 1;
         mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * BN;
-        if (WS) {           // same weight-block key as the producer computes (leader CTA: rank 0)
-          const int m0 = (t / nN) * CL * BM;
-          const int b_row = g.b_row0[seg_of_row(g.segs, m0)] + (t % nN) * BN;
-          if (b_row != b_res) {
-            mbar_wait(smem_u32(&ctrl->bfull), nb & 1);
-            tc_fence_after();
-            ++nb;
-            b_res = b_row;
-          }
-        }
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
           mbar_wait(smem_u32(&ctrl->full[s]), ph);
           tc_fence_after();
           const uint32_t sa = sbase + s * STAGE;
-          const uint32_t sb = WS ? sbres + kb * BSLAB : sa + BM * BK * 2;
+          const uint32_t sb = sa + BM * BK * 2;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
 #pragma unroll
@@ -1050,13 +1003,12 @@ inline bool pdl_enabled() {
   return on != 0;
 }
 
-template <int OP, int CL, bool WS = false>
+template <int OP, int CL>
 static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                      int sm_count, cudaStream_t st) {
   constexpr int BN = 256;
-  static int stages_cfg = env_int(WS ? "MMR_TC_WS_STAGES" : "MMR_TC_STAGES", WS ? 4 : (CL == 2 ? 4 : 3));
-  const int max_stages = WS ? 4 : (CL == 2 ? 4 : 3);   // 32 KB (pair) / 48 KB operand stages + 64 KB of TMA-store staging;
-                                                      // WS: 16 KB A stages next to the resident weights
+  static int stages_cfg = env_int("MMR_TC_STAGES", CL == 2 ? 4 : 3);
+  const int max_stages = CL == 2 ? 4 : 3;   // 32 KB (pair) / 48 KB operand stages + 64 KB of TMA-store staging
   const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
   constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
   CUtensorMap tmA, tmB, tmC;
@@ -1064,22 +1016,14 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
     return cudaErrorUnknown;
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;
-  auto kern = gemm_tc_kernel<BN, OP, CL, WS>;
-  const int smem = WS ? gemm_ws_smem_bytes<BN, CL>(stages) : gemm_smem_bytes<BN, CL>(stages);
+  auto kern = gemm_tc_kernel<BN, OP, CL>;
+  const int smem = gemm_smem_bytes<BN, CL>(stages);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   const int total_rows = g.segs.row0[g.segs.n];
   const int nwork = ((total_rows + CL * BM - 1) / (CL * BM)) * (g.N / BN);
   int grid = nwork * CL < sm_count ? nwork * CL : sm_count;
   grid -= grid % CL;
-  if (WS) {
-    // a CTA (pair) walks work items w0, w0 + wstep, ...; the n-block is t % nN, so it keeps ONE n-block -- and with it
-    // one resident weight block per segment -- iff wstep is a multiple of nN
-    const int nN = g.N / BN;
-    int units = grid / CL;
-    if (units >= nN) units -= units % nN;
-    grid = units * CL;
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1113,13 +1057,6 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   static int pair_min_k = env_int("MMR_TC_PAIR_MIN_K", 512);
   bool pair_ok = pair_cfg != 0 && g.K >= pair_min_k;
   for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
-  // weight-stationary CTA pairs for the K = 256 shapes (opt-in until measured): MMR_TC_WS=1
-  static int ws_cfg = env_int("MMR_TC_WS", 0);
-  if (ws_cfg != 0 && g.K <= WS_KB * BK) {
-    bool ws_ok = true;
-    for (int s = 0; s <= g.segs.n && ws_ok; ++s) ws_ok = g.segs.row0[s] % (2 * BM) == 0;
-    if (ws_ok) return launch_gemm_tc_cl<OP, 2, true>(g, e, a_rows_total, b_rows_total, sm_count, st);
-  }
   if (pair_ok) return launch_gemm_tc_cl<OP, 2>(g, e, a_rows_total, b_rows_total, sm_count, st);
   return launch_gemm_tc_cl<OP, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
 }

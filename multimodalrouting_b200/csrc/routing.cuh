@@ -718,8 +718,12 @@ __global__ void __launch_bounds__(RT_THREADS, MMR_RT_MINB) routing_bwd_kernel(Ro
           else { const float y = pt.a2[r]; g *= y * (1.0f - y) / a.d.act_temperature / (a1 * (1.0f - a1)); }
         }
         if (has_mask) g *= rm;
-        if (a.acts_override) g = 0.f;
-        else g *= pt.a0[r] * (1.0f - pt.a0[r]);
+        if (a.acts_override) {     // the chain ends at the externally supplied prior (routing_and_heads.py:314)
+          if (a.d_acts) a.d_acts[(size_t)b * 10 + r] = g;
+          g = 0.f;
+        } else {
+          g *= pt.a0[r] * (1.0f - pt.a0[r]);
+        }
         pt.misc[32 + r] = g;   // d (activation logit)
       }
     }

@@ -87,7 +87,8 @@ class OverlappedGradReducer:
         torch.cuda.synchronize()
         self._flat = None
         self._rest = None
-        ops.set_grad_overlap(self._on_fusion_grads, self.events)
+        self._mult_params = [p for p in self.mult.parameters() if p.requires_grad]
+        ops.set_grad_overlap(self._on_fusion_grads, self.events)     # raises if another reducer holds the hook
 
     def close(self):
         from . import ops
@@ -98,6 +99,15 @@ class OverlappedGradReducer:
 
     def _on_fusion_grads(self, flat: torch.Tensor, buckets):
         """Called by the autograd node right after the backward kernels were enqueued."""
+        # The slices of `flat` are reduced IN PLACE on the side stream; that is only the gradient if autograd then installs
+        # these very views as p.grad.  With a pre-existing .grad (gradient accumulation, zero_grad(set_to_none=False))
+        # autograd would instead do p.grad += view on the main stream, racing with the collective and dropping the average.
+        stale = [i for i, p in enumerate(self._mult_params) if p.grad is not None]
+        if stale:
+            raise RuntimeError(
+                f"OverlappedGradReducer: {len(stale)} MULTModel parameters already hold a .grad when the backward runs; the "
+                "overlapped all-reduce needs zero_grad(set_to_none=True) before every backward (no gradient accumulation). "
+                "Use dist.allreduce_gradients(...) after the backward instead.")
         early, rest = buckets[:-1], buckets[-1]
         # bucket i holds layer (layers-1-i): completion order
         n = len(early)
@@ -112,6 +122,11 @@ class OverlappedGradReducer:
         """Reduces what is left (late fusion gradients, projector, head) and joins the side stream."""
         cur = torch.cuda.current_stream()
         if self._flat is not None:
+            base = self._flat.untyped_storage().data_ptr()
+            foreign = [p for p in self._mult_params if p.grad is not None and p.grad.untyped_storage().data_ptr() != base]
+            if foreign:
+                raise RuntimeError(f"OverlappedGradReducer: {len(foreign)} gradients are not views of the reduced flat buffer "
+                                   "(something replaced or accumulated into .grad); the averaged values did not reach them")
             lo, hi = self._rest
             if hi > lo:
                 self._reduce(self._flat[lo:hi])

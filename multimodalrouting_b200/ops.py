@@ -182,6 +182,11 @@ _OVERLAP = {"hook": None, "events": None}
 
 
 def set_grad_overlap(hook, events) -> None:
+    """One reducer per process: the hook is consulted by every RouteFusionFn backward.  Installing a second one while the
+    first is active would silently redirect the first module's gradients, so that raises (close() the old one first)."""
+    if hook is not None and _OVERLAP["hook"] is not None and _OVERLAP["hook"] != hook:
+        raise RuntimeError("a gradient-overlap hook is already installed (another OverlappedGradReducer is active); "
+                           "close() it before creating a new one")
     _OVERLAP["hook"], _OVERLAP["events"] = hook, events
 
 
@@ -460,14 +465,15 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     else:
         d_embs = torch.empty(N_ROUTES, B, 256, dtype=torch.float32, device=dev)
         d_poses = torch.empty(0, dtype=torch.float32, device=dev)
-        d_acts = torch.empty(0, dtype=torch.float32, device=dev)
+        # gradient wrt acts_override (the prior chain ends there, routing_and_heads.py:314); zero for masked routes
+        d_acts = torch.zeros(B if acts_override is not None else 0, N_ROUTES, dtype=torch.float32, device=dev)
     # d_route_embs shares the (route, batch) strides of the input embeddings in the C ABI; RoutingFn
     # normalises the inputs to the dense [10,B,256] layout, so the output is dense as well.
     rc = lib.mmr_capsule_routing_bwd(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
                                      _ptr(acts_override), _ptr(route_mask), _ptr(d_logits), _ptr(d_R),
                                      _ptr(scratch), C.byref(g), None if from_poses else _ptr(d_embs),
                                      _ptr(d_poses) if from_poses else None,
-                                     _ptr(d_acts) if from_poses else None, _stream())
+                                     _ptr(d_acts) if (from_poses or acts_override is not None) else None, _stream())
     _lib.check(rc, "mmr_capsule_routing_bwd")
     return d_embs, d_poses, d_acts, flat
 
@@ -480,7 +486,8 @@ def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b
     n = routing_flat_layout(K)["total"]
     if embs is None:
         return e.new_empty(0), e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES), e.new_empty(n)
-    return e.new_empty(N_ROUTES, B, 256), e.new_empty(0), e.new_empty(0), e.new_empty(n)
+    return (e.new_empty(N_ROUTES, B, 256), e.new_empty(0), e.new_empty(B if acts_override is not None else 0, N_ROUTES),
+            e.new_empty(n))
 
 
 def routing_flat_layout(K: int):
@@ -529,6 +536,7 @@ class RoutingFn(torch.autograd.Function):
         ctx.vdt = vdt
         ctx.B = B
         ctx.has = (embs_dense is not None, rm is not None, ao is not None)
+        ctx.ao_shape = tuple(acts_override.shape) if acts_override is not None else None
         tensors = [t for t in (embs_dense, poses_c, acts_c, ao, rm) if t is not None]
         ctx.n_in = len(tensors)
         ctx.save_for_backward(*tensors, caps_w.detach(), pose_to_mc.detach(), embedding.detach(), bias.detach(),
@@ -569,13 +577,90 @@ class RoutingFn(torch.autograd.Function):
         g_mc = flat[lay["pose_to_mc"]:lay["pose_to_mc"] + 64 * 32].view(64, 32)
         g_emb = flat[lay["embedding"]:lay["embedding"] + K * 64].view(K, 64)
         g_bias = flat[lay["bias"]:lay["bias"] + K]
-        head = (None, None, None, g_caps, g_mc, g_emb, g_bias)
+        g_ao = d_acts.view(ctx.ao_shape) if (has_ao and not from_poses and ctx.needs_input_grad[1]) else None
+        head = (None, g_ao, None, g_caps, g_mc, g_emb, g_bias)
         if from_poses:
             return head + (d_poses, d_acts)
         g_pw = [flat[lay["proj_w"] + r * 33 * 256: lay["proj_w"] + (r + 1) * 33 * 256].view(33, 256)
                 for r in range(N_ROUTES)]
         g_pb = [flat[lay["proj_b"] + r * 36: lay["proj_b"] + r * 36 + 33] for r in range(N_ROUTES)]
         return head + tuple(d_embs[r] for r in range(N_ROUTES)) + tuple(g_pw) + tuple(g_pb)
+
+
+# --------------------------------------------------------------------------------------------
+# standalone RoutePrimaryProjector.forward (routing_and_heads.py:111-121)
+@torch.library.custom_op("mmr_b200::projector_fwd", mutates_args=())
+def projector_fwd(embs: Tensor, proj_w: Sequence[Tensor], proj_b: Sequence[Tensor]) -> Tuple[Tensor, Tensor]:
+    """embs fp32 [10,B,256] -> (poses [B,10,32], acts [B,10,1])."""
+    _require_cuda(embs, *proj_w)
+    lib = _lib.load()
+    B = embs.shape[1]
+    rp = RoutingParams()
+    for r in range(N_ROUTES):
+        rp.proj_w[r] = proj_w[r].data_ptr()
+        rp.proj_b[r] = proj_b[r].data_ptr()
+    poses = torch.empty(B, N_ROUTES, 32, dtype=torch.float32, device=embs.device)
+    acts = torch.empty(B, N_ROUTES, 1, dtype=torch.float32, device=embs.device)
+    _lib.check(lib.mmr_projector_fwd(C.byref(rp), _ptr(embs), B * 256, 256, B, _ptr(poses), _ptr(acts), _stream()),
+               "mmr_projector_fwd")
+    return poses, acts
+
+
+@projector_fwd.register_fake
+def _(embs, proj_w, proj_b):
+    B = embs.shape[1]
+    return embs.new_empty(B, N_ROUTES, 32), embs.new_empty(B, N_ROUTES, 1)
+
+
+@torch.library.custom_op("mmr_b200::projector_bwd", mutates_args=())
+def projector_bwd(embs: Tensor, proj_w: Sequence[Tensor], proj_b: Sequence[Tensor], d_poses: Optional[Tensor],
+                  d_acts: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """Returns (d_embs [10,B,256], flat grads: proj_w[10] (33*256 each) | proj_b[10] (36 each, 33 used))."""
+    lib = _lib.load()
+    B = embs.shape[1]
+    dev = embs.device
+    rp = RoutingParams()
+    g = RoutingGrads()
+    flat = torch.zeros(N_ROUTES * (33 * 256 + 36), dtype=torch.float32, device=dev)
+    base = flat.data_ptr()
+    for r in range(N_ROUTES):
+        rp.proj_w[r] = proj_w[r].data_ptr()
+        rp.proj_b[r] = proj_b[r].data_ptr()
+        g.proj_w[r] = base + 4 * (r * 33 * 256)
+        g.proj_b[r] = base + 4 * (N_ROUTES * 33 * 256 + r * 36)
+    scratch = torch.empty(B * 330, dtype=torch.float32, device=dev)
+    d_embs = torch.empty(N_ROUTES, B, 256, dtype=torch.float32, device=dev)
+    _lib.check(lib.mmr_projector_bwd(C.byref(rp), _ptr(embs), B * 256, 256, B, _ptr(d_poses), _ptr(d_acts), _ptr(scratch),
+                                     C.byref(g), _ptr(d_embs), _stream()), "mmr_projector_bwd")
+    return d_embs, flat
+
+
+@projector_bwd.register_fake
+def _(embs, proj_w, proj_b, d_poses, d_acts):
+    return torch.empty_like(embs), embs.new_empty(N_ROUTES * (33 * 256 + 36))
+
+
+class ProjectorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *rest):
+        embs = rest[:N_ROUTES]
+        proj_w = [p.detach() for p in rest[N_ROUTES:2 * N_ROUTES]]
+        proj_b = [p.detach() for p in rest[2 * N_ROUTES:3 * N_ROUTES]]
+        embs_dense = torch.stack([_f32c(e.detach()) for e in embs], dim=0)
+        poses, acts = projector_fwd(embs_dense, proj_w, proj_b)
+        ctx.save_for_backward(embs_dense, *proj_w, *proj_b)
+        return poses, acts
+
+    @staticmethod
+    def backward(ctx, d_poses, d_acts):
+        sv = list(ctx.saved_tensors)
+        embs_dense, proj_w, proj_b = sv[0], sv[1:1 + N_ROUTES], sv[1 + N_ROUTES:]
+        d_embs, flat = projector_bwd(embs_dense, proj_w, proj_b, _f32c(d_poses) if d_poses is not None else None,
+                                     _f32c(d_acts) if d_acts is not None else None)
+        nb = N_ROUTES * 33 * 256
+        g_pw = [flat[r * 33 * 256:(r + 1) * 33 * 256].view(33, 256) for r in range(N_ROUTES)]
+        g_pb = [flat[nb + r * 36: nb + r * 36 + 33] for r in range(N_ROUTES)]
+        return tuple(d_embs[r] for r in range(N_ROUTES)) + tuple(g_pw) + tuple(g_pb)
 
 
 def debug_gemm(engine: int, dtype: int, trans: bool, A: Tensor, B: Tensor, bias: Optional[Tensor]) -> Tensor:

@@ -42,6 +42,21 @@ CASES = {
     "dict_rank1_route": lambda ns: _dict_call(ns, {**ns["ok"]["routes"], "IL": torch.zeros(256)}),
     "dict_rank3_route": lambda ns: _dict_call(ns, {**ns["ok"]["routes"], "IL": torch.zeros(B, 2, 256)}),
     "dict_route_mask_rank3": lambda ns: _dict_call(ns, ns["ok"]["routes"], route_mask=torch.ones(B, 10, 1)),
+    # shapes that would otherwise reach the kernels as raw pointers: the reference fails in F.linear / the broadcasts
+    "dict_route_wrong_width": lambda ns: _dict_call(ns, {**ns["ok"]["routes"], "IL": torch.zeros(B, 128)}),
+    "dict_route_wrong_batch": lambda ns: _dict_call(ns, {**ns["ok"]["routes"], "IL": torch.zeros(B + 1, 256)}),
+    "dict_route_mask_wrong_routes": lambda ns: _dict_call(ns, ns["ok"]["routes"], route_mask=torch.ones(B, 9)),
+    "dict_route_mask_wrong_batch": lambda ns: _dict_call(ns, ns["ok"]["routes"], route_mask=torch.ones(B + 1, 10)),
+    "dict_route_mask_1d_wrong": lambda ns: _dict_call(ns, ns["ok"]["routes"], route_mask=torch.ones(7)),
+    "dict_override_wrong_routes": lambda ns: _dict_call(ns, ns["ok"]["routes"], acts_override=torch.rand(B, 9, 1)),
+    "head_pose_wrong_width": lambda ns: ns["head"](torch.zeros(B, 10, 16), ns["ok"]["act"]),
+    "head_pose_wrong_routes": lambda ns: ns["head"](torch.zeros(B, 9, 32), ns["ok"]["act"]),
+    "head_act_wrong_routes": lambda ns: ns["head"](ns["ok"]["pose"], torch.rand(B, 9)),
+    "head_act_wrong_batch": lambda ns: ns["head"](ns["ok"]["pose"], torch.rand(B + 1, 10)),
+    "head_route_mask_wrong_routes": lambda ns: ns["head"](ns["ok"]["pose"], ns["ok"]["act"], route_mask=torch.ones(B, 9)),
+    "proj_route_wrong_width": lambda ns: ns["proj"]({**ns["ok"]["routes"], "IL": torch.zeros(B, 128)}),
+    "proj_route_wrong_batch": lambda ns: ns["proj"]({**ns["ok"]["routes"], "IL": torch.zeros(B + 1, 256)}),
+    "proj_missing_key": lambda ns: ns["proj"](_without(ns["ok"]["routes"], "LNI")),
     # CapsuleMortalityHead.forward (routing_and_heads.py:200-222)
     "head_act_rank1": lambda ns: ns["head"](ns["ok"]["pose"], torch.rand(10)),
     "head_act_rank3_wide": lambda ns: ns["head"](ns["ok"]["pose"], torch.rand(B, 10, 2)),

@@ -10,7 +10,7 @@ from helpers import ROOT
 
 def test_reference_arm_prints_one_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS="4")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "64"],
                        capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-500:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
@@ -36,5 +36,11 @@ def test_roofline_arithmetic():
     # profiles/r1_step_bytes.md: 7.87 GB of algorithmic GEMM traffic per 512-patient step, linear in the batch
     assert abs(bench.gemm_bytes_per_step(512) - 7.88e9) / 7.88e9 < 0.01
     assert bench.gemm_bytes_per_step(1024) == 2 * bench.gemm_bytes_per_step(512)
-    tf, hbm, src = bench.peaks()
-    assert 1000 < tf < 2500 and 5000 < hbm < 8000 and src in ("measured", "fallback")
+    burst, sust, hbm, src = bench.peaks()
+    assert 1000 < sust <= burst < 2500 and 5000 < hbm < 8000 and src.split()[0] in ("measured", "fallback")
+    # the other BASELINE configs are selectable and change the algorithmic FLOPs
+    bench.WL.update(bench.WORKLOADS["inspect"])
+    try:
+        assert abs(bench.total_flops_per_patient() / 3 - 12.085e9) / 12.085e9 < 0.01
+    finally:
+        bench.WL.update(bench.WORKLOADS["pheno512"])

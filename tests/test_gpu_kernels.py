@@ -181,3 +181,38 @@ def test_routing_reduced_precision_tensor_core_vs_cuda_core(variant, K, masked, 
         e_tc, e_cc = max_rel(res["1"][3][k], ref), max_rel(res["0"][3][k], ref)
         assert bool(torch.isfinite(res["1"][3][k]).all()), k
         assert e_tc <= max(5e-2, 2.0 * e_cc), f"grad {k}: tensor-core {e_tc:.2e} cuda-core {e_cc:.2e}"
+
+
+@pytest.mark.parametrize("B", [1, 19, 64])
+def test_projector_standalone_forward_backward_vs_oracle(B):
+    """RoutePrimaryProjector.forward by itself (routing_and_heads.py:111-121; csrc/projector.cuh): poses / acts and every
+    gradient (route embeddings, the 10 weight / bias pairs) against the oracle's projector_forward, fp32 bar 1e-4."""
+    from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    _, sdp, _ = synth.make_state(K=3, seed=77, sharp=2.0)
+    g = torch.Generator().manual_seed(5)
+    embs = {r: torch.randn(B, 256, generator=g) for r in synth.ROUTES}
+    gp, ga = torch.randn(B, 10, 32, generator=g), torch.randn(B, 10, 1, generator=g)
+    po = {k: v.clone().requires_grad_(True) for k, v in sdp.items()}
+    eo = {r: v.clone().requires_grad_(True) for r, v in embs.items()}
+    poses_o, acts_o = orc.projector_forward(po, eo)
+    ((poses_o * gp).sum() + (acts_o * ga).sum()).backward()
+    proj = rh.RoutePrimaryProjector(256, 32)
+    proj.load_state_dict(sdp)
+    proj = proj.cuda()
+    ed = {r: v.clone().cuda().requires_grad_(True) for r, v in embs.items()}
+    poses, acts = proj(ed)
+    assert tuple(poses.shape) == (B, 10, 32) and tuple(acts.shape) == (B, 10, 1)
+    assert max_rel(poses, poses_o) < 1e-4 and max_rel(acts, acts_o) < 1e-4
+    ((poses * gp.cuda()).sum() + (acts * ga.cuda()).sum()).backward()
+    for r in synth.ROUTES:
+        assert max_rel(ed[r].grad, eo[r].grad) < 1e-4, f"d emb {r}"
+        assert max_rel(proj.proj[r].weight.grad, po[f"proj.{r}.weight"].grad) < 1e-4, f"d W {r}"
+        assert max_rel(proj.proj[r].bias.grad, po[f"proj.{r}.bias"].grad) < 1e-4, f"d b {r}"
+    # only the poses are used downstream (d_acts = None inside autograd)
+    for p in proj.parameters():
+        p.grad = None
+    e2 = {r: v.clone().cuda().requires_grad_(True) for r, v in embs.items()}
+    (proj(e2)[0] * gp.cuda()).sum().backward()
+    e3 = {r: v.clone().requires_grad_(True) for r, v in embs.items()}
+    (orc.projector_forward(sdp, e3)[0] * gp).sum().backward()
+    assert max_rel(e2["LNI"].grad, e3["LNI"].grad) < 1e-4

@@ -532,10 +532,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   forward : A = LN1(x1) , B1 = fc1.weight, epi1 = +bias, ReLU, sign bits ; B2 = fc2.weight, epi2 = +bias
 //   backward: A = dY(fc2) , B1 = fc2.weight^T, epi1 = ReLU' bit mask (dF)  ; B2 = fc1.weight^T, epi2 = row mask
 // (transformer.py:204-215 and its autograd).  Per 128-row tile the A block (64 KB) is staged once; the 1024
-// intermediate columns are produced in four 256-column chunks: GEMM1 -> TMEM acc1 -> epilogue warps (bias / ReLU
-// / mask in registers) -> bf16 into a 128B-swizzled shared-memory block F that is BOTH the TMA-store source
-// for `mid` and the K-major A operand of GEMM2, which accumulates into TMEM acc2.  Unfused, `mid` (237 MB at
-// B=512) is written by one kernel and re-read by the next; here the second read never leaves the SM.
+// intermediate columns are produced in EIGHT 128-column chunks through a two-deep software pipeline:
+//     TMEM  : acc1[2] (2 x 128 columns, ping-pong) + acc2 (256 columns)
+//     smem  : F[2]    (2 x [128 rows x 128 cols] bf16, ping-pong; 128B-swizzled K-major = A operand of GEMM2 AND the
+//                      TMA-store source of `mid`)
+//     MMA   : G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(6) | G2(7)        (single issuing thread)
+//     epi   : two groups of 8 warps; group g drains acc1[g] -> bias / ReLU / mask -> F[g] for chunks c = g (mod 2),
+//             so the tensor pipe always has GEMM2(c) + GEMM1(c+2) queued while chunk c+1 is being converted.
+// The round-1 version (four 256-column chunks, one acc1, one F) serialised GEMM1 -> drain -> GEMM2 per chunk and ran at
+// 36 % tensor-pipe activity, level with the two separate launches (profiles/r2_chain.md).
 // CL = 2 runs CTA pairs (tcgen05 cta_group::2): each CTA stages only half of every weight tile.
 struct ChainProblem {
   Segs segs;            // row space of A / mid / out (same rows)
@@ -549,17 +554,19 @@ struct ChainProblem {
 struct ChainCtrl {
   uint64_t a_full, a_empty;
   uint64_t b_full[8], b_empty[8];
-  uint64_t acc1_full, acc1_empty, f_full, f_empty, acc2_full, acc2_empty;
+  uint64_t acc1_full[2], acc1_empty[2], f_full[2], f_empty[2], acc2_full, acc2_empty;
   uint32_t tmem_base;
 };
 constexpr int CH_EPI_WARPS = 16;
-constexpr int CHAIN_THREADS = 64 + 32 * CH_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, 16 epilogue warps
+constexpr int CHAIN_THREADS = 64 + 32 * CH_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, 2 x 8 epilogue warps
 constexpr int CH_MID = 1024, CH_K = 256, CH_N = 256;     // fixed geometry of the reference FFN (d=256, 4d)
+constexpr int CH_CW = 128;                                // intermediate columns per chunk
+constexpr int CH_NCH = CH_MID / CH_CW;                    // 8 chunks
 constexpr int CH_A_BYTES = BM * CH_K * 2;                 // 64 KB: 4 k-blocks of [128 x 64]
-constexpr int CH_F_BYTES = BM * 256 * 2;                  // 64 KB: one 256-column chunk of the intermediate
+constexpr int CH_F_BYTES = BM * CH_CW * 2;                // 32 KB per F buffer: 2 k-blocks of [128 x 64]
 template <int CL> __host__ __device__ constexpr int chain_bstage_bytes() { return (256 / CL) * BK * 2; }
 template <int CL> __host__ __device__ constexpr int chain_smem_bytes(int stages) {
-  return CH_A_BYTES + CH_F_BYTES + stages * chain_bstage_bytes<CL>() + CH_EPI_WARPS * 64 * 4 + 1024 + 512;
+  return CH_A_BYTES + 2 * CH_F_BYTES + stages * chain_bstage_bytes<CL>() + CH_EPI_WARPS * 64 * 4 + 1024 + 512;
 }
 
 template <int OP1, int OP2, int CL>
@@ -567,12 +574,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmMid,
                 const __grid_constant__ CUtensorMap tmOut, ChainProblem g, int stages) {
-  constexpr int BST = chain_bstage_bytes<CL>();
+  constexpr int BST = chain_bstage_bytes<CL>();            // one stage holds a GEMM2 k-block [256/CL x 64] ...
+  constexpr int B1_BYTES = (CH_CW / CL) * BK * 2;          // ... or a GEMM1 k-block [128/CL x 64] (half of it)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sA = sbase, sF = sbase + CH_A_BYTES, sB = sF + CH_F_BYTES;
-  float* bias_all = reinterpret_cast<float*>(sgen + CH_A_BYTES + CH_F_BYTES + stages * BST);
+  const uint32_t sA = sbase, sF = sbase + CH_A_BYTES, sB = sF + 2 * CH_F_BYTES;
+  float* bias_all = reinterpret_cast<float*>(sgen + CH_A_BYTES + 2 * CH_F_BYTES + stages * BST);
   ChainCtrl* ctrl = reinterpret_cast<ChainCtrl*>(bias_all + CH_EPI_WARPS * 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
@@ -583,8 +591,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(bar(&ctrl->a_full), 1); mbar_init(bar(&ctrl->a_empty), 1);
     for (int s = 0; s < stages; ++s) { mbar_init(bar(&ctrl->b_full[s]), 1); mbar_init(bar(&ctrl->b_empty[s]), 1); }
-    mbar_init(bar(&ctrl->acc1_full), 1); mbar_init(bar(&ctrl->acc1_empty), CH_EPI_WARPS * CL);
-    mbar_init(bar(&ctrl->f_full), CH_EPI_WARPS * CL); mbar_init(bar(&ctrl->f_empty), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(&ctrl->acc1_full[b]), 1); mbar_init(bar(&ctrl->acc1_empty[b]), (CH_EPI_WARPS / 2) * CL);
+      mbar_init(bar(&ctrl->f_full[b]), (CH_EPI_WARPS / 2) * CL); mbar_init(bar(&ctrl->f_empty[b]), 1);
+    }
     mbar_init(bar(&ctrl->acc2_full), 1); mbar_init(bar(&ctrl->acc2_empty), CH_EPI_WARPS * CL);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -596,7 +606,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CL == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 2 * CH_CW;
   // epilogue -> MMA handshakes land on the leader CTA's barriers
   auto arrive_leader = [&](uint64_t* b) {
     if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(b), 0));
@@ -604,8 +614,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ===== TMA producer.  Weight tiles follow the MMA issue order:
-    //       W1(0) | W1(1) W2(0) | W1(2) W2(1) | W1(3) W2(2) | W2(3)   (each item = 4 k-blocks of [256/CL x 64])
+    // ===== TMA producer.  Weight k-blocks follow the MMA issue order:
+    //       W1(0) W1(1) | W2(0) W1(2) | W2(1) W1(3) | ... | W2(5) W1(7) | W2(6) | W2(7)
+    //       W1(c): 4 k-blocks of [128/CL x 64] (rows = intermediate columns of chunk c, k over d = 256)
+    //       W2(c): 2 k-blocks of [256/CL x 64] (rows = output columns, k = the chunk's 128 intermediate columns)
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
@@ -624,83 +636,101 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             else tma_load_2d(sA + kb * (BM * BK * 2), &tmA, kb * BK, m0, full);
           }
         }
-        for (int item = 0; item < 8; ++item) {
-          // items: 0:W1(0) 1:W1(1) 2:W2(0) 3:W1(2) 4:W2(1) 5:W1(3) 6:W2(2) 7:W2(3)
-          const bool is2 = (item == 2 || item == 4 || item >= 6);
-          const int c = item == 0 ? 0 : item == 1 ? 1 : item == 2 ? 0 : item == 3 ? 2 : item == 4 ? 1 : item == 5 ? 3 : item == 6 ? 2 : 3;
-          for (int kb = 0; kb < 4; ++kb, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
-            mbar_wait(bar(&ctrl->b_empty[s]), ph ^ 1);
-            const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->b_full[s]), 0) : bar(&ctrl->b_full[s]);
-            if (rank == 0) mbar_expect_tx(bar(&ctrl->b_full[s]), CL * BST);
-            const uint32_t dst = sB + s * BST;
-            // GEMM1 tile: rows = intermediate columns c*256.. of B1, k = kb*64 of 256
-            // GEMM2 tile: rows = output columns of B2 (256), k = c*256 + kb*64 of 1024
-            const int x = is2 ? c * 256 + kb * BK : kb * BK;
-            const int y = (is2 ? g.b2_row0[seg] : g.b1_row0[seg] + c * 256) + (int)rank * (256 / CL);
-            const CUtensorMap* tm = is2 ? &tmB2 : &tmB1;
-            if (CL == 2) tma_load_2d_pair(dst, tm, x, y, full);
-            else tma_load_2d(dst, tm, x, y, full);
-          }
+        auto load_kblock = [&](const CUtensorMap* tm, int x, int y, uint32_t bytes) {
+          const int s = it % stages;
+          mbar_wait(bar(&ctrl->b_empty[s]), ((it / stages) & 1) ^ 1);
+          const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->b_full[s]), 0) : bar(&ctrl->b_full[s]);
+          if (rank == 0) mbar_expect_tx(bar(&ctrl->b_full[s]), CL * bytes);
+          if (CL == 2) tma_load_2d_pair(sB + s * BST, tm, x, y, full);
+          else tma_load_2d(sB + s * BST, tm, x, y, full);
+          ++it;
+        };
+        auto load_w1 = [&](int c) {
+          for (int kb = 0; kb < CH_K / BK; ++kb)
+            load_kblock(&tmB1, kb * BK, g.b1_row0[seg] + c * CH_CW + (int)rank * (CH_CW / CL), B1_BYTES);
+        };
+        auto load_w2 = [&](int c) {
+          for (int j = 0; j < CH_CW / BK; ++j)
+            load_kblock(&tmB2, c * CH_CW + j * BK, g.b2_row0[seg] + (int)rank * (256 / CL), BST);
+        };
+        load_w1(0);
+        load_w1(1);
+        for (int c = 0; c < CH_NCH; ++c) {
+          load_w2(c);
+          if (c + 2 < CH_NCH) load_w1(c + 2);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc(256, 0, 0, CL * BM);
-      uint32_t it = 0, ti = 0, n1 = 0, n2 = 0;   // n1 / n2: GEMM1 / GEMM2 chunk counters (barrier phases)
+      constexpr uint32_t idesc1 = make_idesc(CH_CW, 0, 0, CL * BM);
+      constexpr uint32_t idesc2 = make_idesc(CH_N, 0, 0, CL * BM);
+      uint32_t it = 0, ti = 0;
+      uint32_t u1[2] = {0, 0}, u2[2] = {0, 0};   // uses of acc1[b] / F[b] so far (barrier phases)
       auto commit = [&](uint64_t* b) {
         if (CL == 2) umma_commit_pair(smem_u32(b)); else umma_commit(smem_u32(b));
       };
-      auto gemm_kblocks = [&](uint32_t a_base, uint32_t acc, bool fresh) {
-        for (int kb = 0; kb < 4; ++kb, ++it) {
-          const int s = it % stages;
-          mbar_wait(bar(&ctrl->b_full[s]), (it / stages) & 1);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(a_base + kb * (BM * BK * 2), 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sB + s * BST, 16, 1024);
+      auto kblock = [&](uint32_t a_addr, uint32_t acc, uint32_t idesc, bool fresh) {
+        const int s = it % stages;
+        mbar_wait(bar(&ctrl->b_full[s]), (it / stages) & 1);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(sB + s * BST, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint32_t accum = (fresh && kb == 0 && k == 0) ? 0u : 1u;
-            if (CL == 2) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-            else umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-          }
-          commit(&ctrl->b_empty[s]);
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint32_t accum = (fresh && k == 0) ? 0u : 1u;
+          if (CL == 2) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+          else umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
         }
+        commit(&ctrl->b_empty[s]);
+        ++it;
+      };
+      auto gemm1 = [&](int b) {          // acc1[b] = A * B1[chunk]^T
+        mbar_wait(bar(&ctrl->acc1_empty[b]), (u1[b] & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < CH_K / BK; ++kb) kblock(sA + kb * (BM * BK * 2), acc1 + b * CH_CW, idesc1, kb == 0);
+        commit(&ctrl->acc1_full[b]);
+        ++u1[b];
+      };
+      auto gemm2 = [&](int b, bool fresh) {   // acc2 (+)= F[b] * B2[:, chunk]^T
+        mbar_wait(bar(&ctrl->f_full[b]), u2[b] & 1);
+        tc_fence_after();
+        for (int j = 0; j < CH_CW / BK; ++j)
+          kblock(sF + b * CH_F_BYTES + j * (BM * BK * 2), acc2, idesc2, fresh && j == 0);
+        commit(&ctrl->f_empty[b]);
+        ++u2[b];
       };
       for (int t = w0; t < nwork; t += wstep, ++ti) {
         mbar_wait(bar(&ctrl->a_full), ti & 1);
         tc_fence_after();
-        for (int c = 0; c <= 4; ++c) {
-          if (c < 4) {            // GEMM1(c): acc1 = A * B1[chunk c]^T
-            mbar_wait(bar(&ctrl->acc1_empty), (n1 & 1) ^ 1);
+        gemm1(0);
+        gemm1(1);
+        for (int c = 0; c < CH_NCH; ++c) {
+          if (c == 0) {
+            mbar_wait(bar(&ctrl->acc2_empty), (ti & 1) ^ 1);
             tc_fence_after();
-            gemm_kblocks(sA, acc1, true);
-            commit(&ctrl->acc1_full);
-            if (c == 3) commit(&ctrl->a_empty);
-            ++n1;
           }
-          if (c > 0) {            // GEMM2(c-1): acc2 += F(c-1) * B2[:, chunk c-1]^T
-            mbar_wait(bar(&ctrl->f_full), n2 & 1);
-            if (c == 1) mbar_wait(bar(&ctrl->acc2_empty), (ti & 1) ^ 1);
-            tc_fence_after();
-            gemm_kblocks(sF, acc2, c == 1);
-            commit(&ctrl->f_empty);
-            if (c == 4) commit(&ctrl->acc2_full);
-            ++n2;
+          gemm2(c & 1, c == 0);
+          if (c == CH_NCH - 1) commit(&ctrl->acc2_full);
+          if (c + 2 < CH_NCH) {
+            gemm1(c & 1);
+            if (c + 2 == CH_NCH - 1) commit(&ctrl->a_empty);   // the last GEMM1 of the tile has been issued
           }
         }
       }
     }
   } else {
-    // ===== 16 epilogue warps: warp w owns TMEM lane quarter (w & 3) and the 64-column slice cq = (w - 2) >> 2
-    //       of each 256-column chunk, i.e. exactly one [32 rows x 64 cols] box of k-block cq of F
-    const int q = warp & 3;
-    const int cq = (warp - 2) >> 2;
-    float* bias_s = bias_all + (warp - 2) * 64;
-    uint32_t ti = 0, n1 = 0;
+    // ===== 2 x 8 epilogue warps.  Group eg drains acc1[eg] into F[eg] for the chunks c = eg (mod 2); inside a group
+    //       warp (q, cq) owns TMEM lane quarter q = warp & 3 and the 64-column slice cq of the chunk, i.e. exactly one
+    //       [32 rows x 64 cols] box of k-block cq of F[eg].  In the final epilogue the same box stages the warp's
+    //       slice cq4 = 2 eg + cq of the 256 output columns.
+    const int wi = warp - 2;
+    const int eg = wi >> 3, q = warp & 3, cq = (wi >> 2) & 1, cq4 = eg * 2 + cq;
+    float* bias_s = bias_all + wi * 64;
+    const uint32_t f_box = sF + (uint32_t)cq4 * (BM * BK * 2) + (uint32_t)q * 4096;   // this warp's 4 KB box
+    const uint32_t f_row = f_box + (uint32_t)lane * 128;
+    uint32_t ti = 0, u = 0;
     for (int t = w0; t < nwork; t += wstep, ++ti) {
       const int m0 = (t * CL + (int)rank) * BM;
       const int seg = seg_of_row(g.segs, m0);
@@ -708,33 +738,31 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int lr = q * 32 + lane;
       const bool row_ok = lr < rows_valid;
       const bool zrow = (rows_valid < BM) && !row_ok;
-      const uint32_t f_box = sF + (uint32_t)cq * (BM * BK * 2) + (uint32_t)q * 4096;   // this warp's 4 KB box of F
-      const uint32_t f_row = f_box + (uint32_t)lane * 128;
       float rmask = 1.f;
       if (OP2 == TEPI_MASK) rmask = (g.rowmask != nullptr && row_ok) ? g.rowmask[m0 + lr] : 1.f;
-      for (int c = 0; c < 4; ++c, ++n1) {
+      for (int c = eg; c < CH_NCH; c += 2, ++u) {
         uint2 bin2 = make_uint2(0, 0);      // ReLU sign bits of this thread's row, columns of (chunk c, slice cq)
         if (OP1 == TEPI_BITS_IN && row_ok)
-          bin2 = *reinterpret_cast<const uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 8 + cq * 2);
+          bin2 = *reinterpret_cast<const uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2);
         if (OP1 == TEPI_BIAS_RELU_BITS) {
-          const float* bsrc = g.bias1 ? g.bias1 + g.b1_row0[seg] + c * 256 + cq * 64 : nullptr;
+          const float* bsrc = g.bias1 ? g.bias1 + g.b1_row0[seg] + c * CH_CW + cq * 64 : nullptr;
           __syncwarp();
           bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
           bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
           __syncwarp();
         }
-        mbar_wait(bar(&ctrl->acc1_full), n1 & 1);
+        mbar_wait(bar(&ctrl->acc1_full[eg]), u & 1);
         tc_fence_after();
-        const uint32_t tacc = acc1 + cq * 64 + ((uint32_t)(q * 32) << 16);
+        const uint32_t tacc = acc1 + eg * CH_CW + cq * 64 + ((uint32_t)(q * 32) << 16);
         uint32_t r0[32], r1[32];
         tmem_ld32_nowait(tacc, r0);
         tmem_ld32_nowait(tacc + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_leader(&ctrl->acc1_empty);      // acc1 may be overwritten by GEMM1(c+1)
-        // F is free once GEMM2 of the previous chunk retired and this warp's previous TMA store has read it
-        mbar_wait(bar(&ctrl->f_empty), (n1 & 1) ^ 1);
+        if (lane == 0) arrive_leader(&ctrl->acc1_empty[eg]);   // acc1[eg] may be overwritten by GEMM1(c+2)
+        // F[eg] is free once GEMM2(c-2) retired and this warp's previous TMA store has read its box
+        mbar_wait(bar(&ctrl->f_empty[eg]), (u & 1) ^ 1);
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
         uint32_t wout0 = 0, wout1 = 0;
@@ -743,16 +771,16 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         fence_async_smem();               // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          arrive_leader(&ctrl->f_full);
-          tma_store_2d(&tmMid, f_box, c * 256 + cq * 64, m0 + q * 32);
+          arrive_leader(&ctrl->f_full[eg]);
+          tma_store_2d(&tmMid, f_box, c * CH_CW + cq * 64, m0 + q * 32);
           tma_store_commit();
         }
         if (OP1 == TEPI_BIAS_RELU_BITS && row_ok)
-          *reinterpret_cast<uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 8 + cq * 2) = make_uint2(wout0, wout1);
+          *reinterpret_cast<uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2) = make_uint2(wout0, wout1);
       }
-      // ---- final epilogue: out = epi2(acc2); F (idle now) is the staging block
+      // ---- final epilogue: out = epi2(acc2); the warp's F box (idle now) is the staging block
       if (OP2 == TEPI_BIAS) {
-        const float* bsrc = g.bias2 ? g.bias2 + g.b2_row0[seg] + cq * 64 : nullptr;
+        const float* bsrc = g.bias2 ? g.bias2 + g.b2_row0[seg] + cq4 * 64 : nullptr;
         __syncwarp();
         bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
         bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
@@ -761,7 +789,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(bar(&ctrl->acc2_full), ti & 1);
       tc_fence_after();
       {
-        const uint32_t tacc = acc2 + cq * 64 + ((uint32_t)(q * 32) << 16);
+        const uint32_t tacc = acc2 + cq4 * 64 + ((uint32_t)(q * 32) << 16);
         uint32_t r0[32], r1[32];
         tmem_ld32_nowait(tacc, r0);
         tmem_ld32_nowait(tacc + 32, r1);
@@ -770,7 +798,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           arrive_leader(&ctrl->acc2_empty);
-          tma_store_wait_read();          // this warp's store of the last intermediate chunk has left F
+          tma_store_wait_read();          // this warp's store of its last intermediate chunk has left the box
         }
         __syncwarp();
         uint32_t dummy;
@@ -779,7 +807,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmOut, f_box, cq * 64, m0 + q * 32);
+          tma_store_2d(&tmOut, f_box, cq4 * 64, m0 + q * 32);
           tma_store_commit();
         }
       }
@@ -1066,12 +1094,12 @@ template <int OP1, int OP2, int CL>
 static cudaError_t launch_chain_tc_cl(const ChainProblem& g, const void* A, const void* B1, int b1_rows, const void* B2,
                                       int b2_rows, void* mid, void* out, int sm_count, cudaStream_t st) {
   static int stages_cfg = env_int("MMR_CHAIN_STAGES", CL == 2 ? 5 : 2);
-  const int max_stages = CL == 2 ? 5 : 2;
+  const int max_stages = CL == 2 ? 5 : 2;     // 64 KB A + 64 KB F[2] + 5 x 16 KB (pairs) / 2 x 32 KB weight stages
   const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
   const int rows = g.segs.row0[g.segs.n];
   CUtensorMap tmA, tmB1, tmB2, tmMid, tmOut;
   if (!make_tmap(&tmA, A, CH_K, (uint64_t)rows, CH_K, BK, BM)) return cudaErrorUnknown;
-  if (!make_tmap(&tmB1, B1, CH_K, (uint64_t)b1_rows, CH_K, BK, 256 / CL)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB1, B1, CH_K, (uint64_t)b1_rows, CH_K, BK, CH_CW / CL)) return cudaErrorUnknown;
   if (!make_tmap(&tmB2, B2, CH_MID, (uint64_t)b2_rows, CH_MID, BK, 256 / CL)) return cudaErrorUnknown;
   if (!make_tmap(&tmMid, mid, CH_MID, (uint64_t)rows, CH_MID, 64, 32)) return cudaErrorUnknown;
   if (!make_tmap(&tmOut, out, CH_N, (uint64_t)rows, CH_N, 64, 32)) return cudaErrorUnknown;

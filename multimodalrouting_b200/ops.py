@@ -577,7 +577,11 @@ class RoutingFn(torch.autograd.Function):
         g_mc = flat[lay["pose_to_mc"]:lay["pose_to_mc"] + 64 * 32].view(64, 32)
         g_emb = flat[lay["embedding"]:lay["embedding"] + K * 64].view(K, 64)
         g_bias = flat[lay["bias"]:lay["bias"] + K]
-        g_ao = d_acts.view(ctx.ao_shape) if (has_ao and not from_poses and ctx.needs_input_grad[1]) else None
+        # Mort never consumes the priors (current_act = ones * mask, d = sum_r R pose: Mort routing_and_heads.py:208-265), so
+        # the reference leaves acts_override.grad = None there; Pheno routes with alpha
+        g_ao = None
+        if has_ao and not from_poses and ctx.needs_input_grad[1] and variant == VARIANT["pheno"]:
+            g_ao = d_acts.view(ctx.ao_shape)
         head = (None, g_ao, None, g_caps, g_mc, g_emb, g_bias)
         if from_poses:
             return head + (d_poses, d_acts)

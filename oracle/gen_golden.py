@@ -74,6 +74,8 @@ CASES = {
                            detach=False, missing=True, mask_mode="full", long=True),
     "mort_missing1": dict(variant="mort", K=2, orig_d_n=256, B=8, seed=1616, sharp=1.0, temp=1.0,
                           detach=False, missing=True, mask_mode="full", long=True),
+    "pheno_override_grad": dict(variant="pheno", K=25, orig_d_n=256, B=4, seed=1818, sharp=2.0, temp=1.5,
+                                detach=False, missing=True, mask_mode="full", override=True, override_grad=True, long=True),
     "mort_override": dict(variant="mort", K=2, orig_d_n=256, B=4, seed=1717, sharp=3.0, temp=1.5,
                           detach=False, missing=True, mask_mode="full", override=True, override_grad=True, long=True),
     # long sequences ("long": only the CPU oracle test iterates them; the GPU tests reach these token counts through the

@@ -17,7 +17,7 @@ GOLDEN_CASES = ["mort_cfg1", "pheno_sharp4", "pheno_warm", "mort_missing", "phen
 # long sequences (PhenoModel's structured_seq_len=256; INSPECT token counts of BASELINE configs[4]): pin the ORACLE to the
 # reference at these token counts; the GPU tests reach them through the oracle (test_bf16_mma_attention_..., tools/stress_shapes.py)
 GOLDEN_LONG = ["pheno_tl256", "pheno_inspect", "pheno_override", "mort_iter2", "pheno_layers2", "mort_proj_all",   # + acts_override, num_routing=2, layers=2, Conv1d on L/N/I
-               "pheno_missing1", "mort_missing1", "mort_override"]   # sharp=1 missing-modality pair; gradient through acts_override
+               "pheno_missing1", "mort_missing1", "mort_override", "pheno_override_grad"]   # sharp=1 missing-modality pair; gradient through acts_override
 
 
 def load_golden(name):

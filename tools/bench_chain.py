@@ -31,3 +31,20 @@ ref_mid = (A[:512].float() @ B1.float().t() + b1).relu()
 ref_out = ref_mid.bfloat16().float() @ B2.float().t() + b2
 print("mid err", float((mid[:512].float() - ref_mid).abs().max() / ref_mid.abs().max()),
       "out err", float((out[:512].float() - ref_out).abs().max() / ref_out.abs().max()))
+# data-gradient pair: dF = (G W2) .* relu' (bits), dH = (dF W1) .* rowmask  -- B1 = fc2.weight^T [1024,256], B2 = fc1.weight^T [256,1024]
+G = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
+W2T = B2.t().contiguous()     # [1024, 256]
+W1T = B1.t().contiguous()     # [256, 1024]
+rowmask = (torch.rand(M, device="cuda", generator=g) < 0.9).float()
+dF = torch.empty(M, 1024, device="cuda", dtype=torch.bfloat16)
+dH = torch.empty(M, 256, device="cuda", dtype=torch.bfloat16)
+rc = lib.mmr_bench_chain(0, M, G.data_ptr(), W2T.data_ptr(), W1T.data_ptr(), None, None, rowmask.data_ptr(),
+                         bits.data_ptr(), dF.data_ptr(), dH.data_ptr(), ITERS, C.byref(ms),
+                         torch.cuda.current_stream().cuda_stream)
+_lib.check(rc, "chain bwd")
+print(f"chain bwd: {ms.value*1e3:.1f} us  {fl/ms.value/1e9:.1f} TFLOP/s")
+keep = (mid[:512] > 0).float()
+ref_dF = (G[:512].float() @ W2T.float().t()) * keep
+ref_dH = (ref_dF.bfloat16().float() @ W1T.float().t()) * rowmask[:512, None]
+print("dF err", float((dF[:512].float() - ref_dF).abs().max() / ref_dF.abs().max()),
+      "dH err", float((dH[:512].float() - ref_dH).abs().max() / ref_dH.abs().max()))

@@ -107,8 +107,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Remote arrive on the peer CTA's barrier.  Default semantics (.release at .cta scope), as CUTLASS's ClusterBarrier::arrive
+// does: the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive, which was 15 % of
+// the chained kernel's stall samples (profiles/r2_chain.md).  What the arrive has to order is covered elsewhere: TMEM reads
+// by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, shared-memory writes for the tensor core by fence.proxy.async.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of the pair; the transaction bytes are credited to the mbarrier at `bar`
 // (a shared::cluster address -- the leader CTA's barrier)
@@ -566,7 +570,7 @@ constexpr int CH_A_BYTES = BM * CH_K * 2;                 // 64 KB: 4 k-blocks o
 constexpr int CH_F_BYTES = BM * CH_CW * 2;                // 32 KB per F buffer: 2 k-blocks of [128 x 64]
 template <int CL> __host__ __device__ constexpr int chain_bstage_bytes() { return (256 / CL) * BK * 2; }
 template <int CL> __host__ __device__ constexpr int chain_smem_bytes(int stages) {
-  return CH_A_BYTES + 2 * CH_F_BYTES + stages * chain_bstage_bytes<CL>() + CH_EPI_WARPS * 64 * 4 + 1024 + 512;
+  return CH_A_BYTES + 2 * CH_F_BYTES + stages * chain_bstage_bytes<CL>() + (CH_MID + CH_N) * 4 + 1024 + 512;
 }
 
 template <int OP1, int OP2, int CL>
@@ -581,7 +585,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t sA = sbase, sF = sbase + CH_A_BYTES, sB = sF + 2 * CH_F_BYTES;
   float* bias_all = reinterpret_cast<float*>(sgen + CH_A_BYTES + 2 * CH_F_BYTES + stages * BST);
-  ChainCtrl* ctrl = reinterpret_cast<ChainCtrl*>(bias_all + CH_EPI_WARPS * 64);
+  ChainCtrl* ctrl = reinterpret_cast<ChainCtrl*>(bias_all + CH_MID + CH_N);   // bias1 [1024] | bias2 [256] of the current segment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
   const int nwork = (g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM);
@@ -727,7 +731,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     //       slice cq4 = 2 eg + cq of the 256 output columns.
     const int wi = warp - 2;
     const int eg = wi >> 3, q = warp & 3, cq = (wi >> 2) & 1, cq4 = eg * 2 + cq;
-    float* bias_s = bias_all + wi * 64;
+    int bias_seg = -1;
     const uint32_t f_box = sF + (uint32_t)cq4 * (BM * BK * 2) + (uint32_t)q * 4096;   // this warp's 4 KB box
     const uint32_t f_row = f_box + (uint32_t)lane * 128;
     uint32_t ti = 0, u = 0;
@@ -740,17 +744,24 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool zrow = (rows_valid < BM) && !row_ok;
       float rmask = 1.f;
       if (OP2 == TEPI_MASK) rmask = (g.rowmask != nullptr && row_ok) ? g.rowmask[m0 + lr] : 1.f;
+      if ((OP1 == TEPI_BIAS_RELU_BITS || OP2 == TEPI_BIAS) && seg != bias_seg) {
+        // the biases depend on the segment only: the 16 epilogue warps (which walk the same tile sequence) refresh the
+        // 5 KB copy together when the segment changes -- no global load sits on a chunk's critical path
+        const int et = threadIdx.x - 64;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        for (int i = et; i < CH_MID + CH_N; i += 32 * CH_EPI_WARPS) {
+          const float* src = i < CH_MID ? g.bias1 : g.bias2;
+          const int off = i < CH_MID ? g.b1_row0[seg] + i : g.b2_row0[seg] + (i - CH_MID);
+          bias_all[i] = src ? src[off] : 0.f;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        bias_seg = seg;
+      }
       for (int c = eg; c < CH_NCH; c += 2, ++u) {
         uint2 bin2 = make_uint2(0, 0);      // ReLU sign bits of this thread's row, columns of (chunk c, slice cq)
         if (OP1 == TEPI_BITS_IN && row_ok)
           bin2 = *reinterpret_cast<const uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2);
-        if (OP1 == TEPI_BIAS_RELU_BITS) {
-          const float* bsrc = g.bias1 ? g.bias1 + g.b1_row0[seg] + c * CH_CW + cq * 64 : nullptr;
-          __syncwarp();
-          bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
-          bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
-          __syncwarp();
-        }
+        const float* bias_s = bias_all + c * CH_CW + cq * 64;
         mbar_wait(bar(&ctrl->acc1_full[eg]), u & 1);
         tc_fence_after();
         const uint32_t tacc = acc1 + eg * CH_CW + cq * 64 + ((uint32_t)(q * 32) << 16);
@@ -779,13 +790,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *reinterpret_cast<uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2) = make_uint2(wout0, wout1);
       }
       // ---- final epilogue: out = epi2(acc2); the warp's F box (idle now) is the staging block
-      if (OP2 == TEPI_BIAS) {
-        const float* bsrc = g.bias2 ? g.bias2 + g.b2_row0[seg] + cq4 * 64 : nullptr;
-        __syncwarp();
-        bias_s[lane] = bsrc ? bsrc[lane] : 0.f;
-        bias_s[lane + 32] = bsrc ? bsrc[lane + 32] : 0.f;
-        __syncwarp();
-      }
+      const float* bias_s = bias_all + CH_MID + cq4 * 64;
       mbar_wait(bar(&ctrl->acc2_full), ti & 1);
       tc_fence_after();
       {

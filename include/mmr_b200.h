@@ -313,12 +313,6 @@ int mmr_debug_gemm(int engine, int dtype, int trans, int M, int N, int K, const 
 int mmr_bench_gemm(int op, int M, int N, int K, const void* A, const void* B, const float* bias,
                    void* C, uint32_t* bits, int iters, float* ms_out, void* stream);
 
-/* Tuning hook for the chained FFN kernel (fc1 + ReLU + fc2, or its data-gradient pair when fwd = 0):
- * average device milliseconds over `iters` launches; M must be a multiple of 256. */
-int mmr_bench_chain(int fwd, int M, const void* A, const void* B1, const void* B2, const float* bias1,
-                    const float* bias2, const float* rowmask, uint32_t* bits, void* mid, void* out,
-                    int iters, float* ms_out, void* stream);
-
 /* Instrumentation (bench / profiling only).  mmr_launch_count: kernels launched by this library
  * since load.  mmr_prof_enable(1) brackets every launch group with CUDA events on the launching
  * stream; mmr_prof_collect synchronises them and returns summed device milliseconds and group counts

@@ -59,7 +59,7 @@ class LossArgs(C.Structure):
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
-           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_bench_chain", "mmr_launch_count",
+           "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
            "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd"]
@@ -116,8 +116,6 @@ def load():
     lib.mmr_debug_gemm.restype = C.c_int
     lib.mmr_bench_gemm.argtypes = [C.c_int] * 4 + [c_fp] * 5 + [C.c_int, C.POINTER(C.c_float), c_fp]
     lib.mmr_bench_gemm.restype = C.c_int
-    lib.mmr_bench_chain.argtypes = [C.c_int, C.c_int] + [c_fp] * 9 + [C.c_int, C.POINTER(C.c_float), c_fp]
-    lib.mmr_bench_chain.restype = C.c_int
     lib.mmr_launch_count.restype = C.c_longlong
     lib.mmr_prof_enable.argtypes = [C.c_int]
     lib.mmr_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]

@@ -106,15 +106,6 @@ static int run_gemm(const Plan& P, const GemmProblem& g, const EpiSpec& sp, int 
   return MMR_OK;
 }
 
-// tcgen05 engine, opt-in (MMR_CHAIN=1): the FFN GEMM pairs run as one chained kernel (gemm_tc.cuh,
-// chain_tc_kernel) that keeps the 1024-wide activation on chip between fc1 and fc2.  Parity-tested; at B=512 it
-// ties the two separate GEMMs (both are bound by the 237 MB write of the activation that the backward needs), so
-// the separate launches stay the default.
-static bool use_chain(const Plan& P) {
-  const char* e = getenv("MMR_CHAIN");
-  return P.tc && e && e[0] == '1';
-}
-
 // tcgen05 engine: bias gradients (column sums of dY) ride along in the weight-gradient kernel
 static bool fuse_colsum(const Plan& P, WgradProblem& w, float* const* dbias) {
   if (!P.tc || getenv("MMR_NO_FUSED_COLSUM")) return false;
@@ -432,19 +423,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       launch_k(ln_rows_fwd_kernel<CT, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
       LAUNCH_OK("ln1_fwd");
     }
-    if (use_chain(P)) {  // fc1 + ReLU + fc2 as one chained kernel: the 1024-wide activation is consumed on chip
-      tc::ChainProblem c; memset(&c, 0, sizeof(c));
-      c.segs = P.q;
-      for (int d = 0; d < NDIR; ++d) { c.b1_row0[d] = (l * 6 + d) * FF; c.b2_row0[d] = (l * 6 + d) * D; }
-      c.bias1 = reinterpret_cast<const float*>(packed + P.o_b1);
-      c.bias2 = reinterpret_cast<const float*>(packed + P.o_b2);
-      c.bits = bits(l);
-      ProfScope ps(PC_GEMM_TC, st);
-      cudaError_t err = tc::launch_chain_tc<tc::TEPI_BIAS_RELU_BITS, tc::TEPI_BIAS>(
-          c, h1(l), packed + P.o_w1, L * 6 * FF, packed + P.o_w2, L * 6 * D, ff(l), delta, st);
-      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 chain ffn_fwd: ") + cudaGetErrorString(err));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-    } else {
+    {
       {  // fc1 + relu
         GemmProblem g = q_problem(h1(l), D, packed + P.o_w1, D, FF, FF, D, l);
         EpiSpec e;
@@ -660,7 +639,6 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   float* g_cur = g_a;   // gradient wrt the layer output (masked)
   float* g_oth = g_b;
   for (int l = L - 1; l >= 0; --l) {
-    const bool chain_bwd = use_chain(P);
     {  // dW2 (reads gc, which the chain overwrites in LN1 backward)
       WgradProblem w = q_wgrad(gc, D, D, ff(l), FF, FF);
       for (int d = 0; d < NDIR; ++d) w.out[d] = gr(ix.layer(d, l, 6));
@@ -670,18 +648,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       if (rc) return rc;
     }
     if (have_dw1) { rc = main_wait(S_DW1); if (rc) return rc; }   // dW1 of the layer above still reads dF
-    if (chain_bwd) {  // dF = (G W2) .* relu' and dH1 = (dF W1) .* mask in one chained kernel
-      tc::ChainProblem c; memset(&c, 0, sizeof(c));
-      c.segs = P.q;
-      for (int d = 0; d < NDIR; ++d) { c.b1_row0[d] = (l * 6 + d) * FF; c.b2_row0[d] = (l * 6 + d) * D; }
-      c.rowmask = maskq;
-      c.bits = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(saved + P.s_bits + (size_t)l * P.l_bits));
-      ProfScope ps(PC_GEMM_TC, st);
-      cudaError_t err = tc::launch_chain_tc<tc::TEPI_BITS_IN, tc::TEPI_MASK>(
-          c, gc, packed + P.o_w2T, L * 6 * FF, packed + P.o_w1T, L * 6 * D, dF, dH, st);
-      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 chain ffn_bwd: ") + cudaGetErrorString(err));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-    } else {  // dF = (G W2) .* relu'   (fc2 data gradient)
+    {  // dF = (G W2) .* relu'   (fc2 data gradient)
       GemmProblem g = q_problem(gc, D, packed + P.o_w2T, D, FF, FF, D, l);
       EpiSpec e;
       e.relu_src = ff(l); e.ld_relu = FF; e.out = dF; e.ldo = FF;
@@ -691,7 +658,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     }
     rc = main_to_side(E_DF);
     if (rc) return rc;
-    if (!chain_bwd) {  // dH1 = dF W1, masked
+    {  // dH1 = dF W1, masked
       GemmProblem g = q_problem(dF, FF, packed + P.o_w1T, FF, D, D, FF, l);
       EpiSpec e;
       e.rowmask = maskq; e.out = dH; e.ldo = D;
@@ -1502,29 +1469,4 @@ int mmr_bench_gemm(int op, int M, int N, int K, const void* A, const void* B, co
 
 /* Tuning hook for the chained FFN kernel: mid[M,1024] = relu(A[M,256] B1[1024,256]^T + b1) (+ sign bits),
  * out[M,256] = mid B2[256,1024]^T + b2 (fwd = 1) or the backward pair (fwd = 0: bit mask, row mask). */
-int mmr_bench_chain(int fwd, int M, const void* A, const void* B1, const void* B2, const float* bias1, const float* bias2,
-                    const float* rowmask, uint32_t* bits, void* mid, void* out, int iters, float* ms_out, void* stream) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (M <= 0 || M % 256 || iters < 1) return fail(MMR_ERR_INVALID_ARG, "bad bench chain size");
-  tc::ChainProblem c; memset(&c, 0, sizeof(c));
-  c.segs = single_seg(M, 1);
-  c.bias1 = bias1; c.bias2 = bias2; c.rowmask = rowmask; c.bits = bits;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaError_t err = cudaSuccess;
-  for (int i = -1; i < iters && err == cudaSuccess; ++i) {
-    if (i == 0) cudaEventRecord(e0, st);
-    if (fwd) err = tc::launch_chain_tc<tc::TEPI_BIAS_RELU_BITS, tc::TEPI_BIAS>(c, A, B1, 1024, B2, 256, mid, out, st);
-    else err = tc::launch_chain_tc<tc::TEPI_BITS_IN, tc::TEPI_MASK>(c, A, B1, 1024, B2, 256, mid, out, st);
-  }
-  cudaEventRecord(e1, st);
-  cudaEventSynchronize(e1);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("bench chain: ") + cudaGetErrorString(err));
-  if (ms_out) *ms_out = ms / iters;
-  return MMR_OK;
-}
-
 }  // extern "C"

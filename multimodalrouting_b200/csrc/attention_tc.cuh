@@ -13,19 +13,17 @@
 //   warps 0-3 / 4-7  softmax + epilogue of head 0 / 1: thread = query row (TMEM lane), scores read with tcgen05.ld,
 //                    rounded to bf16 like the reference's bmm output, key bias added (finfo(bf16).min for padded keys,
 //                    -inf for tile padding), online softmax over 128-key chunks with the running output in registers
-// NH = 1 variant (MMR_ATTN_TC_HEADS=1): one head per CTA (5 warps, 80 KB of shared memory, 256 TMEM columns), so two CTAs
+// NH = 1 variant (the default; MMR_ATTN_TC_HEADS=2 selects head pairs): one head per CTA (5 warps, 80 KB of shared memory, 256 TMEM columns), so two CTAs
 // share an SM and one CTA's TMA / MMA / barrier latencies hide behind the other's softmax; the head pair's Q / K / V tiles
 // are then fetched by both CTAs of the pair (L2 hits).
 // TMEM: S NH x 128 columns, O NH x 64 columns.  Output and statistics are identical in meaning to amma::attn_fwd_kernel
 // (unnormalised bf16 P per chunk, final 1/l scaling, ml = (row max, 1/row sum)), so the mma.sync backward consumes them.
 //
-// Known gap (why it is opt-in besides speed): the K / V boxes of the last chunk extend past the patient's Tk rows into
-// the next patient's rows of the same 2-D row space.  Their scores get a -inf bias and their P is exactly 0, but 0 x NaN
-// is NaN inside the MMA, so a non-finite K / V row of patient b+1 would leak into patient b (the mma.sync kernels zero-fill
-// the rows they stage).  Fix: per-direction 3-D tensor maps [patient][token][column] whose token extent is Tk, so that the
-// TMA unit zero-fills everything past a patient's last key -- implemented as attn_fwd_tc3_kernel (MMR_ATTN_TC_MAP3D=1), same
-// body with a different loader; written after the round's GPU budget was spent, so it still has to see a GPU
-// (tools/round2_first.sh).  The 2-D kernels' SASS is unchanged by that refactor up to one don't-care mask bit.
+// Padding: Q / K / V boxes are fetched through per-direction 3-D tensor maps [patient][token][column] whose token extent is
+// the direction's T, so the TMA unit zero-fills everything past a patient's last token: no box runs on into the next patient's
+// rows (whose scores get a -inf bias and P = 0, but 0 x NaN is NaN inside the MMA).
+// Status (profiles/r2_attention_tc.md): parity-green on a B200 at 48/16/49, 150/70/33 and 512/128/196 tokens; 0.70-0.77x the
+// mma.sync forward at 512 keys and 7-9x slower at the MIMIC token counts, with or without K / V prefetch -- hence opt-in.
 #pragma once
 #include "attention_mma.cuh"
 #include "gemm_tc.cuh"
@@ -68,24 +66,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-// Where the Q / K / V boxes come from.
-//  Load2D: the [rows, columns] row spaces as they are; a box that starts at a patient's row runs on into the next patient's
-//          rows (masked by the key bias; see "Known gap" above).
-//  Load3D: per-direction [patient][token][column] views whose token extent is the direction's T, so that the TMA unit
-//          zero-fills every row past a patient's last token (opt-in MMR_ATTN_TC_MAP3D=1; not yet run on a GPU).
-struct Load2D {
-  const CUtensorMap* q; const CUtensorMap* kv;
-  __device__ __forceinline__ void prefetch(int) const {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(q)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(kv)) : "memory");
-  }
-  __device__ __forceinline__ void load_q(uint32_t dst, int col, int, int row_abs, int, int, uint32_t bar) const {
-    tma_load_2d(dst, q, col, row_abs, bar);
-  }
-  __device__ __forceinline__ void load_kv(uint32_t dst, int col, int, int row_abs, int, int, uint32_t bar) const {
-    tma_load_2d(dst, kv, col, row_abs, bar);
-  }
-};
+// Q / K / V boxes come from per-direction [patient][token][column] views whose token extent is the direction's T, so that
+// the TMA unit zero-fills every row past a patient's last token.
 struct Maps3D { CUtensorMap q[NDIR]; CUtensorMap kv[NDIR]; };
 struct Load3D {
   const Maps3D* m;
@@ -101,8 +83,8 @@ struct Load3D {
   }
 };
 
-// ST = 2 (opt-in MMR_ATTN_TC_PREFETCH=1, not yet run on a GPU): two K / V stages; the TMA loads of chunk c+1 are issued before
-// chunk c is computed, as soon as the MMAs of chunk c-1 -- the last readers of that stage -- have retired.
+// ST = 2: two K / V stages (TMA loads of chunk c+1 issued before chunk c is computed); measured slower with one head per CTA and
+// equal with two (profiles/r2_attention_tc.md), so only ST = 1 is instantiated.
 template <int NH, class Loader, int ST = 1>
 __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnArgs& a) {
   constexpr int CW = NH * 4;            // control warp
@@ -287,46 +269,10 @@ __device__ __forceinline__ void attn_fwd_tc_body(const Loader& ldr, const AttnAr
 
 template <int NH>
 __global__ void __launch_bounds__(threads<NH>(), 3 - NH)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
-  attn_fwd_tc_body<NH>(Load2D{&tmQ, &tmKV}, a);
-}
-template <int NH>
-__global__ void __launch_bounds__(threads<NH>(), 3 - NH)
 attn_fwd_tc3_kernel(const __grid_constant__ Maps3D maps, AttnArgs a) {
   attn_fwd_tc_body<NH>(Load3D{&maps}, a);
 }
-template <int NH>
-__global__ void __launch_bounds__(threads<NH>(), 1)
-attn_fwd_tc_pf_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a) {
-  attn_fwd_tc_body<NH, Load2D, 2>(Load2D{&tmQ, &tmKV}, a);
-}
-
 // host: one launch for all six directions of a layer
-template <int NH>
-static cudaError_t launch_attn_fwd_tc_nh(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnArgs& a, int B, int maxTq,
-                                         cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NH>());
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  dim3 grid((8 / NH) * ((maxTq + QB - 1) / QB), B, NDIR);
-  const char* pf = getenv("MMR_ATTN_TC_PREFETCH");   // two K / V stages (opt-in)
-  if (pf && atoi(pf) == 1) {
-    static bool attr_pf = false;
-    if (!attr_pf) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_pf_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<NH, 2>());
-      if (e != cudaSuccess) return e;
-      attr_pf = true;
-    }
-    attn_fwd_tc_pf_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH, 2>(), st>>>(tmQ, tmKV, a);
-    return cudaGetLastError();
-  }
-  attn_fwd_tc_kernel<NH><<<grid, threads<NH>(), smem_bytes<NH>(), st>>>(tmQ, tmKV, a);
-  return cudaGetLastError();
-}
-
 // [patient][token][column] view of one direction's rows inside a [rows, ld] bf16 matrix: box = 64 columns x 128 tokens x 1 patient
 static bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t tokens, uint64_t patients, uint64_t ld,
                          uint32_t box_tokens) {
@@ -361,19 +307,13 @@ static cudaError_t launch_attn_fwd_tc3_nh(const AttnArgs& a, int B, int maxTq, c
   return cudaGetLastError();
 }
 
+// K / V and Q rows are fetched through per-patient 3-D tensor maps (zero fill past a patient's last token), so no box can
+// pull in the next patient's rows or pad rows (0 x NaN inside the MMA).  The round-1 2-D-map kernel and its two-stage K / V
+// prefetch variant were measured in round 2 (profiles/r2_attention_tc.md: equal or slower) and removed.
 static cudaError_t launch_attn_fwd_tc(const AttnArgs& a, int B, int maxTq, cudaStream_t st) {
-  const char* e3 = getenv("MMR_ATTN_TC_MAP3D");     // per-patient 3-D tensor maps (zero fill past a patient's last token)
-  if (e3 && atoi(e3) == 1) {
-    const char* eh = getenv("MMR_ATTN_TC_HEADS");
-    if (eh && atoi(eh) == 1) return launch_attn_fwd_tc3_nh<1>(a, B, maxTq, st);
-    return launch_attn_fwd_tc3_nh<2>(a, B, maxTq, st);
-  }
-  CUtensorMap tmQ, tmKV;
-  if (!make_tmap(&tmQ, a.qb, (uint64_t)D, (uint64_t)a.q.row0[a.q.n], (uint64_t)D, 64, QB)) return cudaErrorUnknown;
-  if (!make_tmap(&tmKV, a.kvbuf, (uint64_t)a.ldkv, (uint64_t)a.kv.row0[a.kv.n], (uint64_t)a.ldkv, 64, KC)) return cudaErrorUnknown;
-  const char* e = getenv("MMR_ATTN_TC_HEADS");      // heads per CTA: 2 (default) or 1 (two CTAs per SM)
-  if (e && atoi(e) == 1) return launch_attn_fwd_tc_nh<1>(tmQ, tmKV, a, B, maxTq, st);
-  return launch_attn_fwd_tc_nh<2>(tmQ, tmKV, a, B, maxTq, st);
+  const char* eh = getenv("MMR_ATTN_TC_HEADS");     // heads per CTA: 1 (default, two CTAs per SM) or 2
+  if (eh && atoi(eh) == 2) return launch_attn_fwd_tc3_nh<2>(a, B, maxTq, st);
+  return launch_attn_fwd_tc3_nh<1>(a, B, maxTq, st);
 }
 
 }  // namespace atc

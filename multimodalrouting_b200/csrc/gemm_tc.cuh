@@ -204,6 +204,8 @@ struct TcEpi {
   int ld_bits;
   void* out;
   int ldo;
+  int dbg;                    // tuning experiments only (MMR_TC_DBG, tools/bench_gemm.py): 1 = epilogue drains TMEM but neither
+                              // converts nor stores, 2 = no TMA / bit stores, 4 = epilogue only hands the buffer back
 };
 
 constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -466,6 +468,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t buf = i & 1;
       mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
       tc_fence_after();
+      if (e.dbg & 4) {           // experiment: no drain at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->tempty[buf]), 0));
+          else mbar_arrive(smem_u32(&ctrl->tempty[buf]));
+        }
+        continue;
+      }
       const uint32_t tmem_acc = tmem_base + buf * BN + ch * HC + ((uint32_t)(q * 32) << 16);
       const uint32_t stg = cstg_base + (warp - 2) * CSTG_BYTES;     // two 4 KB boxes
       const uint32_t stg_row = stg + lane * 128;
@@ -484,6 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else mbar_arrive(smem_u32(&ctrl->tempty[buf]));
           }
         }
+        if (e.dbg & 1) continue;   // experiment: TMEM drained, nothing converted or stored
         // the staging boxes may still be read by the previous TMA store of this warp
         if (f32_out || cc == 0) {
           if (lane == 0) tma_store_wait_read();
@@ -501,7 +513,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (f32_out || cc == HC / 64 - 1) {
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(e.dbg & 2)) {
             if (f32_out) {
               tma_store_2d(&tmC, stg, n0 + cc * 64, m0 + q * 32);
               tma_store_2d(&tmC, stg + 4096, n0 + cc * 64 + 32, m0 + q * 32);
@@ -513,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (OP == TEPI_BIAS_RELU_BITS && row_ok) {
+      if (OP == TEPI_BIAS_RELU_BITS && row_ok && !(e.dbg & 3)) {
         uint4* bo = reinterpret_cast<uint4*>(e.bits_out + (size_t)(m0 + lr) * e.ld_bits + n0 / 32);
 #pragma unroll
         for (int w4 = 0; w4 < HC / 128; ++w4) bo[w4] = make_uint4(wout[4 * w4], wout[4 * w4 + 1], wout[4 * w4 + 2], wout[4 * w4 + 3]);
@@ -526,304 +538,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (CL == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
     else tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Chained GEMM pair with the 1024-wide intermediate kept on chip between the two products:
-//     mid[r, 0:1024] = epi1( A[r, 0:256] * B1[seg]^T )        (written to HBM once, never re-read here)
-//     out[r, 0:256]  = epi2( mid[r, :]   * B2[seg]^T )
-//   forward : A = LN1(x1) , B1 = fc1.weight, epi1 = +bias, ReLU, sign bits ; B2 = fc2.weight, epi2 = +bias
-//   backward: A = dY(fc2) , B1 = fc2.weight^T, epi1 = ReLU' bit mask (dF)  ; B2 = fc1.weight^T, epi2 = row mask
-// (transformer.py:204-215 and its autograd).  Per 128-row tile the A block (64 KB) is staged once; the 1024
-// intermediate columns are produced in EIGHT 128-column chunks through a two-deep software pipeline:
-//     TMEM  : acc1[2] (2 x 128 columns, ping-pong) + acc2 (256 columns)
-//     smem  : F[2]    (2 x [128 rows x 128 cols] bf16, ping-pong; 128B-swizzled K-major = A operand of GEMM2 AND the
-//                      TMA-store source of `mid`)
-//     MMA   : G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(6) | G2(7)        (single issuing thread)
-//     epi   : two groups of 8 warps; group g drains acc1[g] -> bias / ReLU / mask -> F[g] for chunks c = g (mod 2),
-//             so the tensor pipe always has GEMM2(c) + GEMM1(c+2) queued while chunk c+1 is being converted.
-// The round-1 version (four 256-column chunks, one acc1, one F) serialised GEMM1 -> drain -> GEMM2 per chunk and ran at
-// 36 % tensor-pipe activity, level with the two separate launches (profiles/r2_chain.md).
-// CL = 2 runs CTA pairs (tcgen05 cta_group::2): each CTA stages only half of every weight tile.
-struct ChainProblem {
-  Segs segs;            // row space of A / mid / out (same rows)
-  int b1_row0[6];       // first row of the segment's [1024, 256] block in the stacked B1
-  int b2_row0[6];       // first row of the segment's [256, 1024] block in the stacked B2
-  const float* bias1;   // [stack of 1024] indexed like B1 rows, or null   (forward)
-  const float* bias2;   // [stack of 256]  indexed like B2 rows, or null   (forward)
-  const float* rowmask; // [rows] or null                                   (backward epi2)
-  uint32_t* bits;       // [rows, 32] ReLU sign bits: written (forward) / read (backward)
-};
-struct ChainCtrl {
-  uint64_t a_full, a_empty;
-  uint64_t b_full[8], b_empty[8];
-  uint64_t acc1_full[2], acc1_empty[2], f_full[2], f_empty[2], acc2_full, acc2_empty;
-  uint32_t tmem_base;
-};
-constexpr int CH_EPI_WARPS = 16;
-constexpr int CHAIN_THREADS = 64 + 32 * CH_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, 2 x 8 epilogue warps
-constexpr int CH_MID = 1024, CH_K = 256, CH_N = 256;     // fixed geometry of the reference FFN (d=256, 4d)
-constexpr int CH_CW = 128;                                // intermediate columns per chunk
-constexpr int CH_NCH = CH_MID / CH_CW;                    // 8 chunks
-constexpr int CH_A_BYTES = BM * CH_K * 2;                 // 64 KB: 4 k-blocks of [128 x 64]
-constexpr int CH_F_BYTES = BM * CH_CW * 2;                // 32 KB per F buffer: 2 k-blocks of [128 x 64]
-template <int CL> __host__ __device__ constexpr int chain_bstage_bytes() { return (256 / CL) * BK * 2; }
-template <int CL> __host__ __device__ constexpr int chain_smem_bytes(int stages) {
-  return CH_A_BYTES + 2 * CH_F_BYTES + stages * chain_bstage_bytes<CL>() + (CH_MID + CH_N) * 4 + 1024 + 512;
-}
-
-template <int OP1, int OP2, int CL>
-__global__ void __launch_bounds__(CHAIN_THREADS, 1)
-chain_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
-                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmMid,
-                const __grid_constant__ CUtensorMap tmOut, ChainProblem g, int stages) {
-  constexpr int BST = chain_bstage_bytes<CL>();            // one stage holds a GEMM2 k-block [256/CL x 64] ...
-  constexpr int B1_BYTES = (CH_CW / CL) * BK * 2;          // ... or a GEMM1 k-block [128/CL x 64] (half of it)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sA = sbase, sF = sbase + CH_A_BYTES, sB = sF + 2 * CH_F_BYTES;
-  float* bias_all = reinterpret_cast<float*>(sgen + CH_A_BYTES + 2 * CH_F_BYTES + stages * BST);
-  ChainCtrl* ctrl = reinterpret_cast<ChainCtrl*>(bias_all + CH_MID + CH_N);   // bias1 [1024] | bias2 [256] of the current segment
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
-  const int nwork = (g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM);
-  const int w0 = blockIdx.x / CL, wstep = gridDim.x / CL;
-  auto bar = [&](uint64_t* b) { return smem_u32(b); };
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar(&ctrl->a_full), 1); mbar_init(bar(&ctrl->a_empty), 1);
-    for (int s = 0; s < stages; ++s) { mbar_init(bar(&ctrl->b_full[s]), 1); mbar_init(bar(&ctrl->b_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(&ctrl->acc1_full[b]), 1); mbar_init(bar(&ctrl->acc1_empty[b]), (CH_EPI_WARPS / 2) * CL);
-      mbar_init(bar(&ctrl->f_full[b]), (CH_EPI_WARPS / 2) * CL); mbar_init(bar(&ctrl->f_empty[b]), 1);
-    }
-    mbar_init(bar(&ctrl->acc2_full), 1); mbar_init(bar(&ctrl->acc2_empty), CH_EPI_WARPS * CL);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    if (CL == 2) tmem_alloc_pair(smem_u32(&ctrl->tmem_base), 512);
-    else tmem_alloc(smem_u32(&ctrl->tmem_base), 512);
-  }
-  tc_fence_before();
-  if (CL == 2) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = ctrl->tmem_base;
-  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 2 * CH_CW;
-  // epilogue -> MMA handshakes land on the leader CTA's barriers
-  auto arrive_leader = [&](uint64_t* b) {
-    if (CL == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(b), 0));
-    else mbar_arrive(smem_u32(b));
-  };
-
-  if (warp == 0) {
-    // ===== TMA producer.  Weight k-blocks follow the MMA issue order:
-    //       W1(0) W1(1) | W2(0) W1(2) | W2(1) W1(3) | ... | W2(5) W1(7) | W2(6) | W2(7)
-    //       W1(c): 4 k-blocks of [128/CL x 64] (rows = intermediate columns of chunk c, k over d = 256)
-    //       W2(c): 2 k-blocks of [256/CL x 64] (rows = output columns, k = the chunk's 128 intermediate columns)
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
-      uint32_t it = 0, ti = 0;
-      for (int t = w0; t < nwork; t += wstep, ++ti) {
-        const int m0 = (t * CL + (int)rank) * BM;
-        const int seg = seg_of_row(g.segs, m0);
-        mbar_wait(bar(&ctrl->a_empty), (ti & 1) ^ 1);
-        {
-          const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->a_full), 0) : bar(&ctrl->a_full);
-          if (rank == 0) mbar_expect_tx(bar(&ctrl->a_full), CL * CH_A_BYTES);
-#pragma unroll
-          for (int kb = 0; kb < CH_K / BK; ++kb) {
-            if (CL == 2) tma_load_2d_pair(sA + kb * (BM * BK * 2), &tmA, kb * BK, m0, full);
-            else tma_load_2d(sA + kb * (BM * BK * 2), &tmA, kb * BK, m0, full);
-          }
-        }
-        auto load_kblock = [&](const CUtensorMap* tm, int x, int y, uint32_t bytes) {
-          const int s = it % stages;
-          mbar_wait(bar(&ctrl->b_empty[s]), ((it / stages) & 1) ^ 1);
-          const uint32_t full = CL == 2 ? mapa_u32(bar(&ctrl->b_full[s]), 0) : bar(&ctrl->b_full[s]);
-          if (rank == 0) mbar_expect_tx(bar(&ctrl->b_full[s]), CL * bytes);
-          if (CL == 2) tma_load_2d_pair(sB + s * BST, tm, x, y, full);
-          else tma_load_2d(sB + s * BST, tm, x, y, full);
-          ++it;
-        };
-        auto load_w1 = [&](int c) {
-          for (int kb = 0; kb < CH_K / BK; ++kb)
-            load_kblock(&tmB1, kb * BK, g.b1_row0[seg] + c * CH_CW + (int)rank * (CH_CW / CL), B1_BYTES);
-        };
-        auto load_w2 = [&](int c) {
-          for (int j = 0; j < CH_CW / BK; ++j)
-            load_kblock(&tmB2, c * CH_CW + j * BK, g.b2_row0[seg] + (int)rank * (256 / CL), BST);
-        };
-        load_w1(0);
-        load_w1(1);
-        for (int c = 0; c < CH_NCH; ++c) {
-          load_w2(c);
-          if (c + 2 < CH_NCH) load_w1(c + 2);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc1 = make_idesc(CH_CW, 0, 0, CL * BM);
-      constexpr uint32_t idesc2 = make_idesc(CH_N, 0, 0, CL * BM);
-      uint32_t it = 0, ti = 0;
-      uint32_t u1[2] = {0, 0}, u2[2] = {0, 0};   // uses of acc1[b] / F[b] so far (barrier phases)
-      auto commit = [&](uint64_t* b) {
-        if (CL == 2) umma_commit_pair(smem_u32(b)); else umma_commit(smem_u32(b));
-      };
-      auto kblock = [&](uint32_t a_addr, uint32_t acc, uint32_t idesc, bool fresh) {
-        const int s = it % stages;
-        mbar_wait(bar(&ctrl->b_full[s]), (it / stages) & 1);
-        tc_fence_after();
-        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-        const uint64_t bdesc = make_smem_desc(sB + s * BST, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint32_t accum = (fresh && k == 0) ? 0u : 1u;
-          if (CL == 2) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-          else umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-        }
-        commit(&ctrl->b_empty[s]);
-        ++it;
-      };
-      auto gemm1 = [&](int b) {          // acc1[b] = A * B1[chunk]^T
-        mbar_wait(bar(&ctrl->acc1_empty[b]), (u1[b] & 1) ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < CH_K / BK; ++kb) kblock(sA + kb * (BM * BK * 2), acc1 + b * CH_CW, idesc1, kb == 0);
-        commit(&ctrl->acc1_full[b]);
-        ++u1[b];
-      };
-      auto gemm2 = [&](int b, bool fresh) {   // acc2 (+)= F[b] * B2[:, chunk]^T
-        mbar_wait(bar(&ctrl->f_full[b]), u2[b] & 1);
-        tc_fence_after();
-        for (int j = 0; j < CH_CW / BK; ++j)
-          kblock(sF + b * CH_F_BYTES + j * (BM * BK * 2), acc2, idesc2, fresh && j == 0);
-        commit(&ctrl->f_empty[b]);
-        ++u2[b];
-      };
-      for (int t = w0; t < nwork; t += wstep, ++ti) {
-        mbar_wait(bar(&ctrl->a_full), ti & 1);
-        tc_fence_after();
-        gemm1(0);
-        gemm1(1);
-        for (int c = 0; c < CH_NCH; ++c) {
-          if (c == 0) {
-            mbar_wait(bar(&ctrl->acc2_empty), (ti & 1) ^ 1);
-            tc_fence_after();
-          }
-          gemm2(c & 1, c == 0);
-          if (c == CH_NCH - 1) commit(&ctrl->acc2_full);
-          if (c + 2 < CH_NCH) {
-            gemm1(c & 1);
-            if (c + 2 == CH_NCH - 1) commit(&ctrl->a_empty);   // the last GEMM1 of the tile has been issued
-          }
-        }
-      }
-    }
-  } else {
-    // ===== 2 x 8 epilogue warps.  Group eg drains acc1[eg] into F[eg] for the chunks c = eg (mod 2); inside a group
-    //       warp (q, cq) owns TMEM lane quarter q = warp & 3 and the 64-column slice cq of the chunk, i.e. exactly one
-    //       [32 rows x 64 cols] box of k-block cq of F[eg].  In the final epilogue the same box stages the warp's
-    //       slice cq4 = 2 eg + cq of the 256 output columns.
-    const int wi = warp - 2;
-    const int eg = wi >> 3, q = warp & 3, cq = (wi >> 2) & 1, cq4 = eg * 2 + cq;
-    int bias_seg = -1;
-    const uint32_t f_box = sF + (uint32_t)cq4 * (BM * BK * 2) + (uint32_t)q * 4096;   // this warp's 4 KB box
-    const uint32_t f_row = f_box + (uint32_t)lane * 128;
-    uint32_t ti = 0, u = 0;
-    for (int t = w0; t < nwork; t += wstep, ++ti) {
-      const int m0 = (t * CL + (int)rank) * BM;
-      const int seg = seg_of_row(g.segs, m0);
-      const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
-      const int lr = q * 32 + lane;
-      const bool row_ok = lr < rows_valid;
-      const bool zrow = (rows_valid < BM) && !row_ok;
-      float rmask = 1.f;
-      if (OP2 == TEPI_MASK) rmask = (g.rowmask != nullptr && row_ok) ? g.rowmask[m0 + lr] : 1.f;
-      if ((OP1 == TEPI_BIAS_RELU_BITS || OP2 == TEPI_BIAS) && seg != bias_seg) {
-        // the biases depend on the segment only: the 16 epilogue warps (which walk the same tile sequence) refresh the
-        // 5 KB copy together when the segment changes -- no global load sits on a chunk's critical path
-        const int et = threadIdx.x - 64;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        for (int i = et; i < CH_MID + CH_N; i += 32 * CH_EPI_WARPS) {
-          const float* src = i < CH_MID ? g.bias1 : g.bias2;
-          const int off = i < CH_MID ? g.b1_row0[seg] + i : g.b2_row0[seg] + (i - CH_MID);
-          bias_all[i] = src ? src[off] : 0.f;
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        bias_seg = seg;
-      }
-      for (int c = eg; c < CH_NCH; c += 2, ++u) {
-        uint2 bin2 = make_uint2(0, 0);      // ReLU sign bits of this thread's row, columns of (chunk c, slice cq)
-        if (OP1 == TEPI_BITS_IN && row_ok)
-          bin2 = *reinterpret_cast<const uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2);
-        const float* bias_s = bias_all + c * CH_CW + cq * 64;
-        mbar_wait(bar(&ctrl->acc1_full[eg]), u & 1);
-        tc_fence_after();
-        const uint32_t tacc = acc1 + eg * CH_CW + cq * 64 + ((uint32_t)(q * 32) << 16);
-        uint32_t r0[32], r1[32];
-        tmem_ld32_nowait(tacc, r0);
-        tmem_ld32_nowait(tacc + 32, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_leader(&ctrl->acc1_empty[eg]);   // acc1[eg] may be overwritten by GEMM1(c+2)
-        // F[eg] is free once GEMM2(c-2) retired and this warp's previous TMA store has read its box
-        mbar_wait(bar(&ctrl->f_empty[eg]), (u & 1) ^ 1);
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-        uint32_t wout0 = 0, wout1 = 0;
-        epi_chunk<OP1>(r0, bias_s, 1.f, bin2.x, wout0, zrow, f_row, 0, lane);
-        epi_chunk<OP1>(r1, bias_s + 32, 1.f, bin2.y, wout1, zrow, f_row, 4, lane);
-        fence_async_smem();               // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          arrive_leader(&ctrl->f_full[eg]);
-          tma_store_2d(&tmMid, f_box, c * CH_CW + cq * 64, m0 + q * 32);
-          tma_store_commit();
-        }
-        if (OP1 == TEPI_BIAS_RELU_BITS && row_ok)
-          *reinterpret_cast<uint2*>(g.bits + (size_t)(m0 + lr) * 32 + c * 4 + cq * 2) = make_uint2(wout0, wout1);
-      }
-      // ---- final epilogue: out = epi2(acc2); the warp's F box (idle now) is the staging block
-      const float* bias_s = bias_all + CH_MID + cq4 * 64;
-      mbar_wait(bar(&ctrl->acc2_full), ti & 1);
-      tc_fence_after();
-      {
-        const uint32_t tacc = acc2 + cq4 * 64 + ((uint32_t)(q * 32) << 16);
-        uint32_t r0[32], r1[32];
-        tmem_ld32_nowait(tacc, r0);
-        tmem_ld32_nowait(tacc + 32, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          arrive_leader(&ctrl->acc2_empty);
-          tma_store_wait_read();          // this warp's store of its last intermediate chunk has left the box
-        }
-        __syncwarp();
-        uint32_t dummy;
-        epi_chunk<OP2>(r0, bias_s, rmask, 0u, dummy, zrow, f_row, 0, lane);
-        epi_chunk<OP2>(r1, bias_s + 32, rmask, 0u, dummy, zrow, f_row, 4, lane);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOut, f_box, cq4 * 64, m0 + q * 32);
-          tma_store_commit();
-        }
-      }
-    }
-  }
-  if (warp >= 2 && lane == 0) tma_store_wait_all();
-  tc_fence_before();
-  if (CL == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
-    if (CL == 2) tmem_dealloc_pair(tmem_base, 512);
-    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1051,6 +765,9 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;
   auto kern = gemm_tc_kernel<BN, OP, CL>;
   const int smem = gemm_smem_bytes<BN, CL>(stages);
+  static int dbg_cfg = env_int("MMR_TC_DBG", 0);
+  TcEpi e2 = e;
+  e2.dbg = dbg_cfg;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   const int total_rows = g.segs.row0[g.segs.n];
@@ -1070,7 +787,7 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e, stages);
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, e2, stages);
 }
 
 // a_rows_total / b_rows_total: number of rows physically present in A / B (TMA bounds).
@@ -1085,65 +802,14 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
     if (sm_count <= 0) sm_count = 148;
   }
   // CTA pairs need every segment to start on a 256-row boundary and hold an even number of 128-row tiles
-  // (measured, tools/bench_gemm.py: pairs win for K >= 512, single CTAs for the K = 256 shapes)
+  // (measured, tools/bench_gemm.py, profiles/r2_gemm_experiments.md: with the cheap remote arrive pairs win on every shape
+  // of the path -- K = 256: q/out 28.8 -> 27.1 us, fc1 82.2 -> 75.8 us)
   static int pair_cfg = env_int("MMR_TC_PAIR", 1);
-  static int pair_min_k = env_int("MMR_TC_PAIR_MIN_K", 512);
+  static int pair_min_k = env_int("MMR_TC_PAIR_MIN_K", 256);
   bool pair_ok = pair_cfg != 0 && g.K >= pair_min_k;
   for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
   if (pair_ok) return launch_gemm_tc_cl<OP, 2>(g, e, a_rows_total, b_rows_total, sm_count, st);
   return launch_gemm_tc_cl<OP, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
-}
-
-// mid: bf16 [rows, 1024], out: bf16 [rows, 256]; A bf16 [rows, 256]; B1 stacked [*, 256]; B2 stacked [*, 1024]
-template <int OP1, int OP2, int CL>
-static cudaError_t launch_chain_tc_cl(const ChainProblem& g, const void* A, const void* B1, int b1_rows, const void* B2,
-                                      int b2_rows, void* mid, void* out, int sm_count, cudaStream_t st) {
-  static int stages_cfg = env_int("MMR_CHAIN_STAGES", CL == 2 ? 5 : 2);
-  const int max_stages = CL == 2 ? 5 : 2;     // 64 KB A + 64 KB F[2] + 5 x 16 KB (pairs) / 2 x 32 KB weight stages
-  const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
-  const int rows = g.segs.row0[g.segs.n];
-  CUtensorMap tmA, tmB1, tmB2, tmMid, tmOut;
-  if (!make_tmap(&tmA, A, CH_K, (uint64_t)rows, CH_K, BK, BM)) return cudaErrorUnknown;
-  if (!make_tmap(&tmB1, B1, CH_K, (uint64_t)b1_rows, CH_K, BK, CH_CW / CL)) return cudaErrorUnknown;
-  if (!make_tmap(&tmB2, B2, CH_MID, (uint64_t)b2_rows, CH_MID, BK, 256 / CL)) return cudaErrorUnknown;
-  if (!make_tmap(&tmMid, mid, CH_MID, (uint64_t)rows, CH_MID, 64, 32)) return cudaErrorUnknown;
-  if (!make_tmap(&tmOut, out, CH_N, (uint64_t)rows, CH_N, 64, 32)) return cudaErrorUnknown;
-  auto kern = chain_tc_kernel<OP1, OP2, CL>;
-  const int smem = chain_smem_bytes<CL>(stages);
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  const int nwork = (rows + CL * BM - 1) / (CL * BM);
-  int grid = nwork * CL < sm_count ? nwork * CL : sm_count;
-  grid -= grid % CL;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(CHAIN_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB1, tmB2, tmMid, tmOut, g, stages);
-}
-
-template <int OP1, int OP2>
-static cudaError_t launch_chain_tc(const ChainProblem& g, const void* A, const void* B1, int b1_rows, const void* B2,
-                                   int b2_rows, void* mid, void* out, cudaStream_t st) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
-  static int pair_cfg = env_int("MMR_CHAIN_PAIR", 1);
-  bool pair_ok = pair_cfg != 0;
-  for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
-  if (pair_ok) return launch_chain_tc_cl<OP1, OP2, 2>(g, A, B1, b1_rows, B2, b2_rows, mid, out, sm_count, st);
-  return launch_chain_tc_cl<OP1, OP2, 1>(g, A, B1, b1_rows, B2, b2_rows, mid, out, sm_count, st);
 }
 
 template <int MT>

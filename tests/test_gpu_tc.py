@@ -4,7 +4,6 @@ import pytest
 import torch
 
 from helpers import max_rel
-from test_gpu_fusion import _bf16_case
 
 pytestmark = pytest.mark.gpu
 
@@ -32,11 +31,3 @@ def test_tc_gemm_wgrad(Kr, M, N):
     torch.cuda.synchronize()
     ref = Y.double().t() @ X.double()
     assert max_rel(W, ref) < 1e-5
-
-
-@pytest.mark.parametrize("name", ["pheno_sharp4", "mort_missing", "pheno_odd"])
-def test_bf16_chained_ffn_kernel(name, monkeypatch):
-    """Opt-in chained FFN kernel (fc1 + ReLU + fc2 and its data-gradient pair in one tcgen05 launch each,
-    CTA pairs, intermediate consumed from shared memory): same bf16 parity bar as the default path."""
-    monkeypatch.setenv("MMR_CHAIN", "1")
-    _bf16_case(name, "tc")

@@ -8,7 +8,7 @@ import torch
 
 from gpu_common import run_case
 from helpers import (GOLDEN_CASES, GOLDEN_LONG, check_grad_checksums, fp64_truth, load_golden, max_rel, oracle_grads,
-                     oracle_run, per_patient_err, r_grad_probe, rebuild_case)
+                     oracle_run, per_patient_err, r_grad_probe, rebuild_case, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -119,7 +119,9 @@ def _bf16_case(name, engine):
     for k, t in g64.items():
         if t is None:
             continue
-        e_mine, e_ref = max_rel(out["grads"][k], t), max_rel(g16[k], t)
+        # norm-wise relative error |g - g64| / |g64| (what the golden checksums use): the max-element ratio of two bf16
+        # roundings of an ill-conditioned gradient is itself a heavy-tailed random draw (profiles/r2_parity.md)
+        e_mine, e_ref = rel_err(out["grads"][k], t), rel_err(g16[k], t)
         if e_mine > max(BF16_GRAD_TOL, BF16_SLACK * e_ref):
             worst.append((k, e_mine, e_ref))
     assert not worst, f"{len(worst)} gradients further from fp64 than {BF16_SLACK}x the reference's bf16 path: {worst[:5]}"
@@ -257,7 +259,7 @@ def test_full_size_vs_oracle():
     for k, t in g64.items():
         if t is None:
             continue
-        e_mine, e_ref = max_rel(o16["grads"][k], t), max_rel(g16[k], t)
+        e_mine, e_ref = rel_err(o16["grads"][k], t), rel_err(g16[k], t)
         assert e_mine <= max(BF16_GRAD_TOL, BF16_SLACK * e_ref), f"bf16 grad {k}: {e_mine:.2e} (reference bf16 {e_ref:.2e})"
 
 

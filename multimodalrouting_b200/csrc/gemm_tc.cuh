@@ -211,7 +211,10 @@ struct TcEpi {
 constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int STG_FLOATS = 32 * 36;   // per-warp transpose tile of the weight-gradient epilogue
 
-constexpr int CSTG_BYTES = 8192;      // per epilogue warp: 32 rows x 256 bytes, two 128B-swizzled TMA store boxes
+// TMA-store staging per epilogue warp: one 128B-swizzled [32 rows x 128 bytes] box for bf16 outputs (64 columns per round),
+// two for fp32 outputs (2 x 32 columns per round).  Round 1 staged a warp's whole 128-column slice (8 KB); halving it buys a
+// fifth operand stage for the CTA-pair kernels -- these GEMMs are bound by bytes in flight per SM (profiles/r2_gemm_experiments.md).
+template <bool F32> __host__ __device__ constexpr int cstg_bytes() { return F32 ? 8192 : 4096; }
 
 // TMA store of one [32 rows x 128 bytes] box from shared memory (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int x, int y) {
@@ -326,8 +329,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 // each SM per k-block drop from 48 KB to 32 KB (the measured bound, profiles/r1_gemm_epilogue.md) and a
 // fourth stage fits.  Requires every segment to hold an even number of 128-row tiles.
 template <int BN, int CL> __host__ __device__ constexpr int gemm_stage_bytes() { return (BM + BN / CL) * BK * 2; }
-template <int BN, int CL> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-  return stages * gemm_stage_bytes<BN, CL>() + 8 * CSTG_BYTES + 8 * (BN / 2) * 4 + 1024 + 256;
+template <int BN, int CL, bool F32> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
+  return stages * gemm_stage_bytes<BN, CL>() + 8 * cstg_bytes<F32>() + 8 * (BN / 2) * 4 + 1024 + 256;
 }
 template <int BN, int OP, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -339,6 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t cstg_base = sbase + stages * STAGE;    // 1024-byte aligned (stages are multiples of 1 KB)
+  constexpr int CSTG_BYTES = cstg_bytes<OP == TEPI_F32 || OP == TEPI_BIAS_F32>();
   float* bias_all = reinterpret_cast<float*>(sgen + stages * STAGE + 8 * CSTG_BYTES);
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(bias_all + 8 * (BN / 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -478,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
       const uint32_t tmem_acc = tmem_base + buf * BN + ch * HC + ((uint32_t)(q * 32) << 16);
-      const uint32_t stg = cstg_base + (warp - 2) * CSTG_BYTES;     // two 4 KB boxes
+      const uint32_t stg = cstg_base + (warp - 2) * CSTG_BYTES;     // one (bf16) / two (fp32) 4 KB boxes
       const uint32_t stg_row = stg + lane * 128;
       uint32_t wout[HC / 32];
 #pragma unroll
@@ -496,33 +500,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (e.dbg & 1) continue;   // experiment: TMEM drained, nothing converted or stored
-        // the staging boxes may still be read by the previous TMA store of this warp
-        if (f32_out || cc == 0) {
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-        }
+        // the staging box(es) may still be read by the previous TMA store of this warp
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
         if (f32_out) {   // 64 fp32 columns = two [32 x 32] boxes per round
           epi_chunk<OP>(r0, bias_s + cc * 64, rmask, 0u, wout[2 * cc], zrow, stg_row, 0, lane);
           epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, 0u, wout[2 * cc + 1], zrow, stg_row + 4096, 0, lane);
         } else {         // 64 bf16 columns = one [32 x 64] box per round
           epi_chunk<OP>(r0, bias_s + cc * 64, rmask, OP == TEPI_BITS_IN ? bits[2 * cc] : 0u, wout[2 * cc], zrow,
-                        stg_row + cc * 4096, 0, lane);
+                        stg_row, 0, lane);
           epi_chunk<OP>(r1, bias_s + cc * 64 + 32, rmask, OP == TEPI_BITS_IN ? bits[2 * cc + 1] : 0u, wout[2 * cc + 1],
-                        zrow, stg_row + cc * 4096, 4, lane);
+                        zrow, stg_row, 4, lane);
         }
-        if (f32_out || cc == HC / 64 - 1) {
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(e.dbg & 2)) {
-            if (f32_out) {
-              tma_store_2d(&tmC, stg, n0 + cc * 64, m0 + q * 32);
-              tma_store_2d(&tmC, stg + 4096, n0 + cc * 64 + 32, m0 + q * 32);
-            } else {
-#pragma unroll
-              for (int bx = 0; bx < HC / 64; ++bx) tma_store_2d(&tmC, stg + bx * 4096, n0 + bx * 64, m0 + q * 32);
-            }
-            tma_store_commit();
-          }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(e.dbg & 2)) {
+          tma_store_2d(&tmC, stg, n0 + cc * 64, m0 + q * 32);
+          if (f32_out) tma_store_2d(&tmC, stg + 4096, n0 + cc * 64 + 32, m0 + q * 32);
+          tma_store_commit();
         }
       }
       if (OP == TEPI_BIAS_RELU_BITS && row_ok && !(e.dbg & 3)) {
@@ -754,8 +749,10 @@ template <int OP, int CL>
 static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                      int sm_count, cudaStream_t st) {
   constexpr int BN = 256;
-  static int stages_cfg = env_int("MMR_TC_STAGES", CL == 2 ? 4 : 3);
-  const int max_stages = CL == 2 ? 4 : 3;   // 32 KB (pair) / 48 KB operand stages + 64 KB of TMA-store staging
+  constexpr bool f32_stg = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
+  // 32 KB (pair) / 48 KB operand stages next to 32 KB (bf16) / 64 KB (fp32) of TMA-store staging
+  const int max_stages = CL == 2 ? (f32_stg ? 4 : 5) : (f32_stg ? 3 : 3);
+  static int stages_cfg = env_int("MMR_TC_STAGES", 8);
   const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
   constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
   CUtensorMap tmA, tmB, tmC;
@@ -764,7 +761,7 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;
   auto kern = gemm_tc_kernel<BN, OP, CL>;
-  const int smem = gemm_smem_bytes<BN, CL>(stages);
+  const int smem = gemm_smem_bytes<BN, CL, f32_stg>(stages);
   static int dbg_cfg = env_int("MMR_TC_DBG", 0);
   TcEpi e2 = e;
   e2.dbg = dbg_cfg;

@@ -89,6 +89,17 @@ int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_pa
                          const float* pos_table, void* packed, void* saved, void* scratch,
                          float* routes_out, void* stream);
 
+/* The same forward in two steps, for callers whose weights do not change between calls (evaluation, several forward
+ * passes per optimizer step): mmr_fusion_pack_weights fills `packed` (mmr_fusion_sizes' packed_bytes; depends on layers and
+ * dtype only) from the fp32 parameters -- once per parameter version -- and mmr_route_fusion_fwd_packed runs the forward
+ * from it without re-packing.  `packed` is also what the backward entry points read. */
+int mmr_fusion_pack_weights(const mmr_fusion_dims* dims, const void* const* host_params, void* packed, void* stream);
+int mmr_route_fusion_fwd_packed(const mmr_fusion_dims* dims, const void* const* host_params,
+                                const float* x_l, const float* x_n, const float* x_i,
+                                const float* mL, const float* mN, const float* mI,
+                                const float* pos_table, const void* packed, void* saved, void* scratch,
+                                float* routes_out, void* stream);
+
 /* Backward of the above.  d_routes: fp32 [10,B,256].  host_param_grads: host array of device
  * pointers (same order; NULL entries skipped) to ZERO-INITIALISED fp32 gradient tensors; the
  * gradients are accumulated into them.  dx_*: fp32 [B,T,d_*] outputs or NULL. */

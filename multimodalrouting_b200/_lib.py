@@ -62,7 +62,8 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_capsule_routing_fwd", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
-           "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd"]
+           "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd",
+           "mmr_fusion_pack_weights", "mmr_route_fusion_fwd_packed"]
 
 
 def lib_path() -> str:
@@ -89,6 +90,10 @@ def load():
     lib.mmr_fusion_sizes.restype = C.c_int
     lib.mmr_route_fusion_fwd.argtypes = [C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 12
     lib.mmr_route_fusion_fwd.restype = C.c_int
+    lib.mmr_route_fusion_fwd_packed.argtypes = [C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 12
+    lib.mmr_route_fusion_fwd_packed.restype = C.c_int
+    lib.mmr_fusion_pack_weights.argtypes = [C.POINTER(FusionDims), C.POINTER(c_fp), c_fp, c_fp]
+    lib.mmr_fusion_pack_weights.restype = C.c_int
     lib.mmr_route_fusion_bwd.argtypes = ([C.POINTER(FusionDims), C.POINTER(c_fp)] + [c_fp] * 10 +
                                          [C.POINTER(c_fp)] + [c_fp] * 4)
     lib.mmr_route_fusion_bwd.restype = C.c_int

@@ -294,11 +294,11 @@ static int pack_weights(const Plan& P, const void* const* prm, uint8_t* packed, 
 template <class CT>
 static int fusion_fwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
                       const float* pos, uint8_t* packed, uint8_t* saved, uint8_t* scratch, float* routes,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool do_pack) {
   const ParamIndex ix{P.L};
   const int L = P.L, B = P.B;
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
-  int rc = pack_weights<CT>(P, prm, packed, st);
+  int rc = do_pack ? pack_weights<CT>(P, prm, packed, st) : MMR_OK;   // else: `packed` holds mmr_fusion_pack_weights' output
   if (rc) return rc;
 
   float* fp = reinterpret_cast<float*>(scratch + P.f_p);
@@ -1090,10 +1090,20 @@ int mmr_fusion_sizes(const mmr_fusion_dims* dims, size_t* packed_bytes, size_t* 
   return MMR_OK;
 }
 
-int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
-                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
-                         const float* pos_table, void* packed, void* saved, void* scratch, float* routes_out,
-                         void* stream) {
+int mmr_fusion_pack_weights(const mmr_fusion_dims* dims, const void* const* host_params, void* packed, void* stream) {
+  Plan P;
+  const char* why = "";
+  if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
+  if (!host_params || !packed) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.bf16) return pack_weights<bf16>(P, host_params, (uint8_t*)packed, st);
+  return pack_weights<float>(P, host_params, (uint8_t*)packed, st);
+}
+
+static int route_fusion_fwd_impl(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                                 const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                                 const float* pos_table, void* packed, void* saved, void* scratch, float* routes_out,
+                                 void* stream, bool do_pack) {
   Plan P;
   const char* why = "";
   if (!build_plan(dims, &P, &why)) return fail(MMR_ERR_INVALID_ARG, why);
@@ -1105,9 +1115,25 @@ int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_pa
   ProfScope ps(PC_FUSION_FWD, st);
   if (P.bf16)
     return fusion_fwd<bf16>(P, host_params, x, mask, pos_table, (uint8_t*)packed, (uint8_t*)saved, (uint8_t*)scratch,
-                            routes_out, st);
+                            routes_out, st, do_pack);
   return fusion_fwd<float>(P, host_params, x, mask, pos_table, (uint8_t*)packed, (uint8_t*)saved, (uint8_t*)scratch,
-                           routes_out, st);
+                           routes_out, st, do_pack);
+}
+
+int mmr_route_fusion_fwd(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                         const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                         const float* pos_table, void* packed, void* saved, void* scratch, float* routes_out,
+                         void* stream) {
+  return route_fusion_fwd_impl(dims, host_params, x_l, x_n, x_i, mL, mN, mI, pos_table, packed, saved, scratch, routes_out,
+                               stream, true);
+}
+
+int mmr_route_fusion_fwd_packed(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,
+                                const float* x_n, const float* x_i, const float* mL, const float* mN, const float* mI,
+                                const float* pos_table, const void* packed, void* saved, void* scratch, float* routes_out,
+                                void* stream) {
+  return route_fusion_fwd_impl(dims, host_params, x_l, x_n, x_i, mL, mN, mI, pos_table, const_cast<void*>(packed), saved,
+                               scratch, routes_out, stream, false);
 }
 
 int mmr_route_fusion_bwd_ex(const mmr_fusion_dims* dims, const void* const* host_params, const float* x_l,

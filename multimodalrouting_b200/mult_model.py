@@ -71,6 +71,14 @@ class MULTModel(nn.Module):
         #: "auto" follows torch.autocast like the reference (fp32 outside, bf16 kernels inside)
         self.compute_dtype = "auto"
         self._plist: Optional[List[nn.Parameter]] = None
+        #: The kernels read compute-type copies of the GEMM weights ("packed" weights).  They are rebuilt only when a
+        #: parameter changed (tensor version counters + addresses): evaluation and repeated forward passes between
+        #: optimizer steps pack once.  Inside a CUDA-graph capture version counters cannot be consulted at replay time, so
+        #: the packing is captured with the forward unless the caller declares the weights constant for the life of the
+        #: graph (``static_weights = True``: inference graphs, or a forward/backward graph with the optimizer outside it
+        #: that re-captures / calls ``refresh_packed_weights()`` after every update).
+        self.static_weights = False
+        self._packed = None          # (key, tensor)
 
     def get_network(self, self_type: str = "l", layers: int = -1):
         n_layers = self.layers if layers == -1 else layers
@@ -105,6 +113,37 @@ class MULTModel(nn.Module):
         for lin in (self.proj_pair_ln, self.proj_pair_li, self.proj_pair_ni, self.final_lni):
             ps += [lin.weight, lin.bias]
         return ps
+
+    def _packed_weights(self, params, dtype, engine):
+        """Cached packed weights for the current parameter versions, or None (= pack inside the op)."""
+        p0 = params[0]
+        if not p0.is_cuda or isinstance(p0, torch._subclasses.fake_tensor.FakeTensor):
+            return None
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and not self.static_weights:
+            return None
+        key = (dtype, engine, p0.device, tuple((p.data_ptr(), p._version) for p in params))
+        hit = self._packed
+        if hit is not None and (hit[0] == key or (capturing and hit[0][:3] == key[:3])):
+            return hit[1]
+        if capturing:
+            return None          # nothing cached yet: pack inside the capture
+        with torch.no_grad():
+            packed = ops.route_fusion_pack([p.detach() for p in params], int(self.layers), dtype, engine)
+        self._packed = (key, packed)
+        return packed
+
+    def refresh_packed_weights(self):
+        """Re-packs IN PLACE into the cached buffer (whose address a captured graph may hold) after the parameters
+        were updated outside that graph."""
+        hit = self._packed
+        if hit is None:
+            return
+        dtype, engine = hit[0][0], hit[0][1]
+        params = self._param_list()
+        with torch.no_grad():
+            hit[1].copy_(ops.route_fusion_pack([p.detach() for p in params], int(self.layers), dtype, engine))
+        self._packed = ((dtype, engine, params[0].device, tuple((p.data_ptr(), p._version) for p in params)), hit[1])
 
     def _ensure_float_mask(self, m, B, T, device):
         if m is None:
@@ -150,7 +189,8 @@ class MULTModel(nn.Module):
             plist.append(p.detach() if od == 256 else p)
         plist += params[3:]
         dtype = ops.resolve_dtype(self.compute_dtype)
-        outs = ops.route_fusion(x_l, x_n, x_i, mL, mN, mI, pos, plist, int(self.layers), dtype,
-                                ops.resolve_engine())
+        engine = ops.resolve_engine()
+        outs = ops.route_fusion(x_l, x_n, x_i, mL, mN, mI, pos, plist, int(self.layers), dtype, engine,
+                                self._packed_weights(params, dtype, engine))
         target_dtype = self.final_lni.weight.dtype
         return {r: (o if o.dtype == target_dtype else o.to(target_dtype)) for r, o in zip(ROUTES, outs)}

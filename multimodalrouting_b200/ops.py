@@ -87,36 +87,63 @@ def _ptr_table(ts: Sequence[Optional[Tensor]]):
 
 # --------------------------------------------------------------------------------------------
 # raw ops (opaque to torch.compile, with fake impls)
+def _pack_dims(layers: int, dtype: int, engine: int) -> FusionDims:
+    # the packed-weight layout depends on the depth and the compute dtype only
+    return FusionDims(1, 1, 1, 1, 256, 256, 256, layers, dtype, engine)
+
+
+@torch.library.custom_op("mmr_b200::route_fusion_pack", mutates_args=())
+def route_fusion_pack(params: Sequence[Tensor], layers: int, dtype: int, engine: int) -> Tensor:
+    """Compute-type copies of the GEMM weights (forward and transposed, query scaling and the K/V LayerNorm affine folded
+    in) that the forward and backward kernels read: mmr_fusion_pack_weights.  Valid for one parameter version."""
+    _require_cuda(*params)
+    lib = _lib.load()
+    dims = _pack_dims(layers, dtype, engine)
+    n_expected = lib.mmr_fusion_num_params(C.byref(dims))
+    if n_expected != len(params):
+        raise ValueError(f"route_fusion_pack expects {n_expected} parameter tensors, got {len(params)}")
+    packed = torch.empty(fusion_sizes(dims)[0], dtype=torch.uint8, device=params[0].device)
+    _lib.check(lib.mmr_fusion_pack_weights(C.byref(dims), _ptr_table(params), _ptr(packed), _stream()),
+               "mmr_fusion_pack_weights")
+    return packed
+
+
+@route_fusion_pack.register_fake
+def _(params, layers, dtype, engine):
+    return params[0].new_empty(fusion_sizes(_pack_dims(layers, dtype, engine))[0], dtype=torch.uint8)
+
+
 @torch.library.custom_op("mmr_b200::route_fusion_fwd", mutates_args=())
 def route_fusion_fwd(x_l: Tensor, x_n: Tensor, x_i: Tensor, mL: Optional[Tensor], mN: Optional[Tensor],
-                     mI: Optional[Tensor], pos: Tensor, params: Sequence[Tensor], layers: int, dtype: int,
-                     engine: int) -> Tuple[Tensor, Tensor, Tensor]:
-    _require_cuda(x_l, x_n, x_i, pos, *params)
+                     mI: Optional[Tensor], pos: Tensor, params: Sequence[Tensor], packed: Tensor, layers: int,
+                     dtype: int, engine: int) -> Tuple[Tensor, Tensor]:
+    """MULTModel.forward from packed weights (route_fusion_pack).  Returns (routes [10,B,256], saved-for-backward)."""
+    _require_cuda(x_l, x_n, x_i, pos, packed, *params)
     lib = _lib.load()
     dims = _fusion_dims(x_l, x_n, x_i, layers, dtype, engine)
     n_expected = lib.mmr_fusion_num_params(C.byref(dims))
     if n_expected != len(params):
         raise ValueError(f"route_fusion_fwd expects {n_expected} parameter tensors, got {len(params)}")
     packed_b, saved_b, sf_b, _ = fusion_sizes(dims)
+    if packed.numel() != packed_b or packed.dtype != torch.uint8:
+        raise ValueError(f"route_fusion_fwd: packed weights must be {packed_b} bytes (route_fusion_pack), got {packed.numel()}")
     dev = x_l.device
-    packed = torch.empty(packed_b, dtype=torch.uint8, device=dev)
     saved = torch.empty(saved_b, dtype=torch.uint8, device=dev)
     scratch = torch.empty(sf_b, dtype=torch.uint8, device=dev)
     routes = torch.empty(N_ROUTES, x_l.shape[0], 256, dtype=torch.float32, device=dev)
-    rc = lib.mmr_route_fusion_fwd(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
-                                  _ptr(mN), _ptr(mI), _ptr(pos), _ptr(packed), _ptr(saved), _ptr(scratch),
-                                  _ptr(routes), _stream())
-    _lib.check(rc, "mmr_route_fusion_fwd")
-    return routes, packed, saved
+    rc = lib.mmr_route_fusion_fwd_packed(C.byref(dims), _ptr_table(params), _ptr(x_l), _ptr(x_n), _ptr(x_i), _ptr(mL),
+                                         _ptr(mN), _ptr(mI), _ptr(pos), _ptr(packed), _ptr(saved), _ptr(scratch),
+                                         _ptr(routes), _stream())
+    _lib.check(rc, "mmr_route_fusion_fwd_packed")
+    return routes, saved
 
 
 @route_fusion_fwd.register_fake
-def _(x_l, x_n, x_i, mL, mN, mI, pos, params, layers, dtype, engine):
+def _(x_l, x_n, x_i, mL, mN, mI, pos, params, packed, layers, dtype, engine):
     B = x_l.shape[0]
     # same metadata as the real op: the byte counts come from the (host-only) planner of the C ABI
-    packed_b, saved_b, _, _ = fusion_sizes(_fusion_dims(x_l, x_n, x_i, layers, dtype, engine))
-    return (x_l.new_empty(N_ROUTES, B, 256, dtype=torch.float32), x_l.new_empty(packed_b, dtype=torch.uint8),
-            x_l.new_empty(saved_b, dtype=torch.uint8))
+    _, saved_b, _, _ = fusion_sizes(_fusion_dims(x_l, x_n, x_i, layers, dtype, engine))
+    return (x_l.new_empty(N_ROUTES, B, 256, dtype=torch.float32), x_l.new_empty(saved_b, dtype=torch.uint8))
 
 
 _GRAD_LAYOUTS = {}
@@ -284,14 +311,16 @@ class RouteFusionFn(torch.autograd.Function):
     """MULTModel.forward as one autograd node: 3 sequences + masks + 317 parameters -> 10 routes."""
 
     @staticmethod
-    def forward(ctx, x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, *params):
+    def forward(ctx, x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, packed, *params):
         xs = [_f32c(x.detach()) for x in (x_l, x_n, x_i)]
         ms = [_f32c(m.detach()) if m is not None else None for m in (mL, mN, mI)]
         ps = [p.detach() for p in params]
         for p in ps:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise ValueError("route fusion parameters must be contiguous fp32 tensors")
-        routes, packed, saved = route_fusion_fwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], pos, ps, layers, dtype, engine)
+        if packed is None:
+            packed = route_fusion_pack(ps, layers, dtype, engine)
+        routes, saved = route_fusion_fwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], pos, ps, packed, layers, dtype, engine)
         ctx.save_for_backward(*xs, *[m for m in ms if m is not None], packed, saved, *ps)
         ctx.mask_present = [m is not None for m in ms]
         ctx.cfg = (layers, dtype, engine)
@@ -320,7 +349,7 @@ class RouteFusionFn(torch.autograd.Function):
         else:
             d_all = torch.stack([g.float() if g is not None else torch.zeros(B, 256, device=xs[0].device)
                                  for g in d_routes], dim=0).contiguous()
-        need = [bool(n) for n in ctx.needs_input_grad[10:]]
+        need = [bool(n) for n in ctx.needs_input_grad[11:]]
         hook, events = _OVERLAP["hook"], _OVERLAP["events"]
         handles = [int(e.cuda_event) for e in events[:layers]] if (hook is not None and events) else []
         dxl, dxn, dxi, flat = route_fusion_bwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], ps, packed, saved, d_all,
@@ -342,13 +371,14 @@ class RouteFusionFn(torch.autograd.Function):
                 grads[i] = flat[offs[i]:offs[i] + p.numel()].view(p.shape)
         gi = ctx.needs_input_grad
         return (dxl if gi[0] else None, dxn if gi[1] else None, dxi if gi[2] else None,
-                None, None, None, None, None, None, None, *grads)
+                None, None, None, None, None, None, None, None, *grads)
 
 
 def route_fusion(x_l, x_n, x_i, mL, mN, mI, pos, params: List[Tensor], layers: int, dtype: int,
-                 engine: int) -> Tuple[Tensor, ...]:
+                 engine: int, packed: Optional[Tensor] = None) -> Tuple[Tensor, ...]:
+    """`packed`: output of route_fusion_pack for the CURRENT parameter values, or None to pack inside this call."""
     _require_cuda(x_l, x_n, x_i)
-    return RouteFusionFn.apply(x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, *params)
+    return RouteFusionFn.apply(x_l, x_n, x_i, mL, mN, mI, pos, layers, dtype, engine, packed, *params)
 
 
 # --------------------------------------------------------------------------------------------

@@ -210,6 +210,9 @@ class FusedAdamW(torch.optim.Optimizer):
             _lib.check(lib.mmr_opt_apply(tab, n, C.byref(hp), sp, stream), "mmr_opt_apply")
         if ema is not None:
             ema.update(_exclude=done)      # entries the optimizer does not own (buffers, frozen tensors)
+        # the kernels wrote through raw pointers: tell autograd (and every cache keyed on tensor versions, e.g. MULTModel's
+        # packed weights) that the parameters changed, as an in-place torch op would
+        torch.autograd.graph.increment_version([p for g in self.param_groups for p in g["params"] if p.grad is not None])
         return loss
 
     # ---- torch.optim.AdamW-compatible checkpoints ---------------------------------------------------------

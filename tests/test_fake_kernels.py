@@ -21,7 +21,8 @@ def test_route_fusion_fakes(B, TL, TN, TI, d_n, dtype):
         ms = [torch.empty(B, T, device="cuda") for T in (TL, TN, TI)]
         pos = torch.empty(max(TL, TN, TI), 256, device="cuda")
         params = [torch.empty(s, device="cuda") for s in shapes]
-        routes, packed, saved = ops.route_fusion_fwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], pos, params, 4, dtype, 0)
+        packed = ops.route_fusion_pack(params, 4, dtype, 0)
+        routes, saved = ops.route_fusion_fwd(xs[0], xs[1], xs[2], ms[0], ms[1], ms[2], pos, params, packed, 4, dtype, 0)
         dims = ops._fusion_dims(xs[0], xs[1], xs[2], 4, dtype, 0)
         packed_b, saved_b, _, _ = ops.fusion_sizes(dims)
         assert tuple(routes.shape) == (10, B, 256) and routes.dtype == torch.float32 and routes.device.type == "cuda"

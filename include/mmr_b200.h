@@ -236,6 +236,33 @@ int mmr_sanitize_rows_fwd(const void* x, int in_dtype, float* y, int64_t rows, i
 int mmr_sanitize_rows_bwd(const void* x, int in_dtype, const float* dy, float* dx, int64_t rows, int D, int mode,
                           float max_norm, void* stream);
 
+/* Route-input projections between the modality encoders and the hot path:
+ *   BioClinicalBERT chunk projection  Sequential(LayerNorm(768), Linear(768 -> 256, bias=False))
+ *                                     MIMIC-IV/MortModel/Paired_Cross_Attention/encoders.py:289-293, 472-475   (has_ln = 1)
+ *   CXR token projection              Linear(512 -> 256, bias=False)              encoders.py:620, 747-749     (has_ln = 0)
+ * y[rows, d_out] (fp32) = LN?(x[rows, d_in]) W^T (+ bias).  dtype = MMR_DTYPE_BF16: LayerNorm in fp32, GEMM operands bf16 on
+ * the tcgen05 engine (the reference's autocast flow); MMR_DTYPE_F32: fp32 SIMT GEMM (parity mode).  x is fp32 or bf16
+ * (x_dtype), so an encoder that already emits bf16 is consumed without a cast pass.  W: fp32 [d_out, d_in]; d_in % 128 == 0,
+ * d_in <= 1024; d_out % 256 == 0.  saved (forward -> backward) and scratch sizes from mmr_producer_proj_sizes. */
+typedef struct mmr_proj_dims {
+  int64_t rows;
+  int32_t d_in, d_out;
+  int32_t has_ln, has_bias;
+  int32_t x_dtype;          /* MMR_DTYPE_F32 / MMR_DTYPE_BF16 of x */
+  int32_t dtype;            /* compute dtype, MMR_DTYPE_* */
+  int32_t gemm_engine;      /* MMR_GEMM_* */
+  int32_t reserved;
+} mmr_proj_dims;
+int mmr_producer_proj_sizes(const mmr_proj_dims* dims, size_t* saved_bytes, size_t* scratch_fwd_bytes,
+                            size_t* scratch_bwd_bytes);
+int mmr_producer_proj_fwd(const mmr_proj_dims* dims, const void* x, const float* ln_w, const float* ln_b, const float* W,
+                          const float* bias, float* y, void* saved, void* scratch, void* stream);
+/* dy: fp32 [rows, d_out].  Outputs (each may be NULL): dx fp32 [rows, d_in]; d_ln_w / d_ln_b fp32 [d_in], dW fp32
+ * [d_out, d_in], dbias fp32 [d_out] -- ZERO-INITIALISED accumulators. */
+int mmr_producer_proj_bwd(const mmr_proj_dims* dims, const void* x, const float* ln_w, const float* W, const float* dy,
+                          const void* saved, void* scratch, float* dx, float* d_ln_w, float* d_ln_b, float* dW,
+                          float* dbias, void* stream);
+
 /* Route mask of the missing-modality protocol: replaces build_route_mask_from_presence
  * (MIMIC-IV/PhenoModel/Partial/Cross_Attention/routing_and_heads.py:10-64) / build_route_mask_from_modalities
  * (.../Partial/Cross_Attention/main.py:109-132).  hasL/hasN/hasI: fp32 [B] (1 = available; NULL = available for all);
@@ -334,7 +361,7 @@ int mmr_prof_enable(int on);
 int mmr_prof_collect(double* ms_by_class, long long* n_by_class);
 
 /* sizeof() of the public structs, in declaration order: mmr_fusion_dims, mmr_routing_dims, mmr_routing_params,
- * mmr_routing_grads, mmr_opt_tensor, mmr_opt_hyper, mmr_opt_state, mmr_loss_state, mmr_loss_args.  Lets a foreign-language binding assert that its
+ * mmr_routing_grads, mmr_opt_tensor, mmr_opt_hyper, mmr_opt_state, mmr_loss_state, mmr_loss_args, mmr_proj_dims.  Lets a foreign-language binding assert that its
  * mirror of the structs matches this build (returns the number of entries written, at most n). */
 int mmr_abi_struct_sizes(size_t* out, int n);
 

@@ -45,6 +45,12 @@ class OptHyper(C.Structure):
                 ("has_ema", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ProjDims(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("d_in", C.c_int32), ("d_out", C.c_int32), ("has_ln", C.c_int32),
+                ("has_bias", C.c_int32), ("x_dtype", C.c_int32), ("dtype", C.c_int32), ("gemm_engine", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 OPT_STATE_BYTES = 40     # sizeof(mmr_opt_state): 3 doubles, 2 floats, 2 int32
 LOSS_STATE_BYTES = 48    # sizeof(mmr_loss_state): 7 floats, 2 int32, ticket, 2 reserved
 
@@ -63,7 +69,8 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
            "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd",
-           "mmr_fusion_pack_weights", "mmr_route_fusion_fwd_packed"]
+           "mmr_fusion_pack_weights", "mmr_route_fusion_fwd_packed",
+           "mmr_producer_proj_sizes", "mmr_producer_proj_fwd", "mmr_producer_proj_bwd"]
 
 
 def lib_path() -> str:
@@ -117,6 +124,12 @@ def load():
     lib.mmr_projector_bwd.argtypes = [C.POINTER(RoutingParams), c_fp, C.c_int64, C.c_int64, C.c_int, c_fp, c_fp, c_fp,
                                       C.POINTER(RoutingGrads), c_fp, c_fp]
     lib.mmr_projector_bwd.restype = C.c_int
+    lib.mmr_producer_proj_sizes.argtypes = [C.POINTER(ProjDims)] + [C.POINTER(C.c_size_t)] * 3
+    lib.mmr_producer_proj_sizes.restype = C.c_int
+    lib.mmr_producer_proj_fwd.argtypes = [C.POINTER(ProjDims)] + [c_fp] * 9
+    lib.mmr_producer_proj_fwd.restype = C.c_int
+    lib.mmr_producer_proj_bwd.argtypes = [C.POINTER(ProjDims)] + [c_fp] * 12
+    lib.mmr_producer_proj_bwd.restype = C.c_int
     lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
     lib.mmr_debug_gemm.restype = C.c_int
     lib.mmr_bench_gemm.argtypes = [C.c_int] * 4 + [c_fp] * 5 + [C.c_int, C.POINTER(C.c_float), c_fp]
@@ -145,8 +158,8 @@ def load():
     lib.mmr_loss_scratch_bytes.restype = C.c_size_t
     lib.mmr_loss_fwd_bwd.argtypes = [C.POINTER(LossArgs), c_fp]
     lib.mmr_loss_fwd_bwd.restype = C.c_int
-    sizes = (C.c_size_t * 9)()
-    n = lib.mmr_abi_struct_sizes(sizes, 9)
+    sizes = (C.c_size_t * 10)()
+    n = lib.mmr_abi_struct_sizes(sizes, 10)
     mirrors = (FusionDims, RoutingDims, RoutingParams, RoutingGrads, OptTensor, OptHyper)
     for i, cls in enumerate(mirrors[:n]):
         if C.sizeof(cls) != sizes[i]:
@@ -157,6 +170,9 @@ def load():
     if n < 9 or sizes[7] != LOSS_STATE_BYTES or sizes[8] != C.sizeof(LossArgs):
         raise RuntimeError(f"ABI mismatch: loss structs are {list(sizes[7:n])} bytes, binding expects "
                            f"[{LOSS_STATE_BYTES}, {C.sizeof(LossArgs)}] (stale libmmr_b200.so?)")
+    if n < 10 or sizes[9] != C.sizeof(ProjDims):
+        raise RuntimeError(f"ABI mismatch: mmr_proj_dims is {sizes[9] if n >= 10 else 'absent'} bytes, binding expects "
+                           f"{C.sizeof(ProjDims)} (stale libmmr_b200.so?)")
     _LIB = lib
     return lib
 

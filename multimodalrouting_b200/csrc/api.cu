@@ -17,6 +17,7 @@
 #include "tail.cuh"
 #include "loss.cuh"
 #include "projector.cuh"
+#include "producer.cuh"
 
 using namespace mmr;
 
@@ -1035,14 +1036,16 @@ int mmr_loss_fwd_bwd(const mmr_loss_args* g, void* stream) {
 int mmr_abi_struct_sizes(size_t* out, int n) {
   const size_t sz[] = {sizeof(mmr_fusion_dims), sizeof(mmr_routing_dims), sizeof(mmr_routing_params),
                        sizeof(mmr_routing_grads), sizeof(mmr_opt_tensor), sizeof(mmr_opt_hyper), sizeof(mmr_opt_state),
-                       sizeof(mmr_loss_state), sizeof(mmr_loss_args)};
+                       sizeof(mmr_loss_state), sizeof(mmr_loss_args), sizeof(mmr_proj_dims)};
   const int m = (int)(sizeof(sz) / sizeof(sz[0]));
   int i = 0;
   for (; out && i < n && i < m; ++i) out[i] = sz[i];
   return i;
 }
 
-int mmr_version(void) { return 101; }   // 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd)
+// 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd); 102: + standalone projector, packed-weight
+// forward, producer projections
+int mmr_version(void) { return 102; }
 
 long long mmr_launch_count(void) { return g_launches.load(); }
 
@@ -1412,6 +1415,198 @@ int mmr_projector_bwd(const mmr_routing_params* params, const float* route_embs,
   proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, B, *grads);
   LAUNCH_OK("b_proj");
   return MMR_OK;
+}
+
+// ------------------------------------------------------------ route-input producer projections ---
+struct ProjPlan {
+  long long rows; int rows_pad, din, dout; bool ln, bias, bf16c, tc; int xdt;
+  size_t ct, s_xh, s_stat, saved_bytes, f_w, scratch_fwd, b_dy, b_dxh, b_w, scratch_bwd;
+};
+static int proj_plan(const mmr_proj_dims* d, ProjPlan* P) {
+  if (!d) return fail(MMR_ERR_INVALID_ARG, "null dims");
+  if (d->rows <= 0 || d->rows > (1ll << 30)) return fail(MMR_ERR_INVALID_ARG, "producer projection: bad row count");
+  if (d->d_in % 128 || d->d_in < 128 || d->d_in > 1024) return fail(MMR_ERR_UNSUPPORTED, "producer projection: d_in must be a multiple of 128 in [128, 1024]");
+  if (d->d_out % 256 || d->d_out < 256 || d->d_out > 1024) return fail(MMR_ERR_UNSUPPORTED, "producer projection: d_out must be a multiple of 256 in [256, 1024]");
+  if (d->x_dtype != MMR_DTYPE_F32 && d->x_dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_UNSUPPORTED, "producer projection: x must be fp32 or bf16");
+  if (d->dtype != MMR_DTYPE_F32 && d->dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_INVALID_ARG, "producer projection: bad compute dtype");
+  P->rows = d->rows; P->rows_pad = pad_seg((int)d->rows); P->din = d->d_in; P->dout = d->d_out;
+  P->ln = d->has_ln != 0; P->bias = d->has_bias != 0; P->bf16c = d->dtype == MMR_DTYPE_BF16; P->xdt = d->x_dtype;
+  P->tc = P->bf16c && d->gemm_engine != MMR_GEMM_SIMT;
+  if (d->gemm_engine == MMR_GEMM_TC && !P->bf16c) return fail(MMR_ERR_UNSUPPORTED, "tcgen05 engine requires bf16");
+  P->ct = P->bf16c ? 2 : 4;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align256(n); return r; };
+  P->s_xh = take((size_t)P->rows_pad * P->din * P->ct);       // GEMM operand: LayerNorm(x) (or x) in the compute type
+  P->s_stat = take((size_t)P->rows * 2 * 4);
+  P->saved_bytes = o;
+  o = 0;
+  P->f_w = take((size_t)P->dout * P->din * P->ct);            // W in the compute type
+  P->scratch_fwd = o;
+  o = 0;
+  P->b_dy = take((size_t)P->rows_pad * P->dout * P->ct);
+  P->b_dxh = take((size_t)P->rows_pad * P->din * 4);
+  P->b_w = take((size_t)P->dout * P->din * P->ct);            // W^T in the compute type ([d_in, d_out])
+  P->scratch_bwd = o;
+  return MMR_OK;
+}
+
+int mmr_producer_proj_sizes(const mmr_proj_dims* dims, size_t* saved_bytes, size_t* scratch_fwd_bytes, size_t* scratch_bwd_bytes) {
+  ProjPlan P;
+  int rc = proj_plan(dims, &P);
+  if (rc) return rc;
+  if (saved_bytes) *saved_bytes = P.saved_bytes;
+  if (scratch_fwd_bytes) *scratch_fwd_bytes = P.scratch_fwd;
+  if (scratch_bwd_bytes) *scratch_bwd_bytes = P.scratch_bwd;
+  return MMR_OK;
+}
+
+extern "C++" {
+template <class CT>
+static int proj_fwd_t(const ProjPlan& P, const void* x, const float* ln_w, const float* ln_b, const float* W, const float* bias,
+                      float* y, uint8_t* saved, uint8_t* scratch, cudaStream_t st) {
+  CT* xh = reinterpret_cast<CT*>(saved + P.s_xh);
+  ProjRowArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.rows = P.rows; a.rows_pad = P.rows_pad; a.D = P.din; a.has_ln = P.ln; a.gamma = ln_w; a.beta = ln_b;
+  a.out = xh; a.stat = reinterpret_cast<float*>(saved + P.s_stat);
+  const int blocks = (P.rows_pad + 7) / 8;
+  if (P.xdt == MMR_DTYPE_F32) proj_rows_fwd_kernel<float, CT><<<blocks, 256, 0, st>>>(a);
+  else proj_rows_fwd_kernel<bf16, CT><<<blocks, 256, 0, st>>>(a);
+  LAUNCH_OK("proj_rows_fwd");
+  GemmProblem g; memset(&g, 0, sizeof(g));
+  g.segs = single_seg((int)P.rows, 1); g.segs.row0[1] = P.rows_pad;
+  g.N = P.dout; g.K = P.din; g.A = xh; g.lda = P.din;
+  if (P.tc) {
+    CT* wb = reinterpret_cast<CT*>(scratch + P.f_w);
+    PackJobs pj; memset(&pj, 0, sizeof(pj));
+    pj.n = 1;
+    pj.j[0] = PackJob{W, P.dout, P.din, P.din, nullptr, 1.0f, wb, P.din, nullptr, 0};
+    pack_kernel<CT><<<dim3((P.dout / 32) * (P.din / 32), 1), 256, 0, st>>>(pj);
+    LAUNCH_OK("proj pack");
+    g.B = wb; g.ldb = P.din;
+    tc::TcEpi e; memset(&e, 0, sizeof(e));
+    e.bias = bias; e.out = y; e.ldo = P.dout; e.out_rows = (int)P.rows;
+    ProfScope ps(PC_GEMM_TC, st);
+    cudaError_t err = tc::launch_gemm_tc<tc::TEPI_BIAS_F32>(g, e, P.rows_pad, P.dout, st);
+    if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 producer gemm: ") + cudaGetErrorString(err));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    g.segs.row0[1] = (int)P.rows;       // the SIMT engine guards rows itself: no stores beyond y
+    g.B = W; g.ldb = P.din;
+    EpiParams e; memset(&e, 0, sizeof(e));
+    e.bias = bias; e.out = y; e.ldo = P.dout;
+    launch_gemm_simt<CT, float, EPI_BIAS_F32, CT>(g, e, st);
+    LAUNCH_OK("producer gemm");
+  }
+  return MMR_OK;
+}
+
+}  // extern "C++"
+
+int mmr_producer_proj_fwd(const mmr_proj_dims* dims, const void* x, const float* ln_w, const float* ln_b, const float* W,
+                          const float* bias, float* y, void* saved, void* scratch, void* stream) {
+  ProjPlan P;
+  int rc = proj_plan(dims, &P);
+  if (rc) return rc;
+  if (!x || !W || !y || !saved || !scratch) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (P.ln && (!ln_w || !ln_b)) return fail(MMR_ERR_INVALID_ARG, "has_ln needs ln_w and ln_b");
+  if (P.bias && !bias) return fail(MMR_ERR_INVALID_ARG, "has_bias needs bias");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.bf16c) return proj_fwd_t<bf16>(P, x, ln_w, ln_b, W, P.bias ? bias : nullptr, y, (uint8_t*)saved, (uint8_t*)scratch, st);
+  return proj_fwd_t<float>(P, x, ln_w, ln_b, W, P.bias ? bias : nullptr, y, (uint8_t*)saved, (uint8_t*)scratch, st);
+}
+
+extern "C++" {
+template <class CT>
+static int proj_bwd_t(const ProjPlan& P, const void* x, const float* ln_w, const float* W, const float* dy, const uint8_t* saved,
+                      uint8_t* scratch, float* dx, float* d_ln_w, float* d_ln_b, float* dW, float* dbias, cudaStream_t st) {
+  const CT* xh = reinterpret_cast<const CT*>(saved + P.s_xh);
+  CT* dyc = reinterpret_cast<CT*>(scratch + P.b_dy);
+  float* dxh = reinterpret_cast<float*>(scratch + P.b_dxh);
+  const bool need_dx = dx != nullptr || (P.ln && (d_ln_w || d_ln_b));
+  {
+    int blocks = (int)(((size_t)P.rows_pad * P.dout / 4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cast_rows_kernel<CT><<<blocks, 256, 0, st>>>(dy, P.rows, P.rows_pad, P.dout, dyc);
+    LAUNCH_OK("cast dy");
+  }
+  float* dx_target = P.ln ? dxh : dx;       // without LayerNorm the data gradient is the GEMM output itself
+  if (need_dx && dx_target) {               // dxh[rows, d_in] = dy[rows, d_out] * W[d_out, d_in]
+    GemmProblem g; memset(&g, 0, sizeof(g));
+    g.segs = single_seg((int)P.rows, 1); g.segs.row0[1] = P.rows_pad;
+    g.N = P.din; g.K = P.dout; g.A = dyc; g.lda = P.dout;
+    if (P.tc) {
+      CT* wt = reinterpret_cast<CT*>(scratch + P.b_w);
+      PackJobs pj; memset(&pj, 0, sizeof(pj));
+      pj.n = 1;
+      pj.j[0] = PackJob{W, P.dout, P.din, P.din, nullptr, 1.0f, nullptr, 0, wt, P.dout};
+      pack_kernel<CT><<<dim3((P.dout / 32) * (P.din / 32), 1), 256, 0, st>>>(pj);
+      LAUNCH_OK("proj pack T");
+      g.B = wt; g.ldb = P.dout;
+      tc::TcEpi e; memset(&e, 0, sizeof(e));
+      e.out = dx_target; e.ldo = P.din; e.out_rows = P.ln ? P.rows_pad : (int)P.rows;
+      ProfScope ps(PC_GEMM_TC, st);
+      cudaError_t err = tc::launch_gemm_tc<tc::TEPI_F32>(g, e, P.rows_pad, P.din, st);
+      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 producer dgrad: ") + cudaGetErrorString(err));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      g.segs.row0[1] = (int)P.rows;
+      g.B = W; g.ldb = P.din;
+      EpiParams e; memset(&e, 0, sizeof(e));
+      e.out = dx_target; e.ldo = P.din;
+      launch_gemm_simt<CT, float, EPI_STORE_F32, CT, true>(g, e, st);
+      LAUNCH_OK("producer dgrad");
+    }
+  }
+  if (dW || (P.bias && dbias)) {            // dW[d_out, d_in] = dy^T xh, dbias = column sums of dy
+    WgradProblem w; memset(&w, 0, sizeof(w));
+    w.segs = single_seg((int)P.rows, 1); w.segs.row0[1] = P.rows_pad;
+    w.dY = dyc; w.ldy = P.dout; w.X = xh; w.ldx = P.din; w.M = P.dout; w.N = P.din; w.out[0] = dW; w.ldo = P.din;
+    bool fused_bias = false;
+    if (P.tc && dW) {
+      if (P.bias && dbias) { w.dbias[0] = dbias; w.colsum = 1; fused_bias = true; }
+      ProfScope ps(PC_WGRAD_TC, st);
+      cudaError_t err = tc::launch_wgrad_tc(w, P.rows_pad, P.rows_pad, st);
+      if (err != cudaSuccess) return fail(MMR_ERR_CUDA, std::string("tcgen05 producer wgrad: ") + cudaGetErrorString(err));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (dW) {
+      launch_wgrad_simt<CT, CT>(w, st);
+      LAUNCH_OK("producer wgrad");
+    }
+    if (P.bias && dbias && !fused_bias) {
+      float* o1[6] = {dbias, nullptr, nullptr, nullptr, nullptr, nullptr};
+      int rc = run_colsum<float>(single_seg((int)P.rows, 1), dy, P.dout, 0, P.dout, o1, 1.0f, st, "producer dbias");
+      if (rc) return rc;
+    }
+  }
+  if (P.ln && need_dx) {
+    ProjRowArgs a; memset(&a, 0, sizeof(a));
+    a.x = x; a.rows = P.rows; a.rows_pad = P.rows_pad; a.D = P.din; a.has_ln = 1; a.gamma = ln_w;
+    a.stat = const_cast<float*>(reinterpret_cast<const float*>(saved + P.s_stat));
+    a.dh = dxh; a.dx = dx; a.dgamma = d_ln_w; a.dbeta = d_ln_b;
+    int blocks = (int)((P.rows + 63) / 64);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const int rpb = (int)((P.rows + blocks - 1) / blocks);
+    if (P.xdt == MMR_DTYPE_F32) proj_rows_bwd_kernel<float><<<blocks, 256, 0, st>>>(a, rpb);
+    else proj_rows_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(a, rpb);
+    LAUNCH_OK("proj_rows_bwd");
+  }
+  return MMR_OK;
+}
+
+}  // extern "C++"
+
+int mmr_producer_proj_bwd(const mmr_proj_dims* dims, const void* x, const float* ln_w, const float* W, const float* dy,
+                          const void* saved, void* scratch, float* dx, float* d_ln_w, float* d_ln_b, float* dW, float* dbias,
+                          void* stream) {
+  ProjPlan P;
+  int rc = proj_plan(dims, &P);
+  if (rc) return rc;
+  if (!x || !W || !dy || !saved || !scratch) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (P.ln && !ln_w) return fail(MMR_ERR_INVALID_ARG, "has_ln needs ln_w");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (P.bf16c)
+    return proj_bwd_t<bf16>(P, x, ln_w, W, dy, (const uint8_t*)saved, (uint8_t*)scratch, dx, d_ln_w, d_ln_b, dW, dbias, st);
+  return proj_bwd_t<float>(P, x, ln_w, W, dy, (const uint8_t*)saved, (uint8_t*)scratch, dx, d_ln_w, d_ln_b, dW, dbias, st);
 }
 
 // ----------------------------------------------------------------------------- debug GEMM ---

@@ -204,6 +204,7 @@ struct TcEpi {
   int ld_bits;
   void* out;
   int ldo;
+  int out_rows;               // rows physically present in `out` (TMA store bound); 0 = the padded row space
   int dbg;                    // tuning experiments only (MMR_TC_DBG, tools/bench_gemm.py): 1 = epilogue drains TMEM but neither
                               // converts nor stores, 2 = no TMA / bit stores, 4 = epilogue only hands the buffer back
 };
@@ -756,7 +757,8 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   const int stages = stages_cfg < 1 ? 1 : (stages_cfg > max_stages ? max_stages : stages_cfg);
   constexpr bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
   CUtensorMap tmA, tmB, tmC;
-  if (!make_tmap(&tmC, e.out, (uint64_t)e.ldo, (uint64_t)g.segs.row0[g.segs.n], (uint64_t)e.ldo, f32_out ? 32 : 64, 32, f32_out))
+  const uint64_t c_rows = e.out_rows > 0 ? (uint64_t)e.out_rows : (uint64_t)g.segs.row0[g.segs.n];   // TMA clips rows beyond
+  if (!make_tmap(&tmC, e.out, (uint64_t)e.ldo, c_rows, (uint64_t)e.ldo, f32_out ? 32 : 64, 32, f32_out))
     return cudaErrorUnknown;
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;

@@ -257,12 +257,60 @@ def loss_cases():
     return out
 
 
+def proj_cases():
+    """Route-input projections: the reference's own constructor statements are executed as they are
+    (encoders.py `self.proj = nn.Sequential(nn.LayerNorm(hidden), nn.Linear(hidden, d, bias=False))` and
+    `self.token_proj = nn.Linear(self.token_in_dim, d, bias=False)`), then the resulting torch modules are applied as the
+    encoders do (`chunk_emb = self.proj(chunk_emb)`, `I_seq = self.token_proj(tokens)`).  To keep the fixture small the two
+    chunk cases share one module and the Linear weight gradient is stored as its first rows + (norm, random projection)."""
+    import types
+    ENC = "/root/reference/MIMIC-IV/MortModel/Paired_Cross_Attention/encoders.py"
+    out = {"state": {}}
+    gen = torch.Generator().manual_seed(9100)
+    mods = {}
+    for key, hidden in (("chunk", 768), ("token", 512)):
+        self = types.SimpleNamespace(token_in_dim=hidden)
+        ns = {"nn": torch.nn, "self": self, "hidden": hidden, "d": 256}
+        torch.manual_seed(9100 + hidden)
+        if key == "chunk":
+            a = _anchor(ENC, "self.proj = nn.Sequential(")
+            _inline(ENC, a, a + 3, ns)
+            mods[key] = self.proj
+            with torch.no_grad():        # move the LayerNorm affine away from (1, 0) so that its gradient paths are exercised
+                self.proj[0].weight.add_(0.1 * torch.randn(hidden, generator=gen))
+                self.proj[0].bias.add_(0.1 * torch.randn(hidden, generator=gen))
+        else:
+            a = _anchor(ENC, "self.token_proj = nn.Linear(")
+            _inline(ENC, a, a, ns)
+            mods[key] = self.token_proj
+        out["state"][key] = {k: v.detach().clone() for k, v in mods[key].state_dict().items()}
+    for name, key, rows_shape, hidden in (("chunk768", "chunk", (2, 16), 768), ("chunk768_ragged", "chunk", (37,), 768),
+                                          ("token512", "token", (2, 49), 512)):
+        mod = mods[key]
+        mod.zero_grad(set_to_none=True)
+        x = (torch.randn(*rows_shape, hidden, generator=gen) * 1.5 + 0.3).requires_grad_(True)
+        y = mod(x)
+        dy = torch.randn(y.shape, generator=gen)
+        y.backward(dy)
+        grads = {}
+        for k, v in mod.named_parameters():
+            g = v.grad.detach()
+            if g.dim() == 2:
+                pv = torch.randn(g.numel(), generator=torch.Generator().manual_seed(77)).double()
+                grads[k] = dict(head=g[:8].clone(), norm=float(g.double().norm()), proj=float(g.double().flatten() @ pv))
+            else:
+                grads[k] = g.clone()
+        out[name] = dict(module=key, x=x.detach(), y=y.detach(), dy=dy, dx=x.grad.detach(), grads=grads)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.save(route_mask_case(), os.path.join(GOLD, "tail_route_mask.pt"))
     torch.save(sanitize_cases(), os.path.join(GOLD, "tail_sanitize.pt"))
     torch.save(tail_case(), os.path.join(GOLD, "tail_adamw_ema.pt"))
     torch.save(loss_cases(), os.path.join(GOLD, "tail_loss.pt"))
+    torch.save(proj_cases(), os.path.join(GOLD, "tail_proj.pt"))
     for f in ("tail_sanitize.pt", "tail_adamw_ema.pt", "tail_loss.pt"):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -44,6 +44,17 @@ def sanitize_pheno(x: torch.Tensor) -> torch.Tensor:
     return torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
 
 
+def chunk_projection(x: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """`BioClinBERTEncoder.proj` = Sequential(LayerNorm(hidden), Linear(hidden, d, bias=False)),
+    MortModel/Paired_Cross_Attention/encoders.py:289-293, applied at :472-475."""
+    return torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (x.shape[-1],), ln_w, ln_b), W)
+
+
+def token_projection(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """`token_proj` = Linear(token_in_dim, d, bias=False), encoders.py:620, applied at :747-749."""
+    return torch.nn.functional.linear(x, W)
+
+
 # ---- training tail ------------------------------------------------------------------------------------
 def clip_grad_norm(grads: List[torch.Tensor], max_norm: float) -> float:
     """torch.nn.utils.clip_grad_norm_ (norm_type 2): total = ||(||g_i||)_i||, coef = clamp(max_norm/(total+1e-6), max=1),

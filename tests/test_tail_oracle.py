@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from helpers import ROOT
+from helpers import ROOT, max_rel
 from oracle import tail_oracle as to
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -197,3 +197,19 @@ def test_loss_argument_errors_match_the_reference_drivers():
     # well-formed CPU arguments pass validation and are refused by the device check
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         losses.pheno_train_loss(lg, y, torch.rand(4, 10, 25), torch.rand(4, 10), torch.ones(10))
+
+
+@pytest.mark.parametrize("name", ["chunk768", "chunk768_ragged", "token512"])
+def test_projection_oracle_matches_reference_modules(name):
+    """oracle chunk / token projections vs the outputs of the reference's own module definitions (tail_proj.pt)."""
+    gold = torch.load(os.path.join(GOLD, "tail_proj.pt"), weights_only=False)
+    c = gold[name]
+    st = gold["state"][c["module"]]
+    x = c["x"].clone().requires_grad_(True)
+    if c["module"] == "chunk":
+        y = to.chunk_projection(x, st["0.weight"], st["0.bias"], st["1.weight"])
+    else:
+        y = to.token_projection(x, st["weight"])
+    assert max_rel(y, c["y"]) < 1e-6
+    y.backward(c["dy"])
+    assert max_rel(x.grad, c["dx"]) < 1e-6

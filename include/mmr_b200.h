@@ -339,6 +339,14 @@ typedef struct mmr_loss_args {
 size_t mmr_loss_scratch_bytes(int B);
 int mmr_loss_fwd_bwd(const mmr_loss_args* args, void* stream);
 
+/* Evaluation-time routing statistics: replaces the per-batch `.cpu()` copies and host sums of
+ * evaluate_epoch (MortModel/Paired_Cross_Attention/main.py:1916-1933, 2013-2016).  Accumulates IN PLACE, on the device:
+ *   sums[0][r][k] += sum_b rc_raw[b][r][k]      sums[1][r][k] += sum_b rc_report[b][r][k]   (rc_report may be NULL)
+ *   sums[2][r][k] += sum_b rc_raw[b][r][k] * prim_acts[b][r]       sums[3*10*K + r] += sum_b prim_acts[b][r]
+ * sums: fp32 [3*10*K + 10], zero-initialised once per split; count (may be NULL): device uint64 += B.  rc_raw fp32 or bf16. */
+int mmr_routing_stats_accumulate(const void* rc_raw, int rc_dtype, const float* rc_report, const float* prim_acts, int B,
+                                 int K, float* sums, unsigned long long* count, void* stream);
+
 /* Unit-test hook for the GEMM engines: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) with bf16 (dtype 1)
  * or fp32 (dtype 0) operands, fp32 output.  trans=1 computes C[M,N] = A[Kr,M]^T * B[Kr,N]
  * (the weight-gradient form, reduction over rows). */

@@ -70,7 +70,8 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
            "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd",
            "mmr_fusion_pack_weights", "mmr_route_fusion_fwd_packed",
-           "mmr_producer_proj_sizes", "mmr_producer_proj_fwd", "mmr_producer_proj_bwd"]
+           "mmr_producer_proj_sizes", "mmr_producer_proj_fwd", "mmr_producer_proj_bwd",
+           "mmr_routing_stats_accumulate"]
 
 
 def lib_path() -> str:
@@ -130,6 +131,8 @@ def load():
     lib.mmr_producer_proj_fwd.restype = C.c_int
     lib.mmr_producer_proj_bwd.argtypes = [C.POINTER(ProjDims)] + [c_fp] * 12
     lib.mmr_producer_proj_bwd.restype = C.c_int
+    lib.mmr_routing_stats_accumulate.argtypes = [c_fp, C.c_int, c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp]
+    lib.mmr_routing_stats_accumulate.restype = C.c_int
     lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
     lib.mmr_debug_gemm.restype = C.c_int
     lib.mmr_bench_gemm.argtypes = [C.c_int] * 4 + [c_fp] * 5 + [C.c_int, C.POINTER(C.c_float), c_fp]

@@ -1417,6 +1417,19 @@ int mmr_projector_bwd(const mmr_routing_params* params, const float* route_embs,
   return MMR_OK;
 }
 
+int mmr_routing_stats_accumulate(const void* rc_raw, int rc_dtype, const float* rc_report, const float* prim_acts, int B,
+                                 int K, float* sums, unsigned long long* count, void* stream) {
+  if (!rc_raw || !prim_acts || !sums) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
+  if (B <= 0 || K < 1 || K > MMR_MAX_LABELS) return fail(MMR_ERR_INVALID_ARG, "bad batch / label count");
+  if (rc_dtype != MMR_DTYPE_F32 && rc_dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_UNSUPPORTED, "rc_raw must be fp32 or bf16");
+  RouteStatsArgs a; memset(&a, 0, sizeof(a));
+  a.rc_raw = rc_raw; a.rc_bf16 = rc_dtype == MMR_DTYPE_BF16; a.rc_report = rc_report; a.prim_acts = prim_acts;
+  a.B = B; a.K = K; a.sums = sums; a.count = count;
+  route_stats_kernel<<<10 * K + 10, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_OK("route_stats");
+  return MMR_OK;
+}
+
 // ------------------------------------------------------------ route-input producer projections ---
 struct ProjPlan {
   long long rows; int rows_pad, din, dout; bool ln, bias, bf16c, tc; int xdt;

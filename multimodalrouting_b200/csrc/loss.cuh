@@ -288,4 +288,47 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_stage2_kernel(LossArgs a
   }
 }
 
+// ---- evaluation-time routing statistics (first consumer) -------------------------------
+// evaluate_epoch (MortModel/Paired_Cross_Attention/main.py:1916-1933) copies rc_raw, rc_report and prim_acts of every batch to
+// the host and sums them there; here the three [10, K] sums (and the per-route activation sum) accumulate on the device and are
+// read once per split.  Block = (route, label) column, threads stride over the patients.
+struct RouteStatsArgs {
+  const void* rc_raw; int rc_bf16;     // [B, 10, K]
+  const float* rc_report;              // [B, 10, K] or null
+  const float* prim_acts;              // [B, 10]
+  int B, K;
+  float* sums;                         // [3, 10, K] += (raw, report, raw * act)   then [10] += act
+  unsigned long long* count;           // += B
+};
+__global__ void __launch_bounds__(256) route_stats_kernel(RouteStatsArgs a) {
+  __shared__ float red[3][8];
+  const int col = blockIdx.x, r = col / a.K;            // col = r * K + k; the last 10 blocks (col >= 10 K) sum the activations
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  if (col < 10 * a.K) {
+    for (int b = threadIdx.x; b < a.B; b += 256) {
+      const size_t i = (size_t)b * 10 * a.K + col;
+      const float raw = a.rc_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(a.rc_raw)[i])
+                                  : reinterpret_cast<const float*>(a.rc_raw)[i];
+      s0 += raw;
+      if (a.rc_report) s1 += a.rc_report[i];
+      s2 += raw * a.prim_acts[(size_t)b * 10 + r];
+    }
+  } else {
+    const int rr = col - 10 * a.K;
+    for (int b = threadIdx.x; b < a.B; b += 256) s0 += a.prim_acts[(size_t)b * 10 + rr];
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    const int n = 10 * a.K;
+    if (col < n) { a.sums[col] += t0; a.sums[n + col] += t1; a.sums[2 * n + col] += t2; }   // one block per address
+    else a.sums[3 * n + (col - n)] += t0;
+    if (col == 0 && a.count) *a.count += (unsigned long long)a.B;
+  }
+}
+
 }  // namespace mmr

@@ -304,6 +304,31 @@ def proj_cases():
     return out
 
 
+def route_stats_case():
+    """evaluate_epoch's per-batch accumulation, main.py `rc_raw_cpu = rc_raw.detach().float().cpu()` .. `eff_sum_mat += eff_sum`
+    (1918-1933), executed as it is over three batches (one with bf16 routing coefficients, as the autocast path returns them)."""
+    gen = torch.Generator().manual_seed(9200)
+    K = 25
+    a0 = _anchor(M_MAIN, "rc_raw_cpu    = rc_raw.detach().float().cpu()")
+    a1 = _anchor(M_MAIN, "eff_sum_mat    += eff_sum")
+    ns = {"torch": torch, "rc_raw_sum_mat": None, "rep_sum_mat": None, "eff_sum_mat": None}
+    batches, act_sum, n = [], torch.zeros(10), 0
+    for i, B in enumerate((7, 64, 33)):
+        raw = torch.softmax(torch.randn(B, 10, K, generator=gen), dim=1)
+        if i == 1:
+            raw = raw.bfloat16()
+        rep = torch.softmax(torch.randn(B, 10, K, generator=gen), dim=1)
+        pa = torch.rand(B, 10, generator=gen)
+        ns.update(rc_raw=raw, rc_report=rep, prim_acts=pa)
+        _inline(M_MAIN, a0, a1, ns)
+        act_sum += pa.sum(0)             # main.py: act_sum += prim_acts.sum(dim=0) in the same loop
+        n += B
+        batches.append(dict(rc_raw=raw, rc_report=rep, prim_acts=pa))
+    return dict(K=K, batches=batches, num_samples=n, rc_raw_sum=ns["rc_raw_sum_mat"], rc_report_sum=ns["rep_sum_mat"],
+                eff_sum=ns["eff_sum_mat"], prim_act_sum=act_sum,
+                avg_rc_report=ns["rep_sum_mat"] / max(1, n))    # main.py:2013-2014
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.save(route_mask_case(), os.path.join(GOLD, "tail_route_mask.pt"))
@@ -311,6 +336,7 @@ def main():
     torch.save(tail_case(), os.path.join(GOLD, "tail_adamw_ema.pt"))
     torch.save(loss_cases(), os.path.join(GOLD, "tail_loss.pt"))
     torch.save(proj_cases(), os.path.join(GOLD, "tail_proj.pt"))
+    torch.save(route_stats_case(), os.path.join(GOLD, "tail_route_stats.pt"))
     for f in ("tail_sanitize.pt", "tail_adamw_ema.pt", "tail_loss.pt"):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

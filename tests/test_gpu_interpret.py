@@ -34,8 +34,8 @@ def test_routing_stats_accumulate_like_evaluate_epoch():
     g.replay()
     torch.cuda.synchronize()
     res = acc.result()
-    assert res["num_samples"] == 3 * b["rc_raw"].shape[0]
-    assert max_rel(res["rc_raw_sum"], 3 * b["rc_raw"].float().sum(0).cpu()) < 2e-6
+    assert res["num_samples"] == 2 * b["rc_raw"].shape[0]          # warm-up call + one replay (the capture itself runs nothing)
+    assert max_rel(res["rc_raw_sum"], 2 * b["rc_raw"].float().sum(0).cpu()) < 2e-6
 
 
 def test_routing_stats_rejects_bad_shapes():

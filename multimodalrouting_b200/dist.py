@@ -59,12 +59,14 @@ def allreduce_gradients(modules: Iterable[torch.nn.Module], world_size: int = No
         # (ncclGroupStart / End): one launch instead of one per module
         try:
             from torch.distributed.distributed_c10d import _coalescing_manager
-            with _coalescing_manager(group=group, device=flats[0].device, async_ops=False):
+            cm = _coalescing_manager(group=group, device=flats[0].device, async_ops=False)
+        except (ImportError, TypeError):
+            cm = None              # older / different torch: one call per buffer below
+        if cm is not None:
+            with cm:               # (an error inside propagates: falling through would average twice)
                 for f in flats:
                     dist.all_reduce(f, op=dist.ReduceOp.AVG, group=group)
             return 1
-        except (ImportError, TypeError, RuntimeError):
-            pass                   # older / different torch: fall through to one call per buffer
     for f in flats:
         if nccl:                   # averaged inside the collective: no extra pass over the 79 MB buffer
             dist.all_reduce(f, op=dist.ReduceOp.AVG, group=group)

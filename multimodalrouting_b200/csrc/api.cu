@@ -219,7 +219,7 @@ static bool has_pad(const Segs& s) {
   return false;
 }
 static int zero_pad(const Segs& s, void* buf, size_t ld_bytes, cudaStream_t st) {
-  if (!has_pad(s)) return MMR_OK;
+  if (s.nv == nullptr && !has_pad(s)) return MMR_OK;     // packed query rows: the pad zone is data dependent, always run
   dim3 grid(255, s.n);
   zero_pad_rows_kernel<<<grid, 128, 0, st>>>(s, reinterpret_cast<uint8_t*>(buf), ld_bytes);
   LAUNCH_OK("zero_pad_rows");
@@ -292,6 +292,24 @@ static int pack_weights(const Plan& P, const void* const* prm, uint8_t* packed, 
   return MMR_OK;
 }
 
+// The query row space with its device-side row plan (Segs in mmr_common.cuh; the plan lives in `saved`).
+static Segs query_segs(const Plan& P, const uint8_t* saved) {
+  Segs Q = P.q;
+  const int* plan = reinterpret_cast<const int*>(saved + P.s_plan);
+  Q.nv = plan;
+  for (int d = 0; d < NDIR; ++d) {
+    Q.poff[d] = plan + P.p_poff[dir_qmod(d)];
+    Q.rowpat[d] = plan + P.p_rowpat[dir_qmod(d)];
+  }
+  return Q;
+}
+// MMR_VARLEN=0 keeps the dense query layout (every token has a row); the tcgen05 attention engine needs it (its 3-D
+// tensor maps address [patient][token][column]).
+static bool pack_query_rows(bool tc_attn) {
+  const char* e = getenv("MMR_VARLEN");
+  return !(e && e[0] == '0') && !tc_attn;
+}
+
 template <class CT>
 static int fusion_fwd(const Plan& P, const void* const* prm, const float* const x[3], const float* const mask[3],
                       const float* pos, uint8_t* packed, uint8_t* saved, uint8_t* scratch, float* routes,
@@ -301,6 +319,18 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
   int rc = do_pack ? pack_weights<CT>(P, prm, packed, st) : MMR_OK;   // else: `packed` holds mmr_fusion_pack_weights' output
   if (rc) return rc;
+  const Segs Q = query_segs(P, saved);
+  {  // row plan of the (packed) query space
+    RowPlanArgs a; memset(&a, 0, sizeof(a));
+    int* plan = reinterpret_cast<int*>(saved + P.s_plan);
+    a.B = B; a.pack = pack_query_rows(tc_attention<CT>()) ? 1 : 0; a.nv = plan;
+    for (int m = 0; m < NMOD; ++m) {
+      a.mask[m] = mask[m]; a.T[m] = P.T[m];
+      a.poff[m] = plan + P.p_poff[m]; a.tokrow[m] = plan + P.p_tokrow[m]; a.rowpat[m] = plan + P.p_rowpat[m];
+    }
+    rowplan_kernel<<<NMOD, 1024, 0, st>>>(a);
+    LAUNCH_OK("rowplan");
+  }
 
   float* fp = reinterpret_cast<float*>(scratch + P.f_p);
   float* fy = reinterpret_cast<float*>(scratch + P.f_y);
@@ -337,7 +367,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   // 2. embedding, unimodal encoders, normalised K/V stream, layer-0 query streams
   {
     EmbedArgs a; memset(&a, 0, sizeof(a));
-    a.mod = P.mod; a.q = P.q; a.pos = pos;
+    a.mod = P.mod; a.q = Q; a.pos = pos;
     for (int m = 0; m < NMOD; ++m) {
       a.src[m] = src[m]; a.mask[m] = mask[m];
       a.uni_g[m] = f(ix.uni_ln(m, 0)); a.uni_b[m] = f(ix.uni_ln(m, 1));
@@ -345,8 +375,11 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     for (int d = 0; d < NDIR; ++d) { a.ln0_g[d] = f(ix.layer(d, 0, 8)); a.ln0_b[d] = f(ix.layer(d, 0, 9)); }
     a.xh = xh; a.rstd_e = reinterpret_cast<float*>(saved + P.s_rstd_e); a.u = fu;
     a.xin0 = xin(0); a.h0 = h0(0); a.stat0 = stat0(0); a.maskq = maskq;
+    for (int m = 0; m < NMOD; ++m) a.tokrow[m] = reinterpret_cast<const int*>(saved + P.s_plan) + P.p_tokrow[m];
     embed_fwd_kernel<CT><<<P.MM / ROWS_PER_BLOCK, 256, 0, st>>>(a);
     LAUNCH_OK("embed_fwd");
+    rc = zero_pad(Q, h0(0), (size_t)D * sizeof(CT), st);     // layer-0 Q-projection operand: rows [nv, pad) must be zero
+    if (rc) return rc;
   }
   // 3. K/V projections of every layer at once (LN0 affine folded into the weights)
   {
@@ -362,15 +395,15 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   const float* kmask[NDIR];
   for (int d = 0; d < NDIR; ++d) kmask[d] = mask[dir_kmod(d)];
   int maxTq = 0;
-  for (int d = 0; d < NDIR; ++d) maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d];
+  for (int d = 0; d < NDIR; ++d) maxTq = maxTq > Q.T[d] ? maxTq : Q.T[d];
   CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_single_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
-    g.segs = P.q;
-    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
+    g.segs = Q;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = Q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
     g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = Bw; g.ldb = ldb;
     return g;
   };
@@ -385,7 +418,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     }
     {  // attention
       AttnArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.kv = P.kv;
+      a.q = Q; a.kv = P.kv;
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
       {
@@ -407,7 +440,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
         }
       }
       LAUNCH_OK("attn_fwd");
-      rc = zero_pad(P.q, ob(l), (size_t)D * sizeof(CT), st);
+      rc = zero_pad(Q, ob(l), (size_t)D * sizeof(CT), st);
       if (rc) return rc;
     }
     {  // out projection (+bias); the residual add + mask is fused into the LN1 kernel below
@@ -419,7 +452,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     }
     {  // x1 = (x + attn)*mask ; h1 = LN1(x1)*mask
       LnFwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.x = xin(l); a.delta = delta; a.x_out = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
+      a.q = Q; a.x = xin(l); a.delta = delta; a.x_out = x1(l); a.maskq = maskq; a.out = h1(l); a.stat = stat1(l);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l, 10)); a.beta[d] = f(ix.layer(d, l, 11)); }
       launch_k(ln_rows_fwd_kernel<CT, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
       LAUNCH_OK("ln1_fwd");
@@ -443,7 +476,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     }
     if (l + 1 < L) {  // x_{l+1} = (x1 + ffn)*mask ; h0 = LN0_{l+1}(x_{l+1})*mask
       LnFwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.x = x1(l); a.delta = delta; a.x_out = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
+      a.q = Q; a.x = x1(l); a.delta = delta; a.x_out = xin(l + 1); a.maskq = maskq; a.out = h0(l + 1); a.stat = stat0(l + 1);
       for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.layer(d, l + 1, 8)); a.beta[d] = f(ix.layer(d, l + 1, 9)); }
       launch_k(ln_rows_fwd_kernel<CT, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
       LAUNCH_OK("ln0_fwd");
@@ -451,7 +484,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   }
   {  // x_L = (x1 + ffn)*mask, then the encoder-final LayerNorm (transformer.py:108-113)
     LnFwdArgs a; memset(&a, 0, sizeof(a));
-    a.q = P.q; a.x = x1(L - 1); a.delta = delta; a.x_out = xin(L); a.maskq = maskq; a.out = fy;
+    a.q = Q; a.x = x1(L - 1); a.delta = delta; a.x_out = xin(L); a.maskq = maskq; a.out = fy;
     a.stat = reinterpret_cast<float*>(saved + P.s_statf);
     for (int d = 0; d < NDIR; ++d) { a.gamma[d] = f(ix.enc_ln(d, 0)); a.beta[d] = f(ix.enc_ln(d, 1)); }
     launch_k(ln_rows_fwd_kernel<float, CT>, dim3(P.MQ / ROWS_PER_BLOCK), dim3(256), 0, st, a);
@@ -459,7 +492,8 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   }
   {  // masked-mean pooling of the 9 uni/bi-modal routes
     PoolArgs a; memset(&a, 0, sizeof(a));
-    a.mod = P.mod; a.q = P.q; a.u = fu; a.y = fy; a.routes = routes; a.zcat = zcat; a.cnt = cnt; a.B = B;
+    a.mod = P.mod; a.q = Q; a.u = fu; a.y = fy; a.routes = routes; a.zcat = zcat; a.cnt = cnt; a.B = B;
+    a.maskq = maskq;
     for (int m = 0; m < NMOD; ++m) a.mask[m] = mask[m];
     pool_fwd_kernel<<<dim3(B, 9), 256, 0, st>>>(a);
     LAUNCH_OK("pool_fwd");
@@ -511,6 +545,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   };
   bool have_dw1 = false, have_dwq = false, have_dwo = false;
   const int L = P.L, B = P.B;
+  const Segs Q = query_segs(P, saved);
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
   auto gr = [&](int i) { return reinterpret_cast<float*>(grads[i]); };
   int rc;
@@ -597,7 +632,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   // ---- pooled gradient through the encoder-final LayerNorm ----
   {
     LnBwdArgs a; memset(&a, 0, sizeof(a));
-    a.q = P.q; a.x = xin(L); a.stat = reinterpret_cast<const float*>(saved + P.s_statf); a.maskq = maskq;
+    a.q = Q; a.x = xin(L); a.stat = reinterpret_cast<const float*>(saved + P.s_statf); a.maskq = maskq;
     a.ld2 = 512; a.g_in = nullptr; a.g_out = g_a; a.gc_out = gc;
     for (int d = 0; d < NDIR; ++d) {
       a.dz[d] = d_routes + (size_t)route_of_dir(d) * B * D;
@@ -615,7 +650,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   const float* kmask[NDIR];
   for (int d = 0; d < NDIR; ++d) kmask[d] = mask[dir_kmod(d)];
   int maxTq = 0, maxTk = 0;
-  for (int d = 0; d < NDIR; ++d) { maxTq = maxTq > P.q.T[d] ? maxTq : P.q.T[d]; maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d]; }
+  for (int d = 0; d < NDIR; ++d) { maxTq = maxTq > Q.T[d] ? maxTq : Q.T[d]; maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d]; }
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
@@ -624,15 +659,15 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
-    g.segs = P.q;
-    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = P.q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
+    g.segs = Q;
+    for (int d = 0; d < NDIR; ++d) { g.a_row0[d] = Q.row0[d]; g.b_row0[d] = (l * 6 + d) * nrows_b; }
     g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = Bw; g.ldb = ldb;
     return g;
   };
   auto q_wgrad = [&](const void* dY, int ldy, int M, const void* X, int ldx, int N) {
     WgradProblem w; memset(&w, 0, sizeof(w));
-    w.segs = P.q;
-    for (int d = 0; d < NDIR; ++d) w.x_row0[d] = P.q.row0[d];
+    w.segs = Q;
+    for (int d = 0; d < NDIR; ++d) w.x_row0[d] = Q.row0[d];
     w.dY = dY; w.ldy = ldy; w.X = X; w.ldx = ldx; w.M = M; w.N = N; w.ldo = N;
     return w;
   };
@@ -673,7 +708,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       const bool fused = fuse_colsum(P, w, ob1);
       rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_fc1");
       if (rc) return rc;
-      if (!fused) rc = run_colsum<CT>(P.q, dF, FF, 0, FF, ob1, 1.0f, ws, "b_fc1");
+      if (!fused) rc = run_colsum<CT>(Q, dF, FF, 0, FF, ob1, 1.0f, ws, "b_fc1");
       if (rc) return rc;
       rc = side_record(S_DW1);
       if (rc) return rc;
@@ -683,7 +718,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     gci ^= 1; gc = gcbuf[gci];
     {  // LN1 backward: g_oth = (g_cur + dLN1) * mask ; d out_proj.bias = colsum(g_oth)
       LnBwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.dh = dH; a.x = x1(l); a.stat = stat1(l); a.maskq = maskq; a.g_in = g_cur; a.g_out = g_oth; a.gc_out = gc;
+      a.q = Q; a.dh = dH; a.x = x1(l); a.stat = stat1(l); a.maskq = maskq; a.g_in = g_cur; a.g_out = g_oth; a.gc_out = gc;
       for (int d = 0; d < NDIR; ++d) {
         a.gamma[d] = f(ix.layer(d, l, 10));
         a.dgamma[d] = gr(ix.layer(d, l, 10)); a.dbeta[d] = gr(ix.layer(d, l, 11));
@@ -716,7 +751,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     if (have_dwq) { rc = main_wait(S_DWQ); if (rc) return rc; }   // dWq of the layer above still reads dQ
     {  // attention backward
       AttnArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.kv = P.kv;
+      a.q = Q; a.kv = P.kv;
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = const_cast<CT*>(ob(l));
       a.ml = const_cast<float*>(ml(l)); a.d_o = dO; a.dq = dQ; a.dkv = dKV; a.dvec = dvec;
@@ -742,7 +777,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       }
       LAUNCH_OK("attn_bwd_dq");
       LAUNCH_OK("attn_bwd_dkv");
-      rc = zero_pad(P.q, dQ, (size_t)D * sizeof(CT), st);
+      rc = zero_pad(Q, dQ, (size_t)D * sizeof(CT), st);
       if (rc) return rc;
     }
     rc = main_to_side(E_DQ);
@@ -761,7 +796,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       const bool fused = fuse_colsum(P, w, obq);
       rc = run_wgrad<CT>(P, w, P.MQ, P.MQ, ws, "w_q_proj");
       if (rc) return rc;
-      if (!fused) rc = run_colsum<CT>(P.q, dQ, D, 0, D, obq, 1.0f, ws, "b_q_proj");
+      if (!fused) rc = run_colsum<CT>(Q, dQ, D, 0, D, obq, 1.0f, ws, "b_q_proj");
       if (rc) return rc;
       rc = side_record(S_DWQ);
       if (rc) return rc;
@@ -772,7 +807,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     gci ^= 1; gc = gcbuf[gci];
     {  // LN0 backward: g_cur = (g_oth + dLN0) * mask ; d fc2.bias of the previous layer = colsum(g_cur)
       LnBwdArgs a; memset(&a, 0, sizeof(a));
-      a.q = P.q; a.dh = dH; a.x = xin(l); a.stat = stat0(l); a.maskq = maskq; a.g_in = g_oth; a.g_out = g_cur; a.gc_out = gc;
+      a.q = Q; a.dh = dH; a.x = xin(l); a.stat = stat0(l); a.maskq = maskq; a.g_in = g_oth; a.g_out = g_cur; a.gc_out = gc;
       for (int d = 0; d < NDIR; ++d) {
         a.gamma[d] = f(ix.layer(d, l, 8));
         a.dgamma[d] = gr(ix.layer(d, l, 8)); a.dbeta[d] = gr(ix.layer(d, l, 9));
@@ -839,7 +874,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   // ---- embedding backward ----
   {
     EmbedBwdArgs a; memset(&a, 0, sizeof(a));
-    a.mod = P.mod; a.q = P.q; a.kv = P.kv; a.xh = xh; a.rstd_e = reinterpret_cast<const float*>(saved + P.s_rstd_e);
+    a.mod = P.mod; a.q = Q; a.kv = P.kv; a.xh = xh; a.rstd_e = reinterpret_cast<const float*>(saved + P.s_rstd_e);
+    for (int m = 0; m < NMOD; ++m) a.tokrow[m] = reinterpret_cast<const int*>(saved + P.s_plan) + P.p_tokrow[m];
     a.g0 = g_cur; a.dxh = dxh; a.cnt = cnt; a.B = B;
     for (int m = 0; m < NMOD; ++m) {
       a.mask[m] = mask[m];

@@ -82,12 +82,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnArgs a) {
   float* Vs = smem + ATT_CHUNK * 256;        // [32][256]
   float* Ms = Vs + ATT_CHUNK * 256;          // [32] key keep flags
   const int d = blockIdx.z, b = blockIdx.y;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   if ((int)blockIdx.x * ATT_THREADS >= H * Tq) return;
   const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
   const bool active = i < H * Tq;
   const int h = active ? i / Tq : 0, t = active ? i % Tq : 0;
-  const size_t qrow = (size_t)a.q.row0[d] + (size_t)b * Tq + t;
+  const size_t qrow = (size_t)a.q.row0[d] + (size_t)qs_ + t;
   const CT* qb = reinterpret_cast<const CT*>(a.qb);
   const CT* kvb = reinterpret_cast<const CT*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
@@ -136,12 +138,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(AttnArgs a) {
   float* Vs = smem + ATT_CHUNK * 256;
   float* Ms = Vs + ATT_CHUNK * 256;
   const int d = blockIdx.z, b = blockIdx.y;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   if ((int)blockIdx.x * ATT_THREADS >= H * Tq) return;
   const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
   const bool active = i < H * Tq;
   const int h = active ? i / Tq : 0, t = active ? i % Tq : 0;
-  const size_t qrow = (size_t)a.q.row0[d] + (size_t)b * Tq + t;
+  const size_t qrow = (size_t)a.q.row0[d] + (size_t)qs_ + t;
   const CT* kvb = reinterpret_cast<const CT*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
   const float NEG = neg_fill<CT>();
@@ -187,7 +191,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(AttnArgs a) {
   float* Gs = smem + ATT_CHUNK * 256;         // [32][256] dO
   float* St = Gs + ATT_CHUNK * 256;           // [32][8][3]: m, 1/l, D
   const int d = blockIdx.z, b = blockIdx.y;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   if ((int)blockIdx.x * ATT_THREADS >= H * Tk) return;
   const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
   const bool active = i < H * Tk;
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(AttnArgs a) {
 #pragma unroll
   for (int c = 0; c < 32; ++c) { k[c] = 0.f; v[c] = 0.f; dk[c] = 0.f; dv[c] = 0.f; }
   if (active) { load32<CT>(kvb + h * HD, k); load32<CT>(kvb + D + h * HD, v); }
-  const size_t q0 = (size_t)a.q.row0[d] + (size_t)b * Tq;
+  const size_t q0 = (size_t)a.q.row0[d] + (size_t)qs_;
   const CT* qb = reinterpret_cast<const CT*>(a.qb) + q0 * D;
   const CT* gb = reinterpret_cast<const CT*>(a.d_o) + q0 * D;
   for (int i0 = 0; i0 < Tq; i0 += ATT_CHUNK) {

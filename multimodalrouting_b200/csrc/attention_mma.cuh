@@ -141,14 +141,16 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   pdl_trigger();
   pdl_wait();
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   const int q0 = qc * RC;
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
   const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
   const bf16* qsrc = reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS;
   const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
@@ -279,14 +281,16 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn
   bf16* Vs = Ks + RC * LDS;
   float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
-  const int Tq = a.q.T[d], nk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int nk = a.kv.T[d];
   const int q0 = qc * RC;
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
   const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
   const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
   const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
@@ -384,14 +388,16 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);
   float* St = Ms + RC;           // [64][HG][3]: m, 1/l, D
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   const int q0 = qc * RC;
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG;
   const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * Tq + q0;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
   const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * Tk) * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk : nullptr;
   const int nq16 = (nq + 15) & ~15;
@@ -511,7 +517,9 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   float* Ms = reinterpret_cast<float*>(Gs + RC * LDS);
   float* St = Ms + RC;           // [64 queries][HG][3]
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, kc = blockIdx.x / NHG;
-  const int Tq = a.q.T[d], Tk = a.kv.T[d];
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int Tk = a.kv.T[d];
   const int k0 = kc * RC;
   if (k0 >= Tk) return;
   const int nk = min(RC, Tk - k0);
@@ -519,7 +527,7 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   const int hl = warp % HG, half = warp / HG;
   const int g = lane >> 2, t = lane & 3;
   const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * Tk + k0;
-  const size_t qbase = (size_t)a.q.row0[d] + (size_t)b * Tq;
+  const size_t qbase = (size_t)a.q.row0[d] + (size_t)qs_;
   const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * Tk + k0 : nullptr;
   const int nk16 = (nk + 15) & ~15;
@@ -656,11 +664,13 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 640 / Cfg<HG>::THREADS) attn
   pdl_trigger();
   pdl_wait();
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x;
-  const int nq = a.q.T[d], nk = a.kv.T[d];
+  int qs_, nq;
+  seg_patient(a.q, d, b, qs_, nq);     // this patient's (packed) query rows
+  const int nk = a.kv.T[d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG;
   const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)b * nq;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_;
   const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * nk;
   const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * COLS;
   const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;

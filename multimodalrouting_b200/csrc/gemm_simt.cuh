@@ -20,7 +20,7 @@ __device__ __forceinline__ void gemm_simt_body(const GemmProblem& g, const EpiPa
   const int n0 = bx * 64;
   const int seg = seg_of_row(g.segs, m0);
   const int local0 = m0 - g.segs.row0[seg];
-  const int rows_valid = g.segs.rows[seg] - local0;  // may be <= 0 for pure padding tiles
+  const int rows_valid = seg_rows(g.segs, seg) - local0;  // may be <= 0 for pure padding tiles
   const TA* A = reinterpret_cast<const TA*>(g.A);
   const TB* B = reinterpret_cast<const TB*>(g.B);
   const int lm = t >> 2, lk = (t & 3) * 4;
@@ -174,7 +174,7 @@ __device__ __forceinline__ void wgrad_tile(const TY* dY, int ldy, const TX* X, i
 template <class TY, class TX>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradProblem w, int splits) {
   const int seg = blockIdx.z / splits, sp = blockIdx.z % splits;
-  const int rows = w.segs.rows[seg];
+  const int rows = seg_rows(w.segs, seg);
   const int chunk = (((rows + splits - 1) / splits) + 15) / 16 * 16;
   const int r_begin = sp * chunk;
   const int r_end = min(rows, r_begin + chunk);

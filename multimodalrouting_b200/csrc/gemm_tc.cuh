@@ -353,6 +353,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // work items: 128-row tiles (CL = 1) or 256-row tile pairs (CL = 2), n-block fastest
   const int nwork = ((g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM)) * nN;
   const int w0 = blockIdx.x / CL, wstep = gridDim.x / CL;
+  // packed query rows: the work items past a segment's valid rows (count in device memory) are skipped; the producer, the MMA
+  // issuer and the epilogue warps evaluate the same predicate, so their stage / accumulator counters stay in step
+  auto item_live = [&](int t) -> bool {
+    if (g.segs.nv == nullptr) return true;
+    const int mp = (t / nN) * CL * BM;
+    const int seg = seg_of_row(g.segs, mp);
+    return mp - g.segs.row0[seg] < seg_rows(g.segs, seg);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -382,6 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
       for (int t = w0; t < nwork; t += wstep) {
+        if (!item_live(t)) continue;
         const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN;
         const int seg = seg_of_row(g.segs, m0);
         const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
@@ -411,7 +420,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       uint32_t it = 0, i = 0;
-      for (int t = w0; t < nwork; t += wstep, ++i) {
+      for (int t = w0; t < nwork; t += wstep) {
+        if (!item_live(t)) continue;
         const uint32_t buf = i & 1;
         mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -435,6 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (CL == 2) umma_commit_pair(smem_u32(&ctrl->tfull[buf]));
         else umma_commit(smem_u32(&ctrl->tfull[buf]));
+        ++i;
       }
     }
   } else {
@@ -444,10 +455,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = bias_all + (warp - 2) * HC;
     const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
     uint32_t i = 0;
-    for (int t = w0; t < nwork; t += wstep, ++i) {
+    for (int t = w0; t < nwork; t += wstep) {
+      if (!item_live(t)) continue;
+      const uint32_t i_cur = i++;
       const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN + ch * HC;
       const int seg = seg_of_row(g.segs, m0);
-      const int rows_valid = g.segs.rows[seg] - (m0 - g.segs.row0[seg]);
+      const int rows_valid = seg_rows(g.segs, seg) - (m0 - g.segs.row0[seg]);
       const int lr = q * 32 + lane;                 // accumulator row owned by this thread
       const bool row_ok = lr < rows_valid;
       const bool zrow = (rows_valid < BM) && !row_ok;   // tile-uniform fast path when the tile has no padding rows
@@ -470,8 +483,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < HC / 32; ++j) bias_s[lane + 32 * j] = bsrc ? bsrc[lane + 32 * j] : 0.f;
         __syncwarp();
       }
-      const uint32_t buf = i & 1;
-      mbar_wait(smem_u32(&ctrl->tfull[buf]), (i >> 1) & 1);
+      const uint32_t buf = i_cur & 1;
+      mbar_wait(smem_u32(&ctrl->tfull[buf]), (i_cur >> 1) & 1);
       tc_fence_after();
       if (e.dbg & 4) {           // experiment: no drain at all
         tc_fence_before();
@@ -568,7 +581,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if (i < w.segs.n && (int)blockIdx.z >= sp_tab.first[i]) seg = i;
   const int sp = blockIdx.z - sp_tab.first[seg], splits = sp_tab.first[seg + 1] - sp_tab.first[seg];
   const int m0 = blockIdx.y * (MT * BM), n0 = blockIdx.x * BN;
-  const int rows_pad = w.segs.row0[seg + 1] - w.segs.row0[seg];   // multiple of 128; tail rows are zero
+  // reduction rows: the whole padded segment, or (packed query rows) the valid rows rounded up to a k-block -- rows
+  // [nv, pad256(nv)) are zero in both operands by the q-space contract
+  const int rows_pad = w.segs.nv ? (seg_rows(w.segs, seg) + BK - 1) / BK * BK : w.segs.row0[seg + 1] - w.segs.row0[seg];
   const int kb_total = rows_pad / BK;
   const int kb_per = (kb_total + splits - 1) / splits;
   const int kb_begin = sp * kb_per;

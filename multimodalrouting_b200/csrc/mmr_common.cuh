@@ -32,12 +32,39 @@ __host__ __device__ inline int dir_kmod(int d) {
 }
 
 // A set of up to 6 row segments laid out back to back (128-row aligned starts).
+//
+// Packed query rows (round 2): padded tokens of a query stream contribute nothing to the outputs or the gradients (every
+// q-space tensor is multiplied by the query keep-mask, transformer.py:77-79,111-113), so the query row space holds only the
+// VALID tokens of each patient, back to back.  Their number is data dependent and lives in device memory (one CUDA graph
+// serves every batch): `nv[d]` = valid rows of segment d, `poff[d][b]` = first row of patient b inside the segment
+// (`poff[d][B]` = nv[d]), `rowpat[d][j]` = patient of row j.  `rows[d]` / `T[d]` stay the static upper bounds (allocation, grid
+// sizes).  Null pointers = the dense layout (row = b * T + t): the modality and key/value row spaces, and the query space when
+// packing is off.  Contract for every q-space tensor: rows [nv, pad256(nv)) are zero, rows beyond are never touched.
 struct Segs {
   int n;
   int row0[7];   // padded start row of each segment; row0[n] = total padded rows
-  int rows[6];   // valid rows in the segment
-  int T[6];      // tokens per patient in this segment
+  int rows[6];   // valid rows in the segment (upper bound when nv != nullptr)
+  int T[6];      // tokens per patient in this segment (upper bound when poff != nullptr)
+  const int* nv;          // device [6] or null
+  const int* poff[6];     // device [B + 1] per segment or null
+  const int* rowpat[6];   // device [rows] per segment or null
 };
+
+__device__ __forceinline__ int seg_rows(const Segs& s, int d) { return s.nv ? s.nv[d] : s.rows[d]; }
+// rows [seg_rows, seg_rows_z) of a q-space tensor must be written as zeros (the tcgen05 tiles / CTA pairs read them)
+__device__ __forceinline__ int seg_rows_z(const Segs& s, int d) {
+  if (!s.nv) return s.row0[d + 1] - s.row0[d];
+  const int z = (s.nv[d] + 255) & ~255, cap = s.row0[d + 1] - s.row0[d];
+  return z < cap ? z : cap;
+}
+// first row (relative to the segment) and row count of patient b
+__device__ __forceinline__ void seg_patient(const Segs& s, int d, int b, int& start, int& len) {
+  if (s.poff[d]) { start = s.poff[d][b]; len = s.poff[d][b + 1] - start; }
+  else { start = b * s.T[d]; len = s.T[d]; }
+}
+__device__ __forceinline__ int seg_row_patient(const Segs& s, int d, int local) {
+  return s.rowpat[d] ? s.rowpat[d][local] : local / s.T[d];
+}
 
 __host__ __device__ inline int seg_of_row(const Segs& s, int row) {
   int d = 0;

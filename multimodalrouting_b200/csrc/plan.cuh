@@ -58,6 +58,11 @@ struct Plan {
   size_t s_epair;                         // fp32 [3,B,256] pair embeddings eLN,eLI,eNI
   size_t s_routes;                        // fp32 [10,B,256] copy of the outputs (pair/trimodal bwd)
   size_t s_cnt;                           // fp32 [3,B] valid-token counts (clamped >= 1)
+  // row plan of the packed query space (int32; written by rowplan_kernel in the forward, read by every q-space kernel of
+  // both passes): nv[8] | per query modality m: poff[B+1], tokrow[B*T_m] (token -> row inside the segment, -1 = padded),
+  // rowpat[B*T_m] (row -> patient)
+  size_t s_plan;
+  size_t p_poff[NMOD], p_tokrow[NMOD], p_rowpat[NMOD];   // int32 offsets from s_plan
   size_t saved_bytes;
 
   // ---- forward scratch ----------------------------------------------------------------------
@@ -141,6 +146,15 @@ inline bool build_plan(const mmr_fusion_dims* d, Plan* p, const char** why) {
   p->l_bits = align256(MQ * (FF / 32) * 4); p->s_bits = take(L * p->l_bits);
   p->s_kv = take(MK * L * 2 * D * ct);
   p->s_epair = take(3 * B * D * 4); p->s_routes = take(10 * B * D * 4); p->s_cnt = take(3 * B * 4);
+  {
+    size_t ints = 8;
+    for (int m = 0; m < NMOD; ++m) {
+      p->p_poff[m] = ints; ints += (size_t)B + 1;
+      p->p_tokrow[m] = ints; ints += (size_t)B * p->T[m];
+      p->p_rowpat[m] = ints; ints += (size_t)B * p->T[m];
+    }
+    p->s_plan = take(ints * 4);
+  }
   p->saved_bytes = o;
 
   o = 0;

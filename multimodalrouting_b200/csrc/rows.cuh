@@ -18,6 +18,71 @@ __host__ __device__ inline int pair_of_dir(int d) { const int t[6] = {0, 1, 0, 2
 __host__ __device__ inline int half_of_dir(int d) { const int t[6] = {0, 0, 1, 0, 1, 1}; return t[d]; }
 
 // -------------------------------------------------------------------------------------------
+// Row plan of the packed query space (see Segs in mmr_common.cuh).  One block per modality: counts the valid tokens of every
+// patient (mask != 0), scans the counts into patient offsets and fills the token <-> row maps.  pack = 0 writes the dense
+// identity plan (row = b * T + t for every token).
+struct RowPlanArgs {
+  const float* mask[NMOD];   // [B, T] or null
+  int T[NMOD];
+  int B, pack;
+  int* nv;                   // [8]: nv[d] = valid rows of direction d (query modality d >> 1)
+  int* poff[NMOD]; int* tokrow[NMOD]; int* rowpat[NMOD];
+};
+
+__global__ void __launch_bounds__(1024) rowplan_kernel(RowPlanArgs a) {
+  __shared__ int part[1024];
+  __shared__ int base_s;
+  const int m = blockIdx.x, T = a.T[m], B = a.B, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* mk = a.mask[m];
+  int* poff = a.poff[m];
+  const bool dense = !a.pack || mk == nullptr;
+  // 1. per-patient counts (a warp per patient) into poff[b + 1]
+  for (int b = warp; b < B; b += 32) {
+    int c = 0;
+    if (dense) c = T;
+    else {
+      for (int t = lane; t < T; t += 32) c += mk[(size_t)b * T + t] != 0.f ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) poff[b + 1] = c;
+  }
+  if (tid == 0) { poff[0] = 0; base_s = 0; }
+  __syncthreads();
+  // 2. inclusive scan of poff[1..B] in chunks of 1024
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    int v = b < B ? poff[b + 1] : 0;
+    part[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int add = tid >= o ? part[tid - o] : 0;
+      __syncthreads();
+      part[tid] += add;
+      __syncthreads();
+    }
+    if (b < B) poff[b + 1] = base_s + part[tid];
+    __syncthreads();
+    if (tid == 1023) base_s += part[1023];
+    __syncthreads();
+  }
+  if (tid == 0) { a.nv[2 * m] = base_s; a.nv[2 * m + 1] = base_s; if (m == 0) { a.nv[6] = 0; a.nv[7] = 0; } }
+  // 3. token <-> row maps (a warp per patient, tokens in order)
+  for (int b = warp; b < B; b += 32) {
+    int row = poff[b];
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      const bool ok = t < T && (dense || mk[(size_t)b * T + t] != 0.f);
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      const int rank = __popc(bal & ((1u << lane) - 1u));
+      if (t < T) a.tokrow[m][(size_t)b * T + t] = ok ? row + rank : -1;
+      if (ok) a.rowpat[m][row + rank] = b;
+      row += __popc(bal);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // embed: E = 16*p + pos[t]  (transformer.py:63-72);  unimodal encoder (0 layers) output
 // U = LN_uni(E*m)*m (transformer.py:77-79,108-113); normalised key/value stream XH = (E-mean)*rstd
 // (the affine part of each layer's LN0 is folded into the K/V weights); and for the two
@@ -31,6 +96,7 @@ struct EmbedArgs {
   const float* ln0_g[NDIR]; const float* ln0_b[NDIR];   // layer-0 LN0 of each direction
   void* xh; float* rstd_e; float* u;
   float* xin0; void* h0; float* stat0; float* maskq;
+  const int* tokrow[NMOD];     // token -> row inside the query segment (-1: padded token, no query row)
 };
 
 template <class CT>
@@ -73,10 +139,12 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int d = 2 * m + k;
-    const int qr = a.q.row0[d] + local;
+    const int qrl = valid ? a.tokrow[m][local] : -1;
+    if (qrl < 0) continue;      // padded token: no query row (the rows [nv, pad) of the segment are zeroed by zero_pad)
+    const int qr = a.q.row0[d] + qrl;
     Row8 x0 = z, h0 = z;
     float mu = 0.f, ru = 0.f;
-    if (valid) {
+    {
 #pragma unroll
       for (int i = 0; i < 8; ++i) x0.v[i] = e.v[i] * mval;
       row_stats(x0, mu, ru);
@@ -115,6 +183,18 @@ __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(LnFwdArgs a) {
   const int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= a.q.row0[a.q.n]) return;
   const int d = seg_of_row(a.q, r);
+  const int local = r - a.q.row0[d];
+  if (local >= seg_rows(a.q, d)) {       // not a query row: zero inside the tile-padding zone, untouched beyond it
+    if (local < seg_rows_z(a.q, d)) {
+      Row8 zr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zr.v[i] = 0.f;
+      if (a.delta) row_store<float>(a.x_out + (size_t)r * D, lane, zr);
+      row_store<OT>(reinterpret_cast<OT*>(a.out) + (size_t)r * D, lane, zr);
+      if (lane == 0) { a.stat[2 * (size_t)r] = 0.f; a.stat[2 * (size_t)r + 1] = 0.f; }
+    }
+    return;
+  }
   const float mval = a.maskq[r];
   Row8 x = row_load<float>(a.x + (size_t)r * D, lane);
   if (a.delta) {
@@ -168,7 +248,8 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(LnBwdArgs a) {
   for (int rr = warp; rr < RPB; rr += 8) {
     const int r = r0 + rr;
     const int local = r - a.q.row0[d];
-    const bool valid = local < a.q.rows[d];
+    const bool valid = local < seg_rows(a.q, d);
+    if (!valid && local >= seg_rows_z(a.q, d)) continue;     // beyond the tile-padding zone: never read by anyone
     const float mval = valid ? a.maskq[r] : 0.f;
     Row8 out;
 #pragma unroll
@@ -176,7 +257,7 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(LnBwdArgs a) {
     if (mval != 0.f) {
       Row8 dh;
       if (POOLED) {
-        const int b = local / a.q.T[d];
+        const int b = seg_row_patient(a.q, d, local);
         dh = row_load<float>(a.dz[d] + (size_t)b * D, lane);
         if (a.dz2[d]) {
           Row8 e2 = row_load<float>(a.dz2[d] + (size_t)b * a.ld2, lane);
@@ -239,6 +320,7 @@ struct PoolArgs {
   Segs mod, q;
   const float* u; const float* y;         // unimodal outputs (modality rows), final-LN outputs (q rows)
   const float* mask[NMOD];
+  const float* maskq;                     // [MQ] keep-mask value of every query row
   float* routes;                          // [10,B,256]
   float* zcat;                            // [3,B,512]
   float* cnt;                             // [3,B]
@@ -249,15 +331,19 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolArgs a) {
   const int b = blockIdx.x, which = blockIdx.y, c = threadIdx.x;   // which: 0..2 unimodal, 3..8 directions
   int mod, T, route;
   const float* src;
+  const float* mk;
   if (which < 3) {
     mod = which; T = a.mod.T[mod]; route = which;
     src = a.u + ((size_t)a.mod.row0[mod] + (size_t)b * T) * D;
-  } else {
+    mk = a.mask[mod] ? a.mask[mod] + (size_t)b * T : nullptr;
+  } else {                                  // the patient's (packed) query rows; masked tokens have no row and weight 0
     const int d = which - 3;
-    mod = dir_qmod(d); T = a.q.T[d]; route = route_of_dir(d);
-    src = a.y + ((size_t)a.q.row0[d] + (size_t)b * T) * D;
+    int start;
+    seg_patient(a.q, d, b, start, T);
+    mod = dir_qmod(d); route = route_of_dir(d);
+    src = a.y + ((size_t)a.q.row0[d] + start) * D;
+    mk = a.maskq + a.q.row0[d] + start;
   }
-  const float* mk = a.mask[mod] ? a.mask[mod] + (size_t)b * T : nullptr;
   float acc = 0.f, cnt = 0.f;
   for (int t = 0; t < T; ++t) {
     const float m = mk ? mk[t] : 1.f;
@@ -289,6 +375,7 @@ struct EmbedBwdArgs {
   const float* uni_g[NMOD];
   float* d_uni_g[NMOD]; float* d_uni_b[NMOD];
   float* dsrc[NMOD];               // fp32 [B*T,256] gradient wrt the (projected) inputs, or null
+  const int* tokrow[NMOD];         // token -> row inside the query segment (-1: padded token)
   int B;
 };
 
@@ -335,8 +422,15 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdArgs a) {
     for (int i = 0; i < 8; ++i) { s1 += gt[i]; s2 += gt[i] * xh.v[i]; }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
-    Row8 qa = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m] + local) * D, lane);
-    Row8 qb = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m + 1] + local) * D, lane);
+    const int qrl = a.tokrow[m][local];
+    Row8 qa, qb;
+    if (qrl >= 0) {
+      qa = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m] + qrl) * D, lane);
+      qb = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m + 1] + qrl) * D, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { qa.v[i] = 0.f; qb.v[i] = 0.f; }
+    }
     Row8 o;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -377,21 +471,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
   float* dst = a.colblock > 0 ? a.out[c / a.colblock] : a.out[seg];
   if (dst == nullptr) return;
   dst += a.colblock > 0 ? c % a.colblock : c;
-  const int r_end = min(r0 + 128, a.segs.row0[seg] + a.segs.rows[seg]);
+  const int r_end = min(r0 + 128, a.segs.row0[seg] + seg_rows(a.segs, seg));
   const T* p = reinterpret_cast<const T*>(a.src) + a.col0 + c;
   float s = 0.f;
   for (int r = r0; r < r_end; ++r) s += to_f<T>(p[(size_t)r * a.ld]);
   atomicAdd(dst, s * a.scale);
 }
 
-// Zero the padding rows [rows, pad_seg(rows)) of every segment of a [*, ld_bytes] buffer.
+// Zero the tile-padding rows [seg_rows, seg_rows_z) of every segment of a [*, ld_bytes] buffer (grid.x rows per pass).
 __global__ void zero_pad_rows_kernel(Segs s, uint8_t* buf, size_t ld_bytes) {
   const int seg = blockIdx.y;
-  const int npad = (s.row0[seg + 1] - s.row0[seg]) - s.rows[seg];
-  const int pr = blockIdx.x;
-  if (pr >= npad) return;
-  uint4* row = reinterpret_cast<uint4*>(buf + ((size_t)s.row0[seg] + s.rows[seg] + pr) * ld_bytes);
-  for (size_t i = threadIdx.x; i < ld_bytes / 16; i += blockDim.x) row[i] = make_uint4(0, 0, 0, 0);
+  const int r_begin = seg_rows(s, seg), r_end = seg_rows_z(s, seg);
+  for (int pr = r_begin + blockIdx.x; pr < r_end; pr += gridDim.x) {
+    uint4* row = reinterpret_cast<uint4*>(buf + ((size_t)s.row0[seg] + pr) * ld_bytes);
+    for (size_t i = threadIdx.x; i < ld_bytes / 16; i += blockDim.x) row[i] = make_uint4(0, 0, 0, 0);
+  }
 }
 
 // -------------------------------------------------------------------------------------------

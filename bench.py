@@ -56,12 +56,13 @@ def peaks():
     return 1663.5, 1402.1, 6548.5, "fallback (B200_PROFILING.md / the pool's last measured peaks)"
 
 
-def gemm_flops_per_step(B):
-    """Algorithmic FLOPs of the tensor-core GEMMs (valid rows only), by class."""
+def gemm_flops_per_step(B, q_rows=None):
+    """FLOPs of the tensor-core GEMMs by class.  q_rows = {"l": n, "n": n, "i": n}: query rows actually processed per
+    modality (packed layout: the valid tokens); default: every token (the algorithmic count of SURVEY.md section 8d)."""
     d, f, L = 256, 1024, LAYERS
     T = {"l": WL["TL"], "n": WL["TN"], "i": WL["TI"]}
     dirs = [("l", "n"), ("l", "i"), ("n", "l"), ("n", "i"), ("i", "l"), ("i", "n")]
-    mq = sum(B * T[q] for q, _ in dirs)
+    mq = sum((q_rows[q] if q_rows else B * T[q]) for q, _ in dirs)
     mk = sum(B * T[k] for _, k in dirs)
     fwd_tn = L * mq * (2 * d * d + 2 * d * d + 2 * d * f + 2 * f * d) + mk * 2 * d * (L * 2 * d)
     bwd_tn = fwd_tn            # data gradients mirror the forward GEMMs
@@ -550,7 +551,10 @@ def main():
             _teardown(dist, reducer)
         return
     tf_burst, tf_sust, hbm_peak, src = peaks()
-    fl_tn, fl_wg = gemm_flops_per_step(B)
+    packed = os.environ.get("MMR_VARLEN", "1") != "0" and os.environ.get("MMR_ATTN") != "tc"
+    q_rows = {k: (int((inp[m] != 0).sum()) if packed else B * WL[t]) for k, m, t in (("l", "mL", "TL"), ("n", "mN", "TN"), ("i", "mI", "TI"))}
+    q_dense = {"l": B * WL["TL"], "n": B * WL["TN"], "i": B * WL["TI"]}
+    fl_tn, fl_wg = gemm_flops_per_step(B, q_rows)           # FLOPs the kernels execute (valid query rows)
     t_tn = prof["gemm_tc"]["ms_per_step"] / 1e3
     n_tn = max(prof["gemm_tc"]["launch_groups_per_step"], 1)
     achieved = fl_tn / t_tn / 1e12 if t_tn > 0 else 0.0
@@ -564,6 +568,7 @@ def main():
                 "frac_of_sustained": achieved / tf_sust,
                 "avg_launch_ms": 1e3 * t_tn / n_tn, "launches_per_step": n_tn,
                 "flops_per_launch": fl_tn / n_tn,
+                "flops_counted": "executed by the kernels: packed query rows (valid tokens), dense key/value rows",
                 "wgrad_tc_tflops": (fl_wg / (prof["wgrad_tc"]["ms_per_step"] / 1e3) / 1e12) if prof["wgrad_tc"]["ms_per_step"] > 0 else None,
                 "whole_step_frac_of_tensor_roofline": (value / world) * total_flops_per_patient() / 1e12 / tf_sust,
                 "whole_step_peak": tf_sust,
@@ -603,6 +608,10 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WL["name"], "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": graphed is not None,
+                       "query_rows": (f"packed: {2 * sum(q_rows.values())} of {2 * sum(q_dense.values())} query rows hold a valid "
+                                      f"token (padded tokens contribute nothing to outputs or gradients and get no row); "
+                                      f"the whole-step roofline fraction still counts the dense FLOPs of SURVEY 8d"
+                                      if packed else "dense (MMR_VARLEN=0)"),
                        "packed_weights": ("packed once per parameter version (no optimizer update inside the benchmark step)"
                                           if mult.static_weights else "re-packed inside every step"),
                        "wgrad_side_stream": os.environ.get("MMR_WGRAD_STREAM", "1") != "0",

@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
       }
     }
   }
+  cp_async_wait_all();     // a patient without query rows (packed layout) never entered the loop: K / V may still be landing
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 2; ++i) {

@@ -332,3 +332,39 @@ def test_fp32_edge_shapes_vs_oracle(cfg):
     for n, p in [(n, p) for m in (mult, proj, head) for n, p in m.named_parameters()] + list(xb.items()):
         gg = p.grad
         assert gg is None or bool(torch.isfinite(gg).all()), n
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_packed_query_rows_match_dense_layout_and_oracle(autocast, monkeypatch):
+    """Packed query rows (only valid tokens get a row in the query space; csrc/mmr_common.cuh Segs) against the dense layout
+    (MMR_VARLEN=0) and the oracle, with masks that are NOT prefixes: holes, a patient without any valid L / N / I token, a
+    patient with every token valid, a single valid token."""
+    from oracle import synth
+    c = dict(variant="pheno", K=5, orig_d_n=256, B=6, seed=2024, sharp=1.0, temp=1.0, detach=False, missing=False,
+             mask_mode="full", TL=37, TN=9, TI=18)
+    sdm, sdp, sdh, inp = rebuild_case(c)
+    g = torch.Generator().manual_seed(99)
+    for key, T in (("mL", 37), ("mN", 9), ("mI", 18)):
+        m = (torch.rand(6, T, generator=g) < 0.6).float()
+        m[0] = 0.0                       # no valid token at all
+        m[1] = 1.0                       # every token valid
+        m[2] = 0.0; m[2, T // 2] = 1.0   # a single valid token in the middle
+        inp[key] = m
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MMR_VARLEN", mode)
+        outs[mode] = run_case(c, sdm, sdp, sdh, inp, autocast=autocast)
+    monkeypatch.delenv("MMR_VARLEN")
+    a, b = outs["1"], outs["0"]
+    tol = 2e-2 if autocast else 1e-4
+    for key in ("routes", "logits", "alpha", "R"):
+        assert max_rel(a[key], b[key]) < (1e-3 if autocast else 1e-5), key      # same per-row arithmetic, only the row order differs
+    r32, g32 = oracle_run(c, sdm, sdp, sdh, inp, None, torch.float32)
+    for key in ("routes", "logits", "alpha", "R"):
+        assert max_rel(a[key], r32[key]) < tol, key
+    for k, t in g32.items():
+        if t is None:
+            assert a["grads"][k] is None, k
+            continue
+        assert rel_err(a["grads"][k], b["grads"][k]) < (3e-2 if autocast else 1e-4), f"packed vs dense grad {k}"
+        assert rel_err(a["grads"][k], t) < (8e-2 if autocast else 5e-4), f"grad {k}"

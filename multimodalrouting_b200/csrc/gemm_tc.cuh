@@ -351,15 +351,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks = g.K / BK;
   const int nN = g.N / BN;
   // work items: 128-row tiles (CL = 1) or 256-row tile pairs (CL = 2), n-block fastest
-  const int nwork = ((g.segs.row0[g.segs.n] + CL * BM - 1) / (CL * BM)) * nN;
+  // Work items = the 128-row tiles (CL = 1) / 256-row tile pairs (CL = 2) that hold valid rows, n-block fastest, enumerated
+  // segment by segment.  With packed query rows the valid-row counts live in device memory; every role (producer, MMA issuer,
+  // epilogue warps) derives the same list, so the stage / accumulator counters stay in step and the static round-robin over the
+  // CTAs is balanced to within one item.
+  int vt0[7];
+  vt0[0] = 0;
+#pragma unroll
+  for (int sgi = 0; sgi < 6; ++sgi) {
+    const int rows_s = sgi < g.segs.n ? (g.segs.nv ? seg_rows(g.segs, sgi) : g.segs.row0[sgi + 1] - g.segs.row0[sgi]) : 0;
+    vt0[sgi + 1] = vt0[sgi] + (rows_s + CL * BM - 1) / (CL * BM);
+  }
+  const int nwork = vt0[6] * nN;
   const int w0 = blockIdx.x / CL, wstep = gridDim.x / CL;
-  // packed query rows: the work items past a segment's valid rows (count in device memory) are skipped; the producer, the MMA
-  // issuer and the epilogue warps evaluate the same predicate, so their stage / accumulator counters stay in step
-  auto item_live = [&](int t) -> bool {
-    if (g.segs.nv == nullptr) return true;
-    const int mp = (t / nN) * CL * BM;
-    const int seg = seg_of_row(g.segs, mp);
-    return mp - g.segs.row0[seg] < seg_rows(g.segs, seg);
+  // first row (of the tile / tile pair) of work item t
+  auto item_row = [&](int t) -> int {
+    const int mt = t / nN;
+    int sg = 0;
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+      if (mt >= vt0[i]) sg = i;
+    return g.segs.row0[sg] + (mt - vt0[sg]) * CL * BM;
   };
 
   if (threadIdx.x == 0) {
@@ -390,8 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
       for (int t = w0; t < nwork; t += wstep) {
-        if (!item_live(t)) continue;
-        const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN;
+        const int m0 = item_row(t) + (int)rank * BM, n0 = (t % nN) * BN;
         const int seg = seg_of_row(g.segs, m0);
         const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
         const int b_row = g.b_row0[seg] + n0 + (int)rank * (BN / CL);
@@ -421,7 +432,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       uint32_t it = 0, i = 0;
       for (int t = w0; t < nwork; t += wstep) {
-        if (!item_live(t)) continue;
         const uint32_t buf = i & 1;
         mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -456,9 +466,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
     uint32_t i = 0;
     for (int t = w0; t < nwork; t += wstep) {
-      if (!item_live(t)) continue;
       const uint32_t i_cur = i++;
-      const int m0 = ((t / nN) * CL + (int)rank) * BM, n0 = (t % nN) * BN + ch * HC;
+      const int m0 = item_row(t) + (int)rank * BM, n0 = (t % nN) * BN + ch * HC;
       const int seg = seg_of_row(g.segs, m0);
       const int rows_valid = seg_rows(g.segs, seg) - (m0 - g.segs.row0[seg]);
       const int lr = q * 32 + lane;                 // accumulator row owned by this thread

@@ -561,8 +561,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 TN GEMM, all six directions per launch)",
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                 # dram__bytes_read.sum + dram__bytes_write.sum averaged over the 34 gemm_tc launches of one step,
-                # ncu --set full (profiles/r1_gemm_step.md); algorithmic bytes are 231 MB per launch
-                "traffic": 192.5e6, "traffic_unit": "bytes per launch (ncu dram read+write, mean of the 34 launches of a step)",
+                # ncu --set full (profiles/r2_gemm_step.md, packed query rows; algorithmic bytes ~195 MB per launch).
+                # Other workloads / the dense layout were not captured: null there.
+                "traffic": 161.0e6 if (args.config == "pheno512" and packed and B == 512) else None,
+                "traffic_unit": "bytes per launch (ncu dram read+write, mean of the 34 launches of a step)",
                 "peak_source": f"{src} BURST bf16 (MEASURED_PEAKS.json bf16_tflops): the class is timed alone, eagerly, in a "
                                f"~0.1 s region; frac_of_sustained uses bf16_tflops_sustained",
                 "frac_of_sustained": achieved / tf_sust,

@@ -177,6 +177,9 @@ typedef struct mmr_routing_grads {   /* zero-initialised fp32 accumulators; NULL
 } mmr_routing_grads;
 
 size_t mmr_routing_scratch_bytes(const mmr_routing_dims* dims);
+/* scratch of mmr_capsule_routing_fwd_ex (projector outputs, head matrix and the fp16 votes of the batch: 20 * K * 64 bytes
+ * per patient + ~1.4 KB) */
+size_t mmr_routing_fwd_scratch_bytes(const mmr_routing_dims* dims);
 
 /* Packs capsule.w (and, when params->proj_w[0] != NULL and proj_w_f16 != NULL, the projector weights) into the fp16
  * layouts above.  caps_wt_f16 and caps_w_f16 need 10*K*64*32*2 bytes each, proj_w_f16 10*40*256*2 bytes (16-byte aligned, caller-owned).
@@ -195,6 +198,17 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
                             const float* acts_override, const float* route_mask,
                             float* logits, float* alpha, float* R, float* poses_out,
                             float* acts_out, void* stream);
+
+/* Same call with a caller-owned scratch buffer (mmr_routing_fwd_scratch_bytes, 256-byte aligned; NULL = the call above).
+ * With scratch, vote_dtype = MMR_DTYPE_BF16, the fp16 weight copies and num_routing <= 3 the work is split into
+ * projector / vote GEMM launches over 16-patient tiles and an agreement kernel that gives every patient its own 1-4 warps
+ * (csrc/routing_split.cuh); the backward takes the same path on its own from mmr_routing_scratch_bytes.  MMR_RT_SPLIT=0
+ * in the environment keeps both on the tile-of-4 kernels. */
+int mmr_capsule_routing_fwd_ex(const mmr_routing_dims* dims, const mmr_routing_params* params,
+                               const float* route_embs, const float* poses_in, const float* acts_in,
+                               const float* acts_override, const float* route_mask,
+                               float* logits, float* alpha, float* R, float* poses_out,
+                               float* acts_out, void* scratch, void* stream);
 
 /* Backward: d_logits [B,K], d_R [B,10,K] or NULL.  d_route_embs uses the same strides as
  * route_embs; d_poses [B,10,32] / d_acts [B,10] are written when from_poses=1.  With from_poses=0 and acts_override

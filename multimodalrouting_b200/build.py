@@ -13,7 +13,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libmmr_b200.so")
 SOURCES = ["api.cu"]
 HEADERS = ["mmr_common.cuh", "epilogue.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "plan.cuh", "rows.cuh",
-           "attention.cuh", "attention_mma.cuh", "attention_tc.cuh", "routing.cuh", "tail.cuh", "loss.cuh", os.path.join("..", "..", "include", "mmr_b200.h")]
+           "attention.cuh", "attention_mma.cuh", "attention_tc.cuh", "routing.cuh", "routing_split.cuh", "projector.cuh", "producer.cuh", "tail.cuh", "loss.cuh", os.path.join("..", "..", "include", "mmr_b200.h")]
 
 
 def _nvcc() -> str:

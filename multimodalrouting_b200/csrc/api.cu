@@ -12,6 +12,7 @@
 #include "mmr_common.cuh"
 #include "plan.cuh"
 #include "routing.cuh"
+#include "routing_split.cuh"
 #include "rows.cuh"
 #include "attention_tc.cuh"
 #include "tail.cuh"
@@ -656,6 +657,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
+  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_w_kernel<AHG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
+  static const int bwd_wph = [] { const char* e = getenv("MMR_ATTN_BWD_WPH"); return e ? atoi(e) : 2; }();
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -760,6 +763,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         if (mma_attention<CT>()) {
           if (maxTq <= amma::RC && maxTk <= amma::RC && !getenv("MMR_ATTN_BWD_SPLIT")) {
             // one chunk per sequence: fused dQ + dK/dV kernel (operands staged once, no O / D round trip)
+            if (bwd_wph == 3)
+              launch_k(amma::attn_bwd_fused_w_kernel<AHG, 3>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(AHG * 96),
+                       amma::bwd_fused_smem<AHG>(), st, a);
+            else
             launch_k(amma::attn_bwd_fused_kernel<AHG>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(amma::Cfg<AHG>::THREADS),
                      amma::bwd_fused_smem<AHG>(), st, a);
           } else {
@@ -1080,8 +1087,8 @@ int mmr_abi_struct_sizes(size_t* out, int n) {
 }
 
 // 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd); 102: + standalone projector, packed-weight
-// forward, producer projections
-int mmr_version(void) { return 102; }
+// forward, producer projections; 103: + mmr_capsule_routing_fwd_ex / mmr_routing_fwd_scratch_bytes (split routing path)
+int mmr_version(void) { return 103; }
 
 long long mmr_launch_count(void) { return g_launches.load(); }
 
@@ -1232,10 +1239,19 @@ static int check_routing(const mmr_routing_dims* d) {
   return MMR_OK;
 }
 
+// backward scratch: du | dpc | posem | dG | (split path) pose | zl | G | votes | dposeA;  forward scratch: pose | zl | G | votes
+static size_t rs_fwd_scratch(size_t B, size_t K) {
+  return align256(B * 320 * 4) + align256(B * 10 * 4) + align256(K * 32 * 4) + align256(B * 10 * K * 64 * 2);
+}
 size_t mmr_routing_scratch_bytes(const mmr_routing_dims* d) {
   if (!d || d->B <= 0 || d->K < 1) return 0;
   const size_t B = d->B, K = d->K;
-  return align256(B * 10 * K * 64 * 4) + align256(B * 330 * 4) + align256(B * 320 * 4) + align256(K * 32 * 4) + 256;
+  return align256(B * 10 * K * 64 * 4) + align256(B * 330 * 4) + align256(B * 320 * 4) + align256(K * 32 * 4) +
+         rs_fwd_scratch(B, K) + align256(B * 320 * 4) + align256((size_t)RS_GCOPIES * (K + 1) * 32 * 4) + 256;
+}
+size_t mmr_routing_fwd_scratch_bytes(const mmr_routing_dims* d) {
+  if (!d || d->B <= 0 || d->K < 1) return 0;
+  return rs_fwd_scratch(d->B, d->K) + 256;
 }
 
 }  // extern "C"
@@ -1293,6 +1309,63 @@ static cudaError_t dispatch_routing(const RoutingArgs& a, const RtLaunch& L, boo
   return cudaErrorInvalidValue;
 }
 
+// ---- split path (routing_split.cuh): projector / votes GEMMs + one patient per 1-4 warps for the agreement iterations ----
+static bool rs_enabled(const mmr_routing_dims* d, const mmr_routing_params* p, const void* scratch) {
+  static const bool on = [] { const char* e = getenv("MMR_RT_SPLIT"); return !(e && atoi(e) == 0); }();
+  return on && scratch && d->vote_dtype == MMR_DTYPE_BF16 && p->caps_wt_f16 && p->caps_w_f16 &&
+         (d->from_poses || p->proj_w_f16) && d->num_routing <= RS_NIT;
+}
+static uint8_t* rs_carve_fwd(uint8_t* s, size_t B, size_t K, RsScratch* o) {
+  o->pose = reinterpret_cast<float*>(s); s += align256(B * 320 * 4);
+  o->zl = reinterpret_cast<float*>(s); s += align256(B * 10 * 4);
+  o->G = reinterpret_cast<float*>(s); s += align256(K * 32 * 4);
+  o->votes = reinterpret_cast<__half*>(s); s += align256(B * 10 * K * 64 * 2);
+  o->dposeA = nullptr; o->dGc = nullptr;
+  return s;
+}
+template <int KP>
+static cudaError_t rs_launch_iterate(const RoutingArgs& a, const RsScratch& sc, bool bwd, cudaStream_t st) {
+  using C = RsCfg<KP>;
+  const size_t per = (rs_patient_smem(a.d.K, KP, C::NW) + 15) / 16 * 16, smem = per * C::PPC;
+  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+  const int cap = bwd ? RS_BWD_MINB : 4;
+  per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
+  const int units = (a.d.B + C::PPC - 1) / C::PPC;
+  const int grid = units < 148 * per_sm ? units : 148 * per_sm;
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(rs_iterate_bwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rs_iterate_bwd_kernel<KP><<<grid, 128, smem, st>>>(a, sc);
+  } else {
+    e = cudaFuncSetAttribute(rs_iterate_fwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rs_iterate_fwd_kernel<KP><<<grid, 128, smem, st>>>(a, sc);
+  }
+  return cudaGetLastError();
+}
+static cudaError_t rs_dispatch_iterate(const RoutingArgs& a, const RsScratch& sc, bool bwd, cudaStream_t st) {
+  const int K = a.d.K;
+  if (K <= 2) return rs_launch_iterate<2>(a, sc, bwd, st);
+  if (K <= 4) return rs_launch_iterate<4>(a, sc, bwd, st);
+  if (K <= 8) return rs_launch_iterate<8>(a, sc, bwd, st);
+  if (K <= 16) return rs_launch_iterate<16>(a, sc, bwd, st);
+  return rs_launch_iterate<32>(a, sc, bwd, st);
+}
+// projector (+ G) and votes; returns the number of launches through *n
+static cudaError_t rs_launch_front(const RoutingArgs& a, const RsScratch& sc, cudaStream_t st, int* n) {
+  const int tiles = (a.d.B + 15) / 16, NU = a.d.K * 4;
+  rs_project_kernel<<<dim3(a.d.from_poses ? 1 : tiles, 11), 128, 0, st>>>(a, sc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int S = (2 * 148 + tiles - 1) / tiles;
+  if (S > NU / 8) S = NU / 8;
+  if (S < 1) S = 1;
+  rs_votes_kernel<<<dim3(tiles, S), 256, 0, st>>>(a, sc);
+  *n += 2;
+  return cudaGetLastError();
+}
+
 extern "C" {
 
 int mmr_routing_pack_weights(const mmr_routing_params* params, int K, void* caps_wt_f16, void* caps_w_f16,
@@ -1314,6 +1387,14 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
                             const float* poses_in, const float* acts_in, const float* acts_override,
                             const float* route_mask, float* logits, float* alpha, float* R, float* poses_out,
                             float* acts_out, void* stream) {
+  return mmr_capsule_routing_fwd_ex(dims, params, route_embs, poses_in, acts_in, acts_override, route_mask, logits, alpha, R,
+                                    poses_out, acts_out, nullptr, stream);
+}
+
+int mmr_capsule_routing_fwd_ex(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
+                               const float* poses_in, const float* acts_in, const float* acts_override,
+                               const float* route_mask, float* logits, float* alpha, float* R, float* poses_out,
+                               float* acts_out, void* scratch, void* stream) {
   int rc = check_routing(dims);
   if (rc) return rc;
   if (!params || !logits || !alpha) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
@@ -1323,8 +1404,17 @@ int mmr_capsule_routing_fwd(const mmr_routing_dims* dims, const mmr_routing_para
   a.route_embs = route_embs; a.poses_in = poses_in; a.acts_in = acts_in; a.acts_override = acts_override;
   a.route_mask = route_mask; a.logits = logits; a.alpha = alpha; a.R = R; a.poses_out = poses_out; a.acts_out = acts_out;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const RtLaunch L = routing_launch_cfg(dims, false);
   ProfScope ps(PC_ROUTING, st);
+  if (rs_enabled(dims, params, scratch)) {
+    RsScratch sc;
+    rs_carve_fwd(reinterpret_cast<uint8_t*>(scratch), dims->B, dims->K, &sc);
+    int n = 0;
+    CUDA_OK(rs_launch_front(a, sc, st, &n));
+    CUDA_OK(rs_dispatch_iterate(a, sc, false, st));
+    g_launches.fetch_add(n + 1, std::memory_order_relaxed);
+    return MMR_OK;
+  }
+  const RtLaunch L = routing_launch_cfg(dims, false);
   CUDA_OK(dispatch_routing(a, L, false, st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MMR_OK;
@@ -1363,7 +1453,11 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   float* du = reinterpret_cast<float*>(s); s += align256(B * 10 * KD * 4);
   float* dpc = reinterpret_cast<float*>(s); s += align256(B * 330 * 4);
   float* posem = reinterpret_cast<float*>(s); s += align256(B * 320 * 4);
-  float* dG = reinterpret_cast<float*>(s);
+  float* dG = reinterpret_cast<float*>(s); s += align256(K * 32 * 4);
+  RsScratch sc;
+  s = rs_carve_fwd(s, B, K, &sc);
+  sc.dposeA = reinterpret_cast<float*>(s); s += align256(B * 320 * 4);
+  sc.dGc = reinterpret_cast<float*>(s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUDA_OK(cudaMemsetAsync(dG, 0, K * 32 * 4, st));
   RoutingArgs a; memset(&a, 0, sizeof(a));
@@ -1372,10 +1466,25 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   a.route_mask = route_mask; a.d_logits = d_logits; a.d_R = d_R;
   a.d_route_embs = d_route_embs; a.d_poses = d_poses; a.d_acts = d_acts;
   a.du = du; a.dpc = dpc; a.dG = dG; a.dbias = grads->bias; a.poses_m = posem;
-  const RtLaunch L = routing_launch_cfg(dims, true);
   ProfScope ps(PC_ROUTING, st);
-  CUDA_OK(dispatch_routing(a, L, true, st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  bool split = false;
+  if (rs_enabled(dims, params, scratch)) {
+    int n = 0;
+    CUDA_OK(cudaMemsetAsync(sc.dGc, 0, (size_t)RS_GCOPIES * (K + 1) * 32 * 4, st));
+    CUDA_OK(rs_launch_front(a, sc, st, &n));
+    CUDA_OK(rs_dispatch_iterate(a, sc, true, st));
+    rs_fold_copies_kernel<<<((int)(K + 1) * 32 + 255) / 256, 256, 0, st>>>(sc.dGc, (int)K, dG, grads->bias);
+    CUDA_OK(cudaGetLastError());
+    for (int r = 0; r < 10; ++r) a.d_proj_b[r] = dims->from_poses ? nullptr : grads->proj_b[r];
+    rs_dpose_kernel<<<dim3((dims->B + 15) / 16, 10), 256, 0, st>>>(a, sc);
+    CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(n + 3, std::memory_order_relaxed);
+    split = true;
+  } else {
+    const RtLaunch L = routing_launch_cfg(dims, true);
+    CUDA_OK(dispatch_routing(a, L, true, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   routing_head_grads_kernel<<<(MC * PC + (int)K * MC + 255) / 256, 256, 0, st>>>(dG, params->pose_to_mc, params->embedding, dims->K, grads->pose_to_mc,
                                                grads->embedding);
   LAUNCH_OK("routing_head_grads");
@@ -1395,8 +1504,10 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
       any = any || grads->proj_w[r] != nullptr;
     }
     if (any) { launch_wgrad_batched(w, st); LAUNCH_OK("w_proj"); }
-    proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, dims->B, *grads);
-    LAUNCH_OK("b_proj");
+    if (!split) {      // the split path accumulates the bias gradient inside rs_dpose_kernel
+      proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, dims->B, *grads);
+      LAUNCH_OK("b_proj");
+    }
   }
   return MMR_OK;
 }

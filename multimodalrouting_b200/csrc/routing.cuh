@@ -40,6 +40,7 @@ struct RoutingArgs {
   float* dpc;       // [B,10,33]  gradient wrt projector outputs
   float* dG;        // [K,32]     accumulated gradient wrt G = embedding @ pose_to_mc
   float* dbias;     // [K] or null
+  float* d_proj_b[MMR_ROUTES];   // split path: projector bias gradients (accumulated by rs_dpose_kernel) or null
 };
 
 // per-patient persistent state (floats)

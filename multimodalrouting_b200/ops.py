@@ -440,11 +440,14 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     R = torch.empty(B, N_ROUTES, K, dtype=torch.float32, device=dev)
     poses = torch.empty(B, N_ROUTES, 32, dtype=torch.float32, device=dev)
     acts = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
-    rc = lib.mmr_capsule_routing_fwd(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
-                                     _ptr(acts_override), _ptr(route_mask), _ptr(logits), _ptr(alpha), _ptr(R),
-                                     None if from_poses else _ptr(poses), None if from_poses else _ptr(acts),
-                                     _stream())
-    _lib.check(rc, "mmr_capsule_routing_fwd")
+    # the split path (csrc/routing_split.cuh) stages the projector outputs and the fp16 votes of the batch in scratch
+    scratch = (torch.empty(int(lib.mmr_routing_fwd_scratch_bytes(C.byref(dims))), dtype=torch.uint8, device=dev)
+               if use_tc else None)
+    rc = lib.mmr_capsule_routing_fwd_ex(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
+                                        _ptr(acts_override), _ptr(route_mask), _ptr(logits), _ptr(alpha), _ptr(R),
+                                        None if from_poses else _ptr(poses), None if from_poses else _ptr(acts),
+                                        _ptr(scratch), _stream())
+    _lib.check(rc, "mmr_capsule_routing_fwd_ex")
     return logits, alpha, R, poses, acts, packed
 
 

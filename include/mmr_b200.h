@@ -221,6 +221,15 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
                             const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
                             float* d_acts, void* stream);
 
+/* Same call; fwd_scratch (may be NULL) is the scratch buffer of the mmr_capsule_routing_fwd_ex call on the SAME inputs and
+ * parameters, untouched since: the split path then reuses the projector outputs and votes instead of recomputing them. */
+int mmr_capsule_routing_bwd_ex(const mmr_routing_dims* dims, const mmr_routing_params* params,
+                               const float* route_embs, const float* poses_in, const float* acts_in,
+                               const float* acts_override, const float* route_mask,
+                               const float* d_logits, const float* d_R, void* scratch,
+                               const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
+                               float* d_acts, const void* fwd_scratch, void* stream);
+
 /* Replaces RoutePrimaryProjector.forward alone (routing_and_heads.py:111-121) for callers that use the projector outside
  * forward_capsule_from_route_dict: poses [B,10,32] = (W_r e_r + b_r)[:32], acts [B,10] = sigmoid((W_r e_r + b_r)[32]).
  * route_embs / strides as above; only params->proj_w / proj_b are read.  fp32. */

@@ -65,7 +65,7 @@ class LossArgs(C.Structure):
 
 EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr_fusion_sizes",
            "mmr_route_fusion_fwd", "mmr_route_fusion_bwd", "mmr_route_fusion_bwd_events", "mmr_route_fusion_bwd_ex", "mmr_routing_scratch_bytes",
-           "mmr_capsule_routing_fwd", "mmr_capsule_routing_fwd_ex", "mmr_routing_fwd_scratch_bytes", "mmr_capsule_routing_bwd", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_launch_count",
+           "mmr_capsule_routing_fwd", "mmr_capsule_routing_fwd_ex", "mmr_routing_fwd_scratch_bytes", "mmr_capsule_routing_bwd", "mmr_capsule_routing_bwd_ex", "mmr_debug_gemm", "mmr_bench_gemm", "mmr_launch_count",
            "mmr_prof_enable", "mmr_prof_collect", "mmr_sanitize_rows_fwd", "mmr_sanitize_rows_bwd",
            "mmr_grad_sqnorm", "mmr_opt_prepare", "mmr_opt_apply", "mmr_ema_update", "mmr_route_mask_from_presence", "mmr_routing_pack_weights", "mmr_abi_struct_sizes",
            "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd",
@@ -124,6 +124,9 @@ def load():
     lib.mmr_capsule_routing_bwd.argtypes = ([C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 8 +
                                             [C.POINTER(RoutingGrads)] + [c_fp] * 4)
     lib.mmr_capsule_routing_bwd.restype = C.c_int
+    lib.mmr_capsule_routing_bwd_ex.argtypes = ([C.POINTER(RoutingDims), C.POINTER(RoutingParams)] + [c_fp] * 8 +
+                                               [C.POINTER(RoutingGrads)] + [c_fp] * 5)
+    lib.mmr_capsule_routing_bwd_ex.restype = C.c_int
     lib.mmr_projector_fwd.argtypes = [C.POINTER(RoutingParams), c_fp, C.c_int64, C.c_int64, C.c_int, c_fp, c_fp, c_fp]
     lib.mmr_projector_fwd.restype = C.c_int
     lib.mmr_projector_bwd.argtypes = [C.POINTER(RoutingParams), c_fp, C.c_int64, C.c_int64, C.c_int, c_fp, c_fp, c_fp,

@@ -1087,7 +1087,7 @@ int mmr_abi_struct_sizes(size_t* out, int n) {
 }
 
 // 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd); 102: + standalone projector, packed-weight
-// forward, producer projections; 103: + mmr_capsule_routing_fwd_ex / mmr_routing_fwd_scratch_bytes (split routing path)
+// forward, producer projections; 103: + mmr_capsule_routing_fwd_ex / _bwd_ex / mmr_routing_fwd_scratch_bytes (split routing path)
 int mmr_version(void) { return 103; }
 
 long long mmr_launch_count(void) { return g_launches.load(); }
@@ -1241,7 +1241,8 @@ static int check_routing(const mmr_routing_dims* d) {
 
 // backward scratch: du | dpc | posem | dG | (split path) pose | zl | G | votes | dposeA;  forward scratch: pose | zl | G | votes
 static size_t rs_fwd_scratch(size_t B, size_t K) {
-  return align256(B * 320 * 4) + align256(B * 10 * 4) + align256(K * 32 * 4) + align256(B * 10 * K * 64 * 2);
+  return align256(B * 320 * 4) + align256(B * 10 * 4) + align256(K * 32 * 4) + align256(B * 10 * K * 64 * 2) +
+         align256(B * (RS_NIT - 1) * 320 * 4);
 }
 size_t mmr_routing_scratch_bytes(const mmr_routing_dims* d) {
   if (!d || d->B <= 0 || d->K < 1) return 0;
@@ -1320,6 +1321,7 @@ static uint8_t* rs_carve_fwd(uint8_t* s, size_t B, size_t K, RsScratch* o) {
   o->zl = reinterpret_cast<float*>(s); s += align256(B * 10 * 4);
   o->G = reinterpret_cast<float*>(s); s += align256(K * 32 * 4);
   o->votes = reinterpret_cast<__half*>(s); s += align256(B * 10 * K * 64 * 2);
+  o->qs = reinterpret_cast<float*>(s); s += align256(B * (RS_NIT - 1) * 320 * 4);
   o->dposeA = nullptr; o->dGc = nullptr;
   return s;
 }
@@ -1444,6 +1446,15 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
                             const float* route_mask, const float* d_logits, const float* d_R, void* scratch,
                             const mmr_routing_grads* grads, float* d_route_embs, float* d_poses, float* d_acts,
                             void* stream) {
+  return mmr_capsule_routing_bwd_ex(dims, params, route_embs, poses_in, acts_in, acts_override, route_mask, d_logits, d_R,
+                                    scratch, grads, d_route_embs, d_poses, d_acts, nullptr, stream);
+}
+
+int mmr_capsule_routing_bwd_ex(const mmr_routing_dims* dims, const mmr_routing_params* params, const float* route_embs,
+                               const float* poses_in, const float* acts_in, const float* acts_override,
+                               const float* route_mask, const float* d_logits, const float* d_R, void* scratch,
+                               const mmr_routing_grads* grads, float* d_route_embs, float* d_poses, float* d_acts,
+                               const void* fwd_scratch, void* stream) {
   int rc = check_routing(dims);
   if (rc) return rc;
   if (!params || !d_logits || !scratch || !grads) return fail(MMR_ERR_INVALID_ARG, "null pointer argument");
@@ -1471,7 +1482,14 @@ int mmr_capsule_routing_bwd(const mmr_routing_dims* dims, const mmr_routing_para
   if (rs_enabled(dims, params, scratch)) {
     int n = 0;
     CUDA_OK(cudaMemsetAsync(sc.dGc, 0, (size_t)RS_GCOPIES * (K + 1) * 32 * 4, st));
-    CUDA_OK(rs_launch_front(a, sc, st, &n));
+    if (fwd_scratch) {     // projector outputs, head matrix and votes of the forward call: nothing to recompute
+      float* dposeA = sc.dposeA; float* dGc = sc.dGc;
+      rs_carve_fwd(reinterpret_cast<uint8_t*>(const_cast<void*>(fwd_scratch)), B, K, &sc);
+      sc.dposeA = dposeA; sc.dGc = dGc;
+    } else {
+      sc.qs = nullptr;       // recompute path: the agreement iterations run again inside the backward kernel
+      CUDA_OK(rs_launch_front(a, sc, st, &n));
+    }
     CUDA_OK(rs_dispatch_iterate(a, sc, true, st));
     rs_fold_copies_kernel<<<((int)(K + 1) * 32 + 255) / 256, 256, 0, st>>>(sc.dGc, (int)K, dG, grads->bias);
     CUDA_OK(cudaGetLastError());

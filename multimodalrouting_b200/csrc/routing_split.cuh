@@ -37,6 +37,7 @@ struct RsScratch {
   float* zl;        // [B,10]    activation logits
   float* G;         // [K,32]    embedding @ pose_to_mc
   __half* votes;    // [B,10,K*64]
+  float* qs;        // [B,RS_NIT-1,10,32] routing coefficients q_1 .. q_{nit-1} of the forward call (read by the backward; may be null)
   float* dposeA;    // bwd [B,10,32]: final-aggregation part of d pose_m
   float* dGc;       // bwd [RS_GCOPIES][(K+1)*32]: per-copy accumulators of dG (rows < K) and d bias (row K), zeroed by the host
 };
@@ -150,7 +151,6 @@ __global__ void __launch_bounds__(256) rs_votes_kernel(RoutingArgs a, RsScratch 
       const int idx = tid + 256 * i, p = idx / 80, j4 = idx % 80, b = b0 + p;
       const float4 o = make_float4(v[i].x * rm[i], v[i].y * rm[i], v[i].z * rm[i], v[i].w * rm[i]);
       *reinterpret_cast<float4*>(&pm[p][4 * j4]) = o;
-      if (b < B && a.poses_m && blockIdx.y == 0) *reinterpret_cast<float4*>(a.poses_m + (size_t)b * 320 + 4 * j4) = o;
     }
   }
   __syncthreads();
@@ -315,9 +315,12 @@ __device__ __forceinline__ void rs_stage(const RoutingArgs& a, const RsScratch& 
 }
 
 // forward iterations; on exit q = last routing coefficients; V (when STORE) keeps v_0 .. v_{nit-2}, Q keeps q_1 .. q_{nit-1}
+// qsave (forward kernel): q_it is written there; qload (backward after a forward call with scratch): q_it is read back instead
+// of recomputing the agreement dots and the softmax.  Both point at this patient's [RS_NIT-1][10][32] block or are null.
 template <int KP, bool STORE>
 __device__ __forceinline__ void rs_forward(const RoutingArgs& a, RsGroup<KP>& G, float (&q)[10],
-                                           float (&V)[RS_NIT - 1][RsCfg<KP>::DPL], float (&Q)[RS_NIT - 1][10]) {
+                                           float (&V)[RS_NIT - 1][RsCfg<KP>::DPL], float (&Q)[RS_NIT - 1][10],
+                                           float* qsave, const float* qload) {
   using C = RsCfg<KP>;
   constexpr int DPL = C::DPL;
   const int K = a.d.K, nit = a.d.num_routing;
@@ -345,26 +348,37 @@ __device__ __forceinline__ void rs_forward(const RoutingArgs& a, RsGroup<KP>& G,
 #pragma unroll
         for (int d = 0; d < DPL; ++d) V[it - 1][d] = v[d];
       }
-      float x[10];
+      if (qload) {
 #pragma unroll
-      for (int r = 0; r < 10; ++r) {
-        float f[DPL];
-        rs_ld_u<DPL>(G.urow(r, K), f);
-        float acc = 0.f;
+        for (int r = 0; r < 10; ++r) q[r] = G.kv ? qload[((it - 1) * 10 + r) * 32 + G.k] : 0.f;
+      } else {
+        float x[10];
 #pragma unroll
-        for (int d = 0; d < DPL; ++d) acc = fmaf(f[d], v[d], acc);
-        x[r] = acc;
+        for (int r = 0; r < 10; ++r) {
+          float f[DPL];
+          rs_ld_u<DPL>(G.urow(r, K), f);
+          float acc = 0.f;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) acc = fmaf(f[d], v[d], acc);
+          x[r] = acc;
+        }
+        G.template seg_reduce<10>(x);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {       // softmax over the labels, renormalised (capsule_layers.py:96-100)
+          const float xv = G.kv ? scale * x[r] : -INFINITY;
+          const float mx = rs_kmax<KP>(xv);
+          const float ex = G.kv ? expf(xv - mx) : 0.f;
+          const float pr = ex * (1.0f / rs_ksum<KP>(ex));
+          const float tt = rs_ksum<KP>(pr);
+          q[r] = pr * (1.0f / (tt + 1e-10f));
+        }
+        if (qsave && G.kv && G.seg == 0)
+#pragma unroll
+          for (int r = 0; r < 10; ++r) qsave[((it - 1) * 10 + r) * 32 + G.k] = q[r];
       }
-      G.template seg_reduce<10>(x);
+      if (STORE) {
 #pragma unroll
-      for (int r = 0; r < 10; ++r) {       // softmax over the labels, renormalised (capsule_layers.py:96-100)
-        const float xv = G.kv ? scale * x[r] : -INFINITY;
-        const float mx = rs_kmax<KP>(xv);
-        const float ex = G.kv ? expf(xv - mx) : 0.f;
-        const float pr = ex * (1.0f / rs_ksum<KP>(ex));
-        const float tt = rs_ksum<KP>(pr);
-        q[r] = pr * (1.0f / (tt + 1e-10f));
-        if (STORE) Q[it - 1][r] = q[r];
+        for (int r = 0; r < 10; ++r) Q[it - 1][r] = q[r];
       }
       if (it + 1 < nit) {
 #pragma unroll
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(128, 4) rs_iterate_fwd_kernel(RoutingArgs a, R
   for (int b = blockIdx.x * C::PPC + pg; b < B; b += gridDim.x * C::PPC) {
     rs_stage<KP>(a, s, G, b);
     float q[10], V[RS_NIT - 1][C::DPL], Q[RS_NIT - 1][10];
-    rs_forward<KP, false>(a, G, q, V, Q);
+    rs_forward<KP, false>(a, G, q, V, Q, s.qs ? s.qs + (size_t)b * (RS_NIT - 1) * 320 : nullptr, nullptr);
     // R = q mask / clamp_min(sum_r q mask, 1e-10)   (route_given_pheno)
     float den = 0.f;
 #pragma unroll
@@ -450,8 +464,10 @@ __global__ void __launch_bounds__(128, RS_BWD_MINB) rs_iterate_bwd_kernel(Routin
   for (int j = 0; j < PPL; ++j) accG[j] = 0.f;
   for (int b = blockIdx.x * C::PPC + pg; b < B; b += gridDim.x * C::PPC) {
     rs_stage<KP>(a, s, G, b);
+    if (a.poses_m)       // masked poses: operand of the vote-weight gradient
+      for (int i = G.wp * 32 + G.lane; i < 320; i += C::NW * 32) a.poses_m[(size_t)b * 320 + i] = G.pm[i];
     float q[10], V[RS_NIT - 1][DPL], Q[RS_NIT - 1][10];
-    rs_forward<KP, true>(a, G, q, V, Q);
+    rs_forward<KP, true>(a, G, q, V, Q, nullptr, s.qs ? s.qs + (size_t)b * (RS_NIT - 1) * 320 : nullptr);
     float den = 0.f;
 #pragma unroll
     for (int r = 0; r < 10; ++r) den = fmaf(q[r], G.tab[80 + r], den);
@@ -484,13 +500,41 @@ __global__ void __launch_bounds__(128, RS_BWD_MINB) rs_iterate_bwd_kernel(Routin
     }
     G.template seg_reduce<10>(t);
     // final aggregation: d pose_m[r][p] = c_r sum_k Rn[r][k] ddp[k][p]  -> scratch (rs_dpose_kernel adds du . w^T)
+    if constexpr (KP == 32) {
+      // 80 sums over the 32 labels as a reduce-scatter: every butterfly step halves the values a lane carries
+      // (80 + 5 shuffles instead of 400); lane l ends with the sums v = 16 m + (l & 15), v = r * 8 + j
+      float x[80];
 #pragma unroll
-    for (int r = 0; r < 10; ++r)
+      for (int r = 0; r < 10; ++r)
 #pragma unroll
-      for (int j = 0; j < PPL; ++j) {
-        const float v = rs_ksum<KP>(Rn[r] * ddp[j]) * G.tab[96 + r];
-        if (G.k == 0) s.dposeA[(size_t)b * 320 + r * 32 + G.seg * PPL + j] = v;
+        for (int j = 0; j < 8; ++j) x[r * 8 + j] = Rn[r] * ddp[j];
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        const int o = 1 << st;
+        const bool up = (G.lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < (80 >> (st + 1)); ++i) {
+          // values whose index has bit `st` (of the low four bits) clear / set: x[.. 2i ..], x[.. 2i+1 ..] after compaction
+          const float keep = up ? x[2 * i + 1] : x[2 * i], give = up ? x[2 * i] : x[2 * i + 1];
+          x[i] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+        }
       }
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        const float v = x[m] + __shfl_xor_sync(0xffffffffu, x[m], 16);
+        // after the four compactions x[m] of lane l is the sum of original index 16 m + (l & 15)
+        const int idx = 16 * m + (G.lane & 15), r = idx >> 3, j = idx & 7;
+        if (G.lane < 16) s.dposeA[(size_t)b * 320 + r * 32 + G.seg * PPL + j] = v * G.tab[96 + r];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 10; ++r)
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+          const float v = rs_ksum<KP>(Rn[r] * ddp[j]) * G.tab[96 + r];
+          if (G.k == 0) s.dposeA[(size_t)b * 320 + r * 32 + G.seg * PPL + j] = v;
+        }
+    }
     float dal[10], dact[10], dq[10];
     float dot = 0.f;
 #pragma unroll

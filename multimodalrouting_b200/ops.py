@@ -396,6 +396,16 @@ def routing_pack_bytes(K: int) -> int:
     return 2 * (10 * K * 64 * 32 * 2) + PROJ_PACK_BYTES
 
 
+def _pack_bytes_aligned(K: int) -> int:
+    return (routing_pack_bytes(K) + 255) // 256 * 256
+
+
+def routing_state_bytes(dims: RoutingDims) -> int:
+    """bytes of the buffer the forward hands to the backward in the reduced-precision mode: the fp16 weight copies followed by
+    the forward scratch of the split path (projector outputs, head matrix, fp16 votes; csrc/routing_split.cuh)."""
+    return _pack_bytes_aligned(dims.K) + int(_lib.load().mmr_routing_fwd_scratch_bytes(C.byref(dims)))
+
+
 def _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed=None) -> RoutingParams:
     rp = RoutingParams()
     if packed is not None and packed.numel() > 0:
@@ -430,7 +440,7 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     dev = caps_w.device
     # reduced-precision mode: projector and vote contraction run on tensor cores from fp16 weight copies
     use_tc = vdt == DTYPE_BF16 and os.environ.get("MMR_RT_TC", "1") != "0"
-    packed = torch.empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8, device=dev)
+    packed = torch.empty(routing_state_bytes(dims) if use_tc else 0, dtype=torch.uint8, device=dev)
     rp = _routing_params(proj_w, proj_b, caps_w, pose_to_mc, embedding, bias, packed)
     if use_tc:
         rc = lib.mmr_routing_pack_weights(C.byref(rp), K, rp.caps_wt_f16, rp.caps_w_f16, rp.proj_w_f16, _stream())
@@ -440,13 +450,13 @@ def capsule_routing_fwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
     R = torch.empty(B, N_ROUTES, K, dtype=torch.float32, device=dev)
     poses = torch.empty(B, N_ROUTES, 32, dtype=torch.float32, device=dev)
     acts = torch.empty(B, N_ROUTES, dtype=torch.float32, device=dev)
-    # the split path (csrc/routing_split.cuh) stages the projector outputs and the fp16 votes of the batch in scratch
-    scratch = (torch.empty(int(lib.mmr_routing_fwd_scratch_bytes(C.byref(dims))), dtype=torch.uint8, device=dev)
-               if use_tc else None)
+    # the split path (csrc/routing_split.cuh) stages the projector outputs and the fp16 votes of the batch behind the packed
+    # weights; the backward reads them from there instead of recomputing them
+    scratch = (packed.data_ptr() + _pack_bytes_aligned(K)) if use_tc else None
     rc = lib.mmr_capsule_routing_fwd_ex(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
                                         _ptr(acts_override), _ptr(route_mask), _ptr(logits), _ptr(alpha), _ptr(R),
                                         None if from_poses else _ptr(poses), None if from_poses else _ptr(acts),
-                                        _ptr(scratch), _stream())
+                                        scratch, _stream())
     _lib.check(rc, "mmr_capsule_routing_fwd_ex")
     return logits, alpha, R, poses, acts, packed
 
@@ -457,9 +467,10 @@ def _(embs, rs, bs, poses_in, acts_in, acts_override, route_mask, proj_w, proj_b
     K = embedding.shape[0]
     e = caps_w
     use_tc = vdt == DTYPE_BF16 and os.environ.get("MMR_RT_TC", "1") != "0"
+    dims = _routing_dims(B, K, variant, num_routing, detach_priors, embs is None, temp, floor, ceil, rs, bs, vdt)
     return (e.new_empty(B, K), e.new_empty(B, N_ROUTES), e.new_empty(B, N_ROUTES, K),
             e.new_empty(B, N_ROUTES, 32), e.new_empty(B, N_ROUTES),
-            e.new_empty(routing_pack_bytes(K) if use_tc else 0, dtype=torch.uint8))
+            e.new_empty(routing_state_bytes(dims) if use_tc else 0, dtype=torch.uint8))
 
 
 @torch.library.custom_op("mmr_b200::capsule_routing_bwd", mutates_args=())
@@ -502,12 +513,16 @@ def capsule_routing_bwd(embs: Optional[Tensor], rs: int, bs: int, poses_in: Opti
         d_acts = torch.zeros(B if acts_override is not None else 0, N_ROUTES, dtype=torch.float32, device=dev)
     # d_route_embs shares the (route, batch) strides of the input embeddings in the C ABI; RoutingFn
     # normalises the inputs to the dense [10,B,256] layout, so the output is dense as well.
-    rc = lib.mmr_capsule_routing_bwd(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
-                                     _ptr(acts_override), _ptr(route_mask), _ptr(d_logits), _ptr(d_R),
-                                     _ptr(scratch), C.byref(g), None if from_poses else _ptr(d_embs),
-                                     _ptr(d_poses) if from_poses else None,
-                                     _ptr(d_acts) if (from_poses or acts_override is not None) else None, _stream())
-    _lib.check(rc, "mmr_capsule_routing_bwd")
+    fwd_state = None
+    if packed is not None and packed.numel() >= routing_state_bytes(dims):
+        fwd_state = packed.data_ptr() + _pack_bytes_aligned(K)      # forward scratch of the same call (split path)
+    rc = lib.mmr_capsule_routing_bwd_ex(C.byref(dims), C.byref(rp), _ptr(embs), _ptr(poses_in), _ptr(acts_in),
+                                        _ptr(acts_override), _ptr(route_mask), _ptr(d_logits), _ptr(d_R),
+                                        _ptr(scratch), C.byref(g), None if from_poses else _ptr(d_embs),
+                                        _ptr(d_poses) if from_poses else None,
+                                        _ptr(d_acts) if (from_poses or acts_override is not None) else None,
+                                        fwd_state, _stream())
+    _lib.check(rc, "mmr_capsule_routing_bwd_ex")
     return d_embs, d_poses, d_acts, flat
 
 

@@ -53,7 +53,11 @@ def test_capsule_routing_fakes(K, vdt, monkeypatch):
         logits, alpha, R, poses, acts, packed = out
         assert tuple(logits.shape) == (B, K) and tuple(alpha.shape) == (B, 10) and tuple(R.shape) == (B, 10, K)
         assert tuple(poses.shape) == (B, 10, 32) and tuple(acts.shape) == (B, 10)
-        assert packed.dtype == torch.uint8 and packed.numel() == (ops.routing_pack_bytes(K) if vdt == ops.DTYPE_BF16 else 0)
+        dims = ops._routing_dims(B, K, 1, 3, False, False, 1.0, 0.02, 0.98, B * 256, 256, vdt)
+        # fp16 weight copies + the forward scratch of the split path (projector outputs, head matrix, fp16 votes)
+        assert packed.dtype == torch.uint8 and packed.numel() == (ops.routing_state_bytes(dims) if vdt == ops.DTYPE_BF16 else 0)
+        if vdt == ops.DTYPE_BF16:
+            assert packed.numel() >= ops.routing_pack_bytes(K) + B * 10 * K * 64 * 2 + B * 330 * 4 + K * 32 * 4
         d_embs, d_poses, d_acts, flat = ops.capsule_routing_bwd(embs, B * 256, 256, None, None, None, rm, pw, pb, caps_w, p2m, emb,
                                                                 bias, torch.empty(B, K, device="cuda"), None, B, 1, 3, False, 1.0,
                                                                 0.02, 0.98, vdt, packed)

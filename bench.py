@@ -585,11 +585,16 @@ def main():
     Kl = WL["K"]
     rt_bytes = ((10240 + 40 + 4 * Kl + 40 + 40 * Kl) + (10240 + 4 * Kl + 40 * Kl + 10240)) * B
     rt_gbs = rt_bytes / (rt_ms / 1e3) / 1e9 if rt_ms > 0 else 0.0
-    roofline_routing = {"bound": "hbm", "kernel": "routing_fwd_kernel + routing_bwd_kernel (+ head / vote-weight gradient launches)",
+    split = os.environ.get("MMR_RT_SPLIT", "1") != "0"
+    roofline_routing = {"bound": "hbm",
+                        "kernel": ("rs_project + rs_votes + rs_iterate_fwd | rs_iterate_bwd + rs_dpose (csrc/routing_split.cuh) "
+                                   "+ head / vote-weight gradient launches") if split else
+                                  "routing_fwd_kernel + routing_bwd_kernel (+ head / vote-weight gradient launches)",
                         "achieved": rt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rt_gbs / hbm_peak, "traffic": None,
                         "ms_per_step": rt_ms, "algorithmic_bytes_per_step": rt_bytes,
-                        "note": "K=25: bound by the 1.02 MFLOP/patient vote contraction and phase barriers, not by bytes "
-                                "(16 MB per step = 2.5 us at the HBM peak, below one launch latency)"}
+                        "note": "timed eagerly between CUDA events (launch gaps included); latency / issue bound, not byte bound: "
+                                "the algorithmic bytes of a step take 2.5 us (K=25, B=512) / 39 us (K=2, B=8192) at the HBM peak, "
+                                "the per-patient agreement iterations ~9k dependent warp instructions (profiles/r2_routing.md)"}
     cpu = None
     gpu_ref = None
     if not args.no_gpu_reference and world == 1:

@@ -164,11 +164,11 @@ static Segs single_seg(int rows, int T) {
 // plain fp32 GEMM  C[M,N] (ldc) = A[M,K] (lda) * W^T (+bias), W [N,K] (TRANSB=false) or [K,N] (true)
 template <bool TRANSB>
 static int fp32_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
-                       int M, int N, int K, cudaStream_t st, const char* what) {
+                       int M, int N, int K, cudaStream_t st, const char* what, int tf32 = 0) {
   GemmProblem g;
   memset(&g, 0, sizeof(g));
   g.segs = single_seg(M, 1);
-  g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = W; g.ldb = ldw;
+  g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = W; g.ldb = ldw; g.tf32 = tf32;
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.bias = bias; e.out = C; e.ldo = ldc;
@@ -178,21 +178,21 @@ static int fp32_linear(const float* A, int lda, const float* W, int ldw, const f
 }
 
 static void fp32_problem(GemmProblem* g, EpiParams* e, const float* A, int lda, const float* W, int ldw, const float* bias,
-                         float* C, int ldc, int M, int N, int K) {
+                         float* C, int ldc, int M, int N, int K, int tf32 = 0) {
   memset(g, 0, sizeof(*g));
   g->segs = single_seg(M, 1);
-  g->N = N; g->K = K; g->A = A; g->lda = lda; g->B = W; g->ldb = ldw;
+  g->N = N; g->K = K; g->A = A; g->lda = lda; g->B = W; g->ldb = ldw; g->tf32 = tf32;
   memset(e, 0, sizeof(*e));
   e->bias = bias; e->out = C; e->ldo = ldc;
 }
 
 static int fp32_wgrad(const float* dY, int ldy, const float* X, int ldx, float* out, int ldo, int rows, int M, int N,
-                      cudaStream_t st, const char* what) {
+                      cudaStream_t st, const char* what, int tf32 = 0) {
   if (out == nullptr) return MMR_OK;
   WgradProblem w;
   memset(&w, 0, sizeof(w));
   w.segs = single_seg(rows, 1);
-  w.dY = dY; w.ldy = ldy; w.X = X; w.ldx = ldx; w.M = M; w.N = N; w.out[0] = out; w.ldo = ldo;
+  w.dY = dY; w.ldy = ldy; w.X = X; w.ldx = ldx; w.M = M; w.N = N; w.out[0] = out; w.ldo = ldo; w.tf32 = tf32;
   launch_wgrad_simt<float, float>(w, st);
   LAUNCH_OK(what);
   return MMR_OK;
@@ -316,6 +316,10 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
                       const float* pos, uint8_t* packed, uint8_t* saved, uint8_t* scratch, float* routes,
                       cudaStream_t st, bool do_pack) {
   const ParamIndex ix{P.L};
+  // reduced-precision mode: the small fp32 GEMMs (Conv1d input projections, pair / trimodal composition) contract on tf32
+  // tensor cores (the reference runs these nn.Linear / Conv1d in bf16 under autocast); MMR_TF32=0 keeps the FMA loops
+  static const int tf_on = [] { const char* e = getenv("MMR_TF32"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  const int TF32 = std::is_same<CT, bf16>::value ? tf_on : 0;
   const int L = P.L, B = P.B;
   auto f = [&](int i) { return reinterpret_cast<const float*>(prm[i]); };
   int rc = do_pack ? pack_weights<CT>(P, prm, packed, st) : MMR_OK;   // else: `packed` holds mmr_fusion_pack_weights' output
@@ -361,7 +365,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
   for (int m = 0; m < NMOD; ++m) {
     if (P.din[m] == D) { src[m] = x[m]; continue; }
     float* dst = fp + (size_t)P.mod.row0[m] * D;
-    rc = fp32_linear<false>(x[m], P.din[m], f(ix.proj(m)), P.din[m], nullptr, dst, D, P.mod.rows[m], D, P.din[m], st, "proj");
+    rc = fp32_linear<false>(x[m], P.din[m], f(ix.proj(m)), P.din[m], nullptr, dst, D, P.mod.rows[m], D, P.din[m], st, "proj", TF32);
     if (rc) return rc;
     src[m] = dst;
   }
@@ -504,12 +508,12 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
     MultiGemm mg; mg.n = 3;     // the three pair projections in one launch
     for (int p = 0; p < 3; ++p)
       fp32_problem(&mg.g[p], &mg.e[p], zcat + (size_t)p * B * 512, 512, f(ix.pair(p, 0)), 512, f(ix.pair(p, 1)), ecat + p * D,
-                   3 * D, B, D, 512);
+                   3 * D, B, D, 512, TF32);
     launch_gemm_simt_multi<float, float, EPI_BIAS_F32, float, false>(mg, st);
     LAUNCH_OK("pair_proj");
   }
   rc = fp32_linear<false>(ecat, 3 * D, f(ix.final_lni(0)), 3 * D, f(ix.final_lni(1)), routes + (size_t)9 * B * D, D, B, D,
-                          3 * D, st, "final_lni");
+                          3 * D, st, "final_lni", TF32);
   return rc;
 }
 
@@ -519,6 +523,8 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
                       void* const* grads, float* const dx[3], cudaStream_t st, void* const* layer_events = nullptr,
                       cudaStream_t side = nullptr, void* const* sync_ev = nullptr) {
   const ParamIndex ix{P.L};
+  static const int tf_on = [] { const char* e = getenv("MMR_TF32"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  const int TF32 = std::is_same<CT, bf16>::value ? tf_on : 0;
   // Optional second stream for the weight-gradient kernels.  They depend only on a layer's upstream gradient and saved
   // activations, never feed the data-gradient chain, and are L2/HBM-latency bound, so they can run next to the
   // attention-backward and LayerNorm kernels of the chain.  Nine caller-owned events order the two streams:
@@ -592,9 +598,9 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
 
   // ---- trimodal + pair projections (mult_model.py:174-178) ----
   const float* dz_lni = d_routes + (size_t)9 * B * D;
-  rc = fp32_linear<true>(dz_lni, D, f(ix.final_lni(0)), 3 * D, nullptr, decat, 3 * D, B, 3 * D, D, st, "d_final_lni");
+  rc = fp32_linear<true>(dz_lni, D, f(ix.final_lni(0)), 3 * D, nullptr, decat, 3 * D, B, 3 * D, D, st, "d_final_lni", TF32);
   if (rc) return rc;
-  rc = fp32_wgrad(dz_lni, D, ecat, 3 * D, gr(ix.final_lni(0)), 3 * D, B, D, 3 * D, st, "w_final_lni");
+  rc = fp32_wgrad(dz_lni, D, ecat, 3 * D, gr(ix.final_lni(0)), 3 * D, B, D, 3 * D, st, "w_final_lni", TF32);
   if (rc) return rc;
   {
     Segs sb = single_seg(B, 1);
@@ -605,13 +611,13 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       MultiGemm mg; mg.n = 3;   // d(zcat_p) = d(e_p) W_p for the three pairs in one launch
       for (int p = 0; p < 3; ++p)
         fp32_problem(&mg.g[p], &mg.e[p], decat + p * D, 3 * D, f(ix.pair(p, 0)), 512, nullptr, dzcat + (size_t)p * B * 512, 512, B,
-                     512, D);
+                     512, D, TF32);
       launch_gemm_simt_multi<float, float, EPI_BIAS_F32, float, true>(mg, st);
       LAUNCH_OK("d_pair");
     }
     {
       WgradBatch w; memset(&w, 0, sizeof(w));   // dW_p = d(e_p)^T zcat_p
-      w.nbatch = 3; w.rows = B; w.M = D; w.N = 512; w.ldy = 3 * D; w.ldx = 512; w.ldo = 512;
+      w.nbatch = 3; w.rows = B; w.M = D; w.N = 512; w.ldy = 3 * D; w.ldx = 512; w.ldo = 512; w.tf32 = TF32;
       bool any = false;
       for (int p = 0; p < 3; ++p) {
         w.dY[p] = decat + p * D; w.X[p] = zcat + (size_t)p * B * 512; w.out[p] = gr(ix.pair(p, 0));
@@ -898,10 +904,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
     if (P.din[m] == D) continue;
     const float* dpm = dp + (size_t)P.mod.row0[m] * D;
     if (dx[m]) {
-      rc = fp32_linear<true>(dpm, D, f(ix.proj(m)), P.din[m], nullptr, dx[m], P.din[m], P.mod.rows[m], P.din[m], D, st, "d_proj");
+      rc = fp32_linear<true>(dpm, D, f(ix.proj(m)), P.din[m], nullptr, dx[m], P.din[m], P.mod.rows[m], P.din[m], D, st, "d_proj", TF32);
       if (rc) return rc;
     }
-    rc = fp32_wgrad(dpm, D, x[m], P.din[m], gr(ix.proj(m)), P.din[m], P.mod.rows[m], D, P.din[m], st, "w_proj");
+    rc = fp32_wgrad(dpm, D, x[m], P.din[m], gr(ix.proj(m)), P.din[m], P.mod.rows[m], D, P.din[m], st, "w_proj", TF32);
     if (rc) return rc;
   }
   return MMR_OK;
@@ -1509,6 +1515,7 @@ int mmr_capsule_routing_bwd_ex(const mmr_routing_dims* dims, const mmr_routing_p
   if (grads->caps_w) {   // d w[r] = pose_masked[:, r, :]^T du[:, r, :]
     WgradBatch w; memset(&w, 0, sizeof(w));
     w.nbatch = 10; w.rows = dims->B; w.M = 32; w.N = (int)KD; w.ldy = 320; w.ldx = (int)(10 * KD); w.ldo = (int)KD;
+    w.tf32 = dims->vote_dtype == MMR_DTYPE_BF16 && !(getenv("MMR_TF32") && atoi(getenv("MMR_TF32")) == 0);
     for (int r = 0; r < 10; ++r) { w.dY[r] = posem + r * 32; w.X[r] = du + r * KD; w.out[r] = grads->caps_w + (size_t)r * 32 * KD; }
     launch_wgrad_batched(w, st);
     LAUNCH_OK("w_caps");
@@ -1516,6 +1523,7 @@ int mmr_capsule_routing_bwd_ex(const mmr_routing_dims* dims, const mmr_routing_p
   if (!dims->from_poses) {
     WgradBatch w; memset(&w, 0, sizeof(w));
     w.nbatch = 10; w.rows = dims->B; w.M = 33; w.N = 256; w.ldy = 330; w.ldx = (int)dims->emb_batch_stride; w.ldo = 256;
+    w.tf32 = dims->vote_dtype == MMR_DTYPE_BF16 && !(getenv("MMR_TF32") && atoi(getenv("MMR_TF32")) == 0);
     bool any = false;
     for (int r = 0; r < 10; ++r) {
       w.dY[r] = dpc + r * 33; w.X[r] = route_embs + (size_t)r * dims->emb_route_stride; w.out[r] = grads->proj_w[r];

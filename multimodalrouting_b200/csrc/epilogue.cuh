@@ -25,6 +25,8 @@ struct GemmProblem {
   int lda;
   const void* B;
   int ldb;
+  int tf32;         // CUDA-core engine only: 1 = the staged slabs are contracted with mma.sync tf32 (reduced-precision mode;
+                    // the fp32 parity mode keeps the FMA loop)
 };
 
 struct EpiParams {
@@ -92,6 +94,7 @@ struct WgradProblem {
   int ldo;
   float* dbias[6];    // optional per segment fp32 [M]: += column sums of dY (bias gradient), fused into the
   int colsum;         // tcgen05 weight-gradient kernel when `colsum` is set (launch-uniform)
+  int tf32;           // CUDA-core engine only: contract the staged slabs with mma.sync tf32 (reduced-precision mode)
 };
 
 }  // namespace mmr

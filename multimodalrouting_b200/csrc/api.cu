@@ -598,14 +598,20 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
 
   // ---- trimodal + pair projections (mult_model.py:174-178) ----
   const float* dz_lni = d_routes + (size_t)9 * B * D;
+  // The weight / bias gradients of this tail (4 launches, ~75 us at B = 512) are off the data-gradient chain: they go to the
+  // side stream, which is idle until the last layer's gradients exist.  E_GC0 / E_DF are re-recorded further down.
+  rc = main_to_side(E_GC0);   // fork (after the memset of the accumulators)
+  if (rc) return rc;
   rc = fp32_linear<true>(dz_lni, D, f(ix.final_lni(0)), 3 * D, nullptr, decat, 3 * D, B, 3 * D, D, st, "d_final_lni", TF32);
   if (rc) return rc;
-  rc = fp32_wgrad(dz_lni, D, ecat, 3 * D, gr(ix.final_lni(0)), 3 * D, B, D, 3 * D, st, "w_final_lni", TF32);
+  rc = main_to_side(E_DF);    // d(ecat) is ready
+  if (rc) return rc;
+  rc = fp32_wgrad(dz_lni, D, ecat, 3 * D, gr(ix.final_lni(0)), 3 * D, B, D, 3 * D, ws, "w_final_lni", TF32);
   if (rc) return rc;
   {
     Segs sb = single_seg(B, 1);
     float* o1[6] = {gr(ix.final_lni(1)), nullptr, nullptr, nullptr, nullptr, nullptr};
-    rc = run_colsum<float>(sb, dz_lni, D, 0, D, o1, 1.0f, st, "b_final_lni");
+    rc = run_colsum<float>(sb, dz_lni, D, 0, D, o1, 1.0f, ws, "b_final_lni");
     if (rc) return rc;
     {
       MultiGemm mg; mg.n = 3;   // d(zcat_p) = d(e_p) W_p for the three pairs in one launch
@@ -623,7 +629,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         w.dY[p] = decat + p * D; w.X[p] = zcat + (size_t)p * B * 512; w.out[p] = gr(ix.pair(p, 0));
         any = any || w.out[p] != nullptr;
       }
-      if (any) { launch_wgrad_batched(w, st); LAUNCH_OK("w_pair"); }
+      if (any) { launch_wgrad_batched(w, ws); LAUNCH_OK("w_pair"); }
     }
     {
       ColsumArgs c; memset(&c, 0, sizeof(c));   // the three pair biases: column sums of d(ecat) [B, 768]
@@ -631,7 +637,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       bool any = false;
       for (int p = 0; p < 3; ++p) { c.out[p] = gr(ix.pair(p, 1)); any = any || c.out[p] != nullptr; }
       if (any) {
-        colsum_kernel<float><<<dim3((3 * D + 255) / 256, (B + 127) / 128), 256, 0, st>>>(c);
+        colsum_kernel<float><<<dim3((3 * D + 255) / 256, (B + 127) / 128), 256, 0, ws>>>(c);
         LAUNCH_OK("b_pair");
       }
     }

@@ -584,11 +584,55 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(sgen + stages * STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int seg = 0;
+  int seg = 0, sp, splits;
+  if (sp_tab.first[0] < 0) {
+    // Balanced split-K from the DEVICE-side row counts (packed query rows: the valid rows of a segment are data dependent,
+    // 4.3 k to 25 k at B = 512, while a static table gives every segment the same number of chunks): the gridDim.z chunks
+    // are dealt to the segments in proportion to their k-blocks -- one each, the rest by floor, leftovers to the segment
+    // with the longest chunks -- so every CTA reduces about total / gridDim.z k-blocks.  Every thread computes the same table.
+    const int Z = gridDim.z, n = w.segs.n;
+    int kb[6], cnt[6], total = 0, nonempty = 0;
 #pragma unroll
-  for (int i = 1; i < 6; ++i)
-    if (i < w.segs.n && (int)blockIdx.z >= sp_tab.first[i]) seg = i;
-  const int sp = blockIdx.z - sp_tab.first[seg], splits = sp_tab.first[seg + 1] - sp_tab.first[seg];
+    for (int i = 0; i < 6; ++i) {
+      kb[i] = 0; cnt[i] = 0;
+      if (i < n) {
+        kb[i] = w.segs.nv ? (seg_rows(w.segs, i) + BK - 1) / BK : (w.segs.row0[i + 1] - w.segs.row0[i]) / BK;
+        total += kb[i];
+        if (kb[i] > 0) { cnt[i] = 1; ++nonempty; }
+      }
+    }
+    int rest = Z - nonempty, used = 0;
+    if (total > 0 && rest > 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int add = (int)(((long long)rest * kb[i]) / total);
+        cnt[i] += add; used += add;
+      }
+      for (int left = rest - used; left > 0; --left) {      // at most n iterations
+        int best = 0; long long bv = -1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const long long v = cnt[i] > 0 ? ((long long)kb[i] << 20) / cnt[i] : -1;
+          if (v > bv) { bv = v; best = i; }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (i == best) ++cnt[i];
+      }
+    }
+    int first = 0, z = blockIdx.z;
+    sp = -1; splits = 1;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (sp < 0 && z < first + cnt[i]) { seg = i; sp = z - first; splits = cnt[i]; }
+      first += cnt[i];
+    }
+    if (sp < 0) return;       // more chunks than work (tiny batches)
+  } else {
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+      if (i < w.segs.n && (int)blockIdx.z >= sp_tab.first[i]) seg = i;
+    sp = blockIdx.z - sp_tab.first[seg]; splits = sp_tab.first[seg + 1] - sp_tab.first[seg];
+  }
   const int m0 = blockIdx.y * (MT * BM), n0 = blockIdx.x * BN;
   // reduction rows: the whole padded segment, or (packed query rows) the valid rows rounded up to a k-block -- rows
   // [nv, pad256(nv)) are zero in both operands by the q-space contract
@@ -861,11 +905,20 @@ static cudaError_t launch_wgrad_tc_mt(const WgradProblem& w, const CUtensorMap& 
   }
   for (int s = w.segs.n; s < 6; ++s) tab.first[s + 1] = tab.first[w.segs.n];
   (void)max_kb;
+  // opt-in: measured on one box (gpurun_out/r2c21_*): the class alone 1.03 -> 0.93 ms, but the two-stream step 4.65 -> 4.75 ms --
+  // balanced chunks keep all 148 SMs busy for the whole launch, and the chain's persistent GEMMs (static tile schedule, one
+  // CTA per SM) then wait for every SM; with the static table the short segments' CTAs retire early and free theirs
+  static int bal = env_int("MMR_TC_WGRAD_BAL", 0);
+  int grid_z = tab.first[w.segs.n];
+  if (bal) {        // the kernel derives the chunk table from the device-side row counts (see wgrad_tc_kernel)
+    grid_z = ctas_per_wave / tiles_per_seg > w.segs.n ? ctas_per_wave / tiles_per_seg : w.segs.n;
+    tab.first[0] = -1;
+  }
   auto kern = wgrad_tc_kernel<MT, BN>;
   const int smem = wgrad_smem_bytes<MT, BN>(stages);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
-  dim3 grid((w.N + BN - 1) / BN, (w.M + MT * BM - 1) / (MT * BM), tab.first[w.segs.n]);
+  dim3 grid((w.N + BN - 1) / BN, (w.M + MT * BM - 1) / (MT * BM), grid_z);
   if (pdl_enabled()) return launch_pdl(kern, grid, dim3(NTHREADS), (size_t)smem, st, tmY, tmX, w, tab, stages);
   kern<<<grid, NTHREADS, smem, st>>>(tmY, tmX, w, tab, stages);
   return cudaGetLastError();

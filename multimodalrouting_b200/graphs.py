@@ -13,6 +13,7 @@ private memory pool: read or all-reduce them after the replay, do not free them.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import torch
@@ -31,7 +32,10 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on a high-priority stream (MMR_GRAPH_PRIORITY=0: default priority) so that the chain's kernels are preferred over
+        # the (default-priority) weight-gradient side stream when both have CTAs waiting for an SM
+        prio = os.environ.get("MMR_GRAPH_PRIORITY", "1") == "1"
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=-1) if prio else None):
             self.out = fn()
         torch.cuda.synchronize()
 

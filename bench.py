@@ -531,6 +531,10 @@ def main():
     ws_saved = os.environ.get("MMR_WGRAD_STREAM")
     os.environ["MMR_WGRAD_STREAM"] = "0"      # ... and on ONE stream, so that every kernel class is timed alone
     for _ in range(nprof):          # every rank steps (the gradient all-reduce is a collective)
+        # Issuing a step eagerly takes the host longer than the GPU needs to run it, so the events around a launch would
+        # also time the GPU waiting for the host.  A ~25 ms device-side spin in front of every step lets the host run ahead:
+        # each (event, kernels, event) group is already queued when the GPU reaches it and the interval is device time only.
+        torch.cuda._sleep(int(0.025 * 1.9e9))
         step(False)
     graphed = g_saved
     if ws_saved is None:

@@ -1324,7 +1324,8 @@ static cudaError_t dispatch_routing(const RoutingArgs& a, const RtLaunch& L, boo
 
 // ---- split path (routing_split.cuh): projector / votes GEMMs + one patient per 1-4 warps for the agreement iterations ----
 static bool rs_enabled(const mmr_routing_dims* d, const mmr_routing_params* p, const void* scratch) {
-  static const bool on = [] { const char* e = getenv("MMR_RT_SPLIT"); return !(e && atoi(e) == 0); }();
+  const char* e = getenv("MMR_RT_SPLIT");      // read per call: the tests switch paths inside one process
+  const bool on = !(e && atoi(e) == 0);
   return on && scratch && d->vote_dtype == MMR_DTYPE_BF16 && p->caps_wt_f16 && p->caps_w_f16 &&
          (d->from_poses || p->proj_w_f16) && d->num_routing <= RS_NIT;
 }

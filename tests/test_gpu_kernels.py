@@ -183,6 +183,109 @@ def test_routing_reduced_precision_tensor_core_vs_cuda_core(variant, K, masked, 
         assert e_tc <= max(5e-2, 2.0 * e_cc), f"grad {k}: tensor-core {e_tc:.2e} cuda-core {e_cc:.2e}"
 
 
+@pytest.mark.parametrize("variant,K,nit,masked,B", [
+    ("pheno", 25, 3, True, 45), ("pheno", 25, 1, True, 17), ("pheno", 16, 3, True, 33), ("pheno", 12, 2, False, 40),
+    ("pheno", 8, 3, True, 21), ("mort", 5, 2, True, 50), ("pheno", 3, 3, True, 70), ("mort", 2, 3, True, 130), ("mort", 1, 3, False, 9)])
+def test_routing_split_path_vs_tile_path(variant, K, nit, masked, B, monkeypatch):
+    """Reduced-precision routing, round-2 split path (csrc/routing_split.cuh: projector / vote GEMMs on 16-patient tiles, one
+    patient per 1-4 warps for the agreement iterations; every lane-layout instantiation KP = 2, 4, 8, 16, 32 and num_routing
+    1..3) against the tile-of-4 kernels of the same mode (MMR_RT_SPLIT=0) and the fp32 oracle, ragged last tiles included."""
+    if variant == "mort":
+        from multimodalrouting_b200.MortModel import routing_and_heads as rh
+    else:
+        from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    _, sdp, sdh = synth.make_state(K=K, seed=31 + K, sharp=2.0)
+    g = torch.Generator().manual_seed(100 + K + nit)
+    embs = {r: 0.5 * torch.randn(B, 256, generator=g) for r in synth.ROUTES}
+    rm = None
+    if masked:
+        rm = (torch.rand(B, 10, generator=g) < 0.75).float()
+        rm[0] = 0.0
+        rm[1] = 1.0
+    gl = torch.randn(B, K, generator=g)
+    gR = torch.randn(B, 10, K, generator=g)
+    po = {k: v.clone().requires_grad_(True) for k, v in sdp.items()}
+    ho = {k: v.clone().requires_grad_(True) for k, v in sdh.items()}
+    eo = {r: v.clone().requires_grad_(True) for r, v in embs.items()}
+    lo, ao, Ro = orc.routing_forward(po, ho, eo, variant=variant, route_mask=rm, act_temperature=1.3, num_routing=nit)
+    ((lo * gl).sum() + (Ro * gR).sum()).backward()
+    res = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("MMR_RT_SPLIT", split)
+        proj = rh.RoutePrimaryProjector(256, 32)
+        head = rh.CapsuleMortalityHead(32, 64, nit, 0.0, "EM", num_classes=K)
+        proj.load_state_dict(sdp); head.load_state_dict(sdh)
+        proj, head = proj.cuda(), head.cuda()
+        ed = {r: v.clone().cuda().requires_grad_(True) for r, v in embs.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            l, a, _, R = rh.forward_capsule_from_route_dict(ed, proj, head, route_mask=None if rm is None else rm.cuda(),
+                                                            act_temperature=1.3)
+        ((l.float() * gl.cuda()).sum() + (R.float() * gR.cuda()).sum()).backward()
+        grads = {f"emb {r}": ed[r].grad for r in synth.ROUTES}
+        grads.update({f"proj_w {r}": proj.proj[r].weight.grad for r in synth.ROUTES})
+        grads.update({f"proj_b {r}": proj.proj[r].bias.grad for r in synth.ROUTES})
+        grads.update({"capsule.w": head.capsule.w.grad, "pose_to_mc": head.pose_to_mc.weight.grad,
+                      "embedding": head.embedding.grad, "bias": head.bias.grad})
+        res[split] = (l.float().detach(), a.float().detach(), R.float().detach(), grads)
+    ref_g = {f"emb {r}": eo[r].grad for r in synth.ROUTES}
+    ref_g.update({f"proj_w {r}": po[f"proj.{r}.weight"].grad for r in synth.ROUTES})
+    ref_g.update({f"proj_b {r}": po[f"proj.{r}.bias"].grad for r in synth.ROUTES})
+    ref_g.update({"capsule.w": ho["capsule.w"].grad, "pose_to_mc": ho["pose_to_mc.weight"].grad,
+                  "embedding": ho["embedding"].grad, "bias": ho["bias"].grad})
+    for split in ("0", "1"):
+        l, a, R, _ = res[split]
+        assert max_rel(l, lo) < 2e-2 and max_rel(a, ao) < 2e-2 and max_rel(R, Ro) < 2e-2, split
+        if rm is not None:
+            assert float((a.cpu() * (1 - rm)).abs().max()) == 0.0
+            assert float((R.cpu() * (1 - rm).unsqueeze(-1)).abs().max()) == 0.0
+    # same precision mode, same fp16 weight copies: the two paths differ only in summation order
+    assert max_rel(res["1"][0], res["0"][0].cpu()) < 5e-3 and max_rel(res["1"][2], res["0"][2].cpu()) < 5e-3
+    for k, ref in ref_g.items():
+        if ref is None:
+            continue
+        e_s, e_t = max_rel(res["1"][3][k], ref), max_rel(res["0"][3][k], ref)
+        assert bool(torch.isfinite(res["1"][3][k]).all()), k
+        assert e_s <= max(5e-2, 2.0 * e_t), f"grad {k}: split {e_s:.2e} tile {e_t:.2e}"
+
+
+@pytest.mark.parametrize("variant", ["mort", "pheno"])
+def test_routing_split_path_head_from_poses(variant, monkeypatch):
+    """CapsuleMortalityHead.forward(prim_pose, prim_act, route_mask) under autocast: the from_poses form of the split path
+    (no projector launch; d pose / d act returned) against the tile-of-4 kernels and the fp32 oracle."""
+    if variant == "mort":
+        from multimodalrouting_b200.MortModel import routing_and_heads as rh
+    else:
+        from multimodalrouting_b200.PhenoModel import routing_and_heads as rh
+    K, B = 25, 37
+    _, _, sdh = synth.make_state(K=K, seed=9, sharp=2.0)
+    g = torch.Generator().manual_seed(3)
+    pose = 0.5 * torch.randn(B, 10, 32, generator=g)
+    act = torch.rand(B, 10, generator=g)
+    rm = (torch.rand(B, 10, generator=g) < 0.8).float()
+    gl = torch.randn(B, K, generator=g)
+    ho = {k: v.clone().requires_grad_(True) for k, v in sdh.items()}
+    p0, a0 = pose.clone().requires_grad_(True), act.clone().requires_grad_(True)
+    lo, alo, Ro = orc.capsule_head_forward(ho, p0, a0, rm, variant=variant)
+    (lo * gl).sum().backward()
+    res = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("MMR_RT_SPLIT", split)
+        head = rh.CapsuleMortalityHead(32, 64, 3, 0.0, "EM", num_classes=K)
+        head.load_state_dict(sdh)
+        head = head.cuda()
+        p1, a1 = pose.clone().cuda().requires_grad_(True), act.clone().cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            l, al, R = head(p1, a1, route_mask=rm.cuda())
+        (l.float() * gl.cuda()).sum().backward()
+        res[split] = (l.float().detach(), R.float().detach(), p1.grad, a1.grad, head.capsule.w.grad)
+    for split in ("0", "1"):
+        assert max_rel(res[split][0], lo) < 2e-2 and max_rel(res[split][1], Ro) < 2e-2, split
+    assert max_rel(res["1"][0], res["0"][0].cpu()) < 5e-3
+    for i, ref in ((2, p0.grad), (4, ho["capsule.w"].grad)) + (((3, a0.grad),) if variant == "pheno" else ()):
+        e_s, e_t = max_rel(res["1"][i], ref), max_rel(res["0"][i], ref)
+        assert e_s <= max(5e-2, 2.0 * e_t), f"grad {i}: split {e_s:.2e} tile {e_t:.2e}"
+
+
 @pytest.mark.parametrize("B", [1, 19, 64])
 def test_projector_standalone_forward_backward_vs_oracle(B):
     """RoutePrimaryProjector.forward by itself (routing_and_heads.py:111-121; csrc/projector.cuh): poses / acts and every

@@ -669,8 +669,6 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
   CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
-  CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_w_kernel<AHG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
-  static const int bwd_wph = [] { const char* e = getenv("MMR_ATTN_BWD_WPH"); return e ? atoi(e) : 2; }();
 
   auto q_problem = [&](const void* A, int lda, const void* Bw, int ldb, int nrows_b, int N, int K, int l) {
     GemmProblem g; memset(&g, 0, sizeof(g));
@@ -775,10 +773,6 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
         if (mma_attention<CT>()) {
           if (maxTq <= amma::RC && maxTk <= amma::RC && !getenv("MMR_ATTN_BWD_SPLIT")) {
             // one chunk per sequence: fused dQ + dK/dV kernel (operands staged once, no O / D round trip)
-            if (bwd_wph == 3)
-              launch_k(amma::attn_bwd_fused_w_kernel<AHG, 3>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(AHG * 96),
-                       amma::bwd_fused_smem<AHG>(), st, a);
-            else
             launch_k(amma::attn_bwd_fused_kernel<AHG>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(amma::Cfg<AHG>::THREADS),
                      amma::bwd_fused_smem<AHG>(), st, a);
           } else {

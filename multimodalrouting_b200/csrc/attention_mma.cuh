@@ -71,17 +71,6 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* src, size_t ld, int
   }
 }
 
-template <int HG, int THREADS>
-__device__ __forceinline__ void stage_t(bf16* dst, const bf16* src, size_t ld, int nvalid, int nrows) {
-  constexpr int LDS = Cfg<HG>::LDS, CPR = Cfg<HG>::CPR;
-  for (int idx = threadIdx.x; idx < nrows * CPR; idx += THREADS) {
-    const int r = idx / CPR, c = (idx % CPR) * 8;
-    bf16* d = dst + r * LDS + c;
-    if (r < nvalid) cp_async16(smem_addr(d), src + (size_t)r * ld + c);
-    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-  }
-}
-
 // A fragment (16 rows x 16 k) of a row-major smem tile at (row0, col0)
 template <int LDS>
 __device__ __forceinline__ void frag_a(const bf16* s, int row0, int col0, int lane, uint32_t (&r)[4]) {
@@ -137,7 +126,7 @@ __device__ __forceinline__ void put_c(bf16* s, int row0, int col0, int lane, con
   *reinterpret_cast<uint32_t*>(s + (row0 + g + 8) * LDS + col0 + 2 * t) = pack_bf16(c[2] * s1, c[3] * s1);
 }
 
-template <int HG> constexpr int fwd_smem() { return 3 * RC * Cfg<HG>::LDS * 2 + RC * 4; }
+template <int HG> __host__ __device__ constexpr int fwd_smem() { return 3 * RC * Cfg<HG>::LDS * 2 + RC * 4; }
 template <int HG> constexpr int bwd_smem() { return 4 * RC * Cfg<HG>::LDS * 2 + RC * 4 + RC * HG * 3 * 4; }
 
 // grid: (NHG * ceil(maxTq/64), B, 6)
@@ -278,40 +267,15 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
 }
 
-// ------------------------------------------------------------------------------------------
-// Forward specialised for Tk <= 64 (one key chunk: every MIMIC-IV shape).  No running max / sum / output
-// state survives an m-tile, so the tiles are walked in a rolled loop and the kernel fits 6 CTAs (24 warps)
-// per SM -- the general kernel above is bound by dependent-instruction latency at 16 warps per SM.
-// grid: (NHG * ceil(maxTq/64), B, 6)
+// scores, softmax and P V of one (patient, direction, head group) whose keys fit one chunk; the output tile replaces the
+// Q slot of each (m-tile, head) in shared memory, (max, 1 / sum) go to a.ml
 template <int HG>
-__global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn_fwd_single_kernel(AttnArgs a) {
-  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-  bf16* Ks = Qs + RC * LDS;
-  bf16* Vs = Ks + RC * LDS;
-  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
-  int qs_, Tq;
-  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
-  const int nk = a.kv.T[d];
-  const int q0 = qc * RC;
-  if (q0 >= Tq) return;
-  const int nq = min(RC, Tq - q0);
+__device__ __forceinline__ void fwd_single_compute(const AttnArgs& a, bf16* Qs, const bf16* Ks, const bf16* Vs, const float* Ms,
+                                                   int nq, int nk, size_t qrow0, int hg) {
+  constexpr int LDS = Cfg<HG>::LDS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
   const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
-  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
-  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
-  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
-  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
-  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
-  if (threadIdx.x < RC)
-    Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
-  cp_async_wait_all();
-  __syncthreads();
   const int NT = (nk + 7) >> 3;
 #pragma unroll 1
   for (int i = 0; i < 2; ++i) {
@@ -380,6 +344,43 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn
       if (r1 < nq) { float* p = a.ml + ((qrow0 + r1) * H + h) * 2; p[0] = mx1; p[1] = il1; }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward specialised for Tk <= 64 (one key chunk: every MIMIC-IV shape).  No running max / sum / output
+// state survives an m-tile, so the tiles are walked in a rolled loop and the kernel fits 6 CTAs (24 warps)
+// per SM -- the general kernel above is bound by dependent-instruction latency at 16 warps per SM.
+// grid: (NHG * ceil(maxTq/64), B, 6)
+template <int HG>
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn_fwd_single_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Ks = Qs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int nk = a.kv.T[d];
+  const int q0 = qc * RC;
+  if (q0 >= Tq) return;
+  const int nq = min(RC, Tq - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
+  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
+  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  if (threadIdx.x < RC)
+    Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
+  cp_async_wait_all();
+  __syncthreads();
+  fwd_single_compute<HG>(a, Qs, Ks, Vs, Ms, nq, nk, qrow0, hg);
   __syncthreads();
   unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
 }
@@ -784,182 +785,6 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 640 / Cfg<HG>::THREADS) attn
   for (int i = 0; i < 2; ++i) {
     const int mt = half * 2 + i;
     if (mt * 16 >= nk) break;
-    float dk[4][4], dv[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { dk[n][j] = 0.f; dv[n][j] = 0.f; }
-    uint32_t ka[2][4], va[2][4];
-    frag_a<LDS>(Ks, mt * 16, hl * 32, lane, ka[0]);
-    frag_a<LDS>(Ks, mt * 16, hl * 32 + 16, lane, ka[1]);
-    frag_a<LDS>(Vs, mt * 16, hl * 32, lane, va[0]);
-    frag_a<LDS>(Vs, mt * 16, hl * 32 + 16, lane, va[1]);
-    const float kb0 = Bs[mt * 16 + g], kb1 = Bs[mt * 16 + g + 8];      // this thread's two key rows
-    const float kp0 = Kp[mt * 16 + g], kp1 = Kp[mt * 16 + g + 8];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      if (2 * kk >= NTQ) continue;
-      uint32_t pa[4], dsa[4];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int nt = 2 * kk + e;
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t qb[4], gb[4];
-        frag_b_nk<LDS>(Qs, nt * 8, hl * 32, lane, qb);
-        frag_b_nk<LDS>(Gs, nt * 8, hl * 32, lane, gb);
-        mma16816(s, ka[0], qb[0], qb[1]);
-        mma16816(s, ka[1], qb[2], qb[3]);
-        mma16816(dp, va[0], gb[0], gb[1]);
-        mma16816(dp, va[1], gb[2], gb[3]);
-        const float4 sa = St[(nt * 8 + 2 * t) * HG + hl], sb = St[(nt * 8 + 2 * t + 1) * HG + hl];   // query columns
-        const float p0 = ex2((rbf(s[0]) + kb0 - sa.x) * L2E) * sa.y, p1 = ex2((rbf(s[1]) + kb0 - sb.x) * L2E) * sb.y;
-        const float p2 = ex2((rbf(s[2]) + kb1 - sa.x) * L2E) * sa.y, p3 = ex2((rbf(s[3]) + kb1 - sb.x) * L2E) * sb.y;
-        pa[e * 2] = pack_bf16(p0, p1);
-        pa[e * 2 + 1] = pack_bf16(p2, p3);
-        dsa[e * 2] = pack_bf16(p0 * (dp[0] - sa.z) * kp0, p1 * (dp[1] - sb.z) * kp0);
-        dsa[e * 2 + 1] = pack_bf16(p2 * (dp[2] - sa.z) * kp1, p3 * (dp[3] - sb.z) * kp1);
-      }
-#pragma unroll
-      for (int nc = 0; nc < 2; ++nc) {
-        uint32_t gb[4], qb[4];
-        frag_b_kn<LDS>(Gs, kk * 16, hl * 32 + nc * 16, lane, gb);
-        frag_b_kn<LDS>(Qs, kk * 16, hl * 32 + nc * 16, lane, qb);
-        mma16816(dv[2 * nc], pa, gb[0], gb[1]);
-        mma16816(dv[2 * nc + 1], pa, gb[2], gb[3]);
-        mma16816(dk[2 * nc], dsa, qb[0], qb[1]);
-        mma16816(dk[2 * nc + 1], dsa, qb[2], qb[3]);
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      put_c_global(dkv_out, a.ldkv, mt * 16, hl * 32 + n * 8, lane, dk[n], nk);
-      put_c_global(dkv_out + D, a.ldkv, mt * 16, hl * 32 + n * 8, lane, dv[n], nk);
-    }
-  }
-}
-
-// Same kernel with WPH warps per head and the (head, 16-row tile) work items dealt round-robin over the warps: with two
-// fixed tiles per warp a 48-row sequence (3 tiles) leaves half of the warps idle for half of each pass (13.7 % barrier
-// stalls in profiles/r1_attention.md); packed query rows make the tile count vary per patient on top of that.
-template <int HG, int WPH>
-__global__ void __launch_bounds__(HG * WPH * 32, (HG * WPH * 32) > 128 ? 3 : 5) attn_bwd_fused_w_kernel(AttnArgs a) {
-  constexpr int THREADS = HG * WPH * 32, NW = HG * WPH, LDS = Cfg<HG>::LDS, COLS = Cfg<HG>::COLS;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-  bf16* Gs = Qs + RC * LDS;      // dO
-  bf16* Ks = Gs + RC * LDS;
-  bf16* Vs = Ks + RC * LDS;
-  float* Bs = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
-  float* Kp = Bs + RC;                                   // [64] 1 for kept keys else 0
-  float4* St = reinterpret_cast<float4*>(Kp + RC);       // [64 queries][HG]: m, 1/l, D, -
-  pdl_trigger();
-  pdl_wait();
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x;
-  int qs_, nq;
-  seg_patient(a.q, d, b, qs_, nq);     // this patient's (packed) query rows
-  const int nk = a.kv.T[d];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_;
-  const size_t krow0 = (size_t)a.kv.row0[d] + (size_t)b * nk;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + krow0 * a.ldkv + a.col0 + hg * COLS;
-  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
-  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
-  stage_t<HG, THREADS>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
-  stage_t<HG, THREADS>(Gs, reinterpret_cast<const bf16*>(a.d_o) + qrow0 * D + hg * COLS, D, nq, nq16);
-  stage_t<HG, THREADS>(Ks, kvsrc, a.ldkv, nk, nk16);
-  stage_t<HG, THREADS>(Vs, kvsrc + D, a.ldkv, nk, nk16);
-  if (threadIdx.x < RC) {
-    const float mk = threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f;
-    Bs[threadIdx.x] = key_bias(mk);
-    Kp[threadIdx.x] = mk > 0.f ? 1.f : 0.f;
-  }
-  for (int idx = threadIdx.x; idx < RC * HG; idx += THREADS) {
-    const int r = idx / HG, hh = idx % HG;
-    float2 ml = make_float2(0.f, 0.f);     // 1/l = 0 for tile-padding queries -> P = 0
-    if (r < nq) ml = *reinterpret_cast<const float2*>(a.ml + ((qrow0 + r) * H + hg * HG + hh) * 2);
-    St[idx] = make_float4(ml.x, ml.y, 0.f, 0.f);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  const int NTK = (nk + 7) >> 3, NTQ = (nq + 7) >> 3;
-  bf16* dq_out = reinterpret_cast<bf16*>(a.dq) + qrow0 * D + hg * COLS;
-
-  // ---- pass A: rows = queries ------------------------------------------------------------
-#pragma unroll 1
-  for (int item = warp; item < HG * ((nq + 15) >> 4); item += NW) {
-    const int hl = item % HG, mt = item / HG;
-    uint32_t qa[2][4], ga[2][4];
-    frag_a<LDS>(Qs, mt * 16, hl * 32, lane, qa[0]);
-    frag_a<LDS>(Qs, mt * 16, hl * 32 + 16, lane, qa[1]);
-    frag_a<LDS>(Gs, mt * 16, hl * 32, lane, ga[0]);
-    frag_a<LDS>(Gs, mt * 16, hl * 32 + 16, lane, ga[1]);
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    const float4 st0 = St[r0 * HG + hl], st1 = St[r1 * HG + hl];
-    uint32_t pp[8][2];          // P of this m-tile, packed bf16x2: [nt][0] = row g, [nt][1] = row g+8
-    float dp[8][4];
-    float D0 = 0.f, D1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      pp[nt][0] = pp[nt][1] = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dp[nt][j] = 0.f;
-      if (nt < NTK) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t kb[4], vb[4];
-        frag_b_nk<LDS>(Ks, nt * 8, hl * 32, lane, kb);
-        frag_b_nk<LDS>(Vs, nt * 8, hl * 32, lane, vb);
-        mma16816(s, qa[0], kb[0], kb[1]);
-        mma16816(s, qa[1], kb[2], kb[3]);
-        mma16816(dp[nt], ga[0], vb[0], vb[1]);
-        mma16816(dp[nt], ga[1], vb[2], vb[3]);
-        const float2 kbias = *reinterpret_cast<const float2*>(Bs + nt * 8 + 2 * t);
-        const float p0 = ex2((rbf(s[0]) + kbias.x - st0.x) * L2E) * st0.y;
-        const float p1 = ex2((rbf(s[1]) + kbias.y - st0.x) * L2E) * st0.y;
-        const float p2 = ex2((rbf(s[2]) + kbias.x - st1.x) * L2E) * st1.y;
-        const float p3 = ex2((rbf(s[3]) + kbias.y - st1.x) * L2E) * st1.y;
-        D0 = fmaf(p0, dp[nt][0], fmaf(p1, dp[nt][1], D0));
-        D1 = fmaf(p2, dp[nt][2], fmaf(p3, dp[nt][3], D1));
-        pp[nt][0] = pack_bf16(p0, p1);
-        pp[nt][1] = pack_bf16(p2, p3);
-      }
-    }
-    D0 = quad_sum(D0); D1 = quad_sum(D1);
-    if (t == 0) { St[r0 * HG + hl].z = D0; St[r1 * HG + hl].z = D1; }
-    float dq[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      if (2 * kk >= NTK) continue;
-      uint32_t dsa[4];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int nt = 2 * kk + e;
-        const float2 keep = *reinterpret_cast<const float2*>(Kp + nt * 8 + 2 * t);   // tiles >= NTK: P = 0 already
-        const float p0 = __uint_as_float(pp[nt][0] << 16), p1 = __uint_as_float(pp[nt][0] & 0xffff0000u);
-        const float p2 = __uint_as_float(pp[nt][1] << 16), p3 = __uint_as_float(pp[nt][1] & 0xffff0000u);
-        dsa[e * 2] = pack_bf16(p0 * (dp[nt][0] - D0) * keep.x, p1 * (dp[nt][1] - D0) * keep.y);
-        dsa[e * 2 + 1] = pack_bf16(p2 * (dp[nt][2] - D1) * keep.x, p3 * (dp[nt][3] - D1) * keep.y);
-      }
-#pragma unroll
-      for (int nc = 0; nc < 2; ++nc) {
-        uint32_t kb[4];
-        frag_b_kn<LDS>(Ks, kk * 16, hl * 32 + nc * 16, lane, kb);
-        mma16816(dq[2 * nc], dsa, kb[0], kb[1]);
-        mma16816(dq[2 * nc + 1], dsa, kb[2], kb[3]);
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) put_c_global(dq_out, D, mt * 16, hl * 32 + n * 8, lane, dq[n], nq);
-  }
-  __syncthreads();   // D of every (query, head) visible
-
-  // ---- pass B: rows = keys (transposed tiles) ---------------------------------------------
-  bf16* dkv_out = reinterpret_cast<bf16*>(a.dkv) + krow0 * a.ldkv + a.col0 + hg * COLS;
-#pragma unroll 1
-  for (int item = warp; item < HG * ((nk + 15) >> 4); item += NW) {
-    const int hl = item % HG, mt = item / HG;
     float dk[4][4], dv[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n)

@@ -126,7 +126,7 @@ __device__ __forceinline__ void put_c(bf16* s, int row0, int col0, int lane, con
   *reinterpret_cast<uint32_t*>(s + (row0 + g + 8) * LDS + col0 + 2 * t) = pack_bf16(c[2] * s1, c[3] * s1);
 }
 
-template <int HG> __host__ __device__ constexpr int fwd_smem() { return 3 * RC * Cfg<HG>::LDS * 2 + RC * 4; }
+template <int HG> constexpr int fwd_smem() { return 3 * RC * Cfg<HG>::LDS * 2 + RC * 4; }
 template <int HG> constexpr int bwd_smem() { return 4 * RC * Cfg<HG>::LDS * 2 + RC * 4 + RC * HG * 3 * 4; }
 
 // grid: (NHG * ceil(maxTq/64), B, 6)
@@ -267,15 +267,40 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 512 / Cfg<HG>::THREADS) attn
   unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
 }
 
-// scores, softmax and P V of one (patient, direction, head group) whose keys fit one chunk; the output tile replaces the
-// Q slot of each (m-tile, head) in shared memory, (max, 1 / sum) go to a.ml
+// ------------------------------------------------------------------------------------------
+// Forward specialised for Tk <= 64 (one key chunk: every MIMIC-IV shape).  No running max / sum / output
+// state survives an m-tile, so the tiles are walked in a rolled loop and the kernel fits 6 CTAs (24 warps)
+// per SM -- the general kernel above is bound by dependent-instruction latency at 16 warps per SM.
+// grid: (NHG * ceil(maxTq/64), B, 6)
 template <int HG>
-__device__ __forceinline__ void fwd_single_compute(const AttnArgs& a, bf16* Qs, const bf16* Ks, const bf16* Vs, const float* Ms,
-                                                   int nq, int nk, size_t qrow0, int hg) {
-  constexpr int LDS = Cfg<HG>::LDS;
+__global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn_fwd_single_kernel(AttnArgs a) {
+  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Ks = Qs + RC * LDS;
+  bf16* Vs = Ks + RC * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
+  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
+  int qs_, Tq;
+  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
+  const int nk = a.kv.T[d];
+  const int q0 = qc * RC;
+  if (q0 >= Tq) return;
+  const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
   const int g = lane >> 2, t = lane & 3;
+  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
+  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
+  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
+  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
+  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
+  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
+  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
+  if (threadIdx.x < RC)
+    Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
+  cp_async_wait_all();
+  __syncthreads();
   const int NT = (nk + 7) >> 3;
 #pragma unroll 1
   for (int i = 0; i < 2; ++i) {
@@ -344,43 +369,6 @@ __device__ __forceinline__ void fwd_single_compute(const AttnArgs& a, bf16* Qs, 
       if (r1 < nq) { float* p = a.ml + ((qrow0 + r1) * H + h) * 2; p[0] = mx1; p[1] = il1; }
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// Forward specialised for Tk <= 64 (one key chunk: every MIMIC-IV shape).  No running max / sum / output
-// state survives an m-tile, so the tiles are walked in a rolled loop and the kernel fits 6 CTAs (24 warps)
-// per SM -- the general kernel above is bound by dependent-instruction latency at 16 warps per SM.
-// grid: (NHG * ceil(maxTq/64), B, 6)
-template <int HG>
-__global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn_fwd_single_kernel(AttnArgs a) {
-  constexpr int THREADS = Cfg<HG>::THREADS, LDS = Cfg<HG>::LDS, NHG = Cfg<HG>::NHG, COLS = Cfg<HG>::COLS;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-  bf16* Ks = Qs + RC * LDS;
-  bf16* Vs = Ks + RC * LDS;
-  float* Ms = reinterpret_cast<float*>(Vs + RC * LDS);   // [64] additive key bias
-  const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x % NHG, qc = blockIdx.x / NHG;
-  int qs_, Tq;
-  seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
-  const int nk = a.kv.T[d];
-  const int q0 = qc * RC;
-  if (q0 >= Tq) return;
-  const int nq = min(RC, Tq - q0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = warp % HG, half = warp / HG, h = hg * HG + hl;
-  const int g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = (size_t)a.q.row0[d] + (size_t)qs_ + q0;
-  const bf16* kvsrc = reinterpret_cast<const bf16*>(a.kvbuf) + ((size_t)a.kv.row0[d] + (size_t)b * nk) * a.ldkv + a.col0 + hg * COLS;
-  const float* km = a.kmask[d] ? a.kmask[d] + (size_t)b * nk : nullptr;
-  const int nq16 = (nq + 15) & ~15, nk16 = (nk + 15) & ~15;
-  stage<HG>(Qs, reinterpret_cast<const bf16*>(a.qb) + qrow0 * D + hg * COLS, D, nq, nq16);
-  stage<HG>(Ks, kvsrc, a.ldkv, nk, nk16);
-  stage<HG>(Vs, kvsrc + D, a.ldkv, nk, nk16);
-  if (threadIdx.x < RC)
-    Ms[threadIdx.x] = key_bias(threadIdx.x < nk ? (km ? (km[threadIdx.x] < 0.5f ? 0.f : 1.f) : 1.f) : -1.f);
-  cp_async_wait_all();
-  __syncthreads();
-  fwd_single_compute<HG>(a, Qs, Ks, Vs, Ms, nq, nk, qrow0, hg);
   __syncthreads();
   unstage<HG>(reinterpret_cast<bf16*>(a.o) + qrow0 * D + hg * COLS, D, Qs, nq);
 }

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) rs_votes_kernel(RoutingArgs a, RsScratch 
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-      const int idx = tid + 256 * i, p = idx / 80, j4 = idx % 80, b = b0 + p;
+      const int idx = tid + 256 * i, p = idx / 80, j4 = idx % 80;
       const float4 o = make_float4(v[i].x * rm[i], v[i].y * rm[i], v[i].z * rm[i], v[i].w * rm[i]);
       *reinterpret_cast<float4*>(&pm[p][4 * j4]) = o;
     }

@@ -168,7 +168,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 }
 
 template <int BN> __host__ __device__ constexpr int stage_bytes() { return (BM + BN) * BK * 2; }
-template <int BN> __host__ __device__ constexpr int smem_bytes(int stages) { return stages * stage_bytes<BN>() + 1024 + 256; }
+template <int BN> __host__ __device__ constexpr int smem_bytes(int stages) { return stages * stage_bytes<BN>() + 1024 + 512; }
 
 struct Ctrl {   // lives after the stages
   uint64_t full[8];
@@ -178,7 +178,12 @@ struct Ctrl {   // lives after the stages
   uint64_t tempty[2];     // persistent GEMM: accumulator buffer drained
   uint32_t tmem_base;
   uint32_t pad_;
+  // dynamic tile scheduling (cluster launch control): 16-byte try_cancel responses, one mbarrier pair per slot
+  uint64_t clc_full[4];
+  uint64_t clc_empty[4];
+  uint4 clc_resp[4];
 };
+static_assert(sizeof(Ctrl) <= 512, "Ctrl must fit its shared-memory reserve");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -331,12 +336,21 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 // fourth stage fits.  Requires every segment to hold an even number of 128-row tiles.
 template <int BN, int CL> __host__ __device__ constexpr int gemm_stage_bytes() { return (BM + BN / CL) * BK * 2; }
 template <int BN, int CL, bool F32> __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-  return stages * gemm_stage_bytes<BN, CL>() + 8 * cstg_bytes<F32>() + 8 * (BN / 2) * 4 + 1024 + 256;
+  return stages * gemm_stage_bytes<BN, CL>() + 8 * cstg_bytes<F32>() + 8 * (BN / 2) * 4 + 1024 + 512;
 }
-template <int BN, int OP, int CL>
+// DYN = 1 (CTA pairs only): dynamic tile scheduling through cluster launch control.  The grid holds one cluster per
+// (static) work item; a resident cluster starts with its own item and then CANCELS pending clusters of the grid
+// (clusterlaunchcontrol.try_cancel) and takes over theirs, so the items go to whichever pairs actually hold SMs -- a pair
+// that starts late because the weight-gradient stream or NCCL occupies its SMs simply takes fewer.  The 16-byte response is
+// multicast by the hardware to the same shared-memory offset of both CTAs and completes an mbarrier in each (clc_full);
+// every role reads the item from there and acknowledges on the leader's clc_empty before the slot is reused.  The leader's
+// MMA thread is the scheduler: at the start of item i it looks at the response for item i + 1 and, if that was a
+// cancellation, requests item i + 2.  Items beyond the valid (device-side) count are skipped by every role alike.
+template <int BN, int OP, int CL, int DYN = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmProblem g, TcEpi e, int stages) {
+  static_assert(DYN == 0 || CL == 2, "dynamic scheduling is implemented for CTA pairs");
   constexpr int STAGE = gemm_stage_bytes<BN, CL>();
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -374,6 +388,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     return g.segs.row0[sg] + (mt - vt0[sg]) * CL * BM;
   };
 
+  // item i >= 1 of this cluster travels through slot (i - 1) & 3; its k-th use completes phase k of the slot's barriers
+  auto clc_issue = [&](uint32_t j) {      // leader's scheduler thread
+    const uint32_t sl = (j - 1) & 3u, k = (j - 1) >> 2;
+    mbar_wait(smem_u32(&ctrl->clc_empty[sl]), (k & 1u) ^ 1u);      // every role of both CTAs has read the previous use
+    const uint32_t fb = smem_u32(&ctrl->clc_full[sl]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(fb) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], 16;" ::"r"(mapa_u32(fb, 1)) : "memory");
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+        ::"r"(smem_u32(&ctrl->clc_resp[sl])), "r"(fb) : "memory");
+  };
+  // item index of this cluster's i-th item, -1 when the grid has no pending cluster left; `ack`: this caller is one of the
+  // 18 acknowledging readers (producer lanes, epilogue warps), the scheduler thread reads without acknowledging
+  auto clc_item = [&](uint32_t i, bool ack) -> int {
+    if (i == 0) return (int)(blockIdx.x / CL);
+    const uint32_t sl = (i - 1) & 3u, k = (i - 1) >> 2;
+    mbar_wait(smem_u32(&ctrl->clc_full[sl]), k & 1u);
+    uint32_t valid = 0, x = 0, y = 0, z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 clc_result;\n\t"
+        "ld.shared.b128 clc_result, [%4];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, clc_result;\n\t"
+        "selp.u32 %3, 1, 0, p1;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, clc_result;\n\t}"
+        : "+r"(x), "+r"(y), "+r"(z), "+r"(valid) : "r"(smem_u32(&ctrl->clc_resp[sl])) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the slot is rewritten through the async proxy
+    if (ack) {
+      if (warp >= 2) __syncwarp();        // epilogue warps: every lane has read the slot (the producers call with one lane)
+      if (lane == 0) {
+        if (rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->clc_empty[sl]), 0));
+        else mbar_arrive(smem_u32(&ctrl->clc_empty[sl]));
+      }
+    }
+    return valid ? (int)(x / CL) : -1;
+  };
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&ctrl->full[s]), 1);
@@ -382,6 +432,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&ctrl->tfull[b]), 1);
       mbar_init(smem_u32(&ctrl->tempty[b]), 8 * CL);
+    }
+    if (DYN) {
+      for (int s = 0; s < 4; ++s) {
+        mbar_init(smem_u32(&ctrl->clc_full[s]), 1);
+        mbar_init(smem_u32(&ctrl->clc_empty[s]), 18);     // 2 producer lanes + 16 epilogue warps
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -401,7 +457,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
       uint32_t it = 0;
-      for (int t = w0; t < nwork; t += wstep) {
+      for (uint32_t wi = 0;; ++wi) {
+        int t;
+        if (DYN) {
+          t = clc_item(wi, true);
+          if (t < 0) break;
+          if (t >= nwork) continue;
+        } else {
+          t = w0 + (int)wi * wstep;
+          if (t >= nwork) break;
+        }
         const int m0 = item_row(t) + (int)rank * BM, n0 = (t % nN) * BN;
         const int seg = seg_of_row(g.segs, m0);
         const int a_row = g.a_row0[seg] + (m0 - g.segs.row0[seg]);
@@ -431,7 +496,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(BN, 0, 0, CL * BM);
       uint32_t it = 0, i = 0;
-      for (int t = w0; t < nwork; t += wstep) {
+      if (DYN) clc_issue(1);
+      for (uint32_t wi = 0;; ++wi) {
+        int t;
+        if (DYN) {
+          t = clc_item(wi, false);
+          if (t < 0) break;
+          if (clc_item(wi + 1, false) >= 0) clc_issue(wi + 2);     // never request after a failed cancellation
+          if (t >= nwork) continue;
+        } else {
+          t = w0 + (int)wi * wstep;
+          if (t >= nwork) break;
+        }
         const uint32_t buf = i & 1;
         mbar_wait(smem_u32(&ctrl->tempty[buf]), ((i >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -465,7 +541,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = bias_all + (warp - 2) * HC;
     const bool f32_out = (OP == TEPI_F32 || OP == TEPI_BIAS_F32);
     uint32_t i = 0;
-    for (int t = w0; t < nwork; t += wstep) {
+    for (uint32_t wi = 0;; ++wi) {
+      int t;
+      if (DYN) {
+        t = clc_item(wi, true);
+        if (t < 0) break;
+        if (t >= nwork) continue;
+      } else {
+        t = w0 + (int)wi * wstep;
+        if (t >= nwork) break;
+      }
       const uint32_t i_cur = i++;
       const int m0 = item_row(t) + (int)rank * BM, n0 = (t % nN) * BN + ch * HC;
       const int seg = seg_of_row(g.segs, m0);
@@ -570,7 +655,7 @@ struct WgradSplits { int first[7]; };
 
 template <int MT, int BN> __host__ __device__ constexpr int wgrad_stage_bytes() { return (MT * BM + BN) * BK * 2; }
 template <int MT, int BN> __host__ __device__ constexpr int wgrad_smem_bytes(int stages) {
-  return stages * wgrad_stage_bytes<MT, BN>() + 1024 + 256;
+  return stages * wgrad_stage_bytes<MT, BN>() + 1024 + 512;
 }
 
 template <int MT, int BN>
@@ -814,7 +899,7 @@ inline bool pdl_enabled() {
   return on != 0;
 }
 
-template <int OP, int CL>
+template <int OP, int CL, int DYN = 0>
 static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a_rows_total, int b_rows_total,
                                      int sm_count, cudaStream_t st) {
   constexpr int BN = 256;
@@ -830,7 +915,7 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
     return cudaErrorUnknown;
   if (!make_tmap(&tmA, g.A, (uint64_t)g.K, (uint64_t)a_rows_total, (uint64_t)g.lda, BK, BM)) return cudaErrorUnknown;
   if (!make_tmap(&tmB, g.B, (uint64_t)g.K, (uint64_t)b_rows_total, (uint64_t)g.ldb, BK, BN / CL)) return cudaErrorUnknown;
-  auto kern = gemm_tc_kernel<BN, OP, CL>;
+  auto kern = gemm_tc_kernel<BN, OP, CL, DYN>;
   const int smem = gemm_smem_bytes<BN, CL, f32_stg>(stages);
   static int dbg_cfg = env_int("MMR_TC_DBG", 0);
   TcEpi e2 = e;
@@ -841,6 +926,7 @@ static cudaError_t launch_gemm_tc_cl(const GemmProblem& g, const TcEpi& e, int a
   const int nwork = ((total_rows + CL * BM - 1) / (CL * BM)) * (g.N / BN);
   int grid = nwork * CL < sm_count ? nwork * CL : sm_count;
   grid -= grid % CL;
+  if (DYN) grid = nwork * CL;      // one cluster per static work item; resident clusters cancel the pending ones
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -875,6 +961,11 @@ static cudaError_t launch_gemm_tc(const GemmProblem& g, const TcEpi& e, int a_ro
   static int pair_min_k = env_int("MMR_TC_PAIR_MIN_K", 256);
   bool pair_ok = pair_cfg != 0 && g.K >= pair_min_k;
   for (int s = 0; s <= g.segs.n && pair_ok; ++s) pair_ok = g.segs.row0[s] % (2 * BM) == 0;
+  // dynamic tile scheduling through cluster launch control: opt-in (read per launch: the tests switch it inside one process).
+  // Measured (profiles/r2_experiments_late.md): parity green, the GEMM class alone +1.3 %, the step equal at N = 1, and the
+  // overlapped all-reduce at N = 2 equally slow with it -- the static schedule was not what made the overlap lose.
+  const int clc_cfg = env_int("MMR_TC_CLC", 0);
+  if (pair_ok && clc_cfg) return launch_gemm_tc_cl<OP, 2, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
   if (pair_ok) return launch_gemm_tc_cl<OP, 2>(g, e, a_rows_total, b_rows_total, sm_count, st);
   return launch_gemm_tc_cl<OP, 1>(g, e, a_rows_total, b_rows_total, sm_count, st);
 }

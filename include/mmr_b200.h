@@ -230,6 +230,21 @@ int mmr_capsule_routing_bwd_ex(const mmr_routing_dims* dims, const mmr_routing_p
                                const mmr_routing_grads* grads, float* d_route_embs, float* d_poses,
                                float* d_acts, const void* fwd_scratch, void* stream);
 
+/* Per-patient multi-head attention core (8 heads x 32) on the path's attention kernels, for ONE pair of streams -- what the
+ * attention-fusion variants of the Partial/ model (`CrossAttentionFusion`, `TriTokenAttentionFusion`:
+ * MIMIC-IV/PhenoModel/Partial/Cross_Attention/routing_and_heads.py:103-206) need between their projections:
+ *   o[b, i, h*32:(h+1)*32] = sum_j softmax_j(q_h[b,i] . k_h[b,j] + keymask[b,j]) v_h[b,j]
+ * q: [B*Tq, 256], already scaled by head_dim^-1/2; kv: [B*Tk, 512] = K | V per row; kmask: fp32 [B, Tk] (>= 0.5 keep) or NULL;
+ * o: [B*Tq, 256]; ml: fp32 [B*Tq, 8, 2] (row max, 1 / row sum), saved for the backward.  dtype = MMR_DTYPE_BF16 (bf16 operands,
+ * mma.sync tiles, scores rounded to bf16 before an fp32 softmax like the reference's bmm under autocast) or MMR_DTYPE_F32.
+ * Key masking follows the hot path: padded keys get finfo(bf16).min, so a patient whose keys are all padded
+ * attends uniformly instead of producing NaN; the fusion modules zero such patients afterwards, as the reference intends. */
+int mmr_attention_fwd(int dtype, int B, int Tq, int Tk, const void* q, const void* kv, const float* kmask, void* o, float* ml,
+                      void* stream);
+/* Backward: d_o [B*Tq,256] -> dq [B*Tq,256], dkv [B*Tk,512]; dvec: fp32 [B*Tq, 8] scratch. */
+int mmr_attention_bwd(int dtype, int B, int Tq, int Tk, const void* q, const void* kv, const float* kmask, const void* o,
+                      const float* ml, const void* d_o, void* dq, void* dkv, float* dvec, void* stream);
+
 /* Replaces RoutePrimaryProjector.forward alone (routing_and_heads.py:111-121) for callers that use the projector outside
  * forward_capsule_from_route_dict: poses [B,10,32] = (W_r e_r + b_r)[:32], acts [B,10] = sigmoid((W_r e_r + b_r)[32]).
  * route_embs / strides as above; only params->proj_w / proj_b are read.  fp32. */

@@ -71,7 +71,7 @@ EXPORTS = ["mmr_version", "mmr_last_error_string", "mmr_fusion_num_params", "mmr
            "mmr_loss_scratch_bytes", "mmr_loss_fwd_bwd", "mmr_projector_fwd", "mmr_projector_bwd",
            "mmr_fusion_pack_weights", "mmr_route_fusion_fwd_packed",
            "mmr_producer_proj_sizes", "mmr_producer_proj_fwd", "mmr_producer_proj_bwd",
-           "mmr_routing_stats_accumulate"]
+           "mmr_routing_stats_accumulate", "mmr_attention_fwd", "mmr_attention_bwd"]
 
 
 def lib_path() -> str:
@@ -140,6 +140,10 @@ def load():
     lib.mmr_producer_proj_bwd.restype = C.c_int
     lib.mmr_routing_stats_accumulate.argtypes = [c_fp, C.c_int, c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp]
     lib.mmr_routing_stats_accumulate.restype = C.c_int
+    lib.mmr_attention_fwd.argtypes = [C.c_int] * 4 + [c_fp] * 6
+    lib.mmr_attention_fwd.restype = C.c_int
+    lib.mmr_attention_bwd.argtypes = [C.c_int] * 4 + [c_fp] * 10
+    lib.mmr_attention_bwd.restype = C.c_int
     lib.mmr_debug_gemm.argtypes = [C.c_int] * 6 + [c_fp] * 5
     lib.mmr_debug_gemm.restype = C.c_int
     lib.mmr_bench_gemm.argtypes = [C.c_int] * 4 + [c_fp] * 5 + [C.c_int, C.POINTER(C.c_float), c_fp]

@@ -1093,7 +1093,8 @@ int mmr_abi_struct_sizes(size_t* out, int n) {
 }
 
 // 100: route fusion + routing + tails; 101: + loss tail (mmr_loss_fwd_bwd); 102: + standalone projector, packed-weight
-// forward, producer projections; 103: + mmr_capsule_routing_fwd_ex / _bwd_ex / mmr_routing_fwd_scratch_bytes (split routing path)
+// forward, producer projections; 103: + mmr_capsule_routing_fwd_ex / _bwd_ex / mmr_routing_fwd_scratch_bytes (split routing path),
+// mmr_attention_fwd / bwd (standalone attention core)
 int mmr_version(void) { return 103; }
 
 long long mmr_launch_count(void) { return g_launches.load(); }
@@ -1589,6 +1590,93 @@ int mmr_projector_bwd(const mmr_routing_params* params, const float* route_embs,
   proj_bias_grad_kernel<<<10, 256, 0, st>>>(dpc, B, *grads);
   LAUNCH_OK("b_proj");
   return MMR_OK;
+}
+
+// ---------------------------------------------------------------- standalone attention core ---
+// The path's per-patient attention kernels for ONE (query, key) pair of streams: the consumers outside MULTModel
+// (the Partial/ attention-fusion variants, multimodalrouting_b200/partial_fusion.py) reach them through these two calls.
+}  // extern "C"
+
+template <class CT>
+static int attention_core(bool bwd, int B, int Tq, int Tk, const void* q, const void* kv, const float* kmask, void* o, float* ml,
+                          const void* d_o, void* dq, void* dkv, float* dvec, cudaStream_t st) {
+  AttnArgs a; memset(&a, 0, sizeof(a));
+  a.q = single_seg(B * Tq, Tq); a.kv = single_seg(B * Tk, Tk);
+  a.kmask[0] = kmask;
+  a.qb = q; a.kvbuf = kv; a.ldkv = 2 * D; a.col0 = 0; a.o = o; a.ml = ml;
+  a.d_o = d_o; a.dq = dq; a.dkv = dkv; a.dvec = dvec;
+  const bool mma = std::is_same<CT, bf16>::value;
+  if (!bwd) {
+    ProfScope ps(PC_ATTN_FWD, st);
+    if (mma) {
+      CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
+      CUDA_OK(cudaFuncSetAttribute(amma::attn_fwd_single_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::fwd_smem<AHG>()));
+      dim3 grid(amma::Cfg<AHG>::NHG * ((Tq + amma::RC - 1) / amma::RC), B, 1);
+      if (Tk <= amma::RC) amma::attn_fwd_single_kernel<AHG><<<grid, amma::Cfg<AHG>::THREADS, amma::fwd_smem<AHG>(), st>>>(a);
+      else launch_k(amma::attn_fwd_kernel<AHG>, grid, dim3(amma::Cfg<AHG>::THREADS), amma::fwd_smem<AHG>(), st, a);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+      dim3 grid((H * Tq + ATT_THREADS - 1) / ATT_THREADS, B, 1);
+      attn_fwd_kernel<CT><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+    }
+    LAUNCH_OK("attention_fwd");
+    return MMR_OK;
+  }
+  ProfScope ps(PC_ATTN_BWD, st);
+  if (mma) {
+    CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dq_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
+    CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_fused_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_fused_smem<AHG>()));
+    CUDA_OK(cudaFuncSetAttribute(amma::attn_bwd_dkv_kernel<AHG>, cudaFuncAttributeMaxDynamicSharedMemorySize, amma::bwd_smem<AHG>()));
+    if (Tq <= amma::RC && Tk <= amma::RC) {
+      launch_k(amma::attn_bwd_fused_kernel<AHG>, dim3(amma::Cfg<AHG>::NHG, B, 1), dim3(amma::Cfg<AHG>::THREADS),
+               amma::bwd_fused_smem<AHG>(), st, a);
+    } else {
+      dim3 g1(amma::Cfg<AHG>::NHG * ((Tq + amma::RC - 1) / amma::RC), B, 1);
+      dim3 g2(amma::Cfg<AHG>::NHG * ((Tk + amma::RC - 1) / amma::RC), B, 1);
+      amma::attn_bwd_dq_kernel<AHG><<<g1, amma::Cfg<AHG>::THREADS, amma::bwd_smem<AHG>(), st>>>(a);
+      amma::attn_bwd_dkv_kernel<AHG><<<g2, amma::Cfg<AHG>::THREADS, amma::bwd_smem<AHG>(), st>>>(a);
+    }
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    dim3 g1((H * Tq + ATT_THREADS - 1) / ATT_THREADS, B, 1);
+    dim3 g2((H * Tk + ATT_THREADS - 1) / ATT_THREADS, B, 1);
+    attn_bwd_dq_kernel<CT><<<g1, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+    attn_bwd_dkv_kernel<CT><<<g2, ATT_THREADS, ATT_SMEM_BYTES, st>>>(a);
+  }
+  LAUNCH_OK("attention_bwd");
+  return MMR_OK;
+}
+
+extern "C" {
+
+static int check_attention(int dtype, int B, int Tq, int Tk, const void* q, const void* kv) {
+  if (dtype != MMR_DTYPE_F32 && dtype != MMR_DTYPE_BF16) return fail(MMR_ERR_INVALID_ARG, "attention: dtype must be F32 or BF16");
+  if (B <= 0 || Tq <= 0 || Tk <= 0) return fail(MMR_ERR_INVALID_ARG, "attention: B, Tq, Tk must be positive");
+  if (Tq > 4096 || Tk > 4096) return fail(MMR_ERR_UNSUPPORTED, "attention: sequences longer than 4096 tokens");
+  if (!q || !kv) return fail(MMR_ERR_INVALID_ARG, "attention: null operand");
+  return MMR_OK;
+}
+
+int mmr_attention_fwd(int dtype, int B, int Tq, int Tk, const void* q, const void* kv, const float* kmask, void* o, float* ml,
+                      void* stream) {
+  int rc = check_attention(dtype, B, Tq, Tk, q, kv);
+  if (rc) return rc;
+  if (!o || !ml) return fail(MMR_ERR_INVALID_ARG, "attention: null output");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == MMR_DTYPE_BF16 ? attention_core<bf16>(false, B, Tq, Tk, q, kv, kmask, o, ml, nullptr, nullptr, nullptr, nullptr, st)
+                                 : attention_core<float>(false, B, Tq, Tk, q, kv, kmask, o, ml, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int mmr_attention_bwd(int dtype, int B, int Tq, int Tk, const void* q, const void* kv, const float* kmask, const void* o,
+                      const float* ml, const void* d_o, void* dq, void* dkv, float* dvec, void* stream) {
+  int rc = check_attention(dtype, B, Tq, Tk, q, kv);
+  if (rc) return rc;
+  if (!o || !ml || !d_o || !dq || !dkv || !dvec) return fail(MMR_ERR_INVALID_ARG, "attention: null pointer argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == MMR_DTYPE_BF16
+             ? attention_core<bf16>(true, B, Tq, Tk, q, kv, kmask, const_cast<void*>(o), const_cast<float*>(ml), d_o, dq, dkv, dvec, st)
+             : attention_core<float>(true, B, Tq, Tk, q, kv, kmask, const_cast<void*>(o), const_cast<float*>(ml), d_o, dq, dkv, dvec, st);
 }
 
 int mmr_routing_stats_accumulate(const void* rc_raw, int rc_dtype, const float* rc_report, const float* prim_acts, int B,

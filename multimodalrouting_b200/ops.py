@@ -640,6 +640,69 @@ class RoutingFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# standalone attention core (csrc/api.cu: mmr_attention_fwd / bwd) -- used by partial_fusion.py
+@torch.library.custom_op("mmr_b200::attention_fwd", mutates_args=())
+def attention_fwd(q: Tensor, kv: Tensor, kmask: Optional[Tensor], B: int, Tq: int, Tk: int, dtype: int) -> Tuple[Tensor, Tensor]:
+    """q [B*Tq,256] (pre-scaled), kv [B*Tk,512] = K | V, kmask fp32 [B,Tk] | None -> (o [B*Tq,256], ml [B*Tq,8,2])."""
+    _require_cuda(q, kv)
+    lib = _lib.load()
+    o = torch.empty_like(q)
+    ml = torch.empty(B * Tq, 8, 2, dtype=torch.float32, device=q.device)
+    rc = lib.mmr_attention_fwd(dtype, B, Tq, Tk, _ptr(q), _ptr(kv), _ptr(kmask), _ptr(o), _ptr(ml), _stream())
+    _lib.check(rc, "mmr_attention_fwd")
+    return o, ml
+
+
+@attention_fwd.register_fake
+def _(q, kv, kmask, B, Tq, Tk, dtype):
+    return torch.empty_like(q), q.new_empty(B * Tq, 8, 2, dtype=torch.float32)
+
+
+@torch.library.custom_op("mmr_b200::attention_bwd", mutates_args=())
+def attention_bwd(q: Tensor, kv: Tensor, kmask: Optional[Tensor], o: Tensor, ml: Tensor, d_o: Tensor, B: int, Tq: int,
+                  Tk: int, dtype: int) -> Tuple[Tensor, Tensor]:
+    lib = _lib.load()
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    dvec = torch.empty(B * Tq, 8, dtype=torch.float32, device=q.device)
+    rc = lib.mmr_attention_bwd(dtype, B, Tq, Tk, _ptr(q), _ptr(kv), _ptr(kmask), _ptr(o), _ptr(ml), _ptr(d_o), _ptr(dq),
+                               _ptr(dkv), _ptr(dvec), _stream())
+    _lib.check(rc, "mmr_attention_bwd")
+    return dq, dkv
+
+
+@attention_bwd.register_fake
+def _(q, kv, kmask, o, ml, d_o, B, Tq, Tk, dtype):
+    return torch.empty_like(q), torch.empty_like(kv)
+
+
+class AttentionFn(torch.autograd.Function):
+    """o [B,Tq,256] = per-head softmax(q k^T + key mask) v for q [B,Tq,256] (already scaled), kv [B,Tk,512] = K | V."""
+
+    @staticmethod
+    def forward(ctx, q, kv, kmask):
+        dtype = resolve_dtype()
+        ct = torch.bfloat16 if dtype == DTYPE_BF16 else torch.float32
+        B, Tq, _ = q.shape
+        Tk = kv.shape[1]
+        qc = q.detach().to(ct).reshape(B * Tq, 256).contiguous()
+        kvc = kv.detach().to(ct).reshape(B * Tk, 512).contiguous()
+        km = _f32c(kmask.detach()) if kmask is not None else None
+        o, ml = attention_fwd(qc, kvc, km, B, Tq, Tk, dtype)
+        ctx.save_for_backward(qc, kvc, o, ml, *([km] if km is not None else []))
+        ctx.cfg = (B, Tq, Tk, dtype, q.dtype, kv.dtype)
+        return o.view(B, Tq, 256)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        B, Tq, Tk, dtype, qdt, kvdt = ctx.cfg
+        sv = ctx.saved_tensors
+        qc, kvc, o, ml = sv[:4]
+        km = sv[4] if len(sv) > 4 else None
+        dq, dkv = attention_bwd(qc, kvc, km, o, ml, d_o.to(o.dtype).reshape(B * Tq, 256).contiguous(), B, Tq, Tk, dtype)
+        return dq.view(B, Tq, 256).to(qdt), dkv.view(B, Tk, 512).to(kvdt), None
+
+
+# --------------------------------------------------------------------------------------------
 # standalone RoutePrimaryProjector.forward (routing_and_heads.py:111-121)
 @torch.library.custom_op("mmr_b200::projector_fwd", mutates_args=())
 def projector_fwd(embs: Tensor, proj_w: Sequence[Tensor], proj_b: Sequence[Tensor]) -> Tuple[Tensor, Tensor]:

@@ -133,3 +133,55 @@ def loss_fn(logits: torch.Tensor, y: torch.Tensor, variant: str) -> torch.Tensor
         dl = (logits[:, 1] - logits[:, 0]).unsqueeze(1)
         return F.binary_cross_entropy_with_logits(dl.float(), y[:, :1].float())
     return F.binary_cross_entropy_with_logits(logits.float(), y.float())
+
+
+# ---- attention-fusion modules of the Partial/ variant (partial_fusion.py): seeded parameters -----------------------
+def make_fusion_state(kind: str, seed: int, d: int = 256, ff_mult: int = 4):
+    """state_dict (CPU fp32) for CrossAttentionFusion (kind = "cross") or TriTokenAttentionFusion (kind = "tri") with the
+    reference's key names; weights ~ N(0, 1/fan_in), non-trivial biases and LayerNorm affines."""
+    g = torch.Generator().manual_seed(seed)
+
+    def w(o, i):
+        return torch.randn(o, i, generator=g) / (i ** 0.5)
+
+    def b(n, s=0.1):
+        return s * torch.randn(n, generator=g)
+
+    def ln(pfx, sd):
+        sd[pfx + ".weight"] = 1.0 + 0.2 * torch.randn(d, generator=g)
+        sd[pfx + ".bias"] = b(d)
+
+    sd = {}
+    if kind == "tri":
+        sd["q"] = 0.5 * torch.randn(1, 1, d, generator=g)
+    sd["attn.in_proj_weight"] = w(3 * d, d)
+    sd["attn.in_proj_bias"] = b(3 * d)
+    sd["attn.out_proj.weight"] = w(d, d)
+    sd["attn.out_proj.bias"] = b(d)
+    if kind == "cross":
+        ln("ln1", sd)
+        sd["ff.0.weight"] = w(ff_mult * d, d); sd["ff.0.bias"] = b(ff_mult * d)
+        sd["ff.2.weight"] = w(d, ff_mult * d); sd["ff.2.bias"] = b(d)
+        ln("ln2", sd)
+    else:
+        ln("ln_kv", sd)
+    ln("out.0", sd)
+    sd["out.1.weight"] = w(d, d)
+    sd["out.1.bias"] = b(d)
+    return sd
+
+
+def make_fusion_inputs(B: int, TL: int, TN: int, TI: int, seed: int, d: int = 256):
+    """Three encoder sequences with padding masks: ragged valid lengths, one sample without any N token, one without I."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, T in (("L", TL), ("N", TN), ("I", TI)):
+        out[name] = torch.randn(B, T, d, generator=g)
+        n = torch.randint(1, T + 1, (B,), generator=g)
+        out["m" + name] = (torch.arange(T)[None, :] < n[:, None]).float()
+    if B > 1:
+        out["mN"][1] = 0.0
+    if B > 2:
+        out["mI"][2] = 0.0
+    return out
+

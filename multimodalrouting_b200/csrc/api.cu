@@ -426,6 +426,7 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       a.q = Q; a.kv = P.kv;
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = ob(l); a.ml = ml(l);
+      bool pad_done = false;
       {
         ProfScope ps(PC_ATTN_FWD, st);
         if (tc_attention<CT>()) {
@@ -435,9 +436,10 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
           dim3 grid(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
           int maxTk = 0;
           for (int d = 0; d < NDIR; ++d) maxTk = maxTk > P.kv.T[d] ? maxTk : P.kv.T[d];
-          if (maxTk <= amma::RC && !getenv("MMR_ATTN_FWD_GENERAL"))
+          if (maxTk <= amma::RC && !getenv("MMR_ATTN_FWD_GENERAL")) {
             amma::attn_fwd_single_kernel<AHG><<<grid, amma::Cfg<AHG>::THREADS, amma::fwd_smem<AHG>(), st>>>(a);
-          else
+            pad_done = true;        // the kernel clears rows [nv, pad256(nv)) of its output itself
+          } else
             launch_k(amma::attn_fwd_kernel<AHG>, grid, dim3(amma::Cfg<AHG>::THREADS), amma::fwd_smem<AHG>(), st, a);
         } else {
           dim3 grid((H * maxTq + ATT_THREADS - 1) / ATT_THREADS, B, NDIR);
@@ -445,8 +447,10 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
         }
       }
       LAUNCH_OK("attn_fwd");
-      rc = zero_pad(Q, ob(l), (size_t)D * sizeof(CT), st);
-      if (rc) return rc;
+      if (!pad_done) {
+        rc = zero_pad(Q, ob(l), (size_t)D * sizeof(CT), st);
+        if (rc) return rc;
+      }
     }
     {  // out projection (+bias); the residual add + mask is fused into the LN1 kernel below
       GemmProblem g = q_problem(ob(l), D, packed + P.o_wo, D, D, D, D, l);
@@ -768,6 +772,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       for (int d = 0; d < NDIR; ++d) a.kmask[d] = kmask[d];
       a.qb = qb(l); a.kvbuf = kv; a.ldkv = ldkv; a.col0 = l * 2 * D; a.o = const_cast<CT*>(ob(l));
       a.ml = const_cast<float*>(ml(l)); a.d_o = dO; a.dq = dQ; a.dkv = dKV; a.dvec = dvec;
+      bool pad_done = false;
       {
         ProfScope ps(PC_ATTN_BWD, st);
         if (mma_attention<CT>()) {
@@ -775,6 +780,7 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
             // one chunk per sequence: fused dQ + dK/dV kernel (operands staged once, no O / D round trip)
             launch_k(amma::attn_bwd_fused_kernel<AHG>, dim3(amma::Cfg<AHG>::NHG, B, NDIR), dim3(amma::Cfg<AHG>::THREADS),
                      amma::bwd_fused_smem<AHG>(), st, a);
+            pad_done = true;        // dQ's pad rows are cleared by the kernel
           } else {
           dim3 g1(amma::Cfg<AHG>::NHG * ((maxTq + amma::RC - 1) / amma::RC), B, NDIR);
           dim3 g2(amma::Cfg<AHG>::NHG * ((maxTk + amma::RC - 1) / amma::RC), B, NDIR);
@@ -790,8 +796,10 @@ static int fusion_bwd(const Plan& P, const void* const* prm, const float* const 
       }
       LAUNCH_OK("attn_bwd_dq");
       LAUNCH_OK("attn_bwd_dkv");
-      rc = zero_pad(Q, dQ, (size_t)D * sizeof(CT), st);
-      if (rc) return rc;
+      if (!pad_done) {
+        rc = zero_pad(Q, dQ, (size_t)D * sizeof(CT), st);
+        if (rc) return rc;
+      }
     }
     rc = main_to_side(E_DQ);
     if (rc) return rc;

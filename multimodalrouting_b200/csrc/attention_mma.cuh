@@ -71,6 +71,19 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* src, size_t ld, int
   }
 }
 
+// Rows [nv, pad256(nv)) of a packed q-space tensor must read as zeros (the weight-gradient GEMMs reduce over them).  The
+// CTAs of patient 0 clear them for their own column slice of the attention output / dQ, which replaces a separate
+// zero_pad_rows launch after every attention launch (8 per step).  No-op for dense row spaces without tile padding.
+template <int HG>
+__device__ __forceinline__ void zero_pad_slice(const Segs& q, int d, bf16* slice, int ld) {
+  constexpr int THREADS = Cfg<HG>::THREADS, CPR = Cfg<HG>::CPR;
+  const int r0 = seg_rows(q, d), n = seg_rows_z(q, d) - r0;
+  for (int idx = threadIdx.x; idx < n * CPR; idx += THREADS) {
+    const int r = r0 + idx / CPR, c = (idx % CPR) * 8;
+    *reinterpret_cast<uint4*>(slice + ((size_t)q.row0[d] + r) * ld + c) = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // A fragment (16 rows x 16 k) of a row-major smem tile at (row0, col0)
 template <int LDS>
 __device__ __forceinline__ void frag_a(const bf16* s, int row0, int col0, int lane, uint32_t (&r)[4]) {
@@ -285,6 +298,7 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 768 / Cfg<HG>::THREADS) attn
   seg_patient(a.q, d, b, qs_, Tq);     // this patient's (packed) query rows
   const int nk = a.kv.T[d];
   const int q0 = qc * RC;
+  if (b == 0 && qc == 0) zero_pad_slice<HG>(a.q, d, reinterpret_cast<bf16*>(a.o) + hg * COLS, D);
   if (q0 >= Tq) return;
   const int nq = min(RC, Tq - q0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -667,6 +681,7 @@ __global__ void __launch_bounds__(Cfg<HG>::THREADS, 640 / Cfg<HG>::THREADS) attn
   const int d = blockIdx.z, b = blockIdx.y, hg = blockIdx.x;
   int qs_, nq;
   seg_patient(a.q, d, b, qs_, nq);     // this patient's (packed) query rows
+  if (b == 0) zero_pad_slice<HG>(a.q, d, reinterpret_cast<bf16*>(a.dq) + hg * COLS, D);
   const int nk = a.kv.T[d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = warp % HG, half = warp / HG;

@@ -354,10 +354,16 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolArgs a) {
     mk = a.maskq + a.q.row0[d] + start;
   }
   float acc = 0.f, cnt = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float m = mk ? mk[t] : 1.f;
-    acc += src[(size_t)t * D + c] * m;
-    cnt += m;
+  for (int t0 = 0; t0 < T; t0 += 8) {      // eight tokens' loads in flight per thread; same summation order as a plain loop
+    float v[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = t0 + j < T;
+      m[j] = in ? (mk ? mk[t0 + j] : 1.f) : 0.f;
+      v[j] = in ? src[(size_t)(t0 + j) * D + c] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc += v[j] * m[j]; cnt += m[j]; }
   }
   cnt = fmaxf(cnt, 1.0f);
   const float z = acc / cnt;
@@ -389,7 +395,7 @@ struct EmbedBwdArgs {
 };
 
 template <class CT>
-__global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) embed_bwd_kernel(EmbedBwdArgs a) {
   constexpr int RPB = 64;
   __shared__ float red[8][2][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -407,17 +413,35 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdArgs a) {
     const int local = r - a.mod.row0[m];
     if (local >= a.mod.rows[m]) continue;
     const int b = local / T;
+    // every load that does not depend on another load of the row is requested here, before the first use (the keep-mask,
+    // the token -> query-row map and the pooled-route gradient used to head three separate dependent round trips)
     const float mval = a.mask[m] ? a.mask[m][local] : 1.f;
+    const int qrl = a.tokrow[m][local];
     Row8 xh = row_load<CT>(reinterpret_cast<const CT*>(a.xh) + (size_t)r * D, lane);
     const float rstd = a.rstd_e[r];
     Row8 k0 = row_load<float>(a.dxh + ((size_t)a.kv.row0[kd[0]] + local) * D, lane);
     Row8 k1 = row_load<float>(a.dxh + ((size_t)a.kv.row0[kd[1]] + local) * D, lane);
+    Row8 dz;
+    float cntb = 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dz.v[i] = 0.f;
+    if (a.dz_uni[m]) {
+      dz = row_load<float>(a.dz_uni[m] + (size_t)b * D, lane);
+      cntb = a.cnt[m * a.B + b];
+    }
+    Row8 qa, qb;
+    if (qrl >= 0) {
+      qa = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m] + qrl) * D, lane);
+      qb = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m + 1] + qrl) * D, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { qa.v[i] = 0.f; qb.v[i] = 0.f; }
+    }
     float gt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) gt[i] = k0.v[i] + k1.v[i];
     if (mval != 0.f && a.dz_uni[m]) {
-      Row8 dz = row_load<float>(a.dz_uni[m] + (size_t)b * D, lane);
-      const float sc = mval * mval / a.cnt[m * a.B + b];
+      const float sc = mval * mval / cntb;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float dy = dz.v[i] * sc;
@@ -431,15 +455,6 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedBwdArgs a) {
     for (int i = 0; i < 8; ++i) { s1 += gt[i]; s2 += gt[i] * xh.v[i]; }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
-    const int qrl = a.tokrow[m][local];
-    Row8 qa, qb;
-    if (qrl >= 0) {
-      qa = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m] + qrl) * D, lane);
-      qb = row_load<float>(a.g0 + ((size_t)a.q.row0[2 * m + 1] + qrl) * D, lane);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { qa.v[i] = 0.f; qb.v[i] = 0.f; }
-    }
     Row8 o;
 #pragma unroll
     for (int i = 0; i < 8; ++i)

@@ -333,8 +333,13 @@ static int fusion_fwd(const Plan& P, const void* const* prm, const float* const 
       a.mask[m] = mask[m]; a.T[m] = P.T[m];
       a.poff[m] = plan + P.p_poff[m]; a.tokrow[m] = plan + P.p_tokrow[m]; a.rowpat[m] = plan + P.p_rowpat[m];
     }
-    rowplan_kernel<<<NMOD, 1024, 0, st>>>(a);
-    LAUNCH_OK("rowplan");
+    const dim3 gp((B + 31) / 32, NMOD);
+    rowplan_count_kernel<<<gp, 1024, 0, st>>>(a);
+    LAUNCH_OK("rowplan_count");
+    rowplan_scan_kernel<<<NMOD, 1024, 0, st>>>(a);
+    LAUNCH_OK("rowplan_scan");
+    rowplan_fill_kernel<<<gp, 1024, 0, st>>>(a);
+    LAUNCH_OK("rowplan_fill");
   }
 
   float* fp = reinterpret_cast<float*>(scratch + P.f_p);

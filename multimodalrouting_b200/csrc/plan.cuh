@@ -58,7 +58,7 @@ struct Plan {
   size_t s_epair;                         // fp32 [3,B,256] pair embeddings eLN,eLI,eNI
   size_t s_routes;                        // fp32 [10,B,256] copy of the outputs (pair/trimodal bwd)
   size_t s_cnt;                           // fp32 [3,B] valid-token counts (clamped >= 1)
-  // row plan of the packed query space (int32; written by rowplan_kernel in the forward, read by every q-space kernel of
+  // row plan of the packed query space (int32; written by the rowplan_* kernels in the forward, read by every q-space kernel of
   // both passes): nv[8] | per query modality m: poff[B+1], tokrow[B*T_m] (token -> row inside the segment, -1 = padded),
   // rowpat[B*T_m] (row -> patient)
   size_t s_plan;

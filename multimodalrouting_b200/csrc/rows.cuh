@@ -18,9 +18,9 @@ __host__ __device__ inline int pair_of_dir(int d) { const int t[6] = {0, 1, 0, 2
 __host__ __device__ inline int half_of_dir(int d) { const int t[6] = {0, 0, 1, 0, 1, 1}; return t[d]; }
 
 // -------------------------------------------------------------------------------------------
-// Row plan of the packed query space (see Segs in mmr_common.cuh).  One block per modality: counts the valid tokens of every
-// patient (mask != 0), scans the counts into patient offsets and fills the token <-> row maps.  pack = 0 writes the dense
-// identity plan (row = b * T + t for every token).
+// Row plan of the packed query space (see Segs in mmr_common.cuh): counts the valid tokens of every patient (mask != 0), scans
+// the counts into patient offsets and fills the token <-> row maps.  pack = 0 writes the dense identity plan
+// (row = b * T + t for every token).
 struct RowPlanArgs {
   const float* mask[NMOD];   // [B, T] or null
   int T[NMOD];
@@ -29,27 +29,33 @@ struct RowPlanArgs {
   int* poff[NMOD]; int* tokrow[NMOD]; int* rowpat[NMOD];
 };
 
-__global__ void __launch_bounds__(1024) rowplan_kernel(RowPlanArgs a) {
+// Three launches (round 2): counting and the map fill get one warp PER PATIENT across the grid, only the scan of the B counts
+// is one block per modality.  The single-block form walked 16 patients per warp twice, each behind a dependent load of its
+// mask row: 30 us at B = 512 at the head of every forward call (ncu: 3 CTAs, 8 long-scoreboard stall cycles per instruction).
+// grid (ceil(B / 32), NMOD), 1024 threads
+__global__ void __launch_bounds__(1024) rowplan_count_kernel(RowPlanArgs a) {
+  const int m = blockIdx.y, T = a.T[m], lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 32 + (threadIdx.x >> 5);
+  if (b >= a.B) return;
+  const float* mk = a.mask[m];
+  int c = T;
+  if (a.pack && mk != nullptr) {
+    c = 0;
+    for (int t = lane; t < T; t += 32) c += mk[(size_t)b * T + t] != 0.f ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) a.poff[m][b + 1] = c;
+}
+
+// grid NMOD, 1024 threads: inclusive scan of poff[1..B] in chunks of 1024, nv
+__global__ void __launch_bounds__(1024) rowplan_scan_kernel(RowPlanArgs a) {
   __shared__ int part[1024];
   __shared__ int base_s;
-  const int m = blockIdx.x, T = a.T[m], B = a.B, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* mk = a.mask[m];
+  const int m = blockIdx.x, B = a.B, tid = threadIdx.x;
   int* poff = a.poff[m];
-  const bool dense = !a.pack || mk == nullptr;
-  // 1. per-patient counts (a warp per patient) into poff[b + 1]
-  for (int b = warp; b < B; b += 32) {
-    int c = 0;
-    if (dense) c = T;
-    else {
-      for (int t = lane; t < T; t += 32) c += mk[(size_t)b * T + t] != 0.f ? 1 : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if (lane == 0) poff[b + 1] = c;
-  }
   if (tid == 0) { poff[0] = 0; base_s = 0; }
   __syncthreads();
-  // 2. inclusive scan of poff[1..B] in chunks of 1024
   for (int b0 = 0; b0 < B; b0 += 1024) {
     const int b = b0 + tid;
     int v = b < B ? poff[b + 1] : 0;
@@ -67,18 +73,24 @@ __global__ void __launch_bounds__(1024) rowplan_kernel(RowPlanArgs a) {
     __syncthreads();
   }
   if (tid == 0) { a.nv[2 * m] = base_s; a.nv[2 * m + 1] = base_s; if (m == 0) { a.nv[6] = 0; a.nv[7] = 0; } }
-  // 3. token <-> row maps (a warp per patient, tokens in order)
-  for (int b = warp; b < B; b += 32) {
-    int row = poff[b];
-    for (int t0 = 0; t0 < T; t0 += 32) {
-      const int t = t0 + lane;
-      const bool ok = t < T && (dense || mk[(size_t)b * T + t] != 0.f);
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      const int rank = __popc(bal & ((1u << lane) - 1u));
-      if (t < T) a.tokrow[m][(size_t)b * T + t] = ok ? row + rank : -1;
-      if (ok) a.rowpat[m][row + rank] = b;
-      row += __popc(bal);
-    }
+}
+
+// grid (ceil(B / 32), NMOD), 1024 threads: token <-> row maps (a warp per patient, tokens in order)
+__global__ void __launch_bounds__(1024) rowplan_fill_kernel(RowPlanArgs a) {
+  const int m = blockIdx.y, T = a.T[m], lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 32 + (threadIdx.x >> 5);
+  if (b >= a.B) return;
+  const float* mk = a.mask[m];
+  const bool dense = !a.pack || mk == nullptr;
+  int row = a.poff[m][b];
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool ok = t < T && (dense || mk[(size_t)b * T + t] != 0.f);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int rank = __popc(bal & ((1u << lane) - 1u));
+    if (t < T) a.tokrow[m][(size_t)b * T + t] = ok ? row + rank : -1;
+    if (ok) a.rowpat[m][row + rank] = b;
+    row += __popc(bal);
   }
 }
 

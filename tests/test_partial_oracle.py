@@ -61,3 +61,24 @@ def test_partial_oracle_matches_reference_golden(name):
     c = GOLD[name]["case"]
     out, ins, sd = run_oracle(c)
     compare(name, out, {k: v.grad for k, v in ins.items()}, {k: v.grad for k, v in sd.items()}, 2e-5, 2e-4)
+
+
+def test_partial_fusion_modules_surface_and_loud_cpu_failure():
+    """CPU: the drop-in modules expose exactly the reference's parameter names (the goldens' d_param keys come from the
+    unmodified reference modules) and refuse to run without CUDA instead of falling back."""
+    from multimodalrouting_b200 import partial_fusion as pf
+    cross, tri = pf.CrossAttentionFusion(256, 8, 0.0, "mean"), pf.TriTokenAttentionFusion(256, 8, 0.0)
+    assert sorted(dict(cross.named_parameters())) == sorted(GOLD["cross_mean"]["d_param"])
+    assert sorted(dict(tri.named_parameters())) == sorted(GOLD["tri"]["d_param"])
+    cross.load_state_dict(synth.make_fusion_state("cross", 1), strict=True)
+    tri.load_state_dict(synth.make_fusion_state("tri", 2), strict=True)
+    inp = synth.make_fusion_inputs(2, 5, 4, 3, 9)
+    with pytest.raises(RuntimeError):
+        cross(inp["L"], inp["mL"], inp["N"], inp["mN"])
+    with pytest.raises(RuntimeError):
+        tri(inp["L"], inp["mL"], inp["N"], inp["mN"], inp["I"], inp["mI"])
+    with pytest.raises(NotImplementedError):
+        pf.CrossAttentionFusion(128, 4)(inp["L"][..., :128], inp["mL"], inp["N"][..., :128], inp["mN"])
+    f = pf.build_fusions(256, device="cpu")
+    assert sorted(f) == ["IL", "IN", "LI", "LN", "LNI", "NI", "NL"]
+

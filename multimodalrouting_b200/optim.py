@@ -39,6 +39,7 @@ class EMA:
         self.model_list = list(model_list)
         self.shadow = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in self.model_list]
         self.backup = None
+        self._rebinds = 0          # bumped whenever a shadow entry is replaced by a new tensor (FusedAdamW caches their addresses)
 
     def shadow_by_storage(self) -> Dict[int, Tensor]:
         """live tensor data_ptr -> its shadow tensor (how FusedAdamW finds the EMA slot of a parameter)."""
@@ -58,6 +59,7 @@ class EMA:
             for k, v in m.state_dict().items():
                 if k not in sh:
                     sh[k] = v.detach().clone()
+                    self._rebinds += 1
                     continue
                 if not torch.is_floating_point(v):
                     sh[k].copy_(v)
@@ -66,6 +68,7 @@ class EMA:
                     continue
                 if sh[k].device != v.device or sh[k].dtype != v.dtype:
                     sh[k] = sh[k].to(device=v.device, dtype=v.dtype)
+                    self._rebinds += 1
                 _require_cuda(v)
                 if v.dtype != torch.float32 or not v.is_contiguous() or not sh[k].is_contiguous():
                     raise ValueError("EMA.update expects contiguous fp32 tensors")
@@ -107,7 +110,7 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError(f"Invalid betas: {betas}")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._dev = None           # mmr_opt_state, device resident
-        self._ema_map = (None, None)
+        self._ema_map = (None, None, -1)
         self._tables = {}          # group index -> (pointer key, ctypes table): rebuilt only when a pointer moves
 
     # ---- device-side scalars -------------------------------------------------------------------------
@@ -147,8 +150,8 @@ class FusedAdamW(torch.optim.Optimizer):
         betas = self.param_groups[0]["betas"]
         shadow = None
         if ema is not None:
-            if self._ema_map[0] is not ema:
-                self._ema_map = (ema, ema.shadow_by_storage())
+            if self._ema_map[0] is not ema or self._ema_map[2] != ema._rebinds:     # a rebound shadow tensor invalidates the map
+                self._ema_map = (ema, ema.shadow_by_storage(), ema._rebinds)
             shadow = self._ema_map[1]
         tables: List = []
         done = set()

@@ -101,7 +101,13 @@ class FusedAdamW(torch.optim.Optimizer):
     = clip_grad_norm_(params, 0.3); if grads finite: AdamW step; ema.update() -- in one norm pass, one scalar kernel
     and one update pass over (param, grad, exp_avg, exp_avg_sq, shadow).  The total norm, the clip coefficient, the
     skip flag and the step count live on the device (`total_norm`, `skipped`, `step_count` return 0-dim views), so
-    the step neither syncs the host nor breaks CUDA-graph capture."""
+    the step neither syncs the host nor breaks CUDA-graph capture.
+
+    Two differences from the reference's sequence (main.py:3143-3165), both invisible to the parameters and the EMA of the
+    trained tensors: the clip coefficient is applied inside the update, so `p.grad` still holds the UNCLIPPED gradient after
+    `step()` (read `clip_coef` / `total_norm` instead of re-measuring); and on a skipped (non-finite) step the EMA entries
+    the optimizer does not own -- buffers, frozen tensors -- still take one averaging step towards their (unchanged) values,
+    where the reference `continue`s before `ema.update()`."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0:

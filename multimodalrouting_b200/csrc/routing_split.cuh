@@ -679,7 +679,7 @@ __global__ void rs_fold_copies_kernel(const float* dGc, int K, float* dG, float*
 // ---- d pose = du . w^T + final aggregation; projector data / bias gradient: grid (ceil(B / 16), 10), 256 threads --------
 __global__ void __launch_bounds__(256) rs_dpose_kernel(RoutingArgs a, RsScratch s) {
   __shared__ float part[8][16][33];
-  __shared__ float dps[16][36];
+  __shared__ float dps[16][44];     // columns 33..39 stay zero (k padding of the tf32 tile); pitch 44: conflict-free A fragments
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int B = a.d.B, KD = a.d.K * 64, r = blockIdx.y, b0 = blockIdx.x * 16;
   const bool vl = b0 + g < B, vh = b0 + g + 8 < B;
@@ -708,6 +708,7 @@ __global__ void __launch_bounds__(256) rs_dpose_kernel(RoutingArgs a, RsScratch 
     part[warp][g][n * 8 + 2 * t] = acc[n][0]; part[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
     part[warp][g + 8][n * 8 + 2 * t] = acc[n][2]; part[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
   }
+  if (tid < 16 * 7) dps[tid / 7][33 + tid % 7] = 0.f;
   // operands of the epilogue that do not depend on the contraction: issued before the barrier
   float ex[3], rmv[3];
 #pragma unroll
@@ -752,21 +753,33 @@ __global__ void __launch_bounds__(256) rs_dpose_kernel(RoutingArgs a, RsScratch 
     atomicAdd(a.d_proj_b[r] + tid, sum);
   }
   if (!a.d_route_embs) return;
-  // d e[b][r][c] = sum_j dpc[b][r][j] W_r[j][c]; thread = column, the weights are shared by the 16 patients
-  float o[16];
+  // d e[b][r][c] = sum_j dpc[b][r][j] W_r[j][c]  as [16 patients x 40 (33, zero padded)] . [40 x 256] on mma.sync m16n8k8 tf32
+  // (the gradients keep their exponent range in tf32; the CUDA-core form was 16 x 33 FMAs per thread and, at K = 2 / B = 8192,
+  // the largest item of the routing backward).  Warp w owns columns [32 w, 32 w + 32).
+  {
+    const float* W = a.p.proj_w[r];
+    float c[4][4];
 #pragma unroll
-  for (int p = 0; p < 16; ++p) o[p] = 0.f;
-  const float* w = a.p.proj_w[r] + tid;
-#pragma unroll 11
-  for (int j = 0; j < 33; ++j) {
-    const float w0 = __ldg(w + (size_t)j * 256);
+    for (int n = 0; n < 4; ++n) c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f;
 #pragma unroll
-    for (int p = 0; p < 16; ++p) o[p] = fmaf(dps[p][j], w0, o[p]);
-  }
+    for (int ks = 0; ks < 5; ++ks) {
+      const int j0 = 8 * ks + t, j1 = j0 + 4;
+      const uint32_t a0 = to_tf32(dps[g][j0]), a1 = to_tf32(dps[g + 8][j0]);
+      const uint32_t a2 = to_tf32(dps[g][j1]), a3 = to_tf32(dps[g + 8][j1]);
 #pragma unroll
-  for (int p = 0; p < 16; ++p) {
-    if (b0 + p >= B) break;
-    a.d_route_embs[(size_t)r * a.d.emb_route_stride + (size_t)(b0 + p) * a.d.emb_batch_stride + tid] = o[p];
+      for (int n = 0; n < 4; ++n) {
+        const int col = 32 * warp + 8 * n + g;
+        const uint32_t b0 = j0 < 33 ? to_tf32(__ldg(W + (size_t)j0 * 256 + col)) : 0u;
+        const uint32_t b1 = j1 < 33 ? to_tf32(__ldg(W + (size_t)j1 * 256 + col)) : 0u;
+        mma_tf32(c[n], a0, a1, a2, a3, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int col = 32 * warp + 8 * n + 2 * t;
+      if (vl) *reinterpret_cast<float2*>(a.d_route_embs + (size_t)r * a.d.emb_route_stride + (size_t)(b0 + g) * a.d.emb_batch_stride + col) = make_float2(c[n][0], c[n][1]);
+      if (vh) *reinterpret_cast<float2*>(a.d_route_embs + (size_t)r * a.d.emb_route_stride + (size_t)(b0 + g + 8) * a.d.emb_batch_stride + col) = make_float2(c[n][2], c[n][3]);
+    }
   }
 }
 
